@@ -1,0 +1,145 @@
+/*
+ * tsim.h -- C ABI of the B200-native semantic-search hot path (libtsim.so).
+ *
+ * The reference (cr1m5onk1ng/text_similarity) is pure Python and has no FFI of its own;
+ * its boundary for this path is the Python class surface.  Each entry point below names
+ * the reference lines whose device work it replaces.  The Python mirror of that surface
+ * (text_similarity_b200/, re-exported under the reference's module paths in src/) binds
+ * these symbols with ctypes; INTEGRATION.md shows the stub a maintainer of the reference
+ * would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless it says host;
+ *   - the library never allocates or frees caller-visible memory: outputs and workspace
+ *     are caller-allocated (workspace size from the *_workspace_bytes functions);
+ *   - every call is asynchronous on the CUDA stream passed as `stream` (a cudaStream_t cast
+ *     to void*; NULL = legacy default stream); no hidden synchronisation;
+ *   - return value: TSIM_OK (0) or a negative TSIM_ERR_* code; tsim_last_error() returns a
+ *     thread-local human-readable message for the last failing call on this thread;
+ *   - there is no CPU fallback: an unsupported argument is an error.
+ */
+#ifndef TSIM_H_
+#define TSIM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSIM_ABI_VERSION 1
+
+/* element types */
+#define TSIM_F32 0
+#define TSIM_F16 1
+#define TSIM_BF16 2
+#define TSIM_E4M3 3 /* float8_e4m3fn */
+/* attention-mask element types */
+#define TSIM_I64 10
+#define TSIM_I32 11
+#define TSIM_U8 12 /* also torch.bool */
+
+/* status codes */
+#define TSIM_OK 0
+#define TSIM_ERR_INVALID_ARG (-1)
+#define TSIM_ERR_UNSUPPORTED (-2)
+#define TSIM_ERR_MISALIGNED (-3)
+#define TSIM_ERR_WORKSPACE (-4)
+#define TSIM_ERR_CUDA (-5)
+
+/* search modes */
+#define TSIM_MODE_AUTO 0   /* tensor-core path where supported, exact scan otherwise */
+#define TSIM_MODE_EXACT 1  /* force the float64 exact-scan path for every query */
+#define TSIM_MODE_TENSOR 2 /* require the tcgen05 path (error if unsupported) */
+
+int tsim_version(void);
+const char* tsim_last_error(void);
+
+/* ------------------------------------------------------------------------------------
+ * K1: fused masked mean-pool + L2-normalise + cast.
+ * Replaces AvgPoolingStrategy.forward, reference src/modules/modules.py:158-171 (same
+ * arithmetic inlined at src/models/sentence_encoder.py:35-38):
+ *     out[b,:] = sum_l tok[b,l,:] * mask[b,l] / max(sum_l mask[b,l], 1e-9)
+ * and, when `normalize` != 0, the x / max(||x||, 1e-8) that F.cosine_similarity
+ * (src/pipeline/search_pipeline.py:77) and cos_sim (src/utils/metrics.py:99-100) apply
+ * inside the similarity, hoisted here so the corpus is stored unit-norm.
+ *
+ *   tok   [B, L, D]  TSIM_F32 / F16 / BF16, strides in ELEMENTS (innermost contiguous)
+ *   mask  [B, L]     TSIM_I64 / I32 / U8 / F32, row stride in elements
+ *   out   row b is written at out + out_rows[b] * out_stride (out_rows may be NULL = b),
+ *         as TSIM_F32 / BF16 / E4M3.  E4M3 rows are stored times a per-row power of two
+ *         chosen so the largest element is near 2^7; cosine is scale free and the factor
+ *         is folded into out_inv_norm.
+ *   out_inv_norm [B] float, nullable: 1 / max(||row as stored||, 1e-8), indexed like out rows.
+ *   ws    tsim_pool_workspace_bytes(B, L, D) bytes.
+ * ---------------------------------------------------------------------------------- */
+size_t tsim_pool_workspace_bytes(int64_t B, int64_t L, int64_t D);
+int tsim_pool_norm(const void* tok, int tok_dt, const void* mask, int mask_dt,
+                   int64_t B, int64_t L, int64_t D,
+                   int64_t tok_stride_b, int64_t tok_stride_l, int64_t mask_stride_b,
+                   void* out, int out_dt, int64_t out_stride, const int64_t* out_rows,
+                   float* out_inv_norm, int normalize,
+                   void* ws, size_t ws_bytes, void* stream);
+
+/* 1 / max(||x[i,:]||, 1e-8) for every row of a stored matrix (the norm pass of
+ * F.cosine_similarity, search_pipeline.py:77, done once per corpus instead of once per
+ * query).  x [N, D] TSIM_F32/F16/BF16/E4M3, row stride in elements. */
+int tsim_row_inv_norm(const void* x, int dt, int64_t N, int64_t D, int64_t stride,
+                      float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K2 + K3: exact cosine top-k of Q queries against N corpus rows.
+ * Replaces the per-query loop of SentenceMiningPipeline._search, reference
+ * src/pipeline/search_pipeline.py:73-79 (F.cosine_similarity :77 + torch.topk :78), and
+ * cos_sim + argmax, src/utils/metrics.py:99-101,477.
+ *
+ *   q      [Q, D] q_dt, row stride q_stride elements      (any norm; not modified)
+ *   corpus [N, D] c_dt, row stride c_stride elements      (any norm; not modified)
+ *   corpus_inv_norm [N] float = tsim_row_inv_norm(corpus) (from K1 or the call above);
+ *          may be NULL, then it is computed into the workspace on every call.
+ *   k      results per query, 1 <= k <= 120.
+ *   idx_base           added to corpus row numbers in out_idx (contiguous row shards).
+ *   exclude_self_base  >= 0: corpus row (idx_base + j) == exclude_self_base + query number
+ *                      is skipped (all-pairs mining); -1: off.
+ *   out_score   [Q, k] float   cosine, best first
+ *   out_score64 [Q, k] double  nullable; the float64 value out_score was rounded from
+ *                      (carry it through shard merges so ranking stays exact)
+ *   out_idx     [Q, k] int64   idx_base + row; ties by lower index; -1 past the last row
+ *   out_flags   [Q]    int32   nullable; 1 where the query was answered by the exact-scan
+ *                      fallback (diagnostic)
+ *
+ * Result definition (what is "exact"): rows are ranked by the float64 cosine of the
+ * STORED values, dot / (max(||q||,1e-8) * max(||c||,1e-8)), descending, ties by ascending
+ * index.  The tensor-core pass only nominates candidates; a per-query safety check proves
+ * no row outside the candidates can be in the top-k, otherwise the query is recomputed by
+ * a float64 scan of the whole shard.  Supported: TSIM_MODE_TENSOR needs q_dt == c_dt ==
+ * TSIM_BF16, D % 8 == 0, 16-byte aligned rows; everything else runs the exact scan.
+ * ---------------------------------------------------------------------------------- */
+size_t tsim_search_workspace_bytes(int64_t Q, int64_t N, int64_t D, int k,
+                                   int q_dt, int c_dt, int mode);
+int tsim_search_topk(const void* q, int q_dt, int64_t q_stride,
+                     const void* corpus, int c_dt, int64_t c_stride,
+                     const float* corpus_inv_norm,
+                     int64_t Q, int64_t N, int64_t D, int k,
+                     int64_t idx_base, int64_t exclude_self_base, int mode,
+                     float* out_score, double* out_score64, int64_t* out_idx,
+                     int32_t* out_flags,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K3 (second pass): merge n_lists candidate lists per query into the top k_out, ranked by
+ * (score descending, index ascending); entries with index < 0 are padding.
+ * The reference has no merge: its chunk loop overwrites earlier chunks' results
+ * (src/pipeline/search_pipeline.py:83,88); this is the repaired
+ * intent, and the step after the NCCL all-gather of per-shard results.
+ *   sc [Q, n_lists * k_in] double, ix [Q, n_lists * k_in] int64; n_lists * k_in <= 4096.
+ * ---------------------------------------------------------------------------------- */
+int tsim_merge_topk(const double* sc, const int64_t* ix, int64_t Q, int64_t n_lists,
+                    int k_in, int k_out,
+                    float* out_score, double* out_score64, int64_t* out_idx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSIM_H_ */

@@ -1,0 +1,57 @@
+"""CPU-side checks: libtsim.so builds/loads and exports every symbol include/tsim.h declares;
+host-only entry points behave (no kernel is launched here)."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from text_similarity_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def test_header_symbols_are_exported(lib):
+    from text_similarity_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "tsim.h")).read()
+    declared = set(re.findall(r"\b(tsim_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+def test_version_and_workspace_planning(lib):
+    from text_similarity_b200 import _lib
+    assert lib.tsim_version() == 1
+    # BASELINE configs: workspace stays a small fraction of the 180 GB of HBM
+    for (Q, N, D, k) in [(100, 10_000, 384, 10), (1024, 1_000_000, 768, 10), (4096, 1_250_000, 768, 100),
+                         (32, 12_500_000, 384, 10), (1, 10_000_000, 768, 10)]:
+        nb = lib.tsim_search_workspace_bytes(Q, N, D, k, _lib.BF16, _lib.BF16, _lib.MODE_AUTO)
+        assert 0 < nb < 8e9, (Q, N, D, k, nb)
+    assert lib.tsim_search_workspace_bytes(8, 100, 30, 5, _lib.F32, _lib.F32, _lib.MODE_TENSOR) == 0
+    assert b"TSIM_MODE_TENSOR" in lib.tsim_last_error()
+    assert lib.tsim_search_workspace_bytes(8, 100, 32, 0, _lib.F32, _lib.F32, _lib.MODE_AUTO) == 0
+    assert lib.tsim_pool_workspace_bytes(16, 256, 384) > 0
+
+
+def test_argument_errors_do_not_touch_the_gpu(lib):
+    from text_similarity_b200 import _lib
+    rc = lib.tsim_merge_topk(None, None, 4, 100, 100, 10, None, None, None, None)
+    assert rc == _lib.ERR_INVALID_ARG and b"4096" in lib.tsim_last_error()
+    rc = lib.tsim_row_inv_norm(None, _lib.F32, 10, 0, 0, None, None)
+    assert rc == _lib.ERR_INVALID_ARG
+    rc = lib.tsim_pool_norm(None, _lib.E4M3, None, _lib.I64, 2, 3, 4, 12, 4, 3, None, _lib.F32, 4, None, None, 1, None, 0, None)
+    assert rc == _lib.ERR_INVALID_ARG
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+    from text_similarity_b200 import ops
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.search_topk(torch.randn(2, 8), torch.randn(5, 8), 2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.pool_norm(torch.randn(2, 3, 8), torch.ones(2, 3, dtype=torch.int64))

@@ -1,0 +1,268 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Indices must match exactly (ties -> lower index); scores within the tolerance
+BASELINE.json's north_star states (1e-3 for bf16 inputs, 1e-5 for fp32)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_F32 = 1e-5
+TOL_BF16 = 1e-3
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from text_similarity_b200 import ops as _ops
+    return _ops
+
+
+def _make(N, Q, D, dtype, seed, dup_frac=0.001, normalize=True):
+    g = torch.Generator().manual_seed(seed)
+    corpus = torch.randn(N, D, generator=g)
+    queries = torch.randn(Q, D, generator=g)
+    if normalize:
+        corpus = corpus / corpus.norm(dim=-1, keepdim=True)
+        queries = queries / queries.norm(dim=-1, keepdim=True)
+    ndup = max(2, int(N * dup_frac)) if N >= 8 else 0
+    if ndup:
+        src = torch.randint(0, N, (ndup,), generator=g)
+        dst = torch.randint(0, N, (ndup,), generator=g)
+        corpus[dst] = corpus[src]  # exact duplicate rows -> exact score ties
+    return queries.to(dtype), corpus.to(dtype)
+
+
+def _check(ops, queries, corpus, k, tol, mode="auto", **kw):
+    qd, cd = queries.cuda(), corpus.cuda()
+    s, i, s64, fl = ops.search_topk(qd, cd, k, mode=mode, return_score64=True, return_flags=True, **kw)
+    torch.cuda.synchronize()
+    ev, ei = O.search_exact(queries, corpus, k, idx_base=kw.get("idx_base", 0),
+                            exclude_self_base=kw.get("exclude_self_base", -1))
+    kk = ei.shape[1]
+    gi = i.cpu()[:, :kk]
+    mism = (gi != ei).sum().item()
+    assert mism == 0, f"{mism} index mismatches of {ei.numel()} (flags set: {int(fl.sum())})"
+    assert (i.cpu()[:, kk:] == -1).all()
+    np.testing.assert_allclose(s.cpu().numpy()[:, :kk], ev.numpy(), rtol=0, atol=tol)
+    np.testing.assert_allclose(s64.cpu().numpy()[:, :kk], ev.numpy(), rtol=0, atol=1e-12)
+    return fl.cpu()
+
+
+# ------------------------------------------------------------------------------------ K1
+@pytest.mark.parametrize("tag", ["small", "minilm", "wide"])
+def test_pool_matches_reference_golden(ops, golden, tag):
+    emb = torch.from_numpy(golden[f"pool_{tag}_emb"]).cuda()
+    mask = torch.from_numpy(golden[f"pool_{tag}_mask"]).cuda()
+    out, _ = ops.pool_norm(emb, mask, normalize=False)
+    np.testing.assert_allclose(out.cpu().numpy(), golden[f"pool_{tag}_out"], rtol=0, atol=TOL_F32)
+
+
+@pytest.mark.parametrize("B,L,D", [(1, 1, 8), (3, 17, 100), (16, 64, 384), (16, 256, 768), (64, 33, 1024), (2, 512, 4096)])
+@pytest.mark.parametrize("in_dt", [torch.float32, torch.float16, torch.bfloat16])
+def test_pool_norm_random(ops, B, L, D, in_dt):
+    g = torch.Generator().manual_seed(B * 1000 + L)
+    emb = torch.randn(B, L, D, generator=g).to(in_dt)
+    lens = torch.randint(0, L + 1, (B,), generator=g)
+    lens[0] = L
+    mask = (torch.arange(L)[None] < lens[:, None]).to(torch.int64)
+    for out_dt, tol in ((torch.float32, TOL_F32), (torch.bfloat16, 2 ** -8), (torch.float8_e4m3fn, None)):
+        rows, inv = ops.pool_norm(emb.cuda(), mask.cuda(), out_dtype=out_dt, normalize=True)
+        exp = O.l2_normalize_exact(O.mean_pool_exact(emb, mask))
+        got = rows.cpu().to(torch.float64)
+        if out_dt == torch.float8_e4m3fn:
+            # stored times a per-row power of two: compare directions
+            gotn = got / got.norm(dim=-1, keepdim=True).clamp_min(1e-30)
+            nz = exp.norm(dim=-1) > 0
+            cos = (gotn * exp).sum(-1)[nz]
+            assert (cos > 0.998).all()
+        else:
+            np.testing.assert_allclose(got.numpy(), exp.numpy(), rtol=0, atol=tol * max(1.0, float(exp.abs().max())))
+        n = got.norm(dim=-1).clamp_min(1e-8)
+        np.testing.assert_allclose(inv.cpu().double().numpy() * n.numpy(), 1.0, atol=1e-5)
+    # un-normalised mean == the reference's AvgPoolingStrategy
+    rows, _ = ops.pool_norm(emb.cuda(), mask.cuda(), normalize=False)
+    np.testing.assert_allclose(rows.cpu().numpy(), O.mean_pool_literal(emb.float(), mask).numpy(),
+                               rtol=0, atol=TOL_F32 * 4 if in_dt != torch.float32 else TOL_F32)
+
+
+def test_pool_mask_dtypes_and_scatter(ops):
+    g = torch.Generator().manual_seed(3)
+    emb = torch.randn(6, 9, 32, generator=g)
+    mask = (torch.rand(6, 9, generator=g) > 0.3)
+    exp = O.mean_pool_literal(emb, mask.to(torch.int64))
+    for md in (torch.bool, torch.uint8, torch.int32, torch.int64, torch.float32):
+        out, _ = ops.pool_norm(emb.cuda(), mask.to(md).cuda(), normalize=False)
+        np.testing.assert_allclose(out.cpu().numpy(), exp.numpy(), atol=TOL_F32)
+    big = torch.zeros(10, 32, device="cuda")
+    rows = torch.tensor([9, 0, 4, 2, 7, 5])
+    ops.pool_norm(emb.cuda(), mask.cuda(), normalize=False, out=big, out_rows=rows.cuda())
+    np.testing.assert_allclose(big.cpu()[rows].numpy(), exp.numpy(), atol=TOL_F32)
+    # non-contiguous token view (stride on batch / token axes)
+    wide = torch.randn(6, 9, 64, generator=g)
+    view = wide[:, :, :32]
+    out, _ = ops.pool_norm(view.cuda()[:, :, :], mask.cuda(), normalize=False)
+    np.testing.assert_allclose(out.cpu().numpy(), O.mean_pool_literal(view, mask.to(torch.int64)).numpy(), atol=TOL_F32)
+
+
+def test_row_inv_norm(ops):
+    g = torch.Generator().manual_seed(4)
+    for dt in (torch.float32, torch.float16, torch.bfloat16, torch.float8_e4m3fn):
+        x = torch.randn(1000, 384, generator=g).to(dt)
+        x[5] = 0
+        inv = ops.row_inv_norm(x.cuda()).cpu().double()
+        exp = 1.0 / x.to(torch.float64).norm(dim=-1).clamp_min(1e-8)
+        np.testing.assert_allclose(inv.numpy(), exp.numpy(), rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------ K2/K3 exact scan
+@pytest.mark.parametrize("tag", ["tiny", "mid"])
+def test_exact_scan_on_reference_golden(ops, golden, tag):
+    corpus = torch.from_numpy(golden[f"search_{tag}_corpus"])
+    queries = torch.from_numpy(golden[f"search_{tag}_queries"])
+    k = int(golden[f"search_{tag}_k"])
+    fl = _check(ops, queries, corpus, k, TOL_F32, mode="exact")
+    assert fl.all()
+    # and against what the reference's own ATen calls returned (fp32, unordered)
+    s, i = ops.search_topk(queries.cuda(), corpus.cuda(), k, mode="exact")
+    np.testing.assert_allclose(np.sort(s.cpu().numpy(), 1), np.sort(golden[f"search_{tag}_topk_val"], 1), atol=TOL_F32)
+
+
+@pytest.mark.parametrize("N,Q,D,k", [(1, 1, 8, 1), (5, 3, 16, 10), (33, 9, 50, 4), (10_000, 100, 384, 10),
+                                      (3000, 17, 768, 128), (2500, 5, 96, 1000)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_exact_scan_random(ops, N, Q, D, k, dtype):
+    q, c = _make(N, Q, D, dtype, seed=N + Q)
+    _check(ops, q, c, k, TOL_F32 if dtype == torch.float32 else TOL_BF16, mode="exact")
+
+
+def test_exact_scan_fp8_and_mixed(ops):
+    q, c = _make(2000, 8, 384, torch.float32, seed=9, normalize=False)
+    c8 = (c * 4).to(torch.float8_e4m3fn)
+    _check(ops, q.to(torch.bfloat16), c8, 10, TOL_BF16, mode="exact")
+    _check(ops, q, c.to(torch.float16), 10, TOL_BF16, mode="auto")
+
+
+def test_zero_rows_and_empty(ops):
+    q, c = _make(300, 4, 32, torch.float32, seed=12)
+    c[7] = 0
+    q[1] = 0      # zero query: every cosine is 0 -> rows 0..k-1
+    _check(ops, q, c, 5, TOL_F32, mode="exact")
+    s, i = ops.search_topk(q.cuda(), c[:0].cuda(), 3)
+    assert (i.cpu() == -1).all() and torch.isinf(s.cpu()).all()
+    s, i = ops.search_topk(q[:0].cuda(), c.cuda(), 3)
+    assert s.shape == (0, 3)
+
+
+# ------------------------------------------------------------------------------------ K2/K3 tensor path
+@pytest.mark.parametrize("N,Q,D,k", [
+    (256, 128, 64, 10),          # one tile, one k-block
+    (256, 128, 768, 10),         # one tile, 12 k-blocks
+    (1000, 7, 384, 10),          # ragged everything
+    (4096, 300, 768, 10),
+    (70_000, 130, 384, 5),
+    (50_000, 33, 72, 10),        # D not a multiple of 64 (TMA zero-fills the K tail)
+    (20_000, 64, 768, 24),       # KP = 32
+    (20_000, 40, 768, 50),       # KP = 64
+    (30_000, 40, 768, 100),      # KP = 112 (config-3 k)
+    (9, 4, 64, 10),              # fewer rows than k
+])
+def test_tensor_path_matches_oracle(ops, N, Q, D, k):
+    q, c = _make(N, Q, D, torch.bfloat16, seed=N * 7 + Q)
+    fl = _check(ops, q, c, k, TOL_BF16, mode="tensor")
+    assert fl.float().mean() <= 0.05 or N <= 1000
+
+
+def test_tensor_path_unnormalised_inputs(ops):
+    q, c = _make(20_000, 50, 384, torch.float32, seed=77, normalize=False)
+    c = c * torch.rand(c.shape[0], 1) * 10      # wildly different row norms
+    _check(ops, q.to(torch.bfloat16), c.to(torch.bfloat16), 10, TOL_BF16, mode="tensor")
+
+
+def test_tensor_path_with_precomputed_inv_norm(ops):
+    q, c = _make(30_000, 20, 768, torch.bfloat16, seed=5)
+    inv = ops.row_inv_norm(c.cuda())
+    _check(ops, q, c, 10, TOL_BF16, mode="tensor", corpus_inv_norm=inv)
+
+
+def test_heavy_duplicates_fall_back_and_stay_exact(ops):
+    # 40 identical rows tie for the top: the completeness proof must fail and the exact scan answer
+    q, c = _make(5000, 16, 128, torch.bfloat16, seed=21)
+    c[100:140] = c[4000]
+    c[4000 + 1] = q[0]
+    fl = _check(ops, q, c, 10, TOL_BF16, mode="auto")
+    s, i = ops.search_topk(q.cuda(), c.cuda(), 10, mode="exact")
+    s2, i2 = ops.search_topk(q.cuda(), c.cuda(), 10, mode="auto")
+    assert torch.equal(i, i2) and torch.equal(s, s2)
+
+
+def test_adversarial_ascending_corpus(ops):
+    # rows sorted by increasing similarity to query 0: every row beats the running threshold
+    g = torch.Generator().manual_seed(31)
+    qv = torch.randn(1, 64, generator=g)
+    qv = qv / qv.norm()
+    noise = torch.randn(6000, 64, generator=g)
+    noise = noise - (noise @ qv.T) * qv
+    noise = noise / noise.norm(dim=-1, keepdim=True)
+    alpha = torch.linspace(-0.9, 0.9, 6000)[:, None]
+    c = alpha * qv + (1 - alpha ** 2).sqrt() * noise
+    _check(ops, qv.to(torch.bfloat16), c.to(torch.bfloat16), 10, TOL_BF16, mode="tensor")
+
+
+def test_exclude_self_all_pairs(ops):
+    q, c = _make(3000, 8, 256, torch.bfloat16, seed=41)
+    x = c
+    qd = x[:300]
+    _check(ops, qd, x, 5, TOL_BF16, mode="tensor", exclude_self_base=0)
+    _check(ops, qd, x, 5, TOL_BF16, mode="exact", exclude_self_base=0)
+    # queries are rows 1000..1299 of the corpus, corpus shard starts at global row 500
+    _check(ops, x[1000:1300], x[500:], 5, TOL_BF16, mode="tensor", idx_base=500, exclude_self_base=1000)
+
+
+def test_modes_agree_bitwise(ops):
+    q, c = _make(40_000, 96, 384, torch.bfloat16, seed=51)
+    a = ops.search_topk(q.cuda(), c.cuda(), 10, mode="tensor", return_score64=True)
+    b = ops.search_topk(q.cuda(), c.cuda(), 10, mode="exact", return_score64=True)
+    assert torch.equal(a[1], b[1])
+    assert torch.equal(a[2], b[2])     # same canonical float64 routine on both paths
+
+
+def test_unsupported_is_an_error_not_a_fallback(ops):
+    q, c = _make(100, 4, 30, torch.float32, seed=1)
+    with pytest.raises(ValueError):
+        ops.search_topk(q.cuda(), c.cuda(), 5, mode="tensor")
+    with pytest.raises(RuntimeError):
+        ops.search_topk(q, c, 5)            # CPU tensors: no CPU fallback
+    with pytest.raises(ValueError):
+        ops.search_topk(q.cuda(), c.cuda(), 0)
+
+
+# ------------------------------------------------------------------------------------ merge / shards
+def test_merge_topk_matches_oracle(ops):
+    g = torch.Generator().manual_seed(61)
+    Q, n_lists, k_in, k = 37, 8, 100, 100
+    sc = torch.randn(Q, n_lists * k_in, generator=g, dtype=torch.float64)
+    sc[:, 5] = sc[:, 400]                # equal scores, different rows
+    ix = torch.stack([torch.randperm(10_000, generator=g)[:n_lists * k_in] for _ in range(Q)])
+    ix[:, -7:] = -1                      # padding
+    s, s64, i = ops.merge_topk(sc.cuda(), ix.cuda(), k, n_lists)
+    ev, ei = O.merge_topk_exact(sc, ix, k)
+    assert torch.equal(i.cpu(), ei)
+    assert torch.equal(s64.cpu(), ev)
+
+
+@pytest.mark.parametrize("G", [2, 4, 8])
+def test_fake_shards_plus_merge_equal_single_search(ops, G):
+    q, c = _make(24_000, 70, 384, torch.bfloat16, seed=71)
+    k = 10
+    full = ops.search_topk(q.cuda(), c.cuda(), k, return_score64=True)
+    rows = (c.shape[0] + G - 1) // G
+    parts = [ops.search_topk(q.cuda(), c[r * rows:(r + 1) * rows].cuda(), k, idx_base=r * rows, return_score64=True)
+             for r in range(G)]
+    s64 = torch.cat([p[2] for p in parts], 1)
+    ix = torch.cat([p[1] for p in parts], 1)
+    ms, ms64, mi = ops.merge_topk(s64, ix, k, G)
+    assert torch.equal(mi, full[1]) and torch.equal(ms64, full[2]) and torch.equal(ms, full[0])

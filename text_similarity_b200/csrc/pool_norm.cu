@@ -1,0 +1,347 @@
+// K1: fused masked mean-pool + L2-normalise + cast (fp32 / bf16 / e4m3), and the row
+// inverse-norm pass.  Replaces AvgPoolingStrategy.forward (reference
+// src/modules/modules.py:158-171; same arithmetic at src/models/sentence_encoder.py:35-38),
+// which issues six ATen kernels and materialises a [B,L,D] fp32 mask and product.
+//
+// HBM-bound: algorithmic bytes per call = B*L*D*e_in + B*L*mask_bytes + B*D*e_out + B*4.
+// One pass over the token tensor with 16-byte coalesced loads; masked-out tokens are not
+// read at all.  Grid = B * S CTAs (S = splits of the token axis) sized to >= 2 CTAs per SM;
+// split partial sums go through a small fp32 workspace and the last CTA to finish a row
+// (ticket counter) adds them in a fixed order, so results are deterministic.
+#include "tsim_common.cuh"
+
+namespace tsim {
+
+namespace {
+
+__device__ __forceinline__ float mask_value(const void* mask, int mask_dt, int64_t i) {
+  switch (mask_dt) {
+    case TSIM_I64: return (float)((const int64_t*)mask)[i];
+    case TSIM_I32: return (float)((const int32_t*)mask)[i];
+    case TSIM_U8: return (float)((const uint8_t*)mask)[i];
+    default: return ((const float*)mask)[i];
+  }
+}
+
+template <int DT, int VEC> struct VecLoad;
+template <> struct VecLoad<TSIM_F32, 4> {
+  static __device__ __forceinline__ void ld(const void* p, int64_t i, float* o) {
+    float4 v = __ldg((const float4*)((const float*)p + i));
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
+};
+template <> struct VecLoad<TSIM_F16, 8> {
+  static __device__ __forceinline__ void ld(const void* p, int64_t i, float* o) {
+    uint4 v = __ldg((const uint4*)((const __half*)p + i));
+    const __half2* h = (const __half2*)&v;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { float2 f = __half22float2(h[j]); o[2 * j] = f.x; o[2 * j + 1] = f.y; }
+  }
+};
+template <> struct VecLoad<TSIM_BF16, 8> {
+  static __device__ __forceinline__ void ld(const void* p, int64_t i, float* o) {
+    uint4 v = __ldg((const uint4*)((const __nv_bfloat16*)p + i));
+    const __nv_bfloat162* h = (const __nv_bfloat162*)&v;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); o[2 * j] = f.x; o[2 * j + 1] = f.y; }
+  }
+};
+template <int DT> struct VecLoad<DT, 1> {
+  static __device__ __forceinline__ void ld(const void* p, int64_t i, float* o) { o[0] = Elem<DT>::ld(p, i); }
+};
+
+// deterministic block-wide sum (all threads get the result); red = 32 floats of smem
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum_f32(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < nw; ++i) t += red[i];
+  return t;
+}
+
+__device__ __forceinline__ float round_store(void* out, int out_dt, int64_t i, float v) {
+  switch (out_dt) {
+    case TSIM_F32: ((float*)out)[i] = v; return v;
+    case TSIM_BF16: {
+      __nv_bfloat16 h = __float2bfloat16_rn(v);
+      ((__nv_bfloat16*)out)[i] = h;
+      return __bfloat162float(h);
+    }
+    default: {
+      __nv_fp8_e4m3 h(v);
+      ((__nv_fp8_e4m3*)out)[i] = h;
+      return float(h);
+    }
+  }
+}
+
+struct PoolArgs {
+  const void* tok; const void* mask; int mask_dt;
+  int64_t B, L, D, sb, sl, msb;
+  int S, TL;              // token splits, tokens per split
+  float* partial;         // [B, S, D]
+  int* ticket;            // [B]
+  void* out; int out_dt; int64_t out_stride; const int64_t* out_rows;
+  float* out_inv; int normalize;
+};
+
+template <int DT, int VEC>
+__global__ void __launch_bounds__(256) pool_norm_kernel(PoolArgs a) {
+  extern __shared__ float sm[];           // [rpi][D] partial rows, then reused as pooled[D]
+  __shared__ float red[32];
+  __shared__ int s_last;
+  const int b = blockIdx.x / a.S, sp = blockIdx.x % a.S;
+  const int nvec = (int)(a.D / VEC);
+  const int rpi = max(1, (int)blockDim.x / nvec);
+  const int tid = threadIdx.x;
+  const int r = tid / nvec;
+  const int l0 = sp * a.TL, l1 = min((int)a.L, l0 + a.TL);
+
+  // ---- phase 1: this CTA's token range, reduced over tokens --------------------------
+  // thread (r, v): tokens l0 + r, l0 + r + rpi, ...; columns v*VEC .. v*VEC+VEC-1 (and, when
+  // there are more vector columns than threads, further columns nvec-strided: v += blockDim)
+  for (int v0 = 0; v0 < nvec; v0 += blockDim.x) {
+    const int v = v0 + (rpi > 1 ? tid % nvec : tid);
+    float acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+    if (v < nvec && r < rpi) {
+      const int64_t base = (int64_t)b * a.sb + (int64_t)v * VEC;
+      int l = l0 + r;
+      // 4 independent 16-byte loads in flight per thread
+      for (; l + 3 * rpi < l1; l += 4 * rpi) {
+        float w[4], x[4][VEC];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) w[u] = mask_value(a.mask, a.mask_dt, (int64_t)b * a.msb + l + u * rpi);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (w[u] != 0.f) VecLoad<DT, VEC>::ld(a.tok, base + (int64_t)(l + u * rpi) * a.sl, x[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (w[u] != 0.f) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) acc[j] = fmaf(w[u], x[u][j], acc[j]);
+          }
+        }
+      }
+      for (; l < l1; l += rpi) {
+        float w = mask_value(a.mask, a.mask_dt, (int64_t)b * a.msb + l);
+        if (w != 0.f) {
+          float x[VEC];
+          VecLoad<DT, VEC>::ld(a.tok, base + (int64_t)l * a.sl, x);
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) acc[j] = fmaf(w, x[j], acc[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) sm[(int64_t)r * a.D + (int64_t)v * VEC + j] = acc[j];
+    }
+  }
+  __syncthreads();
+  // fold the rpi sub-rows in a fixed order; result lands in sm[0..D)
+  for (int d = tid; d < a.D; d += blockDim.x) {
+    float t = sm[d];
+    for (int rr = 1; rr < rpi; ++rr) t += sm[(int64_t)rr * a.D + d];
+    if (a.S > 1) a.partial[((int64_t)b * a.S + sp) * a.D + d] = t;
+    else sm[d] = t;
+  }
+
+  // ---- phase 2: the last CTA of row b finalises ---------------------------------------
+  if (a.S > 1) {
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&a.ticket[b], 1) == a.S - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int d = tid; d < a.D; d += blockDim.x) {
+      float t = 0.f;
+      for (int s = 0; s < a.S; ++s) t += __ldcg(&a.partial[((int64_t)b * a.S + s) * a.D + d]);
+      sm[d] = t;
+    }
+  }
+  __syncthreads();
+
+  float cnt = 0.f;
+  for (int l = tid; l < a.L; l += blockDim.x) cnt += mask_value(a.mask, a.mask_dt, (int64_t)b * a.msb + l);
+  cnt = block_sum(cnt, red);
+  const float denom = fmaxf(cnt, kPoolEps);  // modules.py:168
+
+  float ss = 0.f, amax = 0.f;
+  for (int d = tid; d < a.D; d += blockDim.x) {
+    float m = sm[d] / denom;  // modules.py:170
+    sm[d] = m;
+    ss = fmaf(m, m, ss);
+    amax = fmaxf(amax, fabsf(m));
+  }
+  ss = block_sum(ss, red);
+  float scale = 1.f;
+  if (a.normalize) scale = 1.f / fmaxf(sqrtf(ss), (float)kCosEps);
+  if (a.out_dt == TSIM_E4M3) {
+    // per-row power-of-two scale: largest |element| lands in [64, 128) (e4m3 max is 448)
+    float m = amax;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = m;
+    __syncthreads();
+    float bm = 0.f;
+    for (int i = 0; i < (int)((blockDim.x + 31) >> 5); ++i) bm = fmaxf(bm, red[i]);
+    bm *= scale;
+    if (bm > 0.f) {
+      int e;
+      frexpf(bm, &e);  // bm = f * 2^e, f in [0.5, 1)
+      scale *= exp2f((float)(7 - e));
+    }
+  }
+
+  const int64_t orow = a.out_rows ? a.out_rows[b] : (int64_t)b;
+  float ss2 = 0.f;
+  for (int d = tid; d < a.D; d += blockDim.x) {
+    float st = round_store(a.out, a.out_dt, orow * a.out_stride + d, sm[d] * scale);
+    ss2 = fmaf(st, st, ss2);
+  }
+  ss2 = block_sum(ss2, red);
+  if (a.out_inv && tid == 0) a.out_inv[orow] = 1.f / fmaxf(sqrtf(ss2), (float)kCosEps);
+}
+
+template <int DT>
+__global__ void __launch_bounds__(256) row_inv_norm_kernel(const void* x, int64_t N, int64_t D,
+                                                           int64_t stride, float* out) {
+  // one warp per row, lanes stride the row; float accumulation (the value only scales the
+  // approximate scores of the candidate pass; final scores are recomputed in float64)
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const int lane = threadIdx.x & 31;
+  float ss = 0.f;
+  const int64_t base = row * stride;
+  if (DT == TSIM_BF16 && (D % 8 == 0) && (stride % 8 == 0) && (((uintptr_t)x & 15) == 0)) {
+    for (int64_t d = lane * 8; d < D; d += 256) {
+      float v[8];
+      VecLoad<TSIM_BF16, 8>::ld(x, base + d, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss = fmaf(v[j], v[j], ss);
+    }
+  } else {
+    for (int64_t d = lane; d < D; d += 32) {
+      float v = Elem<DT>::ld(x, base + d);
+      ss = fmaf(v, v, ss);
+    }
+  }
+  ss = warp_sum_f32(ss);
+  if (lane == 0) out[row] = 1.f / fmaxf(sqrtf(ss), (float)kCosEps);
+}
+
+template <int DT, int VEC>
+int launch_pool(const PoolArgs& a, cudaStream_t st) {
+  const int nvec = (int)(a.D / VEC);
+  int threads;
+  if (nvec >= 256) threads = 256;
+  else {
+    int rpi = 256 / nvec;
+    threads = nvec * rpi;
+    threads = ((threads + 31) / 32) * 32;
+    if (threads > 256) threads = 256;
+  }
+  const int rpi = threads / nvec > 0 ? threads / nvec : 1;
+  size_t smem = (size_t)rpi * a.D * sizeof(float);
+  if (smem > 200 * 1024) { set_error("pool_norm: D=%lld too large", (long long)a.D); return TSIM_ERR_UNSUPPORTED; }
+  if (smem > 48 * 1024)
+    TSIM_CUDA(cudaFuncSetAttribute(pool_norm_kernel<DT, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pool_norm_kernel<DT, VEC><<<(unsigned)(a.B * a.S), threads, smem, st>>>(a);
+  TSIM_CUDA(cudaGetLastError());
+  return TSIM_OK;
+}
+
+int pool_splits(int64_t B, int64_t L) {
+  int sms = device_sm_count();
+  int64_t want = (2 * (int64_t)sms + B - 1) / B;       // >= 2 CTAs per SM overall
+  int64_t maxs = (L + 7) / 8;                           // >= 8 tokens per CTA
+  int64_t S = want < 1 ? 1 : want;
+  if (S > maxs) S = maxs;
+  if (S < 1) S = 1;
+  return (int)S;
+}
+
+}  // namespace
+
+int launch_row_inv_norm(const void* x, int dt, int64_t N, int64_t D, int64_t stride, float* out,
+                        cudaStream_t st) {
+  if (N == 0) return TSIM_OK;
+  const int wpb = 8;
+  unsigned grid = (unsigned)((N + wpb - 1) / wpb);
+  switch (dt) {
+    case TSIM_F32: row_inv_norm_kernel<TSIM_F32><<<grid, wpb * 32, 0, st>>>(x, N, D, stride, out); break;
+    case TSIM_F16: row_inv_norm_kernel<TSIM_F16><<<grid, wpb * 32, 0, st>>>(x, N, D, stride, out); break;
+    case TSIM_BF16: row_inv_norm_kernel<TSIM_BF16><<<grid, wpb * 32, 0, st>>>(x, N, D, stride, out); break;
+    case TSIM_E4M3: row_inv_norm_kernel<TSIM_E4M3><<<grid, wpb * 32, 0, st>>>(x, N, D, stride, out); break;
+    default: set_error("row_inv_norm: bad dtype %d", dt); return TSIM_ERR_INVALID_ARG;
+  }
+  TSIM_CUDA(cudaGetLastError());
+  return TSIM_OK;
+}
+
+}  // namespace tsim
+
+using namespace tsim;
+
+extern "C" size_t tsim_pool_workspace_bytes(int64_t B, int64_t L, int64_t D) {
+  if (B <= 0 || L <= 0 || D <= 0) return 256;
+  int S = pool_splits(B, L);
+  size_t partial = (S > 1) ? (size_t)B * S * D * sizeof(float) : 0;
+  size_t ticket = (size_t)B * sizeof(int);
+  return ((partial + 255) / 256) * 256 + ((ticket + 255) / 256) * 256 + 256;
+}
+
+extern "C" int tsim_pool_norm(const void* tok, int tok_dt, const void* mask, int mask_dt,
+                              int64_t B, int64_t L, int64_t D, int64_t tok_stride_b,
+                              int64_t tok_stride_l, int64_t mask_stride_b, void* out, int out_dt,
+                              int64_t out_stride, const int64_t* out_rows, float* out_inv_norm,
+                              int normalize, void* ws, size_t ws_bytes, void* stream) {
+  TSIM_CHECK_ARG(B >= 0 && L >= 0 && D > 0, "pool_norm: bad shape B=%lld L=%lld D=%lld", (long long)B, (long long)L, (long long)D);
+  if (B == 0) return TSIM_OK;
+  TSIM_CHECK_ARG(tok && mask && out, "pool_norm: null pointer");
+  TSIM_CHECK_ARG(L > 0, "pool_norm: L must be > 0");
+  TSIM_CHECK_ARG(tok_dt == TSIM_F32 || tok_dt == TSIM_F16 || tok_dt == TSIM_BF16, "pool_norm: token dtype %d unsupported", tok_dt);
+  TSIM_CHECK_ARG(mask_dt == TSIM_I64 || mask_dt == TSIM_I32 || mask_dt == TSIM_U8 || mask_dt == TSIM_F32, "pool_norm: mask dtype %d unsupported", mask_dt);
+  TSIM_CHECK_ARG(out_dt == TSIM_F32 || out_dt == TSIM_BF16 || out_dt == TSIM_E4M3, "pool_norm: output dtype %d unsupported", out_dt);
+  TSIM_CHECK_ARG(out_stride >= D, "pool_norm: out_stride < D");
+  cudaStream_t st = (cudaStream_t)stream;
+  PoolArgs a;
+  a.tok = tok; a.mask = mask; a.mask_dt = mask_dt;
+  a.B = B; a.L = L; a.D = D; a.sb = tok_stride_b; a.sl = tok_stride_l; a.msb = mask_stride_b;
+  a.S = pool_splits(B, L);
+  a.TL = (int)((L + a.S - 1) / a.S);
+  a.out = out; a.out_dt = out_dt; a.out_stride = out_stride; a.out_rows = out_rows;
+  a.out_inv = out_inv_norm; a.normalize = normalize;
+  a.partial = nullptr; a.ticket = nullptr;
+  if (a.S > 1) {
+    size_t partial = (((size_t)B * a.S * D * sizeof(float) + 255) / 256) * 256;
+    size_t need = partial + (size_t)B * sizeof(int);
+    if (!ws || ws_bytes < need) { set_error("pool_norm: workspace too small (%zu < %zu)", ws_bytes, need); return TSIM_ERR_WORKSPACE; }
+    a.partial = (float*)ws;
+    a.ticket = (int*)((char*)ws + partial);
+    TSIM_CUDA(cudaMemsetAsync(a.ticket, 0, (size_t)B * sizeof(int), st));
+  }
+  const int esz = dtype_size(tok_dt);
+  const int vec = 16 / esz;
+  const bool vec_ok = (D % vec == 0) && (tok_stride_b % vec == 0) && (tok_stride_l % vec == 0) &&
+                      (((uintptr_t)tok & 15) == 0);
+  switch (tok_dt) {
+    case TSIM_F32: return vec_ok ? launch_pool<TSIM_F32, 4>(a, st) : launch_pool<TSIM_F32, 1>(a, st);
+    case TSIM_F16: return vec_ok ? launch_pool<TSIM_F16, 8>(a, st) : launch_pool<TSIM_F16, 1>(a, st);
+    default: return vec_ok ? launch_pool<TSIM_BF16, 8>(a, st) : launch_pool<TSIM_BF16, 1>(a, st);
+  }
+}
+
+extern "C" int tsim_row_inv_norm(const void* x, int dt, int64_t N, int64_t D, int64_t stride,
+                                 float* out, void* stream) {
+  TSIM_CHECK_ARG(N >= 0 && D > 0 && stride >= D, "row_inv_norm: bad shape");
+  if (N == 0) return TSIM_OK;
+  TSIM_CHECK_ARG(x && out, "row_inv_norm: null pointer");
+  return launch_row_inv_norm(x, dt, N, D, stride, out, (cudaStream_t)stream);
+}

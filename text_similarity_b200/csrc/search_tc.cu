@@ -1,0 +1,395 @@
+// K2 (tensor-core pass): query x corpus^T on tcgen05 / TMEM, fed by TMA, with the top-k
+// candidate selection fused into the epilogue so the [Q, N] score matrix never exists in HBM.
+//
+// Replaces the per-query loop of SentenceMiningPipeline._search (reference
+// src/pipeline/search_pipeline.py:73-79: one F.cosine_similarity pass over the whole corpus
+// and one torch.topk PER QUERY) and cos_sim's full score matrix (src/utils/metrics.py:99-101).
+//
+// Orientation: queries are the MMA M side (128 per CTA = the 128 TMEM lanes), corpus rows the
+// N side (256 per tile = 256 fp32 TMEM columns), D the K side in 64-element (128-byte) blocks.
+// After a tile's MMAs, TMEM lane i holds query i's 256 dot products; epilogue thread i reads
+// them with tcgen05.ld (32x32b: thread <-> lane), scales by the corpus row's inverse norm and
+// compares with its query's running threshold -- one FMUL + one compare per score, and a rare
+// insertion into that query's private sorted list in shared memory.  Two 256-column
+// accumulator stages (all 512 TMEM columns) let the epilogue of tile t overlap the MMAs of t+1.
+//
+// Work unit = (128-query block, R-row corpus chunk); units are dealt round-robin to one
+// persistent CTA per SM with the query block fastest, so the CTAs that share a corpus chunk
+// run side by side and the chunk is read from HBM once and from L2 by the rest.
+// Each unit leaves its KP best (approx score, row) keys in cand[q][chunk][KP]; full lists raise
+// thr[q] (atomicMax) so later units start with a tight threshold.  select_merge.cu finishes.
+//
+// Roofline: 2*Q*N*D flops on the tensor pipe (Q >~ 240) or N*D*2 bytes from HBM (small Q).
+#include <cuda.h>
+
+#include "tsim_common.cuh"
+
+namespace tsim {
+namespace {
+
+constexpr int BM = 128;        // queries per CTA tile (TMEM lanes)
+constexpr int BN = 256;        // corpus rows per tile (TMEM columns per accumulator stage)
+constexpr int BK = 64;         // bf16 elements per k-block = 128 bytes = one swizzle atom row
+constexpr int UMMA_K = 16;     // bf16 MMA K
+constexpr int kThreads = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
+constexpr int kEpiThreads = 128;
+constexpr int A_BYTES = BM * BK * 2;   // 16 KB
+constexpr int B_BYTES = BN * BK * 2;   // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B, 128-byte rows:
+//   start address >> 4 | LBO (unused for swizzled K-major) = 1 | SBO = 1024 B (8 rows) >> 4 |
+//   version 1 (sm_100) | layout type 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_umma_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3ffff) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// UMMA instruction descriptor: D = f32, A = B = bf16, both K-major, N = 256, M = 128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+struct TcArgs {
+  const float* c_inv;   // [N] inverse norms of the stored corpus rows
+  int64_t Q, N;
+  int kblocks;          // ceil(D / 64)
+  int QB;               // query blocks
+  int64_t R, NC;        // rows per chunk, chunks
+  int64_t n_units;
+  int self_on; int64_t self_off;
+  uint64_t* cand;       // [Q][NC][KP] packed keys
+  uint32_t* thr;        // [Q] ordered-float global thresholds (0 = none yet)
+};
+
+// Rare path: insert (s, row) into this thread's descending list (column `lane` of ls/li).
+// The fill count lives in shared memory (*cntp) and the new threshold is returned, so the hot
+// loop keeps its state in registers across this (non-inlined) call.
+template <int KP>
+__device__ __noinline__ float list_insert(float* ls, uint32_t* li, int* cntp, float thr, float s, uint32_t row) {
+  int cnt = *cntp;
+  int pos = cnt < KP ? cnt : KP - 1;
+  while (pos > 0) {
+    float prev = ls[(pos - 1) * kEpiThreads];
+    if (!(prev < s)) break;            // equal scores keep arrival (= row) order
+    ls[pos * kEpiThreads] = prev;
+    li[pos * kEpiThreads] = li[(pos - 1) * kEpiThreads];
+    --pos;
+  }
+  ls[pos * kEpiThreads] = s;
+  li[pos * kEpiThreads] = row;
+  if (cnt < KP) *cntp = ++cnt;
+  if (cnt == KP) thr = fmaxf(thr, ls[(KP - 1) * kEpiThreads]);
+  return thr;
+}
+
+template <int KP, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c, TcArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment: round the dynamic window up (1 KB of slack is
+  // requested by the launcher).
+  // [STAGES][A 16K | B 32K] | lists | cnorm[2][BN] | list counts | barriers | tmem ptr
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* tiles = smem;
+  float* list_s = (float*)(smem + (size_t)STAGES * STAGE_BYTES);
+  uint32_t* list_i = (uint32_t*)(list_s + KP * kEpiThreads);
+  float* cnorm = (float*)(list_i + KP * kEpiThreads);
+  int* list_n = (int*)(cnorm + 2 * BN);
+  uint64_t* bars = (uint64_t*)(list_n + kEpiThreads);
+  uint64_t* full_bar = bars;                 // [STAGES]  TMA -> MMA
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]  MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]       MMA -> epilogue
+  uint64_t* tempty_bar = tfull_bar + 2;      // [2]       epilogue -> MMA
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_c);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tfull_bar[s]), 1); mbar_init(smem_u32(&tempty_bar[s]), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t u = blockIdx.x; u < a.n_units; u += gridDim.x) {
+        const int64_t chunk = u / a.QB;
+        const int qb = (int)(u % a.QB);
+        const int64_t row0 = chunk * a.R;
+        const int64_t rows = min(a.N, row0 + a.R) - row0;
+        const int ntiles = (int)((rows + BN - 1) / BN);
+        for (int t = 0; t < ntiles; ++t) {
+          for (int kb = 0; kb < a.kblocks; ++kb) {
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+            const uint32_t fb = smem_u32(&full_bar[stage]);
+            mbar_arrive_expect_tx(fb, STAGE_BYTES);
+            const uint32_t sa = smem_u32(tiles + (size_t)stage * STAGE_BYTES);
+            tma_load_2d(sa, &tmap_q, fb, kb * BK, qb * BM);
+            tma_load_2d(sa + A_BYTES, &tmap_c, fb, kb * BK, (int)(row0 + (int64_t)t * BN));
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t aphase = 0;
+      for (int64_t u = blockIdx.x; u < a.n_units; u += gridDim.x) {
+        const int64_t chunk = u / a.QB;
+        const int64_t row0 = chunk * a.R;
+        const int64_t rows = min(a.N, row0 + a.R) - row0;
+        const int ntiles = (int)((rows + BN - 1) / BN);
+        for (int t = 0; t < ntiles; ++t) {
+          mbar_wait(smem_u32(&tempty_bar[acc]), aphase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
+          for (int kb = 0; kb < a.kblocks; ++kb) {
+            mbar_wait(smem_u32(&full_bar[stage]), phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(tiles + (size_t)stage * STAGE_BYTES);
+            const uint64_t adesc = make_umma_desc(sa);
+            const uint64_t bdesc = make_umma_desc(sa + A_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in >>4 units
+              tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), kIdesc, (kb | k) ? 1u : 0u);
+            }
+            tc_commit(smem_u32(&empty_bar[stage]));      // frees the smem stage when the MMAs retire
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          tc_commit(smem_u32(&tfull_bar[acc]));          // accumulator stage complete
+          if (++acc == 2) { acc = 0; aphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: threshold filter + per-query lists =====================
+    const int et = threadIdx.x - 128;            // 0..127 = TMEM lane = query within the block
+    const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
+    float* ls = list_s + et;
+    uint32_t* li = list_i + et;
+    int* cntp = list_n + et;
+    int acc = 0; uint32_t aphase = 0;
+    for (int64_t u = blockIdx.x; u < a.n_units; u += gridDim.x) {
+      const int64_t chunk = u / a.QB;
+      const int qb = (int)(u % a.QB);
+      const int64_t row0 = chunk * a.R;
+      const int64_t rows = min(a.N, row0 + a.R) - row0;
+      const int ntiles = (int)((rows + BN - 1) / BN);
+      const int64_t qg = (int64_t)qb * BM + et;
+      const bool qvalid = qg < a.Q;
+      const int64_t self_row = a.self_on ? a.self_off + qg : -1;
+      *cntp = 0;
+      float thr = qvalid ? -INFINITY : INFINITY;   // padded query lanes never insert
+      for (int t = 0; t < ntiles; ++t) {
+        const int64_t trow0 = row0 + (int64_t)t * BN;
+        const int ncols = (int)min((int64_t)BN, row0 + rows - trow0);
+        // stage the tile's inverse norms (2 per thread) and refresh the shared threshold
+        float n0 = 0.f, n1 = 0.f;
+        if (et < ncols) n0 = __ldg(a.c_inv + trow0 + et);
+        if (et + 128 < ncols) n1 = __ldg(a.c_inv + trow0 + et + 128);
+        if (qvalid) {
+          uint32_t g = __ldcg(a.thr + qg);
+          if (g) thr = fmaxf(thr, ord_to_f32(g));
+        }
+        mbar_wait(smem_u32(&tfull_bar[acc]), aphase);
+        tc_fence_after();
+        float* cn = cnorm + acc * BN;
+        cn[et] = n0;
+        cn[et + 128] = n1;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const uint32_t tbase = tmem_base + lane_addr + (uint32_t)acc * BN;
+        for (int c = 0; c < BN / 32; ++c) {
+          if (c * 32 >= ncols) break;
+          uint32_t v[32];
+          tc_ld32(tbase + c * 32, v);
+          tc_ld_wait();
+          const int lim = ncols - c * 32;   // >= 32 except in the ragged last chunk
+          const float4* cn4 = (const float4*)(cn + c * 32);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 w = cn4[j4];
+            const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j = j4 * 4 + jj;
+              const float s = __uint_as_float(v[j]) * wv[jj];
+              if (s > thr && j < lim) {
+                const int64_t row = trow0 + c * 32 + j;
+                if (row != self_row) thr = list_insert<KP>(ls, li, cntp, thr, s, (uint32_t)row);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+        if (++acc == 2) { acc = 0; aphase ^= 1; }
+      }
+      // flush this unit's list
+      if (qvalid) {
+        const int cnt = *cntp;
+        uint64_t* dst = a.cand + ((size_t)qg * a.NC + chunk) * KP;
+#pragma unroll 4
+        for (int j = 0; j < KP; ++j)
+          dst[j] = j < cnt ? pack_key(ls[j * kEpiThreads], li[j * kEpiThreads]) : 0ull;
+        if (cnt == KP) atomicMax(a.thr + qg, f32_to_ord(ls[(KP - 1) * kEpiThreads]));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, D] tensor map with a [box_rows, 64] box and 128-byte swizzle
+int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t D, int64_t stride_elems, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return TSIM_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)stride_elems * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return TSIM_ERR_CUDA; }
+  return TSIM_OK;
+}
+
+template <int KP, int STAGES>
+int launch_cfg(const CUtensorMap& mq, const CUtensorMap& mc, const TcArgs& a, cudaStream_t st) {
+  size_t smem = 1024 + (size_t)STAGES * STAGE_BYTES + (size_t)KP * kEpiThreads * 8 + 2 * BN * 4 +
+                kEpiThreads * 4 + (2 * STAGES + 4) * 8 + 16;
+  TSIM_CUDA(cudaFuncSetAttribute(search_tc_kernel<KP, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int sms = device_sm_count();
+  unsigned grid = (unsigned)(a.n_units < sms ? a.n_units : sms);
+  search_tc_kernel<KP, STAGES><<<grid, kThreads, smem, st>>>(mq, mc, a);
+  TSIM_CUDA(cudaGetLastError());
+  return TSIM_OK;
+}
+
+}  // namespace
+
+int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_t c_stride,
+                     const float* c_inv, int64_t Q, int64_t N, int64_t D, int self_on, int64_t self_off,
+                     const SearchPlan& p, uint64_t* cand, uint32_t* thr, cudaStream_t st) {
+  CUtensorMap mq, mc;
+  int rc = make_map(&mq, q, Q, D, q_stride, BM);
+  if (rc) return rc;
+  rc = make_map(&mc, corpus, N, D, c_stride, BN);
+  if (rc) return rc;
+  TcArgs a;
+  a.c_inv = c_inv; a.Q = Q; a.N = N;
+  a.kblocks = (int)((D + BK - 1) / BK);
+  a.QB = p.QB; a.R = p.R; a.NC = p.NC; a.n_units = (int64_t)p.QB * p.NC;
+  a.self_on = self_on; a.self_off = self_off;
+  a.cand = cand; a.thr = thr;
+  switch (p.KP) {
+    case 16: return launch_cfg<16, 4>(mq, mc, a, st);
+    case 32: return launch_cfg<32, 3>(mq, mc, a, st);
+    case 64: return launch_cfg<64, 3>(mq, mc, a, st);
+    case 112: return launch_cfg<112, 2>(mq, mc, a, st);
+    default: set_error("search_tc: bad KP %d", p.KP); return TSIM_ERR_INVALID_ARG;
+  }
+}
+
+}  // namespace tsim

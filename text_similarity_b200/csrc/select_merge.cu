@@ -1,0 +1,341 @@
+// K3: second-pass selection over candidate lists.
+//
+//  * select_rescore_kernel  -- per query: gather the packed (approx score, row) keys that the
+//    tensor-core pass left in its per-unit lists, keep the best KP, PROVE that no row outside
+//    them can be in the exact top-k (else flag the query for the float64 scan), recompute the
+//    survivors' cosine in float64 with the canonical warp routine and emit the top-k ranked by
+//    (score desc, row asc).
+//  * merge_exact_lists_kernel -- same ending for the lists written by the exact scan.
+//  * merge_topk_kernel -- tsim_merge_topk: merge of per-shard / per-chunk result lists (the
+//    merge the reference lacks: search_pipeline.py:83,88 overwrites).
+//
+// HBM-bound, tiny: algorithmic bytes = Q * n_lists * k * 12 in + Q * k * 12 out.
+#include "tsim_common.cuh"
+
+namespace tsim {
+namespace {
+
+constexpr int kSelThreads = 256;
+constexpr int kKeyCap = 2048;   // packed keys held in smem by select_rescore
+constexpr int kPairCap = 2048;  // (double, int64) pairs held in smem by the pair merges
+
+__device__ __forceinline__ int next_pow2(int n) {
+  int p = 1;
+  while (p < n) p <<= 1;
+  return p;
+}
+
+// block-wide bitonic sort, DESCENDING, n a power of two, keys in shared memory
+__device__ void sort_keys_desc(uint64_t* a, int n) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          uint64_t x = a[i], y = a[ixj];
+          bool desc = ((i & k) == 0);
+          if (desc ? (x < y) : (x > y)) { a[i] = y; a[ixj] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// (score desc, index asc) order on pairs; idx < 0 (padding) ranks last
+__device__ __forceinline__ bool pair_before(double s1, int64_t i1, double s2, int64_t i2) {
+  bool p1 = i1 < 0, p2 = i2 < 0;
+  if (p1 != p2) return p2;
+  if (p1) return false;
+  if (s1 != s2) return s1 > s2;
+  return i1 < i2;
+}
+
+__device__ void sort_pairs(double* s, int64_t* ix, int n) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          double s1 = s[i], s2 = s[ixj];
+          int64_t i1 = ix[i], i2 = ix[ixj];
+          bool first_block = ((i & k) == 0);
+          bool swap = first_block ? pair_before(s2, i2, s1, i1) : pair_before(s1, i1, s2, i2);
+          if (swap) { s[i] = s2; s[ixj] = s1; ix[i] = i2; ix[ixj] = i1; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// Streaming top-`keep` over `total` source pairs using a kPairCap smem buffer.
+// load(i, &s, &ix) fetches source pair i.  On return s/ix[0..n) is sorted, n <= kPairCap.
+template <class Load>
+__device__ int stream_top_pairs(double* s, int64_t* ix, int* n_sh, int64_t total, int keep, Load load) {
+  if (threadIdx.x == 0) *n_sh = 0;
+  __syncthreads();
+  int64_t cursor = 0;
+  int n = 0;
+  while (cursor < total) {
+    int64_t take = min((int64_t)(kPairCap - n), total - cursor);
+    for (int64_t i = threadIdx.x; i < take; i += blockDim.x) {
+      double v; int64_t id;
+      load(cursor + i, &v, &id);
+      if (id >= 0) {
+        int p = atomicAdd(n_sh, 1);
+        s[p] = v; ix[p] = id;
+      }
+    }
+    cursor += take;
+    __syncthreads();
+    n = *n_sh;
+    if (cursor < total && n > kPairCap / 2) {
+      int np = next_pow2(n);
+      for (int i = n + threadIdx.x; i < np; i += blockDim.x) { s[i] = 0.0; ix[i] = -1; }
+      __syncthreads();
+      sort_pairs(s, ix, np);
+      n = min(n, keep);
+      if (threadIdx.x == 0) *n_sh = n;
+      __syncthreads();
+    }
+  }
+  int np = next_pow2(max(n, 1));
+  for (int i = n + threadIdx.x; i < np; i += blockDim.x) { s[i] = 0.0; ix[i] = -1; }
+  __syncthreads();
+  sort_pairs(s, ix, np);
+  return n;
+}
+
+// Re-evaluate rows ix[0..m) against query row q with the canonical float64 routine, sort by
+// (score desc, row asc) and write the best k.  ix holds LOCAL corpus rows.
+__device__ void rescore_and_emit(double* s, int64_t* ix, int m, const void* qrow, int q_dt,
+                                 const void* corpus, int c_dt, int64_t c_stride, int64_t D, int k,
+                                 int64_t idx_base, float* out_score, double* out_score64,
+                                 int64_t* out_idx) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int csz = dtype_size(c_dt);
+  for (int j = warp; j < m; j += nw) {
+    const char* crow = (const char*)corpus + (size_t)ix[j] * c_stride * csz;
+    double v = warp_exact_cosine(qrow, q_dt, crow, c_dt, D);
+    if (lane == 0) s[j] = v;
+  }
+  int np = next_pow2(max(m, 1));
+  __syncthreads();
+  for (int i = m + threadIdx.x; i < np; i += blockDim.x) { s[i] = 0.0; ix[i] = -1; }
+  __syncthreads();
+  sort_pairs(s, ix, np);
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    bool ok = j < m;
+    out_score[j] = ok ? (float)s[j] : -INFINITY;
+    if (out_score64) out_score64[j] = ok ? s[j] : -INFINITY;
+    out_idx[j] = ok ? idx_base + ix[j] : -1;
+  }
+}
+
+struct SelArgs {
+  const void* q; int q_dt; int64_t q_stride;
+  const void* corpus; int c_dt; int64_t c_stride;
+  int64_t Q, N, D; int k; int64_t idx_base;
+  int KP; int64_t NC;
+  const uint64_t* cand; const uint32_t* thr;
+  int32_t* flag_cnt; int32_t* flag_list;
+  float* out_score; double* out_score64; int64_t* out_idx; int32_t* out_flags;
+};
+
+__global__ void __launch_bounds__(kSelThreads) select_rescore_kernel(SelArgs a) {
+  __shared__ uint64_t keys[kKeyCap];
+  __shared__ double es[128];
+  __shared__ int64_t ei[128];
+  __shared__ int n_sh;
+  __shared__ double red[kSelThreads / 32];
+  const int64_t q = blockIdx.x;
+  const int tid = threadIdx.x;
+  const uint32_t thr_ord = a.thr[q];  // 0: no unit list ever filled -> nothing was dropped
+  const uint64_t* src = a.cand + (size_t)q * a.NC * a.KP;
+  const int64_t total = a.NC * a.KP;
+  if (tid == 0) n_sh = 0;
+  __syncthreads();
+
+  // ---- gather surviving keys; sort; keep the best KP --------------------------------------
+  int64_t cursor = 0;
+  int n = 0;
+  while (cursor < total) {
+    int64_t take = min((int64_t)(kKeyCap - n), total - cursor);
+    for (int64_t i = tid; i < take; i += blockDim.x) {
+      uint64_t key = __ldcg(src + cursor + i);
+      if (key != 0 && (uint32_t)(key >> 32) >= thr_ord) keys[atomicAdd(&n_sh, 1)] = key;
+    }
+    cursor += take;
+    __syncthreads();
+    n = n_sh;
+    if (cursor < total && n > kKeyCap / 2) {
+      int np = next_pow2(n);
+      for (int i = n + tid; i < np; i += blockDim.x) keys[i] = 0;
+      __syncthreads();
+      sort_keys_desc(keys, np);
+      n = min(n, a.KP);
+      if (tid == 0) n_sh = n;
+      __syncthreads();
+    }
+  }
+  {
+    int np = next_pow2(max(n, 1));
+    for (int i = n + tid; i < np; i += blockDim.x) keys[i] = 0;
+    __syncthreads();
+    sort_keys_desc(keys, np);
+  }
+  const int m = min(n, a.KP);
+
+  // ---- ||q|| (float64) for the safety margin -----------------------------------------------
+  const char* qrow = (const char*)a.q + (size_t)q * a.q_stride * dtype_size(a.q_dt);
+  double qq = 0.0;
+  for (int64_t d = tid; d < a.D; d += blockDim.x) {
+    double v = (double)load_elem(qrow, a.q_dt, d);
+    qq = fma(v, v, qq);
+  }
+  qq = warp_sum_f64(qq);
+  if ((tid & 31) == 0) red[tid >> 5] = qq;
+  __syncthreads();
+  qq = 0.0;
+  for (int i = 0; i < kSelThreads / 32; ++i) qq += red[i];
+  const double qn = fmax(sqrt(qq), kCosEps);
+
+  // ---- completeness proof -------------------------------------------------------------------
+  // Every row that is NOT among the candidates has approx <= a_KP (the KP-th best candidate):
+  // it was either evicted from a full unit list or rejected by a threshold that was the minimum
+  // of a full list.  With |approx - exact * ||q||| <= eps * ||q||, a gap a_k - a_KP > 2 eps ||q||
+  // proves such a row (and any candidate ranked beyond KP) is below the exact k-th best.
+  bool flagged = false;
+  if (thr_ord != 0) {
+    int kk = min(a.k, m);
+    float a_k = key_score(keys[kk - 1]);
+    float a_kp = key_score(keys[m - 1]);
+    flagged = !((double)a_k - (double)a_kp > 2.0 * (double)kApproxEps * qn) || (m < a.KP);
+  }
+
+  for (int j = tid; j < m; j += blockDim.x) { ei[j] = (int64_t)key_idx(keys[j]); es[j] = 0.0; }
+  __syncthreads();
+  rescore_and_emit(es, ei, m, qrow, a.q_dt, a.corpus, a.c_dt, a.c_stride, a.D, a.k, a.idx_base,
+                   a.out_score + q * a.k, a.out_score64 ? a.out_score64 + q * a.k : nullptr,
+                   a.out_idx + q * a.k);
+  if (tid == 0) {
+    if (a.out_flags) a.out_flags[q] = flagged ? 1 : 0;
+    if (flagged) a.flag_list[atomicAdd(a.flag_cnt, 1)] = (int32_t)q;
+  }
+}
+
+struct ExMergeArgs {
+  const void* q; int q_dt; int64_t q_stride;
+  const void* corpus; int c_dt; int64_t c_stride;
+  int64_t Q, D; int k; int64_t idx_base; int S;
+  const int32_t* flag_cnt; const int32_t* flag_list;  // null: every query, slot == query
+  const double* ex_score; const uint32_t* ex_idx;     // [slot][S][k]
+  float* out_score; double* out_score64; int64_t* out_idx; int32_t* out_flags;
+};
+
+__global__ void __launch_bounds__(kSelThreads) merge_exact_lists_kernel(ExMergeArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s = (double*)smem_raw;
+  int64_t* ix = (int64_t*)(smem_raw + sizeof(double) * kPairCap);
+  __shared__ int n_sh;
+  const int64_t slot = blockIdx.x;
+  int64_t q = slot;
+  if (a.flag_cnt) {
+    if (slot >= *a.flag_cnt) return;
+    q = a.flag_list[slot];
+  }
+  const double* ss = a.ex_score + (size_t)slot * a.S * a.k;
+  const uint32_t* si = a.ex_idx + (size_t)slot * a.S * a.k;
+  int n = stream_top_pairs(s, ix, &n_sh, (int64_t)a.S * a.k, a.k,
+                           [&](int64_t i, double* v, int64_t* id) {
+                             uint32_t r = si[i];
+                             *v = ss[i];
+                             *id = (r == 0xffffffffu) ? -1 : (int64_t)r;
+                           });
+  const int m = min(n, a.k);
+  __syncthreads();
+  const char* qrow = (const char*)a.q + (size_t)q * a.q_stride * dtype_size(a.q_dt);
+  rescore_and_emit(s, ix, m, qrow, a.q_dt, a.corpus, a.c_dt, a.c_stride, a.D, a.k, a.idx_base,
+                   a.out_score + q * a.k, a.out_score64 ? a.out_score64 + q * a.k : nullptr,
+                   a.out_idx + q * a.k);
+  if (threadIdx.x == 0 && a.out_flags) a.out_flags[q] = 1;
+}
+
+__global__ void __launch_bounds__(kSelThreads) merge_topk_kernel(const double* sc, const int64_t* ix_in,
+                                                                int64_t total, int k_out,
+                                                                float* out_score, double* out_score64,
+                                                                int64_t* out_idx) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int np = next_pow2((int)max(total, (int64_t)1));
+  double* s = (double*)smem_raw;
+  int64_t* ix = (int64_t*)(smem_raw + sizeof(double) * np);
+  const int64_t q = blockIdx.x;
+  for (int i = threadIdx.x; i < np; i += blockDim.x) {
+    bool ok = i < total;
+    s[i] = ok ? sc[q * total + i] : 0.0;
+    ix[i] = ok ? ix_in[q * total + i] : -1;
+  }
+  __syncthreads();
+  sort_pairs(s, ix, np);
+  for (int j = threadIdx.x; j < k_out; j += blockDim.x) {
+    bool ok = j < total && ix[j] >= 0;
+    out_score[q * k_out + j] = ok ? (float)s[j] : -INFINITY;
+    if (out_score64) out_score64[q * k_out + j] = ok ? s[j] : -INFINITY;
+    out_idx[q * k_out + j] = ok ? ix[j] : -1;
+  }
+}
+
+}  // namespace
+
+int launch_select_rescore(const void* q, int q_dt, int64_t q_stride, const void* corpus, int c_dt,
+                          int64_t c_stride, int64_t Q, int64_t N, int64_t D, int k,
+                          int64_t idx_base, const SearchPlan& p, const uint64_t* cand,
+                          const uint32_t* thr, int32_t* flag_cnt, int32_t* flag_list,
+                          float* out_score, double* out_score64, int64_t* out_idx,
+                          int32_t* out_flags, cudaStream_t st) {
+  SelArgs a;
+  a.q = q; a.q_dt = q_dt; a.q_stride = q_stride;
+  a.corpus = corpus; a.c_dt = c_dt; a.c_stride = c_stride;
+  a.Q = Q; a.N = N; a.D = D; a.k = k; a.idx_base = idx_base;
+  a.KP = p.KP; a.NC = p.NC; a.cand = cand; a.thr = thr;
+  a.flag_cnt = flag_cnt; a.flag_list = flag_list;
+  a.out_score = out_score; a.out_score64 = out_score64; a.out_idx = out_idx; a.out_flags = out_flags;
+  select_rescore_kernel<<<(unsigned)Q, kSelThreads, 0, st>>>(a);
+  TSIM_CUDA(cudaGetLastError());
+  return TSIM_OK;
+}
+
+int launch_merge_exact_lists(const void* q, int q_dt, int64_t q_stride, const void* corpus,
+                             int c_dt, int64_t c_stride, int64_t Q, int64_t D, int k,
+                             int64_t idx_base, const SearchPlan& p, const int32_t* flag_cnt,
+                             const int32_t* flag_list, const double* ex_score,
+                             const uint32_t* ex_idx, float* out_score, double* out_score64,
+                             int64_t* out_idx, int32_t* out_flags, cudaStream_t st) {
+  ExMergeArgs a;
+  a.q = q; a.q_dt = q_dt; a.q_stride = q_stride;
+  a.corpus = corpus; a.c_dt = c_dt; a.c_stride = c_stride;
+  a.Q = Q; a.D = D; a.k = k; a.idx_base = idx_base; a.S = p.S;
+  a.flag_cnt = flag_cnt; a.flag_list = flag_list; a.ex_score = ex_score; a.ex_idx = ex_idx;
+  a.out_score = out_score; a.out_score64 = out_score64; a.out_idx = out_idx; a.out_flags = out_flags;
+  size_t smem = (size_t)kPairCap * (sizeof(double) + sizeof(int64_t));
+  merge_exact_lists_kernel<<<(unsigned)Q, kSelThreads, smem, st>>>(a);
+  TSIM_CUDA(cudaGetLastError());
+  return TSIM_OK;
+}
+
+int launch_merge_topk(const double* sc, const int64_t* ix, int64_t Q, int64_t n_lists, int k_in,
+                      int k_out, float* out_score, double* out_score64, int64_t* out_idx,
+                      cudaStream_t st) {
+  int64_t total = n_lists * (int64_t)k_in;
+  int np = 1;
+  while (np < total) np <<= 1;
+  size_t smem = (size_t)np * (sizeof(double) + sizeof(int64_t));
+  if (smem > 48 * 1024)
+    TSIM_CUDA(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  merge_topk_kernel<<<(unsigned)Q, kSelThreads, smem, st>>>(sc, ix, total, k_out, out_score, out_score64, out_idx);
+  TSIM_CUDA(cudaGetLastError());
+  return TSIM_OK;
+}
+
+}  // namespace tsim

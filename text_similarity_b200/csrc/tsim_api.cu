@@ -1,0 +1,198 @@
+// C-ABI entry points of libtsim.so (see include/tsim.h), launch planning and error reporting.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "tsim_common.cuh"
+
+namespace tsim {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int device_sm_count() {
+  // per-device cache; 148 (B200) when no device is visible so that planning still works on a
+  // CPU-only build box
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 148; }
+  if (dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = 148;
+    }
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static bool tensor_shape_ok(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt) {
+  return q_dt == TSIM_BF16 && c_dt == TSIM_BF16 && D % 8 == 0 && D >= 8 && k <= 100 && Q > 0 && N > 0 &&
+         N < (int64_t)0x7fffff00 && Q < (int64_t)0x7fffff00;
+}
+
+int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt, int mode,
+                     bool need_invnorm, SearchPlan* p) {
+  memset(p, 0, sizeof(*p));
+  const int sms = device_sm_count();
+  const bool ok = tensor_shape_ok(Q, N, D, k, q_dt, c_dt);
+  if (mode == TSIM_MODE_TENSOR && !ok) {
+    set_error("search: TSIM_MODE_TENSOR needs bf16 queries and corpus, D %% 8 == 0, k <= 100 "
+              "(got q_dt=%d c_dt=%d D=%lld k=%d)", q_dt, c_dt, (long long)D, k);
+    return TSIM_ERR_UNSUPPORTED;
+  }
+  p->use_tensor = (mode != TSIM_MODE_EXACT) && ok;
+  size_t off = 0;
+  if (p->use_tensor) {
+    p->KP = k <= 10 ? 16 : k <= 24 ? 32 : k <= 52 ? 64 : 112;
+    p->QB = (int)((Q + 127) / 128);
+    int64_t nct = (8 * (int64_t)sms + p->QB - 1) / p->QB;  // aim at ~8 units per SM
+    if (nct < 1) nct = 1;
+    int64_t R = (N + nct - 1) / nct;
+    R = (R + 255) / 256 * 256;
+    if (R < 256) R = 256;
+    if (R > 65536) R = 65536;
+    // bound the candidate buffer (Q * NC * KP * 8 bytes) to ~2 GB
+    while ((double)Q * (double)((N + R - 1) / R) * p->KP * 8.0 > 2.0e9 && R < ((int64_t)1 << 30)) R *= 2;
+    p->R = R;
+    p->NC = (N + R - 1) / R;
+    p->off_cand = off; off = align_up(off + (size_t)Q * p->NC * p->KP * sizeof(uint64_t), 256);
+  }
+  // exact scan (whole-call path, or fallback for flagged queries)
+  int64_t S = (N + 1023) / 1024;
+  if (S < 1) S = 1;
+  if (S > 2 * sms) S = 2 * sms;
+  while (S > 1 && (double)Q * (double)S * k * 12.0 > 5.0e8) S = (S + 1) / 2;
+  int64_t sr = (N + S - 1) / S;
+  sr = (sr + 31) / 32 * 32;
+  if (sr < 32) sr = 32;
+  p->slice_rows = sr;
+  p->S = (int)((N + sr - 1) / sr);
+  if (p->S < 1) p->S = 1;
+  p->off_thr = off; off = align_up(off + (size_t)Q * sizeof(uint32_t), 256);
+  p->off_flagcnt = off; off += 256;
+  p->off_flaglist = off; off = align_up(off + (size_t)Q * sizeof(int32_t), 256);
+  if (need_invnorm && p->use_tensor) { p->off_invnorm = off; off = align_up(off + (size_t)N * sizeof(float), 256); }
+  p->off_ex_score = off; off = align_up(off + (size_t)Q * p->S * k * sizeof(double), 256);
+  p->off_ex_idx = off; off = align_up(off + (size_t)Q * p->S * k * sizeof(uint32_t), 256);
+  p->total = off + 256;
+  return TSIM_OK;
+}
+
+}  // namespace tsim
+
+using namespace tsim;
+
+extern "C" int tsim_version(void) { return TSIM_ABI_VERSION; }
+extern "C" const char* tsim_last_error(void) { return g_err; }
+
+static int check_search_args(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt, int mode) {
+  TSIM_CHECK_ARG(Q >= 0 && N >= 0 && D > 0, "search: bad shape Q=%lld N=%lld D=%lld", (long long)Q, (long long)N, (long long)D);
+  TSIM_CHECK_ARG(k >= 1 && k <= 1024, "search: k=%d out of range [1, 1024]", k);
+  TSIM_CHECK_ARG(dtype_size(q_dt) && dtype_size(c_dt), "search: bad dtype q=%d c=%d", q_dt, c_dt);
+  TSIM_CHECK_ARG(mode >= TSIM_MODE_AUTO && mode <= TSIM_MODE_TENSOR, "search: bad mode %d", mode);
+  TSIM_CHECK_ARG(N < (int64_t)0xfffffff0, "search: N=%lld rows per shard exceeds 2^32", (long long)N);
+  return TSIM_OK;
+}
+
+extern "C" size_t tsim_search_workspace_bytes(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
+                                              int mode) {
+  if (check_search_args(Q, N, D, k, q_dt, c_dt, mode) != TSIM_OK) return 0;
+  SearchPlan p;
+  if (make_search_plan(Q, N, D, k, q_dt, c_dt, mode, /*need_invnorm=*/true, &p) != TSIM_OK) return 0;
+  return p.total;
+}
+
+extern "C" int tsim_search_topk(const void* q, int q_dt, int64_t q_stride, const void* corpus, int c_dt,
+                                int64_t c_stride, const float* corpus_inv_norm, int64_t Q, int64_t N,
+                                int64_t D, int k, int64_t idx_base, int64_t exclude_self_base, int mode,
+                                float* out_score, double* out_score64, int64_t* out_idx,
+                                int32_t* out_flags, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_search_args(Q, N, D, k, q_dt, c_dt, mode);
+  if (rc) return rc;
+  if (Q == 0) return TSIM_OK;
+  TSIM_CHECK_ARG(q && out_score && out_idx, "search: null pointer");
+  TSIM_CHECK_ARG(N == 0 || corpus, "search: null corpus");
+  TSIM_CHECK_ARG(q_stride >= D && c_stride >= D, "search: row stride smaller than D");
+  cudaStream_t st = (cudaStream_t)stream;
+  SearchPlan p;
+  rc = make_search_plan(Q, N, D, k, q_dt, c_dt, mode, true, &p);
+  if (rc) return rc;
+  if (!ws || ws_bytes < p.total) {
+    set_error("search: workspace too small (%zu < %zu bytes)", ws_bytes, p.total);
+    return TSIM_ERR_WORKSPACE;
+  }
+  if (p.use_tensor) {
+    const bool aligned = (((uintptr_t)q & 15) == 0) && (((uintptr_t)corpus & 15) == 0) &&
+                         (q_stride % 8 == 0) && (c_stride % 8 == 0);
+    if (!aligned) {
+      if (mode == TSIM_MODE_TENSOR) {
+        set_error("search: TMA needs 16-byte aligned bases and row strides (multiples of 8 elements)");
+        return TSIM_ERR_MISALIGNED;
+      }
+      p.use_tensor = 0;
+    }
+  }
+  char* w = (char*)ws;
+  uint32_t* thr = (uint32_t*)(w + p.off_thr);
+  int32_t* flag_cnt = (int32_t*)(w + p.off_flagcnt);
+  int32_t* flag_list = (int32_t*)(w + p.off_flaglist);
+  double* ex_score = (double*)(w + p.off_ex_score);
+  uint32_t* ex_idx = (uint32_t*)(w + p.off_ex_idx);
+  const int self_on = exclude_self_base >= 0;
+  const int64_t self_off = exclude_self_base - idx_base;  // local corpus row of query 0's own row
+
+  if (p.use_tensor) {
+    // thr and flag_cnt are adjacent: one memset
+    TSIM_CUDA(cudaMemsetAsync(thr, 0, (p.off_flagcnt + 256) - p.off_thr, st));
+    const float* c_inv = corpus_inv_norm;
+    if (!c_inv) {
+      float* tmp = (float*)(w + p.off_invnorm);
+      rc = launch_row_inv_norm(corpus, c_dt, N, D, c_stride, tmp, st);
+      if (rc) return rc;
+      c_inv = tmp;
+    }
+    rc = launch_search_tc(q, q_stride, corpus, c_stride, c_inv, Q, N, D, self_on, self_off, p,
+                          (uint64_t*)(w + p.off_cand), thr, st);
+    if (rc) return rc;
+    rc = launch_select_rescore(q, q_dt, q_stride, corpus, c_dt, c_stride, Q, N, D, k, idx_base, p,
+                               (const uint64_t*)(w + p.off_cand), thr, flag_cnt, flag_list,
+                               out_score, out_score64, out_idx, out_flags, st);
+    if (rc) return rc;
+    // queries whose candidate set could not be proven complete: float64 scan (usually none)
+    rc = launch_search_exact(q, q_dt, q_stride, corpus, c_dt, c_stride, Q, N, D, k, self_on, self_off, p,
+                             flag_cnt, flag_list, ex_score, ex_idx, st);
+    if (rc) return rc;
+    return launch_merge_exact_lists(q, q_dt, q_stride, corpus, c_dt, c_stride, Q, D, k, idx_base, p,
+                                    flag_cnt, flag_list, ex_score, ex_idx, out_score, out_score64,
+                                    out_idx, out_flags, st);
+  }
+  rc = launch_search_exact(q, q_dt, q_stride, corpus, c_dt, c_stride, Q, N, D, k, self_on, self_off, p,
+                           nullptr, nullptr, ex_score, ex_idx, st);
+  if (rc) return rc;
+  return launch_merge_exact_lists(q, q_dt, q_stride, corpus, c_dt, c_stride, Q, D, k, idx_base, p,
+                                  nullptr, nullptr, ex_score, ex_idx, out_score, out_score64, out_idx,
+                                  out_flags, st);
+}
+
+extern "C" int tsim_merge_topk(const double* sc, const int64_t* ix, int64_t Q, int64_t n_lists, int k_in,
+                               int k_out, float* out_score, double* out_score64, int64_t* out_idx,
+                               void* stream) {
+  TSIM_CHECK_ARG(Q >= 0 && n_lists >= 1 && k_in >= 1 && k_out >= 1, "merge_topk: bad shape");
+  TSIM_CHECK_ARG(n_lists * (int64_t)k_in <= 4096, "merge_topk: n_lists * k_in = %lld exceeds 4096",
+                 (long long)(n_lists * (int64_t)k_in));
+  if (Q == 0) return TSIM_OK;
+  TSIM_CHECK_ARG(sc && ix && out_score && out_idx, "merge_topk: null pointer");
+  return launch_merge_topk(sc, ix, Q, n_lists, k_in, k_out, out_score, out_score64, out_idx,
+                           (cudaStream_t)stream);
+}

@@ -1,0 +1,193 @@
+// Shared device/host helpers for libtsim (B200 / sm_100a).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/tsim.h"
+
+namespace tsim {
+
+constexpr double kCosEps = 1e-8;   // F.cosine_similarity eps, reference search_pipeline.py:77
+constexpr float kPoolEps = 1e-9f;  // clamp in AvgPoolingStrategy, reference modules.py:168
+
+// Relative error bound assumed for a tensor-core (bf16 x bf16 -> fp32) cosine, in units of
+// ||q|| * ||c||.  Candidates are proven complete when the approximate k-th and KP-th best
+// differ by more than 2 * kApproxEps (see select_merge.cu); tests measure the real error.
+constexpr float kApproxEps = 5e-5f;
+
+void set_error(const char* fmt, ...);
+
+#define TSIM_CHECK_ARG(cond, ...)          \
+  do {                                     \
+    if (!(cond)) {                         \
+      ::tsim::set_error(__VA_ARGS__);      \
+      return TSIM_ERR_INVALID_ARG;         \
+    }                                      \
+  } while (0)
+
+#define TSIM_CUDA(call)                                                            \
+  do {                                                                             \
+    cudaError_t e__ = (call);                                                      \
+    if (e__ != cudaSuccess) {                                                      \
+      ::tsim::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),   \
+                        __FILE__, __LINE__);                                       \
+      return TSIM_ERR_CUDA;                                                        \
+    }                                                                              \
+  } while (0)
+
+__host__ __device__ inline int dtype_size(int dt) {
+  switch (dt) {
+    case TSIM_F32: return 4;
+    case TSIM_F16: return 2;
+    case TSIM_BF16: return 2;
+    case TSIM_E4M3: return 1;
+    default: return 0;
+  }
+}
+
+// ---- element loads -------------------------------------------------------------------
+template <int DT> struct Elem;
+template <> struct Elem<TSIM_F32> {
+  using T = float;
+  static __device__ __forceinline__ float ld(const void* p, int64_t i) { return ((const float*)p)[i]; }
+};
+template <> struct Elem<TSIM_F16> {
+  using T = __half;
+  static __device__ __forceinline__ float ld(const void* p, int64_t i) { return __half2float(((const __half*)p)[i]); }
+};
+template <> struct Elem<TSIM_BF16> {
+  using T = __nv_bfloat16;
+  static __device__ __forceinline__ float ld(const void* p, int64_t i) { return __bfloat162float(((const __nv_bfloat16*)p)[i]); }
+};
+template <> struct Elem<TSIM_E4M3> {
+  using T = __nv_fp8_e4m3;
+  static __device__ __forceinline__ float ld(const void* p, int64_t i) {
+    return float(((const __nv_fp8_e4m3*)p)[i]);
+  }
+};
+
+__device__ __forceinline__ float load_elem(const void* p, int dt, int64_t i) {
+  switch (dt) {
+    case TSIM_F32: return Elem<TSIM_F32>::ld(p, i);
+    case TSIM_F16: return Elem<TSIM_F16>::ld(p, i);
+    case TSIM_BF16: return Elem<TSIM_BF16>::ld(p, i);
+    default: return Elem<TSIM_E4M3>::ld(p, i);
+  }
+}
+
+// ---- order-preserving float <-> uint maps (for atomicMax and packed sort keys) ----------
+__host__ __device__ __forceinline__ uint32_t f32_to_ord(float f) {
+#ifdef __CUDA_ARCH__
+  uint32_t b = __float_as_uint(f);
+#else
+  uint32_t b; memcpy(&b, &f, 4);
+#endif
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ord_to_f32(uint32_t o) {
+  uint32_t b = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+  return __uint_as_float(b);
+}
+__device__ __forceinline__ uint64_t f64_to_ord(double d) {
+  uint64_t b = (uint64_t)__double_as_longlong(d);
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+// Packed candidate key: sorting DESCENDING by the 64-bit value ranks by
+// (approximate score descending, row index ascending).  0 is the empty slot.
+__device__ __forceinline__ uint64_t pack_key(float s, uint32_t idx) {
+  return ((uint64_t)f32_to_ord(s) << 32) | (uint64_t)(0xffffffffu - idx);
+}
+__device__ __forceinline__ float key_score(uint64_t k) { return ord_to_f32((uint32_t)(k >> 32)); }
+__device__ __forceinline__ uint32_t key_idx(uint64_t k) { return 0xffffffffu - (uint32_t)k; }
+
+// ---- warp helpers ------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_sum_f32(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// The CANONICAL exact cosine of two stored rows, evaluated by one full warp.
+// Every score the library returns is produced by this routine, whichever path nominated the
+// row, so equal stored rows always yield bit-identical scores (ties -> lower index).
+// Products of bf16/fp16/fp8/fp32 values are exact in float64; lane l sums elements
+// l, l+32, ... sequentially, then a fixed xor-butterfly adds the 32 partials.
+__device__ __forceinline__ double warp_exact_cosine(const void* q, int q_dt, const void* c, int c_dt,
+                                                    int64_t D) {
+  const int lane = threadIdx.x & 31;
+  double dot = 0.0, qq = 0.0, cc = 0.0;
+  for (int64_t d = lane; d < D; d += 32) {
+    double a = (double)load_elem(q, q_dt, d);
+    double b = (double)load_elem(c, c_dt, d);
+    dot = fma(a, b, dot);
+    qq = fma(a, a, qq);
+    cc = fma(b, b, cc);
+  }
+  dot = warp_sum_f64(dot);
+  qq = warp_sum_f64(qq);
+  cc = warp_sum_f64(cc);
+  double qn = fmax(sqrt(qq), kCosEps);
+  double cn = fmax(sqrt(cc), kCosEps);
+  return dot / (qn * cn);
+}
+
+// ---- launch plans shared by the API and the kernels ---------------------------------------
+struct SearchPlan {
+  // tensor path
+  int use_tensor;      // 1: tcgen05 candidate pass + select/rescore
+  int KP;              // per-unit candidate list capacity (16/32/64/128)
+  int QB;              // query blocks of 128
+  int64_t R;           // corpus rows per unit (multiple of 256)
+  int64_t NC;          // corpus chunks = ceil(N / R)
+  // exact path
+  int S;               // corpus slices (CTAs along the corpus) of the exact scan
+  int64_t slice_rows;  // rows per slice
+  // workspace offsets (bytes)
+  size_t off_cand, off_thr, off_flagcnt, off_flaglist, off_invnorm, off_ex_score, off_ex_idx;
+  size_t total;
+};
+
+int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt, int mode,
+                     bool need_invnorm, SearchPlan* plan);
+
+// kernels' host launchers (defined in the .cu files)
+int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_t c_stride,
+                     const float* c_inv, int64_t Q, int64_t N, int64_t D,
+                     int self_on, int64_t self_off, const SearchPlan& p, uint64_t* cand,
+                     uint32_t* thr, cudaStream_t st);
+int launch_select_rescore(const void* q, int q_dt, int64_t q_stride, const void* corpus, int c_dt,
+                          int64_t c_stride, int64_t Q, int64_t N, int64_t D, int k,
+                          int64_t idx_base, const SearchPlan& p, const uint64_t* cand,
+                          const uint32_t* thr, int32_t* flag_cnt, int32_t* flag_list,
+                          float* out_score, double* out_score64, int64_t* out_idx,
+                          int32_t* out_flags, cudaStream_t st);
+int launch_search_exact(const void* q, int q_dt, int64_t q_stride, const void* corpus, int c_dt,
+                        int64_t c_stride, int64_t Q, int64_t N, int64_t D, int k,
+                        int self_on, int64_t self_off, const SearchPlan& p, const int32_t* flag_cnt,
+                        const int32_t* flag_list, double* ex_score, uint32_t* ex_idx,
+                        cudaStream_t st);
+int launch_merge_exact_lists(const void* q, int q_dt, int64_t q_stride, const void* corpus,
+                             int c_dt, int64_t c_stride, int64_t Q, int64_t D, int k,
+                             int64_t idx_base, const SearchPlan& p, const int32_t* flag_cnt,
+                             const int32_t* flag_list, const double* ex_score,
+                             const uint32_t* ex_idx, float* out_score, double* out_score64,
+                             int64_t* out_idx, int32_t* out_flags, cudaStream_t st);
+int launch_merge_topk(const double* sc, const int64_t* ix, int64_t Q, int64_t n_lists, int k_in,
+                      int k_out, float* out_score, double* out_score64, int64_t* out_idx,
+                      cudaStream_t st);
+int launch_row_inv_norm(const void* x, int dt, int64_t N, int64_t D, int64_t stride, float* out,
+                        cudaStream_t st);
+
+int device_sm_count();
+
+}  // namespace tsim

@@ -1,0 +1,206 @@
+"""Tensor-level wrappers over the C ABI (libtsim.so).
+
+torch is used for device memory and streams only; every kernel here is hand-written CUDA for
+sm_100a reached through ctypes.  All functions require CUDA tensors and raise otherwise.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+_DT = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16,
+       torch.float8_e4m3fn: _lib.E4M3}
+_MASK_DT = {torch.int64: _lib.I64, torch.int32: _lib.I32, torch.uint8: _lib.U8, torch.bool: _lib.U8,
+            torch.float32: _lib.F32}
+_MODES = {"auto": _lib.MODE_AUTO, "exact": _lib.MODE_EXACT, "tensor": _lib.MODE_TENSOR}
+
+_workspaces = {}
+
+
+def _require_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("text_similarity_b200 ops need CUDA tensors: there is no CPU fallback")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise ValueError(f"tensors on different devices: {dev} vs {t.device}")
+    return dev
+
+
+def _stream(dev: torch.device) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _workspace(dev: torch.device, nbytes: int, tag: str) -> torch.Tensor:
+    """A per-(device, stream, purpose) scratch buffer that only ever grows."""
+    key = (dev.index, _stream(dev), tag)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
+        _workspaces[key] = ws
+    return ws
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise ValueError(f"unsupported dtype {t.dtype}") from None
+
+
+def pool_norm(token_embeddings: torch.Tensor, attention_mask: torch.Tensor, *,
+              out_dtype: torch.dtype = torch.float32, normalize: bool = True,
+              out: Optional[torch.Tensor] = None, out_rows: Optional[torch.Tensor] = None,
+              out_inv_norm: Optional[torch.Tensor] = None
+              ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K1 -- fused masked mean-pool (+ L2 normalise) + cast.
+
+    token_embeddings [B, L, D] fp32/fp16/bf16, attention_mask [B, L] int64/int32/bool/uint8/fp32.
+    Returns (rows, inv_norm): rows [B, D] in ``out_dtype`` (or written into ``out`` at rows
+    ``out_rows``), inv_norm float32 = 1 / max(||stored row||, 1e-8).
+    Mean pooling follows reference src/modules/modules.py:158-171.
+    """
+    lib = _lib.load()
+    dev = _require_cuda(token_embeddings, attention_mask, out, out_rows, out_inv_norm)
+    if token_embeddings.dim() != 3:
+        raise ValueError("token_embeddings must be [batch, seq_len, embed_size]")  # modules.py:159
+    B, L, D = token_embeddings.shape
+    if attention_mask.shape != (B, L):
+        raise ValueError(f"attention_mask shape {tuple(attention_mask.shape)} != {(B, L)}")
+    tok = token_embeddings if token_embeddings.stride(2) == 1 else token_embeddings.contiguous()
+    mask = attention_mask if attention_mask.stride(1) == 1 else attention_mask.contiguous()
+    if mask.dtype not in _MASK_DT:
+        raise ValueError(f"unsupported mask dtype {mask.dtype}")
+    if out is None:
+        if out_rows is not None:
+            raise ValueError("out_rows needs out")
+        out = torch.empty(B, D, dtype=out_dtype, device=dev)
+    else:
+        if out.dim() != 2 or out.shape[1] != D or out.stride(1) != 1:
+            raise ValueError("out must be [rows, D] with contiguous rows")
+        out_dtype = out.dtype
+    n_out = out.shape[0]
+    if out_inv_norm is None:
+        out_inv_norm = torch.empty(n_out, dtype=torch.float32, device=dev)
+    if out_rows is not None:
+        out_rows = out_rows.to(device=dev, dtype=torch.int64).contiguous()
+        if out_rows.numel() != B:
+            raise ValueError("out_rows must have one entry per batch row")
+    elif n_out < B:
+        raise ValueError("out has fewer rows than the batch")
+    if B == 0:
+        return out, out_inv_norm
+    nbytes = lib.tsim_pool_workspace_bytes(B, L, D)
+    ws = _workspace(dev, nbytes, "pool")
+    with torch.cuda.device(dev):
+        rc = lib.tsim_pool_norm(tok.data_ptr(), _dt(tok), mask.data_ptr(), _MASK_DT[mask.dtype],
+                                B, L, D, tok.stride(0), tok.stride(1), mask.stride(0),
+                                out.data_ptr(), _dt(out), out.stride(0), _ptr(out_rows),
+                                out_inv_norm.data_ptr(), int(bool(normalize)),
+                                ws.data_ptr(), ws.numel(), _stream(dev))
+    _lib.check(rc, "tsim_pool_norm")
+    return out, out_inv_norm
+
+
+def row_inv_norm(x: torch.Tensor) -> torch.Tensor:
+    """1 / max(||x[i]||, 1e-8) per row (float32) of a stored [N, D] matrix."""
+    lib = _lib.load()
+    dev = _require_cuda(x)
+    if x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("x must be [N, D] with contiguous rows")
+    out = torch.empty(x.shape[0], dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.tsim_row_inv_norm(x.data_ptr(), _dt(x), x.shape[0], x.shape[1], x.stride(0),
+                                   out.data_ptr(), _stream(dev))
+    _lib.check(rc, "tsim_row_inv_norm")
+    return out
+
+
+def search_topk(queries: torch.Tensor, corpus: torch.Tensor, k: int, *,
+                corpus_inv_norm: Optional[torch.Tensor] = None, idx_base: int = 0,
+                exclude_self_base: int = -1, mode: str = "auto",
+                return_score64: bool = False, return_flags: bool = False):
+    """K2 + K3 -- exact cosine top-k of every query row against every corpus row.
+
+    Returns (scores float32 [Q, k], idx int64 [Q, k]) best first, ties by lower index, idx -1 /
+    score -inf past the last available row; optionally the float64 scores and the per-query
+    fallback flags.  Replaces the loop at reference src/pipeline/search_pipeline.py:73-79.
+    """
+    lib = _lib.load()
+    dev = _require_cuda(queries, corpus, corpus_inv_norm)
+    if queries.dim() != 2 or corpus.dim() != 2 or queries.shape[1] != corpus.shape[1]:
+        raise ValueError(f"queries {tuple(queries.shape)} and corpus {tuple(corpus.shape)} must be [*, D]")
+    if queries.stride(1) != 1:
+        queries = queries.contiguous()
+    if corpus.stride(1) != 1:
+        corpus = corpus.contiguous()
+    Q, D = queries.shape
+    N = corpus.shape[0]
+    k = int(k)
+    if mode not in _MODES:
+        raise ValueError(f"mode must be one of {sorted(_MODES)}")
+    if corpus_inv_norm is not None:
+        if corpus_inv_norm.dtype != torch.float32 or corpus_inv_norm.numel() != N:
+            raise ValueError("corpus_inv_norm must be float32 [N]")
+        corpus_inv_norm = corpus_inv_norm.contiguous()
+    scores = torch.empty(Q, k, dtype=torch.float32, device=dev)
+    idx = torch.empty(Q, k, dtype=torch.int64, device=dev)
+    s64 = torch.empty(Q, k, dtype=torch.float64, device=dev) if return_score64 else None
+    flags = torch.empty(Q, dtype=torch.int32, device=dev) if return_flags else None
+    nbytes = lib.tsim_search_workspace_bytes(Q, N, D, k, _dt(queries), _dt(corpus), _MODES[mode])
+    if nbytes == 0:
+        _lib.check(_lib.ERR_INVALID_ARG if mode != "tensor" else _lib.ERR_UNSUPPORTED,
+                   "tsim_search_workspace_bytes")
+    ws = _workspace(dev, nbytes, "search")
+    with torch.cuda.device(dev):
+        rc = lib.tsim_search_topk(queries.data_ptr(), _dt(queries), queries.stride(0),
+                                  corpus.data_ptr() if N else None, _dt(corpus), corpus.stride(0) if N else D,
+                                  _ptr(corpus_inv_norm), Q, N, D, k, int(idx_base),
+                                  int(exclude_self_base), _MODES[mode],
+                                  scores.data_ptr(), _ptr(s64), idx.data_ptr(), _ptr(flags),
+                                  ws.data_ptr(), ws.numel(), _stream(dev))
+    _lib.check(rc, "tsim_search_topk")
+    res = [scores, idx]
+    if return_score64:
+        res.append(s64)
+    if return_flags:
+        res.append(flags)
+    return tuple(res)
+
+
+def merge_topk(scores64: torch.Tensor, idx: torch.Tensor, k_out: int, n_lists: int = 1
+               ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """K3 second pass -- merge candidate lists [Q, n_lists * k_in] (float64 scores, int64 rows,
+    -1 = padding) into the top ``k_out`` by (score desc, row asc).
+    Returns (scores float32, scores float64, idx int64)."""
+    lib = _lib.load()
+    dev = _require_cuda(scores64, idx)
+    if scores64.shape != idx.shape or scores64.dim() != 2:
+        raise ValueError("scores64 and idx must both be [Q, n_lists * k_in]")
+    if scores64.dtype != torch.float64 or idx.dtype != torch.int64:
+        raise ValueError("merge_topk takes float64 scores and int64 indices")
+    scores64 = scores64.contiguous()
+    idx = idx.contiguous()
+    Q, total = scores64.shape
+    if total % n_lists:
+        raise ValueError("row length must be n_lists * k_in")
+    out_s = torch.empty(Q, k_out, dtype=torch.float32, device=dev)
+    out_s64 = torch.empty(Q, k_out, dtype=torch.float64, device=dev)
+    out_i = torch.empty(Q, k_out, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.tsim_merge_topk(scores64.data_ptr(), idx.data_ptr(), Q, n_lists, total // n_lists,
+                                 int(k_out), out_s.data_ptr(), out_s64.data_ptr(), out_i.data_ptr(),
+                                 _stream(dev))
+    _lib.check(rc, "tsim_merge_topk")
+    return out_s, out_s64, out_i
