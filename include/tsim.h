@@ -139,6 +139,13 @@ int tsim_merge_topk(const double* sc, const int64_t* ix, int64_t Q, int64_t n_li
                     int k_in, int k_out,
                     float* out_score, double* out_score64, int64_t* out_idx, void* stream);
 
+/* Measurement hook (bench.py / profiling only): when both events are non-NULL, the calling
+ * thread's following tsim_search_topk calls record `start` immediately before and `stop`
+ * immediately after the candidate-pass kernel (tcgen05 search, or the exact scan when that is
+ * the whole-call path) on the call's stream, so the dominant kernel can be timed on its own
+ * launching stream.  Events are cudaEvent_t cast to void*; pass NULL, NULL to switch off. */
+int tsim_set_timing_events(void* start, void* stop);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,7 @@ SIGNATURES = {
     "tsim_search_topk": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p,
                                  c_int64, c_int64, c_int64, c_int, c_int64, c_int64, c_int,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tsim_set_timing_events": (c_int, [c_void_p, c_void_p]),
     "tsim_merge_topk": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p]),
 }

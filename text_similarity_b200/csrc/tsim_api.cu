@@ -8,6 +8,7 @@
 namespace tsim {
 
 static thread_local char g_err[512] = "";
+static thread_local cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -95,6 +96,11 @@ using namespace tsim;
 
 extern "C" int tsim_version(void) { return TSIM_ABI_VERSION; }
 extern "C" const char* tsim_last_error(void) { return g_err; }
+extern "C" int tsim_set_timing_events(void* start, void* stop) {
+  g_ev_start = (cudaEvent_t)start;
+  g_ev_stop = (cudaEvent_t)stop;
+  return TSIM_OK;
+}
 
 static int check_search_args(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt, int mode) {
   TSIM_CHECK_ARG(Q >= 0 && N >= 0 && D > 0, "search: bad shape Q=%lld N=%lld D=%lld", (long long)Q, (long long)N, (long long)D);
@@ -162,9 +168,12 @@ extern "C" int tsim_search_topk(const void* q, int q_dt, int64_t q_stride, const
       if (rc) return rc;
       c_inv = tmp;
     }
+    const bool timed = g_ev_start && g_ev_stop;
+    if (timed) TSIM_CUDA(cudaEventRecord(g_ev_start, st));
     rc = launch_search_tc(q, q_stride, corpus, c_stride, c_inv, Q, N, D, self_on, self_off, p,
                           (uint64_t*)(w + p.off_cand), thr, st);
     if (rc) return rc;
+    if (timed) TSIM_CUDA(cudaEventRecord(g_ev_stop, st));
     rc = launch_select_rescore(q, q_dt, q_stride, corpus, c_dt, c_stride, Q, N, D, k, idx_base, p,
                                (const uint64_t*)(w + p.off_cand), thr, flag_cnt, flag_list,
                                out_score, out_score64, out_idx, out_flags, st);
@@ -177,9 +186,12 @@ extern "C" int tsim_search_topk(const void* q, int q_dt, int64_t q_stride, const
                                     flag_cnt, flag_list, ex_score, ex_idx, out_score, out_score64,
                                     out_idx, out_flags, st);
   }
+  const bool timed = g_ev_start && g_ev_stop;
+  if (timed) TSIM_CUDA(cudaEventRecord(g_ev_start, st));
   rc = launch_search_exact(q, q_dt, q_stride, corpus, c_dt, c_stride, Q, N, D, k, self_on, self_off, p,
                            nullptr, nullptr, ex_score, ex_idx, st);
   if (rc) return rc;
+  if (timed) TSIM_CUDA(cudaEventRecord(g_ev_stop, st));
   return launch_merge_exact_lists(q, q_dt, q_stride, corpus, c_dt, c_stride, Q, D, k, idx_base, p,
                                   nullptr, nullptr, ex_score, ex_idx, out_score, out_score64, out_idx,
                                   out_flags, st);

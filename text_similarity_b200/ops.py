@@ -130,7 +130,9 @@ def row_inv_norm(x: torch.Tensor) -> torch.Tensor:
 def search_topk(queries: torch.Tensor, corpus: torch.Tensor, k: int, *,
                 corpus_inv_norm: Optional[torch.Tensor] = None, idx_base: int = 0,
                 exclude_self_base: int = -1, mode: str = "auto",
-                return_score64: bool = False, return_flags: bool = False):
+                return_score64: bool = False, return_flags: bool = False,
+                out_scores: Optional[torch.Tensor] = None, out_idx: Optional[torch.Tensor] = None,
+                out_score64: Optional[torch.Tensor] = None):
     """K2 + K3 -- exact cosine top-k of every query row against every corpus row.
 
     Returns (scores float32 [Q, k], idx int64 [Q, k]) best first, ties by lower index, idx -1 /
@@ -154,9 +156,16 @@ def search_topk(queries: torch.Tensor, corpus: torch.Tensor, k: int, *,
         if corpus_inv_norm.dtype != torch.float32 or corpus_inv_norm.numel() != N:
             raise ValueError("corpus_inv_norm must be float32 [N]")
         corpus_inv_norm = corpus_inv_norm.contiguous()
-    scores = torch.empty(Q, k, dtype=torch.float32, device=dev)
-    idx = torch.empty(Q, k, dtype=torch.int64, device=dev)
-    s64 = torch.empty(Q, k, dtype=torch.float64, device=dev) if return_score64 else None
+    def _out(t, dtype):
+        if t is None:
+            return torch.empty(Q, k, dtype=dtype, device=dev)
+        if t.shape != (Q, k) or t.dtype != dtype or not t.is_contiguous() or t.device != dev:
+            raise ValueError(f"output tensor must be contiguous {dtype} [{Q}, {k}] on {dev}")
+        return t
+
+    scores = _out(out_scores, torch.float32)
+    idx = _out(out_idx, torch.int64)
+    s64 = _out(out_score64, torch.float64) if (return_score64 or out_score64 is not None) else None
     flags = torch.empty(Q, dtype=torch.int32, device=dev) if return_flags else None
     nbytes = lib.tsim_search_workspace_bytes(Q, N, D, k, _dt(queries), _dt(corpus), _MODES[mode])
     if nbytes == 0:
@@ -172,7 +181,7 @@ def search_topk(queries: torch.Tensor, corpus: torch.Tensor, k: int, *,
                                   ws.data_ptr(), ws.numel(), _stream(dev))
     _lib.check(rc, "tsim_search_topk")
     res = [scores, idx]
-    if return_score64:
+    if return_score64 or out_score64 is not None:
         res.append(s64)
     if return_flags:
         res.append(flags)
