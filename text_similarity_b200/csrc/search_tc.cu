@@ -21,6 +21,7 @@
 //
 // Roofline: 2*Q*N*D flops on the tensor pipe (Q >~ 240) or N*D*2 bytes from HBM (small Q).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "tsim_common.cuh"
 
@@ -96,6 +97,12 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B, 128-byte rows:
@@ -112,34 +119,158 @@ struct TcArgs {
   const float* c_inv;   // [N] inverse norms of the stored corpus rows
   int64_t Q, N;
   int kblocks;          // ceil(D / 64)
-  int QB;               // query blocks
-  int64_t R, NC;        // rows per chunk, chunks
-  int64_t n_units;
+  int QB;               // query blocks of 128
+  int64_t T;            // corpus tiles of 256 rows
+  int sticky;           // 1: CTA <-> (query block, tile residue class), one list per CTA lifetime
+  int Gq;               // sticky: CTAs per query block
+  int64_t tpc;          // round-robin: tiles per corpus chunk
+  int64_t NC;           // candidate lists per query (chunks, or Gq when sticky)
+  int64_t n_units;      // round-robin: QB * NC
   int self_on; int64_t self_off;
   uint64_t* cand;       // [Q][NC][KP] packed keys
   uint32_t* thr;        // [Q] ordered-float global thresholds (0 = none yet)
+  int dbg;              // TSIM_DEBUG bits (diagnosis only): 1 skip A loads, 2 skip MMAs, 4 skip epilogue math
 };
 
-// Rare path: insert (s, row) into this thread's descending list (column `lane` of ls/li).
-// The fill count lives in shared memory (*cntp) and the new threshold is returned, so the hot
-// loop keeps its state in registers across this (non-inlined) call.
-template <int KP>
-__device__ __noinline__ float list_insert(float* ls, uint32_t* li, int* cntp, float thr, float s, uint32_t row) {
-  int cnt = *cntp;
-  int pos = cnt < KP ? cnt : KP - 1;
-  while (pos > 0) {
-    float prev = ls[(pos - 1) * kEpiThreads];
-    if (!(prev < s)) break;            // equal scores keep arrival (= row) order
-    ls[pos * kEpiThreads] = prev;
-    li[pos * kEpiThreads] = li[(pos - 1) * kEpiThreads];
-    --pos;
+// A unit = one candidate list: a query block and the sequence of corpus tiles scanned into it.
+struct Unit { int qb; int64_t slot; int64_t tile0; int64_t tstride; int ntiles; };
+
+// Sticky schedule (few query blocks, the HBM-bound regime): CTA c keeps query block c % QB for its
+// whole life and takes tiles j, j+Gq, ... (j = c / QB): perfect tile balance, neighbouring CTAs
+// stream neighbouring tiles, the QB CTAs that share a tile run side by side (L2), and each query's
+// list -- hence its threshold -- persists over everything the CTA sees.
+// Round-robin schedule (many query blocks, the tensor-bound regime): unit u = (chunk u / QB,
+// query block u % QB) dealt to CTA u % grid; the QB units of one chunk run side by side.
+__device__ __forceinline__ bool get_unit(const TcArgs& a, int it, Unit& un) {
+  if (a.sticky) {
+    if (it > 0 || (int)blockIdx.x >= a.Gq * a.QB) return false;
+    const int j = (int)blockIdx.x / a.QB;
+    un.qb = (int)blockIdx.x % a.QB; un.slot = j; un.tile0 = j; un.tstride = a.Gq;
+    un.ntiles = j < a.T ? (int)((a.T - j + a.Gq - 1) / a.Gq) : 0;
+    return true;
   }
-  ls[pos * kEpiThreads] = s;
-  li[pos * kEpiThreads] = row;
-  if (cnt < KP) *cntp = ++cnt;
-  if (cnt == KP) thr = fmaxf(thr, ls[(KP - 1) * kEpiThreads]);
+  const int64_t u = blockIdx.x + (int64_t)it * gridDim.x;
+  if (u >= a.n_units) return false;
+  const int64_t chunk = u / a.QB;
+  un.qb = (int)(u % a.QB); un.slot = chunk; un.tile0 = chunk * a.tpc; un.tstride = 1;
+  un.ntiles = (int)min(a.tpc, a.T - un.tile0);
+  return true;
+}
+
+// ---- per-query candidate lists -----------------------------------------------------------------
+// Each epilogue thread owns the running top-KP (approx score, row) list of its query, sorted
+// descending, empty slots = (-inf, 0xffffffff).  The hot loop never touches the list: it takes the
+// max of a 32-column chunk and compares it with `thr`.  Only when that fires does the cold path
+// re-read the chunk from TMEM, 8 columns at a time, and insert what qualifies:
+//  * KP == 16 (k <= 10, the headline case): the list lives in REGISTERS for the whole unit and an
+//    insertion is a branch-free 16-step select network (no memory, no dependent-load chain);
+//  * larger KP: the list lives in shared memory as [entry][thread] columns (bank-conflict free)
+//    and the cold path is one non-inlined sorted shift-insertion.
+// A full list's minimum is a valid lower bound of the query's KP-th best anywhere in the corpus,
+// so it is published with atomicMax for every other CTA to filter with.
+struct RegList16 {
+  float a[16]; uint32_t r[16];
+  __device__ __forceinline__ RegList16(float*, uint32_t*) {}
+  __device__ __forceinline__ void reset() {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { a[i] = -INFINITY; r[i] = 0xffffffffu; }
+  }
+  __device__ __forceinline__ float slow(uint32_t taddr, const float* cnp, float thr, int64_t row_base,
+                                        int64_t self_row, int lim, uint32_t* thr_g) {
+    const float thr_in = thr;
+#pragma unroll 1
+    for (int g = 0; g < 4; ++g) {
+      uint32_t w[8];
+      tc_ld8(taddr + g * 8, w);
+      tc_ld_wait();
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int j = g * 8 + jj;
+        const float s = __uint_as_float(w[jj]) * cnp[j];
+        const int64_t row = row_base + j;
+        if (s > thr && j < lim && row != self_row) {
+          // a[] is sorted descending, so (s > a[i]) is monotone in i: entry i becomes the newcomer
+          // where the predicate first turns true, the old a[i-1] after that, and stays otherwise.
+          // Strict '>' puts the newcomer after equal scores (it has the larger row).
+#pragma unroll
+          for (int i = 15; i > 0; --i) {
+            const bool gt = s > a[i], gtp = s > a[i - 1];
+            a[i] = gt ? (gtp ? a[i - 1] : s) : a[i];
+            r[i] = gt ? (gtp ? r[i - 1] : (uint32_t)row) : r[i];
+          }
+          if (s > a[0]) { a[0] = s; r[0] = (uint32_t)row; }
+          thr = fmaxf(thr, a[15]);
+        }
+      }
+    }
+    if (thr > thr_in) atomicMax(thr_g, f32_to_ord(thr));
+    return thr;
+  }
+  __device__ __forceinline__ void flush(uint64_t* dst) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) dst[j] = a[j] > -INFINITY ? pack_key(a[j], r[j]) : 0ull;
+  }
+};
+
+template <int KP>
+__device__ __noinline__ float smem_list_slow(float* ls, uint32_t* li, uint32_t taddr, const float* cnp, float thr,
+                                             int64_t row_base, int64_t self_row, int lim, uint32_t* thr_g) {
+  const float thr_in = thr;
+#pragma unroll 1
+  for (int g = 0; g < 4; ++g) {
+    uint32_t w[8];
+    tc_ld8(taddr + g * 8, w);
+    tc_ld_wait();
+#pragma unroll 1
+    for (int jj = 0; jj < 8; ++jj) {
+      const int j = g * 8 + jj;
+      uint32_t wj = w[0];
+#pragma unroll
+      for (int x = 1; x < 8; ++x) wj = (jj == x) ? w[x] : wj;
+      const float s = __uint_as_float(wj) * cnp[j];
+      const int64_t row = row_base + j;
+      if (s > thr && j < lim && row != self_row) {
+        int pos = KP - 1;                       // the minimum (or an empty slot) drops out
+        while (pos > 0) {
+          const float prev = ls[(pos - 1) * kEpiThreads];
+          if (!(prev < s)) break;               // equal scores keep arrival (= row) order
+          ls[pos * kEpiThreads] = prev;
+          li[pos * kEpiThreads] = li[(pos - 1) * kEpiThreads];
+          --pos;
+        }
+        ls[pos * kEpiThreads] = s;
+        li[pos * kEpiThreads] = (uint32_t)row;
+        thr = fmaxf(thr, ls[(KP - 1) * kEpiThreads]);
+      }
+    }
+  }
+  if (thr > thr_in) atomicMax(thr_g, f32_to_ord(thr));
   return thr;
 }
+
+template <int KP>
+struct SmemList {
+  float* ls; uint32_t* li;
+  __device__ __forceinline__ SmemList(float* s, uint32_t* i) : ls(s), li(i) {}
+  __device__ __forceinline__ void reset() {
+#pragma unroll 4
+    for (int j = 0; j < KP; ++j) { ls[j * kEpiThreads] = -INFINITY; li[j * kEpiThreads] = 0xffffffffu; }
+  }
+  __device__ __forceinline__ float slow(uint32_t taddr, const float* cnp, float thr, int64_t row_base,
+                                        int64_t self_row, int lim, uint32_t* thr_g) {
+    return smem_list_slow<KP>(ls, li, taddr, cnp, thr, row_base, self_row, lim, thr_g);
+  }
+  __device__ __forceinline__ void flush(uint64_t* dst) {
+#pragma unroll 4
+    for (int j = 0; j < KP; ++j) {
+      const float sc = ls[j * kEpiThreads];
+      dst[j] = sc > -INFINITY ? pack_key(sc, li[j * kEpiThreads]) : 0ull;
+    }
+  }
+};
+
+template <int KP> struct ListFor { using type = SmemList<KP>; };
+template <> struct ListFor<16> { using type = RegList16; };
 
 template <int KP, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -153,8 +284,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   float* list_s = (float*)(smem + (size_t)STAGES * STAGE_BYTES);
   uint32_t* list_i = (uint32_t*)(list_s + KP * kEpiThreads);
   float* cnorm = (float*)(list_i + KP * kEpiThreads);
-  int* list_n = (int*)(cnorm + 2 * BN);
-  uint64_t* bars = (uint64_t*)(list_n + kEpiThreads);
+  uint64_t* bars = (uint64_t*)(cnorm + 2 * BN);
   uint64_t* full_bar = bars;                 // [STAGES]  TMA -> MMA
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]  MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]       MMA -> epilogue
@@ -186,20 +316,17 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int64_t u = blockIdx.x; u < a.n_units; u += gridDim.x) {
-        const int64_t chunk = u / a.QB;
-        const int qb = (int)(u % a.QB);
-        const int64_t row0 = chunk * a.R;
-        const int64_t rows = min(a.N, row0 + a.R) - row0;
-        const int ntiles = (int)((rows + BN - 1) / BN);
-        for (int t = 0; t < ntiles; ++t) {
+      Unit un;
+      for (int it = 0; get_unit(a, it, un); ++it) {
+        for (int t = 0; t < un.ntiles; ++t) {
+          const int row0 = (int)((un.tile0 + (int64_t)t * un.tstride) * BN);
           for (int kb = 0; kb < a.kblocks; ++kb) {
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
             const uint32_t fb = smem_u32(&full_bar[stage]);
-            mbar_arrive_expect_tx(fb, STAGE_BYTES);
+            mbar_arrive_expect_tx(fb, (a.dbg & 1) ? B_BYTES : STAGE_BYTES);
             const uint32_t sa = smem_u32(tiles + (size_t)stage * STAGE_BYTES);
-            tma_load_2d(sa, &tmap_q, fb, kb * BK, qb * BM);
-            tma_load_2d(sa + A_BYTES, &tmap_c, fb, kb * BK, (int)(row0 + (int64_t)t * BN));
+            if (!(a.dbg & 1)) tma_load_2d(sa, &tmap_q, fb, kb * BK, un.qb * BM);
+            tma_load_2d(sa + A_BYTES, &tmap_c, fb, kb * BK, row0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -210,12 +337,9 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t aphase = 0;
-      for (int64_t u = blockIdx.x; u < a.n_units; u += gridDim.x) {
-        const int64_t chunk = u / a.QB;
-        const int64_t row0 = chunk * a.R;
-        const int64_t rows = min(a.N, row0 + a.R) - row0;
-        const int ntiles = (int)((rows + BN - 1) / BN);
-        for (int t = 0; t < ntiles; ++t) {
+      Unit un;
+      for (int it = 0; get_unit(a, it, un); ++it) {
+        for (int t = 0; t < un.ntiles; ++t) {
           mbar_wait(smem_u32(&tempty_bar[acc]), aphase ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
@@ -227,6 +351,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             const uint64_t bdesc = make_umma_desc(sa + A_BYTES);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
+              if (a.dbg & 2) break;
               // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in >>4 units
               tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), kIdesc, (kb | k) ? 1u : 0u);
             }
@@ -242,30 +367,25 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     // ===================== epilogue: threshold filter + per-query lists =====================
     const int et = threadIdx.x - 128;            // 0..127 = TMEM lane = query within the block
     const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
-    float* ls = list_s + et;
-    uint32_t* li = list_i + et;
-    int* cntp = list_n + et;
+    typename ListFor<KP>::type list(list_s + et, list_i + et);
     int acc = 0; uint32_t aphase = 0;
-    for (int64_t u = blockIdx.x; u < a.n_units; u += gridDim.x) {
-      const int64_t chunk = u / a.QB;
-      const int qb = (int)(u % a.QB);
-      const int64_t row0 = chunk * a.R;
-      const int64_t rows = min(a.N, row0 + a.R) - row0;
-      const int ntiles = (int)((rows + BN - 1) / BN);
-      const int64_t qg = (int64_t)qb * BM + et;
+    Unit un;
+    for (int it = 0; get_unit(a, it, un); ++it) {
+      const int64_t qg = (int64_t)un.qb * BM + et;
       const bool qvalid = qg < a.Q;
       const int64_t self_row = a.self_on ? a.self_off + qg : -1;
-      *cntp = 0;
+      uint32_t* thr_g = a.thr + (qvalid ? qg : 0);
+      list.reset();
       float thr = qvalid ? -INFINITY : INFINITY;   // padded query lanes never insert
-      for (int t = 0; t < ntiles; ++t) {
-        const int64_t trow0 = row0 + (int64_t)t * BN;
-        const int ncols = (int)min((int64_t)BN, row0 + rows - trow0);
+      for (int t = 0; t < un.ntiles; ++t) {
+        const int64_t trow0 = (un.tile0 + (int64_t)t * un.tstride) * BN;
+        const int ncols = (int)min((int64_t)BN, a.N - trow0);
         // stage the tile's inverse norms (2 per thread) and refresh the shared threshold
         float n0 = 0.f, n1 = 0.f;
         if (et < ncols) n0 = __ldg(a.c_inv + trow0 + et);
         if (et + 128 < ncols) n1 = __ldg(a.c_inv + trow0 + et + 128);
         if (qvalid) {
-          uint32_t g = __ldcg(a.thr + qg);
+          const uint32_t g = __ldcg(thr_g);
           if (g) thr = fmaxf(thr, ord_to_f32(g));
         }
         mbar_wait(smem_u32(&tfull_bar[acc]), aphase);
@@ -275,27 +395,26 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         cn[et + 128] = n1;
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const uint32_t tbase = tmem_base + lane_addr + (uint32_t)acc * BN;
-        for (int c = 0; c < BN / 32; ++c) {
-          if (c * 32 >= ncols) break;
+        const int nchunks = (a.dbg & 4) ? 0 : (ncols + 31) / 32;
+#pragma unroll 1
+        for (int c = 0; c < nchunks; ++c) {
           uint32_t v[32];
           tc_ld32(tbase + c * 32, v);
           tc_ld_wait();
-          const int lim = ncols - c * 32;   // >= 32 except in the ragged last chunk
+          // hot path: 32 FMUL + FMNMX3 tree + one compare
           const float4* cn4 = (const float4*)(cn + c * 32);
+          float mx = -INFINITY;
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 w = cn4[j4];
-            const float wv[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const int j = j4 * 4 + jj;
-              const float s = __uint_as_float(v[j]) * wv[jj];
-              if (s > thr && j < lim) {
-                const int64_t row = trow0 + c * 32 + j;
-                if (row != self_row) thr = list_insert<KP>(ls, li, cntp, thr, s, (uint32_t)row);
-              }
-            }
+            const float a0 = __uint_as_float(v[j4 * 4 + 0]) * w.x, a1 = __uint_as_float(v[j4 * 4 + 1]) * w.y;
+            const float a2 = __uint_as_float(v[j4 * 4 + 2]) * w.z, a3 = __uint_as_float(v[j4 * 4 + 3]) * w.w;
+            mx = fmaxf(mx, fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)));
           }
+          // Cold path, taken by the WHOLE warp when any lane has a candidate (tcgen05.ld is
+          // .sync.aligned: it must not run under divergence); rare once the lists are warm.
+          if (__any_sync(0xffffffffu, mx > thr))
+            thr = list.slow(tbase + c * 32, cn + c * 32, thr, trow0 + c * 32, self_row, ncols - c * 32, thr_g);
         }
         tc_fence_before();
         __syncwarp();
@@ -303,14 +422,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         if (++acc == 2) { acc = 0; aphase ^= 1; }
       }
       // flush this unit's list
-      if (qvalid) {
-        const int cnt = *cntp;
-        uint64_t* dst = a.cand + ((size_t)qg * a.NC + chunk) * KP;
-#pragma unroll 4
-        for (int j = 0; j < KP; ++j)
-          dst[j] = j < cnt ? pack_key(ls[j * kEpiThreads], li[j * kEpiThreads]) : 0ull;
-        if (cnt == KP) atomicMax(a.thr + qg, f32_to_ord(ls[(KP - 1) * kEpiThreads]));
-      }
+      if (qvalid) list.flush(a.cand + ((size_t)qg * a.NC + un.slot) * KP);
     }
   }
 
@@ -358,10 +470,10 @@ int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t D, int64_t 
 template <int KP, int STAGES>
 int launch_cfg(const CUtensorMap& mq, const CUtensorMap& mc, const TcArgs& a, cudaStream_t st) {
   size_t smem = 1024 + (size_t)STAGES * STAGE_BYTES + (size_t)KP * kEpiThreads * 8 + 2 * BN * 4 +
-                kEpiThreads * 4 + (2 * STAGES + 4) * 8 + 16;
+                (2 * STAGES + 4) * 8 + 16;
   TSIM_CUDA(cudaFuncSetAttribute(search_tc_kernel<KP, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int sms = device_sm_count();
-  unsigned grid = (unsigned)(a.n_units < sms ? a.n_units : sms);
+  unsigned grid = a.sticky ? (unsigned)(a.Gq * a.QB) : (unsigned)(a.n_units < sms ? a.n_units : sms);
   search_tc_kernel<KP, STAGES><<<grid, kThreads, smem, st>>>(mq, mc, a);
   TSIM_CUDA(cudaGetLastError());
   return TSIM_OK;
@@ -373,16 +485,20 @@ int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_
                      const float* c_inv, int64_t Q, int64_t N, int64_t D, int self_on, int64_t self_off,
                      const SearchPlan& p, uint64_t* cand, uint32_t* thr, cudaStream_t st) {
   CUtensorMap mq, mc;
-  int rc = make_map(&mq, q, Q, D, q_stride, BM);
+  // q holds QB * 128 rows (the API pads the last query block with zero rows)
+  int rc = make_map(&mq, q, (int64_t)p.QB * BM, D, q_stride, BM);
   if (rc) return rc;
   rc = make_map(&mc, corpus, N, D, c_stride, BN);
   if (rc) return rc;
   TcArgs a;
   a.c_inv = c_inv; a.Q = Q; a.N = N;
   a.kblocks = (int)((D + BK - 1) / BK);
-  a.QB = p.QB; a.R = p.R; a.NC = p.NC; a.n_units = (int64_t)p.QB * p.NC;
+  a.QB = p.QB; a.T = (N + BN - 1) / BN; a.sticky = p.sticky; a.Gq = p.Gq; a.tpc = p.R / BN;
+  a.NC = p.NC; a.n_units = (int64_t)p.QB * p.NC;
   a.self_on = self_on; a.self_off = self_off;
   a.cand = cand; a.thr = thr;
+  const char* dbg = getenv("TSIM_DEBUG");
+  a.dbg = dbg ? atoi(dbg) : 0;
   switch (p.KP) {
     case 16: return launch_cfg<16, 4>(mq, mc, a, st);
     case 32: return launch_cfg<32, 3>(mq, mc, a, st);

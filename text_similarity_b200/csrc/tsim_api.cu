@@ -57,6 +57,14 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
   if (p->use_tensor) {
     p->KP = k <= 10 ? 16 : k <= 24 ? 32 : k <= 52 ? 64 : 112;
     p->QB = (int)((Q + 127) / 128);
+    const int64_t T = (N + 255) / 256;
+    if (p->QB <= sms && (sms % p->QB) * 100 <= 3 * sms) {
+      // few query blocks: sticky schedule (see search_tc.cu), one candidate list per CTA
+      p->sticky = 1;
+      p->Gq = sms / p->QB;
+      if (p->Gq > T) p->Gq = (int)T;
+      if (p->Gq < 1) p->Gq = 1;
+    }
     int64_t nct = (8 * (int64_t)sms + p->QB - 1) / p->QB;  // aim at ~8 units per SM
     if (nct < 1) nct = 1;
     int64_t R = (N + nct - 1) / nct;
@@ -66,7 +74,7 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
     // bound the candidate buffer (Q * NC * KP * 8 bytes) to ~2 GB
     while ((double)Q * (double)((N + R - 1) / R) * p->KP * 8.0 > 2.0e9 && R < ((int64_t)1 << 30)) R *= 2;
     p->R = R;
-    p->NC = (N + R - 1) / R;
+    p->NC = p->sticky ? p->Gq : (N + R - 1) / R;
     p->off_cand = off; off = align_up(off + (size_t)Q * p->NC * p->KP * sizeof(uint64_t), 256);
   }
   // exact scan (whole-call path, or fallback for flagged queries)
@@ -83,6 +91,9 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
   p->off_thr = off; off = align_up(off + (size_t)Q * sizeof(uint32_t), 256);
   p->off_flagcnt = off; off += 256;
   p->off_flaglist = off; off = align_up(off + (size_t)Q * sizeof(int32_t), 256);
+  if (p->use_tensor && Q % 128 != 0) {  // zero-padded copy of the queries (TMA out-of-bounds fill is slow)
+    p->off_qpad = off; off = align_up(off + (size_t)p->QB * 128 * D * 2, 256);
+  }
   if (need_invnorm && p->use_tensor) { p->off_invnorm = off; off = align_up(off + (size_t)N * sizeof(float), 256); }
   p->off_ex_score = off; off = align_up(off + (size_t)Q * p->S * k * sizeof(double), 256);
   p->off_ex_idx = off; off = align_up(off + (size_t)Q * p->S * k * sizeof(uint32_t), 256);
@@ -168,9 +179,19 @@ extern "C" int tsim_search_topk(const void* q, int q_dt, int64_t q_stride, const
       if (rc) return rc;
       c_inv = tmp;
     }
+    const void* qt = q;
+    int64_t qt_stride = q_stride;
+    if (Q % 128 != 0) {
+      char* qp = w + p.off_qpad;
+      const size_t rowb = (size_t)D * 2;
+      TSIM_CUDA(cudaMemsetAsync(qp + (size_t)Q * rowb, 0, ((size_t)p.QB * 128 - Q) * rowb, st));
+      TSIM_CUDA(cudaMemcpy2DAsync(qp, rowb, q, (size_t)q_stride * 2, rowb, (size_t)Q, cudaMemcpyDeviceToDevice, st));
+      qt = qp;
+      qt_stride = D;
+    }
     const bool timed = g_ev_start && g_ev_stop;
     if (timed) TSIM_CUDA(cudaEventRecord(g_ev_start, st));
-    rc = launch_search_tc(q, q_stride, corpus, c_stride, c_inv, Q, N, D, self_on, self_off, p,
+    rc = launch_search_tc(qt, qt_stride, corpus, c_stride, c_inv, Q, N, D, self_on, self_off, p,
                           (uint64_t*)(w + p.off_cand), thr, st);
     if (rc) return rc;
     if (timed) TSIM_CUDA(cudaEventRecord(g_ev_stop, st));

@@ -147,13 +147,15 @@ struct SearchPlan {
   int use_tensor;      // 1: tcgen05 candidate pass + select/rescore
   int KP;              // per-unit candidate list capacity (16/32/64/128)
   int QB;              // query blocks of 128
-  int64_t R;           // corpus rows per unit (multiple of 256)
-  int64_t NC;          // corpus chunks = ceil(N / R)
+  int sticky;          // 1: each CTA keeps one query block and strides over tiles (few query blocks)
+  int Gq;              // sticky: CTAs per query block
+  int64_t R;           // round-robin: corpus rows per unit (multiple of 256)
+  int64_t NC;          // candidate lists per query: chunks ceil(N / R), or Gq when sticky
   // exact path
   int S;               // corpus slices (CTAs along the corpus) of the exact scan
   int64_t slice_rows;  // rows per slice
   // workspace offsets (bytes)
-  size_t off_cand, off_thr, off_flagcnt, off_flaglist, off_invnorm, off_ex_score, off_ex_idx;
+  size_t off_cand, off_thr, off_flagcnt, off_flaglist, off_invnorm, off_qpad, off_ex_score, off_ex_idx;
   size_t total;
 };
 
