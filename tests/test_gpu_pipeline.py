@@ -1,0 +1,141 @@
+"""GPU tests of the reference-facing surface: the same imports and calls a script written against
+cr1m5onk1ng/text_similarity makes, checked against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def stack():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from src.configurations.config import ModelParameters, SearchConfiguration
+    from src.models.sentence_encoder import SentenceTransformerWrapper
+    from src.modules.modules import AvgPoolingStrategy
+    from text_similarity_b200.utils import SyntheticTokenizer, minilm_l6_encoder, synthetic_sentences
+    params = SearchConfiguration(model_parameters=ModelParameters(model_name="minilm-l6-shaped", hidden_size=384),
+                                 model="synthetic-minilm", save_path="./results", tokenizer=SyntheticTokenizer(),
+                                 sequence_max_len=64, batch_size=16, device=torch.device("cuda"))
+    bert = minilm_l6_encoder(seed=0, layers=2)
+    model = SentenceTransformerWrapper(pooler=AvgPoolingStrategy(params), merge_strategy=None, loss=None,
+                                       params=params, context_embedder=bert, parallel_mode=False)
+    corpus = synthetic_sentences(300, seed=1)
+    corpus[200] = corpus[13]            # duplicate sentences -> exact ties
+    queries = synthetic_sentences(9, seed=2) + [corpus[50]]
+    return params, model, corpus, queries
+
+
+def test_encode_text_matches_per_sentence_torch(stack):
+    params, model, corpus, _ = stack
+    docs = corpus[:40]
+    emb = model.encode_text(docs)
+    assert emb.shape == (40, 384) and emb.dtype == torch.float32 and emb.is_cuda
+    assert model.get_sentence_embedding_dimension() == 384
+    tok = params.tokenizer
+    with torch.no_grad():
+        for i in (0, 7, 39):
+            enc = tok(text=[docs[i]], max_length=params.sequence_max_len)
+            t = model.context_embedder(input_ids=enc["input_ids"].cuda(), attention_mask=enc["attention_mask"].cuda())[0]
+            exp = O.mean_pool_literal(t.cpu(), enc["attention_mask"])
+            np.testing.assert_allclose(emb[i].cpu().numpy(), exp[0].numpy(), atol=2e-5)
+    as_np = model.encode(docs[:5], output_np=True)
+    assert isinstance(as_np, np.ndarray) and as_np.shape == (5, 384)
+    np.testing.assert_allclose(as_np, emb[:5].cpu().numpy(), atol=2e-5)
+
+
+def test_pooler_and_onnx_wrapper_follow_reference(stack, golden):
+    from src.dataset.dataset import EmbeddingsFeatures
+    from src.models.sentence_encoder import OnnxSentenceTransformerWrapper
+    from src.modules.modules import AvgPoolingStrategy
+    params, model, _, _ = stack
+    pooler = AvgPoolingStrategy(params)
+    assert len(pooler.state_dict()) == 0
+    emb = torch.from_numpy(golden["pool_minilm_emb"]).cuda()
+    mask = torch.from_numpy(golden["pool_minilm_mask"]).cuda()
+    feats = EmbeddingsFeatures(input_ids=torch.zeros_like(mask), attention_mask=mask)
+    np.testing.assert_allclose(pooler(emb, feats).cpu().numpy(), golden["pool_minilm_out"], atol=1e-5)
+    with pytest.raises(AssertionError):
+        pooler(emb[0], feats)
+    onnx = OnnxSentenceTransformerWrapper(params=params, context_embedder=model.context_embedder).cuda().eval()
+    enc = params.tokenizer(text=["w1 w2 w3", "w4"], max_length=32)
+    with torch.no_grad():
+        got = onnx(enc["input_ids"].cuda(), enc["attention_mask"].cuda())
+        tok = model.context_embedder(input_ids=enc["input_ids"].cuda(), attention_mask=enc["attention_mask"].cuda())[0]
+    np.testing.assert_allclose(got.cpu().numpy(), O.mean_pool_literal(tok.cpu(), enc["attention_mask"]).numpy(), atol=2e-5)
+
+
+def test_sentence_mining_pipeline_text(stack):
+    from src.pipeline.search_pipeline import SentenceMiningPipeline
+    params, model, corpus, queries = stack
+    pipe = SentenceMiningPipeline(10_000, params=params, model=model, corpus=corpus, name="teacher")
+    res = pipe(queries, 5)                       # the call the reference's eval scripts make
+    assert sorted(res) == list(range(len(queries)))
+    rows, inv = model.encode_text_normalized(corpus, torch.bfloat16)
+    qrows, _ = model.encode_text_normalized(queries, torch.bfloat16)
+    ev, ei = O.search_exact(qrows.cpu(), rows.cpu(), 5)
+    for qi in range(len(queries)):
+        assert [c for c, _ in res[qi]] == ei[qi].tolist()
+        assert all(text == corpus[c] for c, text in res[qi])
+    assert res[len(queries) - 1][0][0] == 50      # the query copied from corpus[50] finds it first
+    # stored rows are unit norm up to bf16 rounding and inv_norm describes the stored rows
+    n = rows.float().norm(dim=-1).cpu()
+    assert (n - 1).abs().max() < 1e-2
+    np.testing.assert_allclose((inv.cpu() * n).numpy(), 1.0, atol=1e-5)
+    # chunked search (several chunks + merge) returns the same thing
+    pipe_small = SentenceMiningPipeline(37, params=params, model=model, corpus=corpus, name="chunked")
+    res2 = pipe_small._search(queries, None, 5)
+    assert {q: [c for c, _ in v] for q, v in res2.items()} == {q: [c for c, _ in v] for q, v in res.items()}
+
+
+def test_sentence_mining_pipeline_tensors(stack):
+    from src.pipeline.search_pipeline import SentenceMiningPipeline
+    params, model, _, _ = stack
+    g = torch.Generator().manual_seed(3)
+    corpus = torch.randn(5000, 384, generator=g)
+    queries = torch.randn(12, 384, generator=g)
+    pipe = SentenceMiningPipeline(2048, params=params, model=model)
+    # fp32 tensors: answered by the float64 exact scan, 1e-5 tolerance
+    out = pipe._search(queries.cuda(), corpus.cuda(), 7, return_embeddings=True)
+    ev, ei = O.search_exact(queries, corpus, 7)
+    for qi in range(12):
+        assert torch.equal(out[qi].cpu(), corpus[ei[qi]])
+    s, i = pipe.search_tensors(queries.cuda(), 7)
+    assert torch.equal(i.cpu(), ei)
+    np.testing.assert_allclose(s.cpu().numpy(), ev.numpy(), atol=1e-5)
+    # bf16 tensors: tcgen05 path, k larger than the corpus is clamped (reference clamps by #queries, A6)
+    cb = corpus[:9].to(torch.bfloat16)
+    s, i = pipe.search_tensors(queries.to(torch.bfloat16).cuda(), 100, corpus=cb.cuda())
+    assert i.shape == (12, 9)
+    assert torch.equal(i.cpu(), O.search_exact(queries.to(torch.bfloat16), cb, 9)[1])
+
+
+def test_semantic_search_pipeline_surface(stack, tmp_path):
+    from src.pipeline.search_pipeline import SemanticSearchPipeline
+    params, model, corpus, queries = stack
+    pipe = SemanticSearchPipeline(str(tmp_path / "index"), params=params, model=model, corpus=list(corpus[:120]))
+    hits = pipe(queries, 3)
+    assert all(len(v) == 3 and all(isinstance(t, str) for t in v) for v in hits.values())
+    assert hits[len(queries) - 1][0] == corpus[50]
+    assert pipe.num_indexed() == 120
+    pipe.add_to_index(["w1 w2 w3 w4", queries[0]])
+    assert pipe.num_indexed() == 122 and pipe(queries[:1], 1)[0] == [queries[0]]
+    pipe.remove_from_index([121, 9999])
+    assert pipe.num_indexed() == 121 and pipe(queries[:1], 1)[0] != [queries[0]]
+    again = SemanticSearchPipeline(str(tmp_path / "index"), params=params, model=model, corpus=list(corpus[:120]))
+    assert again(queries, 3) == hits                     # reloaded from index_path
+
+
+def test_cos_sim_surface(golden):
+    from src.utils.metrics import cos_sim, cos_sim_topk
+    a = torch.from_numpy(golden["cossim_a"])
+    b = torch.from_numpy(golden["cossim_b"])
+    np.testing.assert_allclose(cos_sim(a.cuda(), b.cuda()).cpu().numpy(), golden["cossim_out"], atol=1e-5)
+    np.testing.assert_allclose(cos_sim(a[0].cuda(), b.cuda()).cpu().numpy(), golden["cossim_1d_out"], atol=1e-5)
+    s, i = cos_sim_topk(a.cuda(), b.cuda(), 3)
+    assert torch.equal(i.cpu(), O.search_exact(a, b, 3)[1])
+    with pytest.raises(RuntimeError):
+        cos_sim(a, b)

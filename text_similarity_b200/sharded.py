@@ -22,6 +22,30 @@ def shard_bounds(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
     return begin, min(n_rows, begin + per)
 
 
+def gather_shard_results(score64: torch.Tensor, idx: torch.Tensor, group, bufs=None
+                         ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The ONE collective of the search: all-gather every rank's [Q, k] (float64 score, int64 global
+    row) lists and lay them out as [Q, world * k] merge input (rank-major inside a query row).
+    Works on any backend (NCCL over NVLink in production, gloo in the CPU tests)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    Q, k = idx.shape
+    if bufs is None:
+        send = torch.empty(2, Q, k, dtype=torch.int64, device=idx.device)
+        recv = torch.empty(world * 2, Q, k, dtype=torch.int64, device=idx.device)
+    else:
+        send, recv = bufs
+    if score64.data_ptr() != send[0].data_ptr():
+        send[0].copy_(score64.contiguous().view(torch.int64))
+    if idx.data_ptr() != send[1].data_ptr():
+        send[1].copy_(idx)
+    dist.all_gather_into_tensor(recv, send, group=group)  # output = inputs concatenated on dim 0
+    recv = recv.view(world, 2, Q, k)
+    s64 = recv[:, 0].view(torch.float64).permute(1, 0, 2).reshape(Q, world * k)
+    rows = recv[:, 1].permute(1, 0, 2).reshape(Q, world * k)
+    return s64, rows
+
+
 class ShardedCorpus:
     """One rank's block of the corpus embedding matrix plus what the search needs with it."""
 
@@ -51,22 +75,19 @@ class ShardedCorpus:
         """Global top-k on every rank: (scores float32 [Q, k], global rows int64 [Q, k])."""
         if self.world == 1:
             return self.search_local(queries, k, exclude_self_base=exclude_self_base, mode=mode)
-        import torch.distributed as dist
         Q = queries.shape[0]
         key = (Q, k)
         bufs = self._gather_buf.get(key)
         if bufs is None:
             send = torch.empty(2, Q, k, dtype=torch.int64, device=queries.device)
-            recv = torch.empty(self.world, 2, Q, k, dtype=torch.int64, device=queries.device)
+            recv = torch.empty(self.world * 2, Q, k, dtype=torch.int64, device=queries.device)
             bufs = self._gather_buf[key] = (send, recv)
         send, recv = bufs
         # the search kernels write their float64 scores and int64 rows straight into the send buffer
         ops.search_topk(queries, self.shard, k, corpus_inv_norm=self.inv_norm, idx_base=self.idx_base,
                         exclude_self_base=exclude_self_base, mode=mode,
                         out_score64=send[0].view(torch.float64), out_idx=send[1])
-        dist.all_gather_into_tensor(recv, send, group=self.group)
-        s64 = recv[:, 0].view(torch.float64).permute(1, 0, 2).reshape(Q, self.world * k)
-        idx = recv[:, 1].permute(1, 0, 2).reshape(Q, self.world * k)
+        s64, idx = gather_shard_results(send[0].view(torch.float64), send[1], self.group, bufs)
         scores, _, rows = ops.merge_topk(s64, idx, k, self.world)
         return scores, rows
 
