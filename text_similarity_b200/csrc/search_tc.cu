@@ -34,9 +34,18 @@ constexpr int BK = 64;         // bf16 elements per k-block = 128 bytes = one sw
 constexpr int UMMA_K = 16;     // bf16 MMA K
 constexpr int kThreads = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
 constexpr int kEpiThreads = 128;
-constexpr int A_BYTES = BM * BK * 2;   // 16 KB
-constexpr int B_BYTES = BN * BK * 2;   // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int A_BYTES = BM * BK * 2;   // 16 KB: 128 query rows x 128 bytes
+// B (corpus) bytes per CTA per stage: all 256 rows of the tile for a lone CTA, 128 rows for each CTA
+// of a pair (cta_group::2: the MMA reads the other half from the peer's shared memory)
+template <bool PAIR> struct Cfg {
+  static constexpr int B_ROWS = PAIR ? BN / 2 : BN;
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;       // 48 KB lone, 32 KB per CTA of a pair
+  static constexpr int MMA_M = PAIR ? 2 * BM : BM;
+  // UMMA instruction descriptor: D = f32, A = B = bf16, both K-major, N = 256, M = 128 / 256
+  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                    ((uint32_t)(MMA_M >> 4) << 24);
+};
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -67,6 +76,43 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+// 2-CTA variants: the peer's TMA signals the LEADER's barrier; the leader's commit reaches both CTAs
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -112,14 +158,12 @@ __device__ __forceinline__ uint64_t make_umma_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3ffff) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-// UMMA instruction descriptor: D = f32, A = B = bf16, both K-major, N = 256, M = 128
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 struct TcArgs {
   const float* c_inv;   // [N] inverse norms of the stored corpus rows
   int64_t Q, N;
   int kblocks;          // ceil(D / 64)
-  int QB;               // query blocks of 128
+  int QB;               // query blocks (128 queries; 256 when CTA pairs are used)
   int64_t T;            // corpus tiles of 256 rows
   int sticky;           // 1: CTA <-> (query block, tile residue class), one list per CTA lifetime
   int Gq;               // sticky: CTAs per query block
@@ -141,15 +185,16 @@ struct Unit { int qb; int64_t slot; int64_t tile0; int64_t tstride; int ntiles; 
 // list -- hence its threshold -- persists over everything the CTA sees.
 // Round-robin schedule (many query blocks, the tensor-bound regime): unit u = (chunk u / QB,
 // query block u % QB) dealt to CTA u % grid; the QB units of one chunk run side by side.
-__device__ __forceinline__ bool get_unit(const TcArgs& a, int it, Unit& un) {
+// `wid` / `nw` = this worker's index and the number of workers (CTAs, or CTA pairs).
+__device__ __forceinline__ bool get_unit(const TcArgs& a, int it, int wid, int nw, Unit& un) {
   if (a.sticky) {
-    if (it > 0 || (int)blockIdx.x >= a.Gq * a.QB) return false;
-    const int j = (int)blockIdx.x / a.QB;
-    un.qb = (int)blockIdx.x % a.QB; un.slot = j; un.tile0 = j; un.tstride = a.Gq;
+    if (it > 0 || wid >= a.Gq * a.QB) return false;
+    const int j = wid / a.QB;
+    un.qb = wid % a.QB; un.slot = j; un.tile0 = j; un.tstride = a.Gq;
     un.ntiles = j < a.T ? (int)((a.T - j + a.Gq - 1) / a.Gq) : 0;
     return true;
   }
-  const int64_t u = blockIdx.x + (int64_t)it * gridDim.x;
+  const int64_t u = wid + (int64_t)it * nw;
   if (u >= a.n_units) return false;
   const int64_t chunk = u / a.QB;
   un.qb = (int)(u % a.QB); un.slot = chunk; un.tile0 = chunk * a.tpc; un.tstride = 1;
@@ -272,19 +317,21 @@ struct SmemList {
 template <int KP> struct ListFor { using type = SmemList<KP>; };
 template <> struct ListFor<16> { using type = RegList16; };
 
-template <int KP, int STAGES>
+template <int KP, int STAGES, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c, TcArgs a) {
   extern __shared__ unsigned char smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment: round the dynamic window up (1 KB of slack is
   // requested by the launcher).
-  // [STAGES][A 16K | B 32K] | lists | cnorm[2][BN] | list counts | barriers | tmem ptr
+  // [STAGES][A 16K | B 32K] | lists | cnorm[2 acc][4 warps][BN] | barriers | tmem ptr
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int B_BYTES = Cfg<PAIR>::B_BYTES;
+  constexpr int STAGE_BYTES = Cfg<PAIR>::STAGE_BYTES;
   unsigned char* tiles = smem;
   float* list_s = (float*)(smem + (size_t)STAGES * STAGE_BYTES);
   uint32_t* list_i = (uint32_t*)(list_s + KP * kEpiThreads);
   float* cnorm = (float*)(list_i + KP * kEpiThreads);
-  uint64_t* bars = (uint64_t*)(cnorm + 2 * BN);
+  uint64_t* bars = (uint64_t*)(cnorm + 2 * 4 * BN);
   uint64_t* full_bar = bars;                 // [STAGES]  TMA -> MMA
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]  MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]       MMA -> epilogue
@@ -292,6 +339,11 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // a pair = cluster of 2 CTAs: rank 0 (leader) issues the MMAs for both, each CTA loads its own 128
+  // queries and its own half of the corpus tile, and scans its own 128 TMEM lanes
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int wid = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int nw = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -299,16 +351,21 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tfull_bar[s]), 1); mbar_init(smem_u32(&tempty_bar[s]), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tfull_bar[s]), 1); mbar_init(smem_u32(&tempty_bar[s]), PAIR ? 8 : 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();   // barrier inits visible to the peer before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -317,28 +374,36 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       Unit un;
-      for (int it = 0; get_unit(a, it, un); ++it) {
+      for (int it = 0; get_unit(a, it, wid, nw, un); ++it) {
         for (int t = 0; t < un.ntiles; ++t) {
           const int row0 = (int)((un.tile0 + (int64_t)t * un.tstride) * BN);
           for (int kb = 0; kb < a.kblocks; ++kb) {
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-            const uint32_t fb = smem_u32(&full_bar[stage]);
-            mbar_arrive_expect_tx(fb, (a.dbg & 1) ? B_BYTES : STAGE_BYTES);
             const uint32_t sa = smem_u32(tiles + (size_t)stage * STAGE_BYTES);
-            if (!(a.dbg & 1)) tma_load_2d(sa, &tmap_q, fb, kb * BK, un.qb * BM);
-            tma_load_2d(sa + A_BYTES, &tmap_c, fb, kb * BK, row0);
+            if (PAIR) {
+              // both CTAs' bytes land on the leader's barrier; only the leader arms it (for both)
+              const uint32_t fb = map_to_cta(smem_u32(&full_bar[stage]), 0);
+              if (rank == 0) mbar_arrive_expect_tx(smem_u32(&full_bar[stage]), 2 * STAGE_BYTES);
+              tma_load_2d_pair(sa, &tmap_q, fb, kb * BK, un.qb * (2 * BM) + (int)rank * BM);
+              tma_load_2d_pair(sa + A_BYTES, &tmap_c, fb, kb * BK, row0 + (int)rank * (BN / 2));
+            } else {
+              const uint32_t fb = smem_u32(&full_bar[stage]);
+              mbar_arrive_expect_tx(fb, (a.dbg & 1) ? B_BYTES : STAGE_BYTES);
+              if (!(a.dbg & 1)) tma_load_2d(sa, &tmap_q, fb, kb * BK, un.qb * BM);
+              tma_load_2d(sa + A_BYTES, &tmap_c, fb, kb * BK, row0);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (the pair's leader issues for both CTAs) =====================
+    if (lane == 0 && rank == 0) {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t aphase = 0;
       Unit un;
-      for (int it = 0; get_unit(a, it, un); ++it) {
+      for (int it = 0; get_unit(a, it, wid, nw, un); ++it) {
         for (int t = 0; t < un.ntiles; ++t) {
           mbar_wait(smem_u32(&tempty_bar[acc]), aphase ^ 1);
           tc_fence_after();
@@ -353,12 +418,15 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             for (int k = 0; k < BK / UMMA_K; ++k) {
               if (a.dbg & 2) break;
               // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in >>4 units
-              tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), kIdesc, (kb | k) ? 1u : 0u);
+              if (PAIR) tc_mma_bf16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), Cfg<PAIR>::IDESC, (kb | k) ? 1u : 0u);
+              else tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), Cfg<PAIR>::IDESC, (kb | k) ? 1u : 0u);
             }
-            tc_commit(smem_u32(&empty_bar[stage]));      // frees the smem stage when the MMAs retire
+            // frees the smem stage (in both CTAs of a pair) when the MMAs retire
+            if (PAIR) tc_commit_pair(smem_u32(&empty_bar[stage])); else tc_commit(smem_u32(&empty_bar[stage]));
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          tc_commit(smem_u32(&tfull_bar[acc]));          // accumulator stage complete
+          // accumulator stage complete: wake the epilogue warps (of both CTAs)
+          if (PAIR) tc_commit_pair(smem_u32(&tfull_bar[acc])); else tc_commit(smem_u32(&tfull_bar[acc]));
           if (++acc == 2) { acc = 0; aphase ^= 1; }
         }
       }
@@ -370,30 +438,37 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     typename ListFor<KP>::type list(list_s + et, list_i + et);
     int acc = 0; uint32_t aphase = 0;
     Unit un;
-    for (int it = 0; get_unit(a, it, un); ++it) {
-      const int64_t qg = (int64_t)un.qb * BM + et;
+    for (int it = 0; get_unit(a, it, wid, nw, un); ++it) {
+      const int64_t qg = PAIR ? (int64_t)un.qb * (2 * BM) + rank * BM + et : (int64_t)un.qb * BM + et;
       const bool qvalid = qg < a.Q;
       const int64_t self_row = a.self_on ? a.self_off + qg : -1;
       uint32_t* thr_g = a.thr + (qvalid ? qg : 0);
       list.reset();
       float thr = qvalid ? -INFINITY : INFINITY;   // padded query lanes never insert
+      // Tile metadata (the 256 inverse norms, 8 per lane, and the query's shared threshold) is
+      // fetched one tile ahead so its global-load latency hides behind the previous tile's work.
+      float nreg[8];
+      uint32_t gthr = 0;
+      auto fetch_meta = [&](int t) {
+        const int64_t r0 = (un.tile0 + (int64_t)t * un.tstride) * BN;
+        const int nc = (int)min((int64_t)BN, a.N - r0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) nreg[i] = (lane + 32 * i < nc) ? __ldg(a.c_inv + r0 + lane + 32 * i) : 0.f;
+        gthr = qvalid ? __ldcg(thr_g) : 0u;
+      };
+      if (un.ntiles > 0) fetch_meta(0);
       for (int t = 0; t < un.ntiles; ++t) {
         const int64_t trow0 = (un.tile0 + (int64_t)t * un.tstride) * BN;
         const int ncols = (int)min((int64_t)BN, a.N - trow0);
-        // stage the tile's inverse norms (2 per thread) and refresh the shared threshold
-        float n0 = 0.f, n1 = 0.f;
-        if (et < ncols) n0 = __ldg(a.c_inv + trow0 + et);
-        if (et + 128 < ncols) n1 = __ldg(a.c_inv + trow0 + et + 128);
-        if (qvalid) {
-          const uint32_t g = __ldcg(thr_g);
-          if (g) thr = fmaxf(thr, ord_to_f32(g));
-        }
+        // each epilogue warp keeps a private copy of the tile's inverse norms: no cross-warp barrier
+        float* cn = cnorm + (acc * 4 + (warp & 3)) * BN;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cn[lane + 32 * i] = nreg[i];
+        if (gthr) thr = fmaxf(thr, ord_to_f32(gthr));
+        __syncwarp();
+        if (t + 1 < un.ntiles) fetch_meta(t + 1);
         mbar_wait(smem_u32(&tfull_bar[acc]), aphase);
         tc_fence_after();
-        float* cn = cnorm + acc * BN;
-        cn[et] = n0;
-        cn[et + 128] = n1;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
         const uint32_t tbase = tmem_base + lane_addr + (uint32_t)acc * BN;
         const int nchunks = (a.dbg & 4) ? 0 : (ncols + 31) / 32;
 #pragma unroll 1
@@ -418,7 +493,10 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[acc]), 0));   // the leader's MMA thread waits
+          else mbar_arrive(smem_u32(&tempty_bar[acc]));
+        }
         if (++acc == 2) { acc = 0; aphase ^= 1; }
       }
       // flush this unit's list
@@ -427,10 +505,12 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   }
 
   tc_fence_before();
-  __syncthreads();
+  // a pair stays alive together: the leader's MMAs read the peer's shared memory until the last commit
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -467,15 +547,28 @@ int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t D, int64_t 
   return TSIM_OK;
 }
 
-template <int KP, int STAGES>
+template <int KP, int STAGES, bool PAIR>
 int launch_cfg(const CUtensorMap& mq, const CUtensorMap& mc, const TcArgs& a, cudaStream_t st) {
-  size_t smem = 1024 + (size_t)STAGES * STAGE_BYTES + (size_t)KP * kEpiThreads * 8 + 2 * BN * 4 +
+  size_t smem = 1024 + (size_t)STAGES * Cfg<PAIR>::STAGE_BYTES + (size_t)KP * kEpiThreads * 8 + 2 * 4 * BN * 4 +
                 (2 * STAGES + 4) * 8 + 16;
-  TSIM_CUDA(cudaFuncSetAttribute(search_tc_kernel<KP, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int sms = device_sm_count();
-  unsigned grid = a.sticky ? (unsigned)(a.Gq * a.QB) : (unsigned)(a.n_units < sms ? a.n_units : sms);
-  search_tc_kernel<KP, STAGES><<<grid, kThreads, smem, st>>>(mq, mc, a);
-  TSIM_CUDA(cudaGetLastError());
+  auto kern = search_tc_kernel<KP, STAGES, PAIR>;
+  TSIM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int sms = device_sm_count();
+  const int workers = PAIR ? sms / 2 : sms;
+  int64_t nwork = a.sticky ? (int64_t)a.Gq * a.QB : (a.n_units < workers ? a.n_units : workers);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(PAIR ? 2 * nwork : nwork));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TSIM_CUDA(cudaLaunchKernelEx(&cfg, kern, mq, mc, a));
   return TSIM_OK;
 }
 
@@ -485,10 +578,11 @@ int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_
                      const float* c_inv, int64_t Q, int64_t N, int64_t D, int self_on, int64_t self_off,
                      const SearchPlan& p, uint64_t* cand, uint32_t* thr, cudaStream_t st) {
   CUtensorMap mq, mc;
-  // q holds QB * 128 rows (the API pads the last query block with zero rows)
-  int rc = make_map(&mq, q, (int64_t)p.QB * BM, D, q_stride, BM);
+  const int qrows = p.pair ? 2 * BM : BM;
+  // q holds QB * qrows rows (the API pads the last query block with zero rows)
+  int rc = make_map(&mq, q, (int64_t)p.QB * qrows, D, q_stride, BM);
   if (rc) return rc;
-  rc = make_map(&mc, corpus, N, D, c_stride, BN);
+  rc = make_map(&mc, corpus, N, D, c_stride, p.pair ? BN / 2 : BN);
   if (rc) return rc;
   TcArgs a;
   a.c_inv = c_inv; a.Q = Q; a.N = N;
@@ -499,13 +593,23 @@ int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_
   a.cand = cand; a.thr = thr;
   const char* dbg = getenv("TSIM_DEBUG");
   a.dbg = dbg ? atoi(dbg) : 0;
-  switch (p.KP) {
-    case 16: return launch_cfg<16, 4>(mq, mc, a, st);
-    case 32: return launch_cfg<32, 3>(mq, mc, a, st);
-    case 64: return launch_cfg<64, 3>(mq, mc, a, st);
-    case 112: return launch_cfg<112, 2>(mq, mc, a, st);
-    default: set_error("search_tc: bad KP %d", p.KP); return TSIM_ERR_INVALID_ARG;
+  if (p.pair) {
+    switch (p.KP) {
+      case 16: return launch_cfg<16, 6, true>(mq, mc, a, st);
+      case 32: return launch_cfg<32, 5, true>(mq, mc, a, st);
+      case 64: return launch_cfg<64, 4, true>(mq, mc, a, st);
+      case 112: return launch_cfg<112, 3, true>(mq, mc, a, st);
+    }
+  } else {
+    switch (p.KP) {
+      case 16: return launch_cfg<16, 4, false>(mq, mc, a, st);
+      case 32: return launch_cfg<32, 3, false>(mq, mc, a, st);
+      case 64: return launch_cfg<64, 3, false>(mq, mc, a, st);
+      case 112: return launch_cfg<112, 2, false>(mq, mc, a, st);
+    }
   }
+  set_error("search_tc: bad KP %d", p.KP);
+  return TSIM_ERR_INVALID_ARG;
 }
 
 }  // namespace tsim

@@ -1,6 +1,7 @@
 // C-ABI entry points of libtsim.so (see include/tsim.h), launch planning and error reporting.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "tsim_common.cuh"
@@ -56,16 +57,21 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
   size_t off = 0;
   if (p->use_tensor) {
     p->KP = k <= 10 ? 16 : k <= 24 ? 32 : k <= 52 ? 64 : 112;
-    p->QB = (int)((Q + 127) / 128);
+    // more than one 128-query block: CTA pairs (cta_group::2) share each corpus tile between two SMs
+    const char* nopair = getenv("TSIM_NO_PAIR");
+    p->pair = (Q > 128 && !(nopair && nopair[0] == '1')) ? 1 : 0;
+    const int qrows = p->pair ? 256 : 128;
+    const int workers = p->pair ? sms / 2 : sms;
+    p->QB = (int)((Q + qrows - 1) / qrows);
     const int64_t T = (N + 255) / 256;
-    if (p->QB <= sms && (sms % p->QB) * 100 <= 3 * sms) {
+    if (p->QB <= workers && (workers % p->QB) * 100 <= 3 * workers) {
       // few query blocks: sticky schedule (see search_tc.cu), one candidate list per CTA
       p->sticky = 1;
-      p->Gq = sms / p->QB;
+      p->Gq = workers / p->QB;
       if (p->Gq > T) p->Gq = (int)T;
       if (p->Gq < 1) p->Gq = 1;
     }
-    int64_t nct = (8 * (int64_t)sms + p->QB - 1) / p->QB;  // aim at ~8 units per SM
+    int64_t nct = (8 * (int64_t)workers + p->QB - 1) / p->QB;  // aim at ~8 units per worker
     if (nct < 1) nct = 1;
     int64_t R = (N + nct - 1) / nct;
     R = (R + 255) / 256 * 256;
@@ -91,8 +97,8 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
   p->off_thr = off; off = align_up(off + (size_t)Q * sizeof(uint32_t), 256);
   p->off_flagcnt = off; off += 256;
   p->off_flaglist = off; off = align_up(off + (size_t)Q * sizeof(int32_t), 256);
-  if (p->use_tensor && Q % 128 != 0) {  // zero-padded copy of the queries (TMA out-of-bounds fill is slow)
-    p->off_qpad = off; off = align_up(off + (size_t)p->QB * 128 * D * 2, 256);
+  if (p->use_tensor && Q % (p->pair ? 256 : 128) != 0) {  // zero-padded copy of the queries (TMA OOB fill is slow)
+    p->off_qpad = off; off = align_up(off + (size_t)p->QB * (p->pair ? 256 : 128) * D * 2, 256);
   }
   if (need_invnorm && p->use_tensor) { p->off_invnorm = off; off = align_up(off + (size_t)N * sizeof(float), 256); }
   p->off_ex_score = off; off = align_up(off + (size_t)Q * p->S * k * sizeof(double), 256);
@@ -181,10 +187,11 @@ extern "C" int tsim_search_topk(const void* q, int q_dt, int64_t q_stride, const
     }
     const void* qt = q;
     int64_t qt_stride = q_stride;
-    if (Q % 128 != 0) {
+    const int qrows = p.pair ? 256 : 128;
+    if (Q % qrows != 0) {
       char* qp = w + p.off_qpad;
       const size_t rowb = (size_t)D * 2;
-      TSIM_CUDA(cudaMemsetAsync(qp + (size_t)Q * rowb, 0, ((size_t)p.QB * 128 - Q) * rowb, st));
+      TSIM_CUDA(cudaMemsetAsync(qp + (size_t)Q * rowb, 0, ((size_t)p.QB * qrows - Q) * rowb, st));
       TSIM_CUDA(cudaMemcpy2DAsync(qp, rowb, q, (size_t)q_stride * 2, rowb, (size_t)Q, cudaMemcpyDeviceToDevice, st));
       qt = qp;
       qt_stride = D;

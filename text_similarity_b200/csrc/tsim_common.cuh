@@ -146,7 +146,8 @@ struct SearchPlan {
   // tensor path
   int use_tensor;      // 1: tcgen05 candidate pass + select/rescore
   int KP;              // per-unit candidate list capacity (16/32/64/128)
-  int QB;              // query blocks of 128
+  int pair;            // 1: CTA pairs (cta_group::2), query blocks of 256
+  int QB;              // query blocks of 128 (256 when pair)
   int sticky;          // 1: each CTA keeps one query block and strides over tiles (few query blocks)
   int Gq;              // sticky: CTAs per query block
   int64_t R;           // round-robin: corpus rows per unit (multiple of 256)
