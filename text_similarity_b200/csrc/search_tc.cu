@@ -164,7 +164,10 @@ struct TcArgs {
   int64_t Q, N;
   int kblocks;          // ceil(D / 64)
   int QB;               // query blocks (128 queries; 256 when CTA pairs are used)
-  int64_t T;            // corpus tiles of 256 rows
+  int64_t T;            // corpus tiles (of 256 rows) THIS launch scans (see tile_mode)
+  int tile_mode;        // 0: tiles 0..T-1; 1: the sample tiles i * tile_stride; 2: every tile that is not a sample tile
+  int64_t tile_stride;  // distance between sample tiles (modes 1, 2)
+  int64_t slot_base;    // first candidate-list slot this launch writes
   int sticky;           // 1: CTA <-> (query block, tile residue class), one list per CTA lifetime
   int Gq;               // sticky: CTAs per query block
   int64_t tpc;          // round-robin: tiles per corpus chunk
@@ -175,6 +178,14 @@ struct TcArgs {
   uint32_t* thr;        // [Q] ordered-float global thresholds (0 = none yet)
   int dbg;              // TSIM_DEBUG bits (diagnosis only): 1 skip A loads, 2 skip MMAs, 4 skip epilogue math
 };
+
+// Logical tile number of this launch -> tile of the corpus.  A bootstrap launch (mode 1) scans a
+// strided sample so every query gets a good threshold before the main launch (mode 2) scans the rest.
+__device__ __forceinline__ int64_t actual_tile(const TcArgs& a, int64_t u) {
+  if (a.tile_mode == 1) return u * a.tile_stride;
+  if (a.tile_mode == 2) return u + u / (a.tile_stride - 1) + 1;
+  return u;
+}
 
 // A unit = one candidate list: a query block and the sequence of corpus tiles scanned into it.
 struct Unit { int qb; int64_t slot; int64_t tile0; int64_t tstride; int ntiles; };
@@ -376,7 +387,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       Unit un;
       for (int it = 0; get_unit(a, it, wid, nw, un); ++it) {
         for (int t = 0; t < un.ntiles; ++t) {
-          const int row0 = (int)((un.tile0 + (int64_t)t * un.tstride) * BN);
+          const int row0 = (int)(actual_tile(a, un.tile0 + (int64_t)t * un.tstride) * BN);
           for (int kb = 0; kb < a.kblocks; ++kb) {
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
             const uint32_t sa = smem_u32(tiles + (size_t)stage * STAGE_BYTES);
@@ -450,7 +461,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       float nreg[8];
       uint32_t gthr = 0;
       auto fetch_meta = [&](int t) {
-        const int64_t r0 = (un.tile0 + (int64_t)t * un.tstride) * BN;
+        const int64_t r0 = actual_tile(a, un.tile0 + (int64_t)t * un.tstride) * BN;
         const int nc = (int)min((int64_t)BN, a.N - r0);
 #pragma unroll
         for (int i = 0; i < 8; ++i) nreg[i] = (lane + 32 * i < nc) ? __ldg(a.c_inv + r0 + lane + 32 * i) : 0.f;
@@ -458,7 +469,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       };
       if (un.ntiles > 0) fetch_meta(0);
       for (int t = 0; t < un.ntiles; ++t) {
-        const int64_t trow0 = (un.tile0 + (int64_t)t * un.tstride) * BN;
+        const int64_t trow0 = actual_tile(a, un.tile0 + (int64_t)t * un.tstride) * BN;
         const int ncols = (int)min((int64_t)BN, a.N - trow0);
         // each epilogue warp keeps a private copy of the tile's inverse norms: no cross-warp barrier
         float* cn = cnorm + (acc * 4 + (warp & 3)) * BN;
@@ -500,7 +511,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         if (++acc == 2) { acc = 0; aphase ^= 1; }
       }
       // flush this unit's list
-      if (qvalid) list.flush(a.cand + ((size_t)qg * a.NC + un.slot) * KP);
+      if (qvalid) list.flush(a.cand + ((size_t)qg * a.NC + a.slot_base + un.slot) * KP);
     }
   }
 
@@ -576,7 +587,7 @@ int launch_cfg(const CUtensorMap& mq, const CUtensorMap& mc, const TcArgs& a, cu
 
 int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_t c_stride,
                      const float* c_inv, int64_t Q, int64_t N, int64_t D, int self_on, int64_t self_off,
-                     const SearchPlan& p, uint64_t* cand, uint32_t* thr, cudaStream_t st) {
+                     const SearchPlan& p, int pass, uint64_t* cand, uint32_t* thr, cudaStream_t st) {
   CUtensorMap mq, mc;
   const int qrows = p.pair ? 2 * BM : BM;
   // q holds QB * qrows rows (the API pads the last query block with zero rows)
@@ -587,8 +598,12 @@ int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_
   TcArgs a;
   a.c_inv = c_inv; a.Q = Q; a.N = N;
   a.kblocks = (int)((D + BK - 1) / BK);
-  a.QB = p.QB; a.T = (N + BN - 1) / BN; a.sticky = p.sticky; a.Gq = p.Gq; a.tpc = p.R / BN;
+  const int64_t T = (N + BN - 1) / BN;
+  a.QB = p.QB; a.sticky = p.sticky; a.Gq = p.Gq; a.tpc = p.R / BN;
   a.NC = p.NC; a.n_units = (int64_t)p.QB * p.NC;
+  // pass 0: the whole corpus in one launch; pass 1: bootstrap sample; pass 2: everything else
+  a.tile_mode = pass; a.tile_stride = p.boot_stride; a.slot_base = pass == 2 ? p.Gq : 0;
+  a.T = pass == 1 ? p.boot_tiles : pass == 2 ? T - p.boot_tiles : T;
   a.self_on = self_on; a.self_off = self_off;
   a.cand = cand; a.thr = thr;
   const char* dbg = getenv("TSIM_DEBUG");

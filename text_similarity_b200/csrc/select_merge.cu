@@ -225,6 +225,47 @@ __global__ void __launch_bounds__(kSelThreads) select_rescore_kernel(SelArgs a) 
   }
 }
 
+// Between the bootstrap launch and the main launch: the KP-th best key of the union of a query's
+// bootstrap lists (slots 0..Gq-1) is a lower bound of its KP-th best over the whole corpus.
+__global__ void __launch_bounds__(kSelThreads) tighten_kernel(const uint64_t* cand, uint32_t* thr, int64_t NC, int KP,
+                                                              int nslots) {
+  __shared__ uint64_t keys[kKeyCap];
+  __shared__ int n_sh;
+  const int64_t q = blockIdx.x;
+  const int tid = threadIdx.x;
+  const uint64_t* src = cand + (size_t)q * NC * KP;
+  const int64_t total = (int64_t)nslots * KP;
+  const uint32_t thr_ord = thr[q];
+  if (tid == 0) n_sh = 0;
+  __syncthreads();
+  int64_t cursor = 0;
+  int n = 0;
+  while (cursor < total) {
+    int64_t take = min((int64_t)(kKeyCap - n), total - cursor);
+    for (int64_t i = tid; i < take; i += blockDim.x) {
+      uint64_t key = __ldcg(src + cursor + i);
+      if (key != 0 && (uint32_t)(key >> 32) >= thr_ord) keys[atomicAdd(&n_sh, 1)] = key;
+    }
+    cursor += take;
+    __syncthreads();
+    n = n_sh;
+    if (cursor < total && n > kKeyCap / 2) {
+      int np = next_pow2(n);
+      for (int i = n + tid; i < np; i += blockDim.x) keys[i] = 0;
+      __syncthreads();
+      sort_keys_desc(keys, np);
+      n = min(n, KP);
+      if (tid == 0) n_sh = n;
+      __syncthreads();
+    }
+  }
+  int np = next_pow2(max(n, 1));
+  for (int i = n + tid; i < np; i += blockDim.x) keys[i] = 0;
+  __syncthreads();
+  sort_keys_desc(keys, np);
+  if (tid == 0 && n >= KP) atomicMax(thr + q, (uint32_t)(keys[KP - 1] >> 32));
+}
+
 struct ExMergeArgs {
   const void* q; int q_dt; int64_t q_stride;
   const void* corpus; int c_dt; int64_t c_stride;
@@ -302,6 +343,12 @@ int launch_select_rescore(const void* q, int q_dt, int64_t q_stride, const void*
   a.flag_cnt = flag_cnt; a.flag_list = flag_list;
   a.out_score = out_score; a.out_score64 = out_score64; a.out_idx = out_idx; a.out_flags = out_flags;
   select_rescore_kernel<<<(unsigned)Q, kSelThreads, 0, st>>>(a);
+  TSIM_CUDA(cudaGetLastError());
+  return TSIM_OK;
+}
+
+int launch_tighten(int64_t Q, const SearchPlan& p, const uint64_t* cand, uint32_t* thr, cudaStream_t st) {
+  tighten_kernel<<<(unsigned)Q, kSelThreads, 0, st>>>(cand, thr, p.NC, p.KP, p.Gq);
   TSIM_CUDA(cudaGetLastError());
   return TSIM_OK;
 }

@@ -70,6 +70,14 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
       p->Gq = workers / p->QB;
       if (p->Gq > T) p->Gq = (int)T;
       if (p->Gq < 1) p->Gq = 1;
+      // Bootstrap: with >= 16 queries the per-CTA lists' warm-up (every early score is a candidate)
+      // costs more than two extra launches; scan 2 strided sample tiles per worker first and turn
+      // their union's KP-th best into every query's starting threshold.
+      const char* noboot = getenv("TSIM_NO_BOOT");
+      if (Q >= 16 && T >= 32 * (int64_t)p->Gq && !(noboot && noboot[0] == '1')) {
+        p->boot_stride = T / (2 * (int64_t)p->Gq);                      // >= 16
+        p->boot_tiles = (T + p->boot_stride - 1) / p->boot_stride;      // every multiple of the stride below T
+      }
     }
     int64_t nct = (8 * (int64_t)workers + p->QB - 1) / p->QB;  // aim at ~8 units per worker
     if (nct < 1) nct = 1;
@@ -80,7 +88,7 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
     // bound the candidate buffer (Q * NC * KP * 8 bytes) to ~2 GB
     while ((double)Q * (double)((N + R - 1) / R) * p->KP * 8.0 > 2.0e9 && R < ((int64_t)1 << 30)) R *= 2;
     p->R = R;
-    p->NC = p->sticky ? p->Gq : (N + R - 1) / R;
+    p->NC = p->sticky ? (p->boot_tiles ? 2 * p->Gq : p->Gq) : (N + R - 1) / R;
     p->off_cand = off; off = align_up(off + (size_t)Q * p->NC * p->KP * sizeof(uint64_t), 256);
   }
   // exact scan (whole-call path, or fallback for flagged queries)
@@ -198,8 +206,15 @@ extern "C" int tsim_search_topk(const void* q, int q_dt, int64_t q_stride, const
     }
     const bool timed = g_ev_start && g_ev_stop;
     if (timed) TSIM_CUDA(cudaEventRecord(g_ev_start, st));
+    uint64_t* cand = (uint64_t*)(w + p.off_cand);
+    if (p.boot_tiles) {
+      rc = launch_search_tc(qt, qt_stride, corpus, c_stride, c_inv, Q, N, D, self_on, self_off, p, 1, cand, thr, st);
+      if (rc) return rc;
+      rc = launch_tighten(Q, p, cand, thr, st);
+      if (rc) return rc;
+    }
     rc = launch_search_tc(qt, qt_stride, corpus, c_stride, c_inv, Q, N, D, self_on, self_off, p,
-                          (uint64_t*)(w + p.off_cand), thr, st);
+                          p.boot_tiles ? 2 : 0, cand, thr, st);
     if (rc) return rc;
     if (timed) TSIM_CUDA(cudaEventRecord(g_ev_stop, st));
     rc = launch_select_rescore(q, q_dt, q_stride, corpus, c_dt, c_stride, Q, N, D, k, idx_base, p,

@@ -150,6 +150,8 @@ struct SearchPlan {
   int QB;              // query blocks of 128 (256 when pair)
   int sticky;          // 1: each CTA keeps one query block and strides over tiles (few query blocks)
   int Gq;              // sticky: CTAs per query block
+  int64_t boot_tiles;  // > 0: a bootstrap launch scans this many strided sample tiles first
+  int64_t boot_stride; //      distance between sample tiles
   int64_t R;           // round-robin: corpus rows per unit (multiple of 256)
   int64_t NC;          // candidate lists per query: chunks ceil(N / R), or Gq when sticky
   // exact path
@@ -166,8 +168,9 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
 // kernels' host launchers (defined in the .cu files)
 int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_t c_stride,
                      const float* c_inv, int64_t Q, int64_t N, int64_t D,
-                     int self_on, int64_t self_off, const SearchPlan& p, uint64_t* cand,
+                     int self_on, int64_t self_off, const SearchPlan& p, int pass, uint64_t* cand,
                      uint32_t* thr, cudaStream_t st);
+int launch_tighten(int64_t Q, const SearchPlan& p, const uint64_t* cand, uint32_t* thr, cudaStream_t st);
 int launch_select_rescore(const void* q, int q_dt, int64_t q_stride, const void* corpus, int c_dt,
                           int64_t c_stride, int64_t Q, int64_t N, int64_t D, int k,
                           int64_t idx_base, const SearchPlan& p, const uint64_t* cand,
