@@ -98,7 +98,7 @@ int tsim_row_inv_norm(const void* x, int dt, int64_t N, int64_t D, int64_t strid
  *   corpus [N, D] c_dt, row stride c_stride elements      (any norm; not modified)
  *   corpus_inv_norm [N] float = tsim_row_inv_norm(corpus) (from K1 or the call above);
  *          may be NULL, then it is computed into the workspace on every call.
- *   k      results per query, 1 <= k <= 120.
+ *   k      results per query, 1 <= k <= 1024 (k <= 100 on the tensor-core path).
  *   idx_base           added to corpus row numbers in out_idx (contiguous row shards).
  *   exclude_self_base  >= 0: corpus row (idx_base + j) == exclude_self_base + query number
  *                      is skipped (all-pairs mining); -1: off.
@@ -114,7 +114,8 @@ int tsim_row_inv_norm(const void* x, int dt, int64_t N, int64_t D, int64_t strid
  * index.  The tensor-core pass only nominates candidates; a per-query safety check proves
  * no row outside the candidates can be in the top-k, otherwise the query is recomputed by
  * a float64 scan of the whole shard.  Supported: TSIM_MODE_TENSOR needs q_dt == c_dt ==
- * TSIM_BF16, D % 8 == 0, 16-byte aligned rows; everything else runs the exact scan.
+ * TSIM_BF16 (D % 8 == 0) or TSIM_E4M3 (D % 16 == 0), 16-byte aligned rows, k <= 100;
+ * everything else runs the exact scan.
  * ---------------------------------------------------------------------------------- */
 size_t tsim_search_workspace_bytes(int64_t Q, int64_t N, int64_t D, int k,
                                    int q_dt, int c_dt, int mode);

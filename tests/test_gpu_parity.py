@@ -188,6 +188,32 @@ def test_tensor_path_with_precomputed_inv_norm(ops):
     _check(ops, q, c, 10, TOL_BF16, mode="tensor", corpus_inv_norm=inv)
 
 
+@pytest.mark.parametrize("N,Q,D,k", [(50_000, 1, 384, 10), (50_000, 32, 384, 10), (70_000, 300, 768, 10),
+                                      (20_000, 17, 400, 24), (300, 5, 128, 10)])
+def test_fp8_tensor_path_matches_oracle(ops, N, Q, D, k):
+    # e4m3 queries AND corpus (BASELINE config 4 storage): tcgen05 kind::f8f6f4 nominates, float64 re-scores
+    q, c = _make(N, Q, D, torch.float32, seed=N + D)
+    scale = torch.rand(N, 1) * 3 + 0.5                     # per-row scales: cosine is scale free
+    c8 = (c * 64 * scale).to(torch.float8_e4m3fn)
+    q8 = (q * 64).to(torch.float8_e4m3fn)
+    fl = _check(ops, q8, c8, k, TOL_BF16, mode="tensor")
+    assert fl.float().mean() <= 0.05 or N <= 1000
+
+
+def test_fp8_store_from_pool_kernel_then_search(ops):
+    g = torch.Generator().manual_seed(17)
+    tok = torch.randn(600, 12, 384, generator=g)
+    mask = (torch.rand(600, 12, generator=g) > 0.2).to(torch.int64)
+    mask[:, 0] = 1
+    rows, inv = ops.pool_norm(tok.cuda(), mask.cuda(), out_dtype=torch.float8_e4m3fn, normalize=True)
+    q = rows[:40].clone()
+    s, i = ops.search_topk(q, rows, 5, corpus_inv_norm=inv, mode="tensor")
+    ev, ei = O.search_exact(q.cpu(), rows.cpu(), 5)
+    assert torch.equal(i.cpu(), ei)
+    assert (i[:, 0].cpu() == torch.arange(40)).all()        # every query finds itself first
+    np.testing.assert_allclose(s.cpu().numpy(), ev.numpy(), atol=TOL_BF16)
+
+
 def test_heavy_duplicates_fall_back_and_stay_exact(ops):
     # 40 identical rows tie for the top: the completeness proof must fail and the exact scan answer
     q, c = _make(5000, 16, 128, torch.bfloat16, seed=21)

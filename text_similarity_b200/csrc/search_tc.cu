@@ -30,21 +30,23 @@ namespace {
 
 constexpr int BM = 128;        // queries per CTA tile (TMEM lanes)
 constexpr int BN = 256;        // corpus rows per tile (TMEM columns per accumulator stage)
-constexpr int BK = 64;         // bf16 elements per k-block = 128 bytes = one swizzle atom row
-constexpr int UMMA_K = 16;     // bf16 MMA K
+constexpr int BK_BYTES = 128;  // bytes per row per k-block = one 128-byte swizzle atom row (64 bf16 / 128 e4m3)
+constexpr int UMMA_K_BYTES = 32;  // one MMA consumes 32 bytes of K per row (K = 16 bf16 / 32 e4m3)
 constexpr int kThreads = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
 constexpr int kEpiThreads = 128;
-constexpr int A_BYTES = BM * BK * 2;   // 16 KB: 128 query rows x 128 bytes
+constexpr int A_BYTES = BM * BK_BYTES;   // 16 KB: 128 query rows x 128 bytes
 // B (corpus) bytes per CTA per stage: all 256 rows of the tile for a lone CTA, 128 rows for each CTA
 // of a pair (cta_group::2: the MMA reads the other half from the peer's shared memory)
 template <bool PAIR> struct Cfg {
   static constexpr int B_ROWS = PAIR ? BN / 2 : BN;
-  static constexpr int B_BYTES = B_ROWS * BK * 2;
+  static constexpr int B_BYTES = B_ROWS * BK_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;       // 48 KB lone, 32 KB per CTA of a pair
   static constexpr int MMA_M = PAIR ? 2 * BM : BM;
-  // UMMA instruction descriptor: D = f32, A = B = bf16, both K-major, N = 256, M = 128 / 256
-  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                                    ((uint32_t)(MMA_M >> 4) << 24);
+  // UMMA instruction descriptor: D = f32 (bit 4), A/B format at bits 7/10 (kind::f16: 1 = bf16;
+  // kind::f8f6f4: 0 = e4m3), both K-major, N = 256, M = 128 / 256
+  static constexpr uint32_t IDESC_BF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                         ((uint32_t)(MMA_M >> 4) << 24);
+  static constexpr uint32_t IDESC_E4M3 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(MMA_M >> 4) << 24);
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -90,20 +92,32 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t cta_
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  // default semantics (release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id): a
+  // cluster-scope release would cost a full memory barrier per tile; the TMEM hand-off is ordered
+  // by tcgen05.fence::before_thread_sync / after_thread_sync around the barrier
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
-__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                                 uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
+template <bool FP8>
+__device__ __forceinline__ void tc_mma_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  if constexpr (FP8)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -122,14 +136,23 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
+template <bool FP8>
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                       uint32_t accumulate) {
+  if constexpr (FP8)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
@@ -162,7 +185,7 @@ __device__ __forceinline__ uint64_t make_umma_desc(uint32_t smem_addr) {
 struct TcArgs {
   const float* c_inv;   // [N] inverse norms of the stored corpus rows
   int64_t Q, N;
-  int kblocks;          // ceil(D / 64)
+  int kblocks;          // ceil(D * element size / 128)
   int QB;               // query blocks (128 queries; 256 when CTA pairs are used)
   int64_t T;            // corpus tiles (of 256 rows) THIS launch scans (see tile_mode)
   int tile_mode;        // 0: tiles 0..T-1; 1: the sample tiles i * tile_stride; 2: every tile that is not a sample tile
@@ -231,11 +254,16 @@ struct RegList16 {
 #pragma unroll
     for (int i = 0; i < 16; ++i) { a[i] = -INFINITY; r[i] = 0xffffffffu; }
   }
+  // gm0..gm3: this lane's maxima over the chunk's four 8-column groups; a group is re-read only if
+  // some lane of the warp has a candidate in it (warp-uniform test: tcgen05.ld is .sync.aligned)
   __device__ __forceinline__ float slow(uint32_t taddr, const float* cnp, float thr, int64_t row_base,
-                                        int64_t self_row, int lim, uint32_t* thr_g) {
+                                        int64_t self_row, int lim, uint32_t* thr_g, float gm0, float gm1,
+                                        float gm2, float gm3) {
     const float thr_in = thr;
 #pragma unroll 1
     for (int g = 0; g < 4; ++g) {
+      const float gm = g == 0 ? gm0 : g == 1 ? gm1 : g == 2 ? gm2 : gm3;
+      if (!__any_sync(0xffffffffu, gm > thr)) continue;
       uint32_t w[8];
       tc_ld8(taddr + g * 8, w);
       tc_ld_wait();
@@ -270,10 +298,13 @@ struct RegList16 {
 
 template <int KP>
 __device__ __noinline__ float smem_list_slow(float* ls, uint32_t* li, uint32_t taddr, const float* cnp, float thr,
-                                             int64_t row_base, int64_t self_row, int lim, uint32_t* thr_g) {
+                                             int64_t row_base, int64_t self_row, int lim, uint32_t* thr_g,
+                                             float gm0, float gm1, float gm2, float gm3) {
   const float thr_in = thr;
 #pragma unroll 1
   for (int g = 0; g < 4; ++g) {
+    const float gm = g == 0 ? gm0 : g == 1 ? gm1 : g == 2 ? gm2 : gm3;
+    if (!__any_sync(0xffffffffu, gm > thr)) continue;
     uint32_t w[8];
     tc_ld8(taddr + g * 8, w);
     tc_ld_wait();
@@ -313,8 +344,9 @@ struct SmemList {
     for (int j = 0; j < KP; ++j) { ls[j * kEpiThreads] = -INFINITY; li[j * kEpiThreads] = 0xffffffffu; }
   }
   __device__ __forceinline__ float slow(uint32_t taddr, const float* cnp, float thr, int64_t row_base,
-                                        int64_t self_row, int lim, uint32_t* thr_g) {
-    return smem_list_slow<KP>(ls, li, taddr, cnp, thr, row_base, self_row, lim, thr_g);
+                                        int64_t self_row, int lim, uint32_t* thr_g, float gm0, float gm1,
+                                        float gm2, float gm3) {
+    return smem_list_slow<KP>(ls, li, taddr, cnp, thr, row_base, self_row, lim, thr_g, gm0, gm1, gm2, gm3);
   }
   __device__ __forceinline__ void flush(uint64_t* dst) {
 #pragma unroll 4
@@ -328,7 +360,7 @@ struct SmemList {
 template <int KP> struct ListFor { using type = SmemList<KP>; };
 template <> struct ListFor<16> { using type = RegList16; };
 
-template <int KP, int STAGES, bool PAIR>
+template <int KP, int STAGES, bool PAIR, bool FP8>
 __global__ void __launch_bounds__(kThreads, 1)
 search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c, TcArgs a) {
   extern __shared__ unsigned char smem_raw[];
@@ -338,6 +370,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int B_BYTES = Cfg<PAIR>::B_BYTES;
   constexpr int STAGE_BYTES = Cfg<PAIR>::STAGE_BYTES;
+  constexpr int BK = FP8 ? BK_BYTES : BK_BYTES / 2;       // elements per k-block (TMA coordinates are in elements)
+  constexpr uint32_t IDESC = FP8 ? Cfg<PAIR>::IDESC_E4M3 : Cfg<PAIR>::IDESC_BF16;
   unsigned char* tiles = smem;
   float* list_s = (float*)(smem + (size_t)STAGES * STAGE_BYTES);
   uint32_t* list_i = (uint32_t*)(list_s + KP * kEpiThreads);
@@ -426,11 +460,11 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             const uint64_t adesc = make_umma_desc(sa);
             const uint64_t bdesc = make_umma_desc(sa + A_BYTES);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
+            for (int k = 0; k < BK_BYTES / UMMA_K_BYTES; ++k) {
               if (a.dbg & 2) break;
-              // advance 32 bytes (16 bf16) inside the 128-byte swizzle row: +2 in >>4 units
-              if (PAIR) tc_mma_bf16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), Cfg<PAIR>::IDESC, (kb | k) ? 1u : 0u);
-              else tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), Cfg<PAIR>::IDESC, (kb | k) ? 1u : 0u);
+              // advance 32 bytes (16 bf16 / 32 e4m3) inside the 128-byte swizzle row: +2 in >>4 units
+              if (PAIR) tc_mma_pair<FP8>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (kb | k) ? 1u : 0u);
+              else tc_mma<FP8>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (kb | k) ? 1u : 0u);
             }
             // frees the smem stage (in both CTAs of a pair) when the MMAs retire
             if (PAIR) tc_commit_pair(smem_u32(&empty_bar[stage])); else tc_commit(smem_u32(&empty_bar[stage]));
@@ -487,20 +521,24 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           uint32_t v[32];
           tc_ld32(tbase + c * 32, v);
           tc_ld_wait();
-          // hot path: 32 FMUL + FMNMX3 tree + one compare
+          // hot path: 32 FMUL + FMNMX3 tree (kept per 8-column group) + one compare
           const float4* cn4 = (const float4*)(cn + c * 32);
-          float mx = -INFINITY;
+          float gm[4];
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 w = cn4[j4];
-            const float a0 = __uint_as_float(v[j4 * 4 + 0]) * w.x, a1 = __uint_as_float(v[j4 * 4 + 1]) * w.y;
-            const float a2 = __uint_as_float(v[j4 * 4 + 2]) * w.z, a3 = __uint_as_float(v[j4 * 4 + 3]) * w.w;
-            mx = fmaxf(mx, fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)));
+          for (int g = 0; g < 4; ++g) {
+            const float4 w0 = cn4[2 * g], w1 = cn4[2 * g + 1];
+            const float a0 = __uint_as_float(v[g * 8 + 0]) * w0.x, a1 = __uint_as_float(v[g * 8 + 1]) * w0.y;
+            const float a2 = __uint_as_float(v[g * 8 + 2]) * w0.z, a3 = __uint_as_float(v[g * 8 + 3]) * w0.w;
+            const float a4 = __uint_as_float(v[g * 8 + 4]) * w1.x, a5 = __uint_as_float(v[g * 8 + 5]) * w1.y;
+            const float a6 = __uint_as_float(v[g * 8 + 6]) * w1.z, a7 = __uint_as_float(v[g * 8 + 7]) * w1.w;
+            gm[g] = fmaxf(fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)), fmaxf(fmaxf(a4, a5), fmaxf(a6, a7)));
           }
+          const float mx = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
           // Cold path, taken by the WHOLE warp when any lane has a candidate (tcgen05.ld is
           // .sync.aligned: it must not run under divergence); rare once the lists are warm.
           if (__any_sync(0xffffffffu, mx > thr))
-            thr = list.slow(tbase + c * 32, cn + c * 32, thr, trow0 + c * 32, self_row, ncols - c * 32, thr_g);
+            thr = list.slow(tbase + c * 32, cn + c * 32, thr, trow0 + c * 32, self_row, ncols - c * 32, thr_g,
+                            gm[0], gm[1], gm[2], gm[3]);
         }
         tc_fence_before();
         __syncwarp();
@@ -543,26 +581,26 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 row-major [rows, D] tensor map with a [box_rows, 64] box and 128-byte swizzle
-int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t D, int64_t stride_elems, int box_rows) {
+// 2-D row-major [rows, D] tensor map (bf16 or 1-byte e4m3) with a [box_rows, 128 bytes] box and 128-byte swizzle
+int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t D, int64_t stride_elems, int box_rows, int esz) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return TSIM_ERR_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)stride_elems * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)stride_elems * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(BK_BYTES / esz), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(m, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return TSIM_ERR_CUDA; }
   return TSIM_OK;
 }
 
-template <int KP, int STAGES, bool PAIR>
+template <int KP, int STAGES, bool PAIR, bool FP8>
 int launch_cfg(const CUtensorMap& mq, const CUtensorMap& mc, const TcArgs& a, cudaStream_t st) {
   size_t smem = 1024 + (size_t)STAGES * Cfg<PAIR>::STAGE_BYTES + (size_t)KP * kEpiThreads * 8 + 2 * 4 * BN * 4 +
                 (2 * STAGES + 4) * 8 + 16;
-  auto kern = search_tc_kernel<KP, STAGES, PAIR>;
+  auto kern = search_tc_kernel<KP, STAGES, PAIR, FP8>;
   TSIM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int sms = device_sm_count();
   const int workers = PAIR ? sms / 2 : sms;
@@ -585,19 +623,20 @@ int launch_cfg(const CUtensorMap& mq, const CUtensorMap& mc, const TcArgs& a, cu
 
 }  // namespace
 
-int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_t c_stride,
+int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_t c_stride, int dt,
                      const float* c_inv, int64_t Q, int64_t N, int64_t D, int self_on, int64_t self_off,
                      const SearchPlan& p, int pass, uint64_t* cand, uint32_t* thr, cudaStream_t st) {
   CUtensorMap mq, mc;
   const int qrows = p.pair ? 2 * BM : BM;
   // q holds QB * qrows rows (the API pads the last query block with zero rows)
-  int rc = make_map(&mq, q, (int64_t)p.QB * qrows, D, q_stride, BM);
+  const int esz = dt == TSIM_E4M3 ? 1 : 2;
+  int rc = make_map(&mq, q, (int64_t)p.QB * qrows, D, q_stride, BM, esz);
   if (rc) return rc;
-  rc = make_map(&mc, corpus, N, D, c_stride, p.pair ? BN / 2 : BN);
+  rc = make_map(&mc, corpus, N, D, c_stride, p.pair ? BN / 2 : BN, esz);
   if (rc) return rc;
   TcArgs a;
   a.c_inv = c_inv; a.Q = Q; a.N = N;
-  a.kblocks = (int)((D + BK - 1) / BK);
+  a.kblocks = (int)((D * esz + BK_BYTES - 1) / BK_BYTES);
   const int64_t T = (N + BN - 1) / BN;
   a.QB = p.QB; a.sticky = p.sticky; a.Gq = p.Gq; a.tpc = p.R / BN;
   a.NC = p.NC; a.n_units = (int64_t)p.QB * p.NC;
@@ -608,21 +647,24 @@ int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_
   a.cand = cand; a.thr = thr;
   const char* dbg = getenv("TSIM_DEBUG");
   a.dbg = dbg ? atoi(dbg) : 0;
-  if (p.pair) {
-    switch (p.KP) {
-      case 16: return launch_cfg<16, 6, true>(mq, mc, a, st);
-      case 32: return launch_cfg<32, 5, true>(mq, mc, a, st);
-      case 64: return launch_cfg<64, 4, true>(mq, mc, a, st);
-      case 112: return launch_cfg<112, 3, true>(mq, mc, a, st);
-    }
-  } else {
-    switch (p.KP) {
-      case 16: return launch_cfg<16, 4, false>(mq, mc, a, st);
-      case 32: return launch_cfg<32, 3, false>(mq, mc, a, st);
-      case 64: return launch_cfg<64, 3, false>(mq, mc, a, st);
-      case 112: return launch_cfg<112, 2, false>(mq, mc, a, st);
-    }
+#define TSIM_DISPATCH(FP8)                                                       \
+  if (p.pair) {                                                                  \
+    switch (p.KP) {                                                              \
+      case 16: return launch_cfg<16, 6, true, FP8>(mq, mc, a, st);               \
+      case 32: return launch_cfg<32, 5, true, FP8>(mq, mc, a, st);               \
+      case 64: return launch_cfg<64, 4, true, FP8>(mq, mc, a, st);               \
+      case 112: return launch_cfg<112, 3, true, FP8>(mq, mc, a, st);             \
+    }                                                                            \
+  } else {                                                                       \
+    switch (p.KP) {                                                              \
+      case 16: return launch_cfg<16, 4, false, FP8>(mq, mc, a, st);              \
+      case 32: return launch_cfg<32, 3, false, FP8>(mq, mc, a, st);              \
+      case 64: return launch_cfg<64, 3, false, FP8>(mq, mc, a, st);              \
+      case 112: return launch_cfg<112, 2, false, FP8>(mq, mc, a, st);            \
+    }                                                                            \
   }
+  if (dt == TSIM_E4M3) { TSIM_DISPATCH(true) } else { TSIM_DISPATCH(false) }
+#undef TSIM_DISPATCH
   set_error("search_tc: bad KP %d", p.KP);
   return TSIM_ERR_INVALID_ARG;
 }

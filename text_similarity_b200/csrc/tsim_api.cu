@@ -39,8 +39,9 @@ int device_sm_count() {
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 static bool tensor_shape_ok(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt) {
-  return q_dt == TSIM_BF16 && c_dt == TSIM_BF16 && D % 8 == 0 && D >= 8 && k <= 100 && Q > 0 && N > 0 &&
-         N < (int64_t)0x7fffff00 && Q < (int64_t)0x7fffff00;
+  const bool bf16 = q_dt == TSIM_BF16 && c_dt == TSIM_BF16 && D % 8 == 0 && D >= 8;
+  const bool e4m3 = q_dt == TSIM_E4M3 && c_dt == TSIM_E4M3 && D % 16 == 0 && D >= 16;
+  return (bf16 || e4m3) && k <= 100 && Q > 0 && N > 0 && N < (int64_t)0x7fffff00 && Q < (int64_t)0x7fffff00;
 }
 
 int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt, int mode,
@@ -49,7 +50,7 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
   const int sms = device_sm_count();
   const bool ok = tensor_shape_ok(Q, N, D, k, q_dt, c_dt);
   if (mode == TSIM_MODE_TENSOR && !ok) {
-    set_error("search: TSIM_MODE_TENSOR needs bf16 queries and corpus, D %% 8 == 0, k <= 100 "
+    set_error("search: TSIM_MODE_TENSOR needs bf16 (D %% 8 == 0) or e4m3 (D %% 16 == 0) queries AND corpus, k <= 100 "
               "(got q_dt=%d c_dt=%d D=%lld k=%d)", q_dt, c_dt, (long long)D, k);
     return TSIM_ERR_UNSUPPORTED;
   }
@@ -106,7 +107,7 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
   p->off_flagcnt = off; off += 256;
   p->off_flaglist = off; off = align_up(off + (size_t)Q * sizeof(int32_t), 256);
   if (p->use_tensor && Q % (p->pair ? 256 : 128) != 0) {  // zero-padded copy of the queries (TMA OOB fill is slow)
-    p->off_qpad = off; off = align_up(off + (size_t)p->QB * (p->pair ? 256 : 128) * D * 2, 256);
+    p->off_qpad = off; off = align_up(off + (size_t)p->QB * (p->pair ? 256 : 128) * D * dtype_size(q_dt), 256);
   }
   if (need_invnorm && p->use_tensor) { p->off_invnorm = off; off = align_up(off + (size_t)N * sizeof(float), 256); }
   p->off_ex_score = off; off = align_up(off + (size_t)Q * p->S * k * sizeof(double), 256);
@@ -164,11 +165,12 @@ extern "C" int tsim_search_topk(const void* q, int q_dt, int64_t q_stride, const
     return TSIM_ERR_WORKSPACE;
   }
   if (p.use_tensor) {
+    const int per16 = 16 / dtype_size(c_dt);
     const bool aligned = (((uintptr_t)q & 15) == 0) && (((uintptr_t)corpus & 15) == 0) &&
-                         (q_stride % 8 == 0) && (c_stride % 8 == 0);
+                         (q_stride % per16 == 0) && (c_stride % per16 == 0);
     if (!aligned) {
       if (mode == TSIM_MODE_TENSOR) {
-        set_error("search: TMA needs 16-byte aligned bases and row strides (multiples of 8 elements)");
+        set_error("search: TMA needs 16-byte aligned bases and row strides");
         return TSIM_ERR_MISALIGNED;
       }
       p.use_tensor = 0;
@@ -198,9 +200,9 @@ extern "C" int tsim_search_topk(const void* q, int q_dt, int64_t q_stride, const
     const int qrows = p.pair ? 256 : 128;
     if (Q % qrows != 0) {
       char* qp = w + p.off_qpad;
-      const size_t rowb = (size_t)D * 2;
+      const size_t rowb = (size_t)D * dtype_size(q_dt);
       TSIM_CUDA(cudaMemsetAsync(qp + (size_t)Q * rowb, 0, ((size_t)p.QB * qrows - Q) * rowb, st));
-      TSIM_CUDA(cudaMemcpy2DAsync(qp, rowb, q, (size_t)q_stride * 2, rowb, (size_t)Q, cudaMemcpyDeviceToDevice, st));
+      TSIM_CUDA(cudaMemcpy2DAsync(qp, rowb, q, (size_t)q_stride * dtype_size(q_dt), rowb, (size_t)Q, cudaMemcpyDeviceToDevice, st));
       qt = qp;
       qt_stride = D;
     }
@@ -208,12 +210,12 @@ extern "C" int tsim_search_topk(const void* q, int q_dt, int64_t q_stride, const
     if (timed) TSIM_CUDA(cudaEventRecord(g_ev_start, st));
     uint64_t* cand = (uint64_t*)(w + p.off_cand);
     if (p.boot_tiles) {
-      rc = launch_search_tc(qt, qt_stride, corpus, c_stride, c_inv, Q, N, D, self_on, self_off, p, 1, cand, thr, st);
+      rc = launch_search_tc(qt, qt_stride, corpus, c_stride, c_dt, c_inv, Q, N, D, self_on, self_off, p, 1, cand, thr, st);
       if (rc) return rc;
       rc = launch_tighten(Q, p, cand, thr, st);
       if (rc) return rc;
     }
-    rc = launch_search_tc(qt, qt_stride, corpus, c_stride, c_inv, Q, N, D, self_on, self_off, p,
+    rc = launch_search_tc(qt, qt_stride, corpus, c_stride, c_dt, c_inv, Q, N, D, self_on, self_off, p,
                           p.boot_tiles ? 2 : 0, cand, thr, st);
     if (rc) return rc;
     if (timed) TSIM_CUDA(cudaEventRecord(g_ev_stop, st));

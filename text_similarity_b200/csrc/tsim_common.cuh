@@ -166,7 +166,7 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
                      bool need_invnorm, SearchPlan* plan);
 
 // kernels' host launchers (defined in the .cu files)
-int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_t c_stride,
+int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_t c_stride, int dt,
                      const float* c_inv, int64_t Q, int64_t N, int64_t D,
                      int self_on, int64_t self_off, const SearchPlan& p, int pass, uint64_t* cand,
                      uint32_t* thr, cudaStream_t st);
