@@ -1,0 +1,184 @@
+"""GPU parity at the shapes BASELINE.json names.  Small enough cases are compared row for row with
+the CPU oracle; at full size the checks are size-independent properties: planted answers with known
+order, float64 recomputation of every returned score from gathered rows, a sampled lower-bound test
+of the k-th score, sortedness, and shards + merge == one search."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from text_similarity_b200 import ops as _ops
+    return _ops
+
+
+def _unit_rows(n, d, seed, dtype, dev="cuda", scale=1.0):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    out = torch.empty(n, d, dtype=dtype, device=dev)
+    for s in range(0, n, 1 << 18):
+        m = min(1 << 18, n - s)
+        x = torch.randn(m, d, generator=g, device=dev)
+        out[s:s + m] = (x / x.norm(dim=-1, keepdim=True) * scale).to(dtype)
+    return out
+
+
+def _recompute(queries, corpus, idx):
+    """float64 cosine of returned (query, row) pairs from gathered rows, on the CPU."""
+    q = queries.cpu().to(torch.float64)
+    rows = corpus[idx.reshape(-1).to(corpus.device)].cpu().to(torch.float64).reshape(*idx.shape, -1)
+    dot = (rows * q[:, None, :]).sum(-1)
+    return dot / (q.norm(dim=-1).clamp_min(1e-8)[:, None] * rows.norm(dim=-1).clamp_min(1e-8))
+
+
+# ---------------------------------------------------------------------------- config 1
+def test_config1_minilm_encoder_10k_sentences_fp32(ops):
+    """MiniLM-L6-shaped random-init encoder, 10k synthetic sentences, 100 queries, exact top-10 (the
+    reference's own CPU-runnable case) through the reference-facing classes."""
+    from src.configurations.config import ModelParameters, SearchConfiguration
+    from src.models.sentence_encoder import SentenceTransformerWrapper
+    from src.modules.modules import AvgPoolingStrategy
+    from src.pipeline.search_pipeline import SentenceMiningPipeline
+    from text_similarity_b200.utils import SyntheticTokenizer, minilm_l6_encoder, synthetic_sentences
+    params = SearchConfiguration(model_parameters=ModelParameters(model_name="minilm-l6", hidden_size=384),
+                                 model="synthetic", save_path=".", tokenizer=SyntheticTokenizer(),
+                                 sequence_max_len=64, batch_size=16, device=torch.device("cuda"))
+    model = SentenceTransformerWrapper(pooler=AvgPoolingStrategy(params), merge_strategy=None, loss=None,
+                                       params=params, context_embedder=minilm_l6_encoder(0), parallel_mode=False)
+    corpus_text = synthetic_sentences(10_000, seed=0, min_words=2, max_words=62)
+    query_text = synthetic_sentences(100, seed=1, min_words=2, max_words=62)
+    corpus = model.encode_text(corpus_text)          # fp32, un-normalised, as the reference returns
+    queries = model.encode_text(query_text)
+    assert corpus.shape == (10_000, 384) and corpus.dtype == torch.float32
+    pipe = SentenceMiningPipeline(4096, params=params, model=model, name="cfg1")   # 3 chunks + merge
+    s, i = pipe.search_tensors(queries, 10, corpus=corpus)
+    ev, ei = O.search_exact(queries.cpu(), corpus.cpu(), 10)
+    assert torch.equal(i.cpu(), ei)
+    np.testing.assert_allclose(s.cpu().numpy(), ev.numpy(), atol=1e-5)
+    # against the reference's literal fp32 loop: same rows except where its fp32 noise reorders near-ties
+    lv, li = O.search_literal(queries.cpu(), corpus.cpu(), 10)
+    for q in range(100):
+        if set(li[q].tolist()) != set(ei[q].tolist()):
+            full = np.sort(O.cosine_scores_exact(queries[q:q + 1].cpu(), corpus.cpu()).numpy()[0])[::-1]
+            assert full[9] - full[10] < 1e-6
+    np.testing.assert_allclose(np.sort(lv.numpy(), 1)[:, ::-1], ev.numpy(), atol=1e-5)
+    # the text-in / dict-out call of the eval scripts on a slice (bf16 unit-norm store, tcgen05 path)
+    pipe2 = SentenceMiningPipeline(1 << 20, params=params, model=model, corpus=corpus_text[:2000], name="cfg1-text")
+    res = pipe2(query_text[:10], 10)
+    rows, _ = model.encode_text_normalized(corpus_text[:2000], torch.bfloat16)
+    qrows, _ = model.encode_text_normalized(query_text[:10], torch.bfloat16)
+    _, ei2 = O.search_exact(qrows.cpu(), rows.cpu(), 10)
+    assert [[c for c, _ in res[q]] for q in range(10)] == ei2.tolist()
+
+
+# ---------------------------------------------------------------------------- config 2 (full size)
+def test_config2_1m_x_768_bf16_1024_queries_top10(ops):
+    N, D, Q, k = 1_000_000, 768, 1024, 10
+    corpus = _unit_rows(N, D, 1234, torch.bfloat16)
+    queries = _unit_rows(Q, D, 4321, torch.bfloat16)
+    # planted answers: for the first 64 queries, 10 rows with cosine 0.90, 0.85, ... (known order)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    planted = torch.randperm(N, generator=g, device="cuda")[:64 * k].reshape(64, k)
+    alphas = torch.linspace(0.9, 0.45, k, device="cuda")
+    for qi in range(64):
+        qv = queries[qi].float()
+        qv = qv / qv.norm()
+        u = torch.randn(k, D, generator=g, device="cuda")
+        u = u - (u @ qv)[:, None] * qv
+        u = u / u.norm(dim=-1, keepdim=True)
+        corpus[planted[qi]] = (alphas[:, None] * qv + (1 - alphas ** 2).sqrt()[:, None] * u).to(torch.bfloat16)
+    corpus[777_777] = corpus[planted[0, 0]]          # an exact duplicate of query 0's best row
+    inv = ops.row_inv_norm(corpus)
+    s, i, s64, fl = ops.search_topk(queries, corpus, k, corpus_inv_norm=inv, mode="tensor",
+                                    return_score64=True, return_flags=True)
+    torch.cuda.synchronize()
+    assert fl.sum().item() <= 2
+    ic = i.cpu()
+    # planted rows come back in their known order (query 0 has its duplicate pair: lower row first)
+    for qi in range(1, 64):
+        assert ic[qi].tolist() == planted[qi].cpu().tolist()
+    first = sorted([planted[0, 0].item(), 777_777])
+    assert ic[0, :2].tolist() == first and ic[0, 2:].tolist() == planted[0, 1:k - 1].cpu().tolist()
+    assert s64[0, 0].item() == s64[0, 1].item()
+    # best first, ties by row
+    d = s64[:, 1:] - s64[:, :-1]
+    assert (d <= 0).all()
+    assert ((i[:, 1:] > i[:, :-1]) | (d < 0)).all()
+    # every returned score equals the float64 cosine recomputed from the gathered rows
+    rec = _recompute(queries, corpus, i)
+    np.testing.assert_allclose(s64.cpu().numpy(), rec.numpy(), atol=1e-12)
+    np.testing.assert_allclose(s.cpu().numpy(), rec.numpy(), atol=1e-3)
+    # sampled lower bound: no row of a 20k-row sample (outside the answer) beats the k-th score
+    sample = torch.randperm(N, generator=g, device="cuda")[:20_000]
+    sub = O.cosine_scores_exact(queries[:128].cpu(), corpus[sample].cpu())
+    hit = (sample.cpu()[None, None, :] == ic[:128, :, None]).any(1)
+    sub[hit] = -1.0
+    assert (sub.max(dim=1).values <= s64[:128, -1].cpu()).all()
+    # 4 fake shards + merge == one search, bit for bit
+    per = N // 4
+    parts = [ops.search_topk(queries, corpus[r * per:(r + 1) * per], k, corpus_inv_norm=inv[r * per:(r + 1) * per],
+                             idx_base=r * per, return_score64=True) for r in range(4)]
+    ms, ms64, mi = ops.merge_topk(torch.cat([p[2] for p in parts], 1), torch.cat([p[1] for p in parts], 1), k, 4)
+    assert torch.equal(mi, i) and torch.equal(ms64, s64)
+
+
+# ---------------------------------------------------------------------------- config 3 (k = 100, sharded)
+def test_config3_shape_k100_4096_queries_sharded(ops):
+    N, D, Q, k, G = 200_000, 768, 4096, 100, 8
+    corpus = _unit_rows(N, D, 11, torch.bfloat16)
+    corpus[150_000:150_050] = corpus[10:60]            # 50 duplicated rows
+    queries = _unit_rows(Q, D, 12, torch.bfloat16)
+    full = ops.search_topk(queries, corpus, k, return_score64=True, return_flags=True)
+    per = N // G
+    parts = [ops.search_topk(queries, corpus[r * per:(r + 1) * per], k, idx_base=r * per, return_score64=True)
+             for r in range(G)]
+    ms, ms64, mi = ops.merge_topk(torch.cat([p[2] for p in parts], 1), torch.cat([p[1] for p in parts], 1), k, G)
+    assert torch.equal(mi, full[1]) and torch.equal(ms64, full[2])
+    sel = torch.arange(0, Q, 64)
+    ev, ei = O.search_exact(queries[sel].cpu(), corpus.cpu(), k)
+    assert torch.equal(full[1][sel].cpu(), ei)
+    np.testing.assert_allclose(full[2][sel].cpu().numpy(), ev.numpy(), atol=1e-12)
+    assert full[3].float().mean().item() < 0.05
+
+
+# ---------------------------------------------------------------------------- config 4 (fp8 stream, small batches)
+@pytest.mark.parametrize("Q", [1, 8, 32])
+def test_config4_shape_fp8_stream_small_batches(ops, Q):
+    N, D, k = 1_000_000, 384, 10
+    corpus = _unit_rows(N, D, 21, torch.float8_e4m3fn, scale=64.0)
+    queries = _unit_rows(Q, D, 22 + Q, torch.float8_e4m3fn, scale=64.0)
+    s, i, s64, fl = ops.search_topk(queries, corpus, k, mode="tensor", return_score64=True, return_flags=True)
+    ev, ei = O.search_exact(queries.cpu(), corpus.cpu(), k)
+    assert torch.equal(i.cpu(), ei)
+    np.testing.assert_allclose(s64.cpu().numpy(), ev.numpy(), atol=1e-12)
+    assert fl.sum().item() == 0
+
+
+# ---------------------------------------------------------------------------- config 5 (all pairs, top-5, self excluded)
+def test_config5_shape_all_pairs_top5_self_excluded(ops):
+    N, D, k = 100_000, 768, 5
+    x = _unit_rows(N, D, 31, torch.bfloat16)
+    x[90_000:90_100] = x[100:200]                      # near-duplicate mining: 100 exact duplicate pairs
+    inv = ops.row_inv_norm(x)
+    idx = torch.empty(N, k, dtype=torch.int64, device="cuda")
+    s64 = torch.empty(N, k, dtype=torch.float64, device="cuda")
+    for b in range(0, N, 16_384):                      # query tiles = corpus row blocks
+        e = min(N, b + 16_384)
+        _, idx[b:e], s64[b:e] = ops.search_topk(x[b:e], x, k, corpus_inv_norm=inv, exclude_self_base=b,
+                                                return_score64=True)
+    assert not (idx == torch.arange(N, device="cuda")[:, None]).any()
+    # each duplicated row's nearest neighbour is its copy, at cosine 1 (up to float64 rounding)
+    assert torch.equal(idx[100:200, 0].cpu(), torch.arange(90_000, 90_100))
+    assert torch.equal(idx[90_000:90_100, 0].cpu(), torch.arange(100, 200))
+    assert (s64[100:200, 0] - 1).abs().max().item() < 1e-12
+    sel = torch.randperm(N, generator=torch.Generator().manual_seed(3))[:200]
+    ev, ei = O.search_exact(x[sel.cuda()].cpu(), x.cpu(), k + 1)
+    for n, r in enumerate(sel.tolist()):
+        exp = [c for c in ei[n].tolist() if c != r][:k]
+        assert idx[r].cpu().tolist() == exp
