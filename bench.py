@@ -145,7 +145,7 @@ def cpu_reference_qps(N_full: int, D: int, k: int, budget_s: float = 20.0, reps:
     return qps_full, cores, sample, per_call * done
 
 
-def run_reference(args):
+def run_reference(args, out_fd):
     N, D, Q, k = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -164,10 +164,24 @@ def run_reference(args):
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(out_fd, line)
+
+
+def _claim_stdout() -> int:
+    """Keep stdout for the ONE JSON line: libraries (NCCL prints its version banner to stdout on some
+    boxes) get stderr instead.  Returns the fd to write the JSON line to."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return saved
+
+
+def _emit(fd: int, line: dict) -> None:
+    os.write(fd, (json.dumps(line) + "\n").encode())
 
 
 def main():
+    out_fd = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -180,7 +194,7 @@ def main():
     ap.add_argument("--small-q", default="1,32", help="extra HBM-regime batch sizes reported under 'regimes' (N=1)")
     args = ap.parse_args()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, out_fd)
 
     from text_similarity_b200 import _lib, ops
     from text_similarity_b200.sharded import ShardedCorpus
@@ -321,6 +335,11 @@ def main():
     else:
         roofline = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": gbs / peaks["hbm_gbs"], "traffic": None}
+    if world == 1 and args.workload == DEFAULT_WORKLOAD and Q == WORKLOADS[DEFAULT_WORKLOAD][2]:
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload, one ncu --set full
+        # capture (profiles/r01_search_tc_bench_q4096.ncu_raw.txt)
+        roofline["traffic"] = 80.62e9 + 0.09e9
+        roofline["traffic_source"] = "profiles/r01_search_tc_bench_q4096.ncu_raw.txt"
     roofline.update({"kernel": "search_tc_kernel", "kernel_ms": kern_ms, "peak_source": peaks["source"],
                      "algorithmic_flops": flops, "algorithmic_bytes": bytes_alg})
 
@@ -345,7 +364,7 @@ def main():
             "gpu_launches": launches_per_step * steps,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "regimes": regimes,
         }
-        print(json.dumps(line), flush=True)
+        _emit(out_fd, line)
     if dist:
         dist.destroy_process_group()
 

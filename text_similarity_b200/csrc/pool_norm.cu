@@ -209,31 +209,89 @@ __global__ void __launch_bounds__(256) pool_norm_kernel(PoolArgs a) {
   if (a.out_inv && tid == 0) a.out_inv[orow] = 1.f / fmaxf(sqrtf(ss2), (float)kCosEps);
 }
 
+// Sum of squares of one 16-byte vector of a stored row.
+template <int DT> struct SqVec;
+template <> struct SqVec<TSIM_F32> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ float sq(const uint4& raw) {
+    const float* f = (const float*)&raw;
+    return f[0] * f[0] + f[1] * f[1] + f[2] * f[2] + f[3] * f[3];
+  }
+};
+template <> struct SqVec<TSIM_F16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ float sq(const uint4& raw) {
+    const __half2* h = (const __half2*)&raw;
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { float2 f = __half22float2(h[j]); s = fmaf(f.x, f.x, s); s = fmaf(f.y, f.y, s); }
+    return s;
+  }
+};
+template <> struct SqVec<TSIM_BF16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ float sq(const uint4& raw) {
+    const __nv_bfloat162* h = (const __nv_bfloat162*)&raw;
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); s = fmaf(f.x, f.x, s); s = fmaf(f.y, f.y, s); }
+    return s;
+  }
+};
+template <> struct SqVec<TSIM_E4M3> {
+  static constexpr int N = 16;
+  static __device__ __forceinline__ float sq(const uint4& raw) {
+    const __nv_fp8_e4m3* e = (const __nv_fp8_e4m3*)&raw;
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { const float v = float(e[j]); s = fmaf(v, v, s); }
+    return s;
+  }
+};
+
+// One warp per row, four rows in flight per warp, grid-stride over rows; float accumulation (the
+// value only scales the approximate scores of the candidate pass; final scores are recomputed in
+// float64).  HBM-bound: N*D*e bytes in, N*4 out.
 template <int DT>
 __global__ void __launch_bounds__(256) row_inv_norm_kernel(const void* x, int64_t N, int64_t D,
-                                                           int64_t stride, float* out) {
-  // one warp per row, lanes stride the row; float accumulation (the value only scales the
-  // approximate scores of the candidate pass; final scores are recomputed in float64)
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= N) return;
+                                                           int64_t stride, float* out, int vec_ok) {
   const int lane = threadIdx.x & 31;
-  float ss = 0.f;
-  const int64_t base = row * stride;
-  if (DT == TSIM_BF16 && (D % 8 == 0) && (stride % 8 == 0) && (((uintptr_t)x & 15) == 0)) {
-    for (int64_t d = lane * 8; d < D; d += 256) {
-      float v[8];
-      VecLoad<TSIM_BF16, 8>::ld(x, base + d, v);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  constexpr int R = 4;
+  constexpr int VN = SqVec<DT>::N;
+  const int esz = 16 / VN;
+  for (int64_t row0 = gw * R; row0 < N; row0 += nwarps * R) {
+    float ss[R];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) ss = fmaf(v[j], v[j], ss);
+    for (int r = 0; r < R; ++r) ss[r] = 0.f;
+    if (vec_ok) {
+      for (int64_t d = (int64_t)lane * VN; d < D; d += 32 * VN) {
+        uint4 raw[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int64_t row = row0 + r < N ? row0 + r : N - 1;
+          raw[r] = __ldg((const uint4*)((const unsigned char*)x + (row * stride + d) * esz));
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) ss[r] += SqVec<DT>::sq(raw[r]);
+      }
+    } else {
+      for (int64_t d = lane; d < D; d += 32) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int64_t row = row0 + r < N ? row0 + r : N - 1;
+          const float v = Elem<DT>::ld(x, row * stride + d);
+          ss[r] = fmaf(v, v, ss[r]);
+        }
+      }
     }
-  } else {
-    for (int64_t d = lane; d < D; d += 32) {
-      float v = Elem<DT>::ld(x, base + d);
-      ss = fmaf(v, v, ss);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float t = warp_sum_f32(ss[r]);
+      if (lane == 0 && row0 + r < N) out[row0 + r] = 1.f / fmaxf(sqrtf(t), (float)kCosEps);
     }
   }
-  ss = warp_sum_f32(ss);
-  if (lane == 0) out[row] = 1.f / fmaxf(sqrtf(ss), (float)kCosEps);
 }
 
 template <int DT, int VEC>
@@ -272,14 +330,19 @@ int pool_splits(int64_t B, int64_t L) {
 int launch_row_inv_norm(const void* x, int dt, int64_t N, int64_t D, int64_t stride, float* out,
                         cudaStream_t st) {
   if (N == 0) return TSIM_OK;
+  const int esz = dtype_size(dt);
+  if (!esz) { set_error("row_inv_norm: bad dtype %d", dt); return TSIM_ERR_INVALID_ARG; }
+  const int per16 = 16 / esz;
+  const int vec_ok = (D % per16 == 0) && (stride % per16 == 0) && (((uintptr_t)x & 15) == 0);
   const int wpb = 8;
-  unsigned grid = (unsigned)((N + wpb - 1) / wpb);
+  int64_t want = (N + 4 * wpb - 1) / (4 * wpb);
+  const int64_t cap = (int64_t)device_sm_count() * 8;      // persistent: 8 CTAs per SM, grid-stride over rows
+  unsigned grid = (unsigned)(want < cap ? want : cap);
   switch (dt) {
-    case TSIM_F32: row_inv_norm_kernel<TSIM_F32><<<grid, wpb * 32, 0, st>>>(x, N, D, stride, out); break;
-    case TSIM_F16: row_inv_norm_kernel<TSIM_F16><<<grid, wpb * 32, 0, st>>>(x, N, D, stride, out); break;
-    case TSIM_BF16: row_inv_norm_kernel<TSIM_BF16><<<grid, wpb * 32, 0, st>>>(x, N, D, stride, out); break;
-    case TSIM_E4M3: row_inv_norm_kernel<TSIM_E4M3><<<grid, wpb * 32, 0, st>>>(x, N, D, stride, out); break;
-    default: set_error("row_inv_norm: bad dtype %d", dt); return TSIM_ERR_INVALID_ARG;
+    case TSIM_F32: row_inv_norm_kernel<TSIM_F32><<<grid, wpb * 32, 0, st>>>(x, N, D, stride, out, vec_ok); break;
+    case TSIM_F16: row_inv_norm_kernel<TSIM_F16><<<grid, wpb * 32, 0, st>>>(x, N, D, stride, out, vec_ok); break;
+    case TSIM_BF16: row_inv_norm_kernel<TSIM_BF16><<<grid, wpb * 32, 0, st>>>(x, N, D, stride, out, vec_ok); break;
+    default: row_inv_norm_kernel<TSIM_E4M3><<<grid, wpb * 32, 0, st>>>(x, N, D, stride, out, vec_ok); break;
   }
   TSIM_CUDA(cudaGetLastError());
   return TSIM_OK;
