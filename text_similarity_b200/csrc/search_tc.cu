@@ -249,7 +249,7 @@ __device__ __forceinline__ bool get_unit(const TcArgs& a, int it, int wid, int n
 // so it is published with atomicMax for every other CTA to filter with.
 struct RegList16 {
   float a[16]; uint32_t r[16];
-  __device__ __forceinline__ RegList16(float*, uint32_t*) {}
+  __device__ __forceinline__ RegList16(float*, uint32_t*, int*) {}
   __device__ __forceinline__ void reset() {
 #pragma unroll
     for (int i = 0; i < 16; ++i) { a[i] = -INFINITY; r[i] = 0xffffffffu; }
@@ -296,11 +296,17 @@ struct RegList16 {
   }
 };
 
+// Larger lists (KP = 32 / 64 / 112) live in shared memory UNSORTED: a newcomer overwrites the current
+// minimum and the new minimum is found by one pipelined scan of KP independent loads (a sorted
+// shift would be a chain of ~KP/2 dependent load/store steps).  *statep packs the fill count (low 16
+// bits) and the slot of the minimum (high 16 bits).  Which of several equal minima is evicted does
+// not matter: every dropped row still has approx <= the final KP-th best (see select_merge.cu).
 template <int KP>
-__device__ __noinline__ float smem_list_slow(float* ls, uint32_t* li, uint32_t taddr, const float* cnp, float thr,
+__device__ __noinline__ float smem_list_slow(float* ls, uint32_t* li, int* statep, uint32_t taddr, const float* cnp, float thr,
                                              int64_t row_base, int64_t self_row, int lim, uint32_t* thr_g,
                                              float gm0, float gm1, float gm2, float gm3) {
   const float thr_in = thr;
+  int cnt = *statep & 0xffff, minpos = *statep >> 16;
 #pragma unroll 1
   for (int g = 0; g < 4; ++g) {
     const float gm = g == 0 ? gm0 : g == 1 ? gm1 : g == 2 ? gm2 : gm3;
@@ -317,36 +323,42 @@ __device__ __noinline__ float smem_list_slow(float* ls, uint32_t* li, uint32_t t
       const float s = __uint_as_float(wj) * cnp[j];
       const int64_t row = row_base + j;
       if (s > thr && j < lim && row != self_row) {
-        int pos = KP - 1;                       // the minimum (or an empty slot) drops out
-        while (pos > 0) {
-          const float prev = ls[(pos - 1) * kEpiThreads];
-          if (!(prev < s)) break;               // equal scores keep arrival (= row) order
-          ls[pos * kEpiThreads] = prev;
-          li[pos * kEpiThreads] = li[(pos - 1) * kEpiThreads];
-          --pos;
-        }
+        const int pos = cnt < KP ? cnt : minpos;
         ls[pos * kEpiThreads] = s;
         li[pos * kEpiThreads] = (uint32_t)row;
-        thr = fmaxf(thr, ls[(KP - 1) * kEpiThreads]);
+        if (cnt < KP) ++cnt;
+        if (cnt == KP) {                        // full: locate the new minimum
+          float m = ls[0];
+          int mp = 0;
+#pragma unroll 8
+          for (int i = 1; i < KP; ++i) {
+            const float v = ls[i * kEpiThreads];
+            if (v < m) { m = v; mp = i; }
+          }
+          minpos = mp;
+          thr = fmaxf(thr, m);
+        }
       }
     }
   }
+  *statep = cnt | (minpos << 16);
   if (thr > thr_in) atomicMax(thr_g, f32_to_ord(thr));
   return thr;
 }
 
 template <int KP>
 struct SmemList {
-  float* ls; uint32_t* li;
-  __device__ __forceinline__ SmemList(float* s, uint32_t* i) : ls(s), li(i) {}
+  float* ls; uint32_t* li; int* cntp;
+  __device__ __forceinline__ SmemList(float* s, uint32_t* i, int* n) : ls(s), li(i), cntp(n) {}
   __device__ __forceinline__ void reset() {
 #pragma unroll 4
     for (int j = 0; j < KP; ++j) { ls[j * kEpiThreads] = -INFINITY; li[j * kEpiThreads] = 0xffffffffu; }
+    *cntp = 0;
   }
   __device__ __forceinline__ float slow(uint32_t taddr, const float* cnp, float thr, int64_t row_base,
                                         int64_t self_row, int lim, uint32_t* thr_g, float gm0, float gm1,
                                         float gm2, float gm3) {
-    return smem_list_slow<KP>(ls, li, taddr, cnp, thr, row_base, self_row, lim, thr_g, gm0, gm1, gm2, gm3);
+    return smem_list_slow<KP>(ls, li, cntp, taddr, cnp, thr, row_base, self_row, lim, thr_g, gm0, gm1, gm2, gm3);
   }
   __device__ __forceinline__ void flush(uint64_t* dst) {
 #pragma unroll 4
@@ -366,7 +378,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   extern __shared__ unsigned char smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment: round the dynamic window up (1 KB of slack is
   // requested by the launcher).
-  // [STAGES][A 16K | B 32K] | lists | cnorm[2 acc][4 warps][BN] | barriers | tmem ptr
+  // [STAGES][A 16K | B 32K] | lists | cnorm[2 acc][4 warps][BN] | list fill counts | barriers | tmem ptr
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int B_BYTES = Cfg<PAIR>::B_BYTES;
   constexpr int STAGE_BYTES = Cfg<PAIR>::STAGE_BYTES;
@@ -376,7 +388,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   float* list_s = (float*)(smem + (size_t)STAGES * STAGE_BYTES);
   uint32_t* list_i = (uint32_t*)(list_s + KP * kEpiThreads);
   float* cnorm = (float*)(list_i + KP * kEpiThreads);
-  uint64_t* bars = (uint64_t*)(cnorm + 2 * 4 * BN);
+  int* list_n = (int*)(cnorm + 2 * 4 * BN);
+  uint64_t* bars = (uint64_t*)(list_n + kEpiThreads);
   uint64_t* full_bar = bars;                 // [STAGES]  TMA -> MMA
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]  MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]       MMA -> epilogue
@@ -480,7 +493,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     // ===================== epilogue: threshold filter + per-query lists =====================
     const int et = threadIdx.x - 128;            // 0..127 = TMEM lane = query within the block
     const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
-    typename ListFor<KP>::type list(list_s + et, list_i + et);
+    typename ListFor<KP>::type list(list_s + et, list_i + et, list_n + et);
     int acc = 0; uint32_t aphase = 0;
     Unit un;
     for (int it = 0; get_unit(a, it, wid, nw, un); ++it) {
@@ -599,7 +612,7 @@ int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t D, int64_t 
 template <int KP, int STAGES, bool PAIR, bool FP8>
 int launch_cfg(const CUtensorMap& mq, const CUtensorMap& mc, const TcArgs& a, cudaStream_t st) {
   size_t smem = 1024 + (size_t)STAGES * Cfg<PAIR>::STAGE_BYTES + (size_t)KP * kEpiThreads * 8 + 2 * 4 * BN * 4 +
-                (2 * STAGES + 4) * 8 + 16;
+                kEpiThreads * 4 + (2 * STAGES + 4) * 8 + 16;
   auto kern = search_tc_kernel<KP, STAGES, PAIR, FP8>;
   TSIM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int sms = device_sm_count();
@@ -639,10 +652,11 @@ int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_
   a.kblocks = (int)((D * esz + BK_BYTES - 1) / BK_BYTES);
   const int64_t T = (N + BN - 1) / BN;
   a.QB = p.QB; a.sticky = p.sticky; a.Gq = p.Gq; a.tpc = p.R / BN;
-  a.NC = p.NC; a.n_units = (int64_t)p.QB * p.NC;
+  a.NC = p.NC;
   // pass 0: the whole corpus in one launch; pass 1: bootstrap sample; pass 2: everything else
-  a.tile_mode = pass; a.tile_stride = p.boot_stride; a.slot_base = pass == 2 ? p.Gq : 0;
+  a.tile_mode = pass; a.tile_stride = p.boot_stride; a.slot_base = pass == 2 ? p.boot_slots : 0;
   a.T = pass == 1 ? p.boot_tiles : pass == 2 ? T - p.boot_tiles : T;
+  a.n_units = (int64_t)p.QB * ((a.T + a.tpc - 1) / (a.tpc > 0 ? a.tpc : 1));
   a.self_on = self_on; a.self_off = self_off;
   a.cand = cand; a.thr = thr;
   const char* dbg = getenv("TSIM_DEBUG");

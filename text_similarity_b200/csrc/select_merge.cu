@@ -348,7 +348,7 @@ int launch_select_rescore(const void* q, int q_dt, int64_t q_stride, const void*
 }
 
 int launch_tighten(int64_t Q, const SearchPlan& p, const uint64_t* cand, uint32_t* thr, cudaStream_t st) {
-  tighten_kernel<<<(unsigned)Q, kSelThreads, 0, st>>>(cand, thr, p.NC, p.KP, p.Gq);
+  tighten_kernel<<<(unsigned)Q, kSelThreads, 0, st>>>(cand, thr, p.NC, p.KP, (int)p.boot_slots);
   TSIM_CUDA(cudaGetLastError());
   return TSIM_OK;
 }

@@ -78,6 +78,7 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
       if (Q >= 16 && T >= 32 * (int64_t)p->Gq && !(noboot && noboot[0] == '1')) {
         p->boot_stride = T / (2 * (int64_t)p->Gq);                      // >= 16
         p->boot_tiles = (T + p->boot_stride - 1) / p->boot_stride;      // every multiple of the stride below T
+        p->boot_slots = p->Gq;
       }
     }
     int64_t nct = (8 * (int64_t)workers + p->QB - 1) / p->QB;  // aim at ~8 units per worker
@@ -89,7 +90,23 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
     // bound the candidate buffer (Q * NC * KP * 8 bytes) to ~2 GB
     while ((double)Q * (double)((N + R - 1) / R) * p->KP * 8.0 > 2.0e9 && R < ((int64_t)1 << 30)) R *= 2;
     p->R = R;
-    p->NC = p->sticky ? (p->boot_tiles ? 2 * p->Gq : p->Gq) : (N + R - 1) / R;
+    if (!p->sticky) {
+      // Round-robin units start every list cold.  For k > 10 (lists of 32+ entries, insertion in shared
+      // memory) that warm-up dominates, so a ~3 % strided sample is scanned first and its KP-th best
+      // becomes every unit's starting threshold.
+      const int64_t tpc = R / 256;
+      const char* noboot = getenv("TSIM_NO_BOOT");
+      if (p->KP >= 32 && T >= 24 * tpc && !(noboot && noboot[0] == '1')) {
+        int64_t want = T / 32;
+        want = (want + tpc - 1) / tpc * tpc;                             // whole chunks of sample tiles
+        p->boot_stride = T / want;                                       // >= 16
+        p->boot_tiles = (T + p->boot_stride - 1) / p->boot_stride;
+        p->boot_slots = (p->boot_tiles + tpc - 1) / tpc;
+      }
+      p->NC = p->boot_tiles ? p->boot_slots + (T - p->boot_tiles + tpc - 1) / tpc : (T + tpc - 1) / tpc;
+    } else {
+      p->NC = p->boot_tiles ? 2 * p->Gq : p->Gq;
+    }
     p->off_cand = off; off = align_up(off + (size_t)Q * p->NC * p->KP * sizeof(uint64_t), 256);
   }
   // exact scan (whole-call path, or fallback for flagged queries)

@@ -152,6 +152,7 @@ struct SearchPlan {
   int Gq;              // sticky: CTAs per query block
   int64_t boot_tiles;  // > 0: a bootstrap launch scans this many strided sample tiles first
   int64_t boot_stride; //      distance between sample tiles
+  int64_t boot_slots;  //      candidate-list slots written by the bootstrap launch (the main launch follows)
   int64_t R;           // round-robin: corpus rows per unit (multiple of 256)
   int64_t NC;          // candidate lists per query: chunks ceil(N / R), or Gq when sticky
   // exact path
