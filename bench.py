@@ -117,14 +117,15 @@ def make_shard(rows: int, D: int, seed: int, dev) -> torch.Tensor:
     return out
 
 
-def cpu_reference_qps(N_full: int, D: int, k: int, budget_s: float = 20.0, reps: int = 1):
+def cpu_reference_qps(N_full: int, D: int, k: int, budget_s: float = 12.0):
     """The reference's CPU search (cos_sim + topk, metrics.py:99-101 + search_pipeline.py:78, as
-    restated in oracle/oracle.py) on a bounded sample, all host threads; scaled linearly in N."""
+    restated in oracle/oracle.py) on a bounded sample of the workload, all host threads, repeated
+    for about `budget_s` seconds; scaled linearly in N to the full corpus (stated in `sample`)."""
     from oracle import oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    n_s = min(N_full, 250_000)
-    q_s = 64
+    n_s = min(N_full, 500_000)
+    q_s = 128
     g = torch.Generator().manual_seed(1234)
     corpus = torch.randn(n_s, D, generator=g)
     queries = torch.randn(q_s, D, generator=g)
@@ -135,14 +136,13 @@ def cpu_reference_qps(N_full: int, D: int, k: int, budget_s: float = 20.0, reps:
         O.search_cos_sim_literal(queries, corpus, k)
         done += 1
         el = time.perf_counter() - t0
-        if done >= reps and (el > budget_s / 2 or done >= 8):
+        if el >= budget_s or done >= 200:
             break
     per_call = el / done
-    qps_sample = q_s / per_call
-    qps_full = qps_sample * n_s / N_full
-    sample = (f"{q_s} fp32 queries x {n_s} rows x {D} (cos_sim + torch.topk, {done} reps, "
-              f"{per_call:.2f} s each); scaled linearly to {N_full} rows")
-    return qps_full, cores, sample, per_call * done
+    qps_full = (q_s / per_call) * n_s / N_full
+    sample = (f"{q_s} fp32 queries x {n_s} rows x {D} (cos_sim + torch.topk), {done} reps in {el:.1f} s "
+              f"({per_call:.3f} s each) on {cores} threads; scaled linearly in N to {N_full} rows")
+    return qps_full, cores, sample, el
 
 
 def run_reference(args, out_fd):
@@ -152,7 +152,7 @@ def run_reference(args, out_fd):
         return
     steps = max(1, args.steps)
     t0 = time.perf_counter()
-    qps, cores, sample, spent = cpu_reference_qps(N, D, k, budget_s=min(120.0, 6.0 * steps), reps=min(steps, 8))
+    qps, cores, sample, spent = cpu_reference_qps(N, D, k, budget_s=min(90.0, max(10.0, 3.0 * steps)))
     ms_per_step = Q / qps * 1e3
     line = {
         "impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
@@ -346,7 +346,7 @@ def main():
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload ----------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        qps, cores, sample, _ = cpu_reference_qps(N, D, k, budget_s=20.0)
+        qps, cores, sample, _ = cpu_reference_qps(N, D, k, budget_s=12.0)
         cpu_baseline = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample}
 
     launches_per_step = 4 + (1 if world > 1 else 0)

@@ -139,3 +139,44 @@ def test_cos_sim_surface(golden):
     assert torch.equal(i.cpu(), O.search_exact(a, b, 3)[1])
     with pytest.raises(RuntimeError):
         cos_sim(a, b)
+
+
+def test_ranking_pipeline_and_helpers(stack):
+    from src.pipeline.ranking_pipeline import RankingPipeline
+    from src.utils.utils import most_similar_vectors
+    from text_similarity_b200.ranking import assign_to_centroids, near_duplicates
+    params, model, corpus, queries = stack
+
+    class LengthCrossEncoder:                       # stand-in cross-encoder: prefers short passages
+        def predict(self, pairs):
+            return [1.0 / (1 + len(p[1])) for p in pairs]
+
+    pipe = RankingPipeline(LengthCrossEncoder(), 10_000, params=params, model=model, name="rank")
+    out = pipe(queries[:3], corpus[:100], top_k=5)
+    assert len(out) == 3
+    for res in out:
+        hits = res["results"]
+        assert len(hits) == 5 and all("cross-score" in h and h["text"] == corpus[h["corpus_id"]] for h in hits)
+        assert [h["cross-score"] for h in hits] == sorted((h["cross-score"] for h in hits), reverse=True)
+        assert abs(res["avg_score"] - sum(res["cross_scores"]) / 5) < 1e-12
+    # retrieval part == the exact search
+    rows, _ = model.encode_text_normalized(corpus[:100], torch.bfloat16)
+    qrows, _ = model.encode_text_normalized(queries[:3], torch.bfloat16)
+    _, ei = O.search_exact(qrows.cpu(), rows.cpu(), 5)
+    assert [sorted(h["corpus_id"] for h in r["results"]) for r in out] == [sorted(x) for x in ei.tolist()]
+
+    g = torch.Generator().manual_seed(9)
+    vecs = torch.randn(500, 64, generator=g)
+    best = most_similar_vectors(vecs[17].cuda(), vecs.cuda(), n=3)
+    _, ei = O.search_exact(vecs[17:18], vecs, 3)
+    assert [torch.equal(b.cpu(), vecs[i]) for b, i in zip(best, ei[0].tolist())] == [True] * 3
+
+    cent = torch.randn(7, 64, generator=g)
+    lab = assign_to_centroids(vecs.cuda(), cent.cuda())
+    assert torch.equal(lab.cpu(), O.cosine_scores_exact(vecs, cent).argmax(1))
+
+    x = torch.nn.functional.normalize(torch.randn(3000, 128, generator=g), dim=-1).to(torch.bfloat16)
+    x[2000] = x[5]
+    x[2500] = x[5]
+    dup = near_duplicates(x.cuda(), threshold=0.99, k=3)
+    assert dup == {5: [2000, 2500], 2000: [5, 2500], 2500: [5, 2000]}

@@ -4,8 +4,8 @@
 // which issues six ATen kernels and materialises a [B,L,D] fp32 mask and product.
 //
 // HBM-bound: algorithmic bytes per call = B*L*D*e_in + B*L*mask_bytes + B*D*e_out + B*4.
-// One pass over the token tensor with 16-byte coalesced loads; masked-out tokens are not
-// read at all.  Grid = B * S CTAs (S = splits of the token axis) sized to >= 2 CTAs per SM;
+// One pass over the token tensor with 16-byte coalesced loads; trailing padding is not read at
+// all and masked tokens never enter the sum.  Grid = B * S CTAs (S = splits of the token axis) sized to >= 2 CTAs per SM;
 // split partial sums go through a small fp32 workspace and the last CTA to finish a row
 // (ticket counter) adds them in a fixed order, so results are deterministic.
 #include "tsim_common.cuh"
@@ -90,7 +90,7 @@ struct PoolArgs {
 
 template <int DT, int VEC>
 __global__ void __launch_bounds__(256) pool_norm_kernel(PoolArgs a) {
-  extern __shared__ float sm[];           // [rpi][D] partial rows, then reused as pooled[D]
+  extern __shared__ float sm[];           // [rpi][D] partial rows (then reused as pooled[D]) | [TL] token weights
   __shared__ float red[32];
   __shared__ int s_last;
   const int b = blockIdx.x / a.S, sp = blockIdx.x % a.S;
@@ -101,8 +101,23 @@ __global__ void __launch_bounds__(256) pool_norm_kernel(PoolArgs a) {
   const int l0 = sp * a.TL, l1 = min((int)a.L, l0 + a.TL);
 
   // ---- phase 1: this CTA's token range, reduced over tokens --------------------------
+  // The range's token weights are staged in shared memory and its last non-zero weight located, so
+  // the inner loop is branch-free: unconditional 16-byte loads (8 in flight per thread) up to the
+  // last real token; trailing padding (the common mask shape 1..1 0..0) is never read.
+  float* wts = sm + (size_t)rpi * a.D;    // [TL]
+  __shared__ int s_lend;
+  if (tid == 0) s_lend = l0;
+  __syncthreads();
+  for (int l = l0 + tid; l < l1; l += blockDim.x) {
+    const float w = mask_value(a.mask, a.mask_dt, (int64_t)b * a.msb + l);
+    wts[l - l0] = w;
+    if (w != 0.f) atomicMax(&s_lend, l + 1);
+  }
+  __syncthreads();
+  const int lend = s_lend;
   // thread (r, v): tokens l0 + r, l0 + r + rpi, ...; columns v*VEC .. v*VEC+VEC-1 (and, when
   // there are more vector columns than threads, further columns nvec-strided: v += blockDim)
+  constexpr int UN = 8;
   for (int v0 = 0; v0 < nvec; v0 += blockDim.x) {
     const int v = v0 + (rpi > 1 ? tid % nvec : tid);
     float acc[VEC];
@@ -111,25 +126,21 @@ __global__ void __launch_bounds__(256) pool_norm_kernel(PoolArgs a) {
     if (v < nvec && r < rpi) {
       const int64_t base = (int64_t)b * a.sb + (int64_t)v * VEC;
       int l = l0 + r;
-      // 4 independent 16-byte loads in flight per thread
-      for (; l + 3 * rpi < l1; l += 4 * rpi) {
-        float w[4], x[4][VEC];
+      for (; l + (UN - 1) * rpi < lend; l += UN * rpi) {
+        float x[UN][VEC];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) w[u] = mask_value(a.mask, a.mask_dt, (int64_t)b * a.msb + l + u * rpi);
+        for (int u = 0; u < UN; ++u) VecLoad<DT, VEC>::ld(a.tok, base + (int64_t)(l + u * rpi) * a.sl, x[u]);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (w[u] != 0.f) VecLoad<DT, VEC>::ld(a.tok, base + (int64_t)(l + u * rpi) * a.sl, x[u]);
-        }
+        for (int u = 0; u < UN; ++u) {
+          const float w = wts[l + u * rpi - l0];
+          if (w != 0.f) {      // a masked token's values must not reach the sum (they may be Inf/NaN)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (w[u] != 0.f) {
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) acc[j] = fmaf(w[u], x[u][j], acc[j]);
+            for (int j = 0; j < VEC; ++j) acc[j] = fmaf(w, x[u][j], acc[j]);
           }
         }
       }
-      for (; l < l1; l += rpi) {
-        float w = mask_value(a.mask, a.mask_dt, (int64_t)b * a.msb + l);
+      for (; l < lend; l += rpi) {
+        const float w = wts[l - l0];
         if (w != 0.f) {
           float x[VEC];
           VecLoad<DT, VEC>::ld(a.tok, base + (int64_t)l * a.sl, x);
@@ -306,7 +317,7 @@ int launch_pool(const PoolArgs& a, cudaStream_t st) {
     if (threads > 256) threads = 256;
   }
   const int rpi = threads / nvec > 0 ? threads / nvec : 1;
-  size_t smem = (size_t)rpi * a.D * sizeof(float);
+  size_t smem = ((size_t)rpi * a.D + a.TL) * sizeof(float);
   if (smem > 200 * 1024) { set_error("pool_norm: D=%lld too large", (long long)a.D); return TSIM_ERR_UNSUPPORTED; }
   if (smem > 48 * 1024)
     TSIM_CUDA(cudaFuncSetAttribute(pool_norm_kernel<DT, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
