@@ -292,3 +292,56 @@ def test_fake_shards_plus_merge_equal_single_search(ops, G):
     ix = torch.cat([p[1] for p in parts], 1)
     ms, ms64, mi = ops.merge_topk(s64, ix, k, G)
     assert torch.equal(mi, full[1]) and torch.equal(ms64, full[2]) and torch.equal(ms, full[0])
+
+
+# ------------------------------------------------------------------------------------ randomized sweep
+def test_randomized_shapes_dtypes_modes(ops):
+    """Seeded random sweep over shapes, dtypes, k, modes, shard offsets and self-exclusion (the
+    hypothesis-style kernel-vs-oracle test of SURVEY.md section 4, kept deterministic)."""
+    rng = np.random.default_rng(20260)
+    for trial in range(48):
+        dtype = [torch.bfloat16, torch.float8_e4m3fn, torch.float32, torch.float16][trial % 4]
+        step = 16 if dtype == torch.float8_e4m3fn else 8
+        D = int(rng.integers(1, 60)) * step
+        N = int(rng.choice([1, 7, 255, 256, 257, 1000, 5000, 40_000]))
+        Q = int(rng.choice([1, 2, 31, 127, 128, 129, 255, 256, 300, 700]))
+        k = int(rng.choice([1, 3, 10, 11, 24, 25, 52, 53, 100]))
+        g = torch.Generator().manual_seed(trial)
+        c = torch.randn(N, D, generator=g)
+        q = torch.randn(Q, D, generator=g)
+        if N > 10:
+            c[N // 3] = c[1]
+            c[N - 1] = c[1]
+        if dtype == torch.float8_e4m3fn:
+            c, q = c * 8, q * 8
+        c, q = c.to(dtype), q.to(dtype)
+        kw = {}
+        if trial % 3 == 1:
+            kw["idx_base"] = int(rng.integers(0, 10_000))
+        if trial % 5 == 2 and N > Q:
+            q = c[:Q].clone()
+            kw["exclude_self_base"] = kw.get("idx_base", 0)
+        mode = "auto" if dtype in (torch.float32, torch.float16) else ("tensor" if trial % 2 == 0 else "auto")
+        tol = TOL_F32 if dtype == torch.float32 else TOL_BF16
+        try:
+            _check(ops, q, c, k, tol, mode=mode, **kw)
+        except AssertionError as e:
+            raise AssertionError(f"trial {trial}: dtype={dtype} N={N} Q={Q} D={D} k={k} mode={mode} {kw}: {e}") from e
+
+
+def test_strided_rows_and_views(ops):
+    g = torch.Generator().manual_seed(88)
+    big = torch.randn(6000, 512, generator=g).to(torch.bfloat16)
+    qbig = torch.randn(300, 512, generator=g).to(torch.bfloat16)
+    c = big[:, :256]            # row stride 512 elements, TMA path reads the view directly
+    q = qbig[:, :256]
+    s, i = ops.search_topk(q.cuda()[:, :], c.cuda(), 10, mode="tensor")      # contiguous copies on device
+    big_d, qbig_d = big.cuda(), qbig.cuda()
+    s2, i2 = ops.search_topk(qbig_d[:, :256], big_d[:, :256], 10, mode="tensor")   # genuine strided views
+    ev, ei = O.search_exact(q, c, 10)
+    assert torch.equal(i.cpu(), ei) and torch.equal(i2.cpu(), ei)
+    # a misaligned view cannot take the TMA path: "tensor" must say so, "auto" must still be exact
+    with pytest.raises(ValueError):
+        ops.search_topk(qbig_d[:, 1:257], big_d[:, 1:257], 10, mode="tensor")
+    s3, i3 = ops.search_topk(qbig_d[:, 1:257], big_d[:, 1:257], 10, mode="auto")
+    assert torch.equal(i3.cpu(), O.search_exact(qbig[:, 1:257], big[:, 1:257], 10)[1])

@@ -87,6 +87,10 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
     R = (R + 255) / 256 * 256;
     if (R < 256) R = 256;
     if (R > 65536) R = 65536;
+    if (const char* cr = getenv("TSIM_CHUNK_ROWS")) {     // experiment knob: rows per round-robin unit
+      int64_t v = atoll(cr);
+      if (v >= 256) R = v / 256 * 256;
+    }
     // bound the candidate buffer (Q * NC * KP * 8 bytes) to ~2 GB
     while ((double)Q * (double)((N + R - 1) / R) * p->KP * 8.0 > 2.0e9 && R < ((int64_t)1 << 30)) R *= 2;
     p->R = R;
