@@ -147,6 +147,10 @@ int tsim_merge_topk(const double* sc, const int64_t* ix, int64_t Q, int64_t n_li
  * launching stream.  Events are cudaEvent_t cast to void*; pass NULL, NULL to switch off. */
 int tsim_set_timing_events(void* start, void* stop);
 
+/* Number of CUDA kernels this library has launched in the process so far (bench.py reports the
+ * difference over its timed region as `gpu_launches`). */
+uint64_t tsim_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -323,6 +323,7 @@ int launch_pool(const PoolArgs& a, cudaStream_t st) {
     TSIM_CUDA(cudaFuncSetAttribute(pool_norm_kernel<DT, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   pool_norm_kernel<DT, VEC><<<(unsigned)(a.B * a.S), threads, smem, st>>>(a);
   TSIM_CUDA(cudaGetLastError());
+  count_launch();
   return TSIM_OK;
 }
 
@@ -356,6 +357,7 @@ int launch_row_inv_norm(const void* x, int dt, int64_t N, int64_t D, int64_t str
     default: row_inv_norm_kernel<TSIM_E4M3><<<grid, wpb * 32, 0, st>>>(x, N, D, stride, out, vec_ok); break;
   }
   TSIM_CUDA(cudaGetLastError());
+  count_launch();
   return TSIM_OK;
 }
 

@@ -172,6 +172,7 @@ int launch_search_exact(const void* q, int q_dt, int64_t q_stride, const void* c
   dim3 grid((unsigned)p.S, (unsigned)gy);
   search_exact_kernel<<<grid, kExThreads, smem, st>>>(a);
   TSIM_CUDA(cudaGetLastError());
+  count_launch();
   return TSIM_OK;
 }
 

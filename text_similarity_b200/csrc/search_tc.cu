@@ -631,6 +631,7 @@ int launch_cfg(const CUtensorMap& mq, const CUtensorMap& mc, const TcArgs& a, cu
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   TSIM_CUDA(cudaLaunchKernelEx(&cfg, kern, mq, mc, a));
+  count_launch();
   return TSIM_OK;
 }
 

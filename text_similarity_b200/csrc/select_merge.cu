@@ -344,12 +344,14 @@ int launch_select_rescore(const void* q, int q_dt, int64_t q_stride, const void*
   a.out_score = out_score; a.out_score64 = out_score64; a.out_idx = out_idx; a.out_flags = out_flags;
   select_rescore_kernel<<<(unsigned)Q, kSelThreads, 0, st>>>(a);
   TSIM_CUDA(cudaGetLastError());
+  count_launch();
   return TSIM_OK;
 }
 
 int launch_tighten(int64_t Q, const SearchPlan& p, const uint64_t* cand, uint32_t* thr, cudaStream_t st) {
   tighten_kernel<<<(unsigned)Q, kSelThreads, 0, st>>>(cand, thr, p.NC, p.KP, (int)p.boot_slots);
   TSIM_CUDA(cudaGetLastError());
+  count_launch();
   return TSIM_OK;
 }
 
@@ -368,6 +370,7 @@ int launch_merge_exact_lists(const void* q, int q_dt, int64_t q_stride, const vo
   size_t smem = (size_t)kPairCap * (sizeof(double) + sizeof(int64_t));
   merge_exact_lists_kernel<<<(unsigned)Q, kSelThreads, smem, st>>>(a);
   TSIM_CUDA(cudaGetLastError());
+  count_launch();
   return TSIM_OK;
 }
 
@@ -382,6 +385,7 @@ int launch_merge_topk(const double* sc, const int64_t* ix, int64_t Q, int64_t n_
     TSIM_CUDA(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   merge_topk_kernel<<<(unsigned)Q, kSelThreads, smem, st>>>(sc, ix, total, k_out, out_score, out_score64, out_idx);
   TSIM_CUDA(cudaGetLastError());
+  count_launch();
   return TSIM_OK;
 }
 

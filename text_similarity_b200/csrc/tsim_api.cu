@@ -10,6 +10,8 @@ namespace tsim {
 
 static thread_local char g_err[512] = "";
 static thread_local cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -81,26 +83,30 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
         p->boot_slots = p->Gq;
       }
     }
-    int64_t nct = (8 * (int64_t)workers + p->QB - 1) / p->QB;  // aim at ~8 units per worker
-    if (nct < 1) nct = 1;
-    int64_t R = (N + nct - 1) / nct;
-    R = (R + 255) / 256 * 256;
-    if (R < 256) R = 256;
-    if (R > 65536) R = 65536;
-    if (const char* cr = getenv("TSIM_CHUNK_ROWS")) {     // experiment knob: rows per round-robin unit
-      int64_t v = atoll(cr);
-      if (v >= 256) R = v / 256 * 256;
-    }
-    // bound the candidate buffer (Q * NC * KP * 8 bytes) to ~2 GB
-    while ((double)Q * (double)((N + R - 1) / R) * p->KP * 8.0 > 2.0e9 && R < ((int64_t)1 << 30)) R *= 2;
-    p->R = R;
     if (!p->sticky) {
-      // Round-robin units start every list cold.  For k > 10 (lists of 32+ entries, insertion in shared
-      // memory) that warm-up dominates, so a ~3 % strided sample is scanned first and its KP-th best
-      // becomes every unit's starting threshold.
-      const int64_t tpc = R / 256;
+      // Round-robin units (many query blocks).  Every unit starts its lists cold, so a ~3 % strided
+      // sample is scanned first (bootstrap launch) and its KP-th best becomes every unit's starting
+      // threshold; with warm thresholds short units (16K rows) win: the units that share a corpus chunk
+      // drift less, so the chunk is re-read from DRAM less often (measured +2.5 % at k = 10, +14 % at
+      // k = 100 over 64K-row units).  Small corpora keep one launch and long units.
       const char* noboot = getenv("TSIM_NO_BOOT");
-      if (p->KP >= 32 && T >= 24 * tpc && !(noboot && noboot[0] == '1')) {
+      const bool boot = T >= 24 * 64 && !(noboot && noboot[0] == '1');
+      int64_t nct = (8 * (int64_t)workers + p->QB - 1) / p->QB;  // aim at >= ~8 units per worker
+      if (nct < 1) nct = 1;
+      int64_t R = (N + nct - 1) / nct;
+      R = (R + 255) / 256 * 256;
+      if (R < 256) R = 256;
+      const int64_t rcap = boot ? 16384 : 65536;
+      if (R > rcap) R = rcap;
+      if (const char* cr = getenv("TSIM_CHUNK_ROWS")) {     // experiment knob: rows per unit
+        int64_t v = atoll(cr);
+        if (v >= 256) R = v / 256 * 256;
+      }
+      // bound the candidate buffer (Q * NC * KP * 8 bytes) to ~2 GB
+      while ((double)Q * (double)((N + R - 1) / R) * p->KP * 8.0 > 2.0e9 && R < ((int64_t)1 << 30)) R *= 2;
+      p->R = R;
+      const int64_t tpc = R / 256;
+      if (boot && T >= 24 * tpc) {
         int64_t want = T / 32;
         want = (want + tpc - 1) / tpc * tpc;                             // whole chunks of sample tiles
         p->boot_stride = T / want;                                       // >= 16
@@ -109,6 +115,7 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
       }
       p->NC = p->boot_tiles ? p->boot_slots + (T - p->boot_tiles + tpc - 1) / tpc : (T + tpc - 1) / tpc;
     } else {
+      p->R = 256;
       p->NC = p->boot_tiles ? 2 * p->Gq : p->Gq;
     }
     p->off_cand = off; off = align_up(off + (size_t)Q * p->NC * p->KP * sizeof(uint64_t), 256);
@@ -143,6 +150,7 @@ using namespace tsim;
 
 extern "C" int tsim_version(void) { return TSIM_ABI_VERSION; }
 extern "C" const char* tsim_last_error(void) { return g_err; }
+extern "C" uint64_t tsim_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 extern "C" int tsim_set_timing_events(void* start, void* stop) {
   g_ev_start = (cudaEvent_t)start;
   g_ev_stop = (cudaEvent_t)stop;

@@ -196,5 +196,6 @@ int launch_row_inv_norm(const void* x, int dt, int64_t N, int64_t D, int64_t str
                         cudaStream_t st);
 
 int device_sm_count();
+void count_launch();   // bumps the counter behind tsim_launch_count()
 
 }  // namespace tsim
