@@ -31,6 +31,23 @@ def timeit(fn, reps=20, flush=None):
     return t[len(t) // 2]
 
 
+def timeit_rotating(fns, rounds=8):
+    """Back-to-back launches over DISTINCT input buffers (each larger than what L2 keeps of the
+    previous ones; no flush kernel in between, so no dirty lines of a flush are written back
+    during the measured kernel): one event pair around the whole train, time per launch."""
+    for f in fns:
+        f()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(rounds):
+        for f in fns:
+            f()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / (rounds * len(fns))
+
+
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 print(f"HBM peak used for fractions: {peak} GB/s")
 for (B, L, D, in_dt, out_dt) in [(16, 256, 384, torch.float32, torch.float32), (16, 256, 768, torch.float32, torch.bfloat16),
@@ -44,6 +61,15 @@ for (B, L, D, in_dt, out_dt) in [(16, 256, 384, torch.float32, torch.float32), (
     nbytes = tok.numel() * tok.element_size() + mask.numel() * 8 + out.numel() * out.element_size() + B * 4
     print(f"K1 pool_norm B={B} L={L} D={D} {str(in_dt)[6:]}->{str(out_dt)[6:]}: {ms * 1e3:8.1f} us  "
           f"{nbytes / ms / 1e6:7.0f} GB/s  ({nbytes / ms / 1e6 / peak * 100:5.1f}% of HBM peak, {nbytes / 1e6:.1f} MB)")
+    if nbytes > 64e6:
+        # sustained: a train of launches rotating over input copies totalling >= 1 GB (>> the 126 MB L2)
+        ncopy = max(3, int(1.0e9 // nbytes) + 1)
+        toks = [tok] + [tok.clone() for _ in range(ncopy - 1)]
+        fns = [(lambda t=t: ops.pool_norm(t, mask, out=out, out_inv_norm=inv, normalize=True)) for t in toks]
+        ms_r = timeit_rotating(fns)
+        print(f"   rotating {ncopy} inputs, launch train: {ms_r * 1e3:8.1f} us  {nbytes / ms_r / 1e6:7.0f} GB/s  "
+              f"({nbytes / ms_r / 1e6 / peak * 100:5.1f}% of HBM peak)")
+        del toks, fns
     # the six-kernel ATen sequence the reference issues (modules.py:160-170) on the same GPU, for scale
     def aten():
         m = mask.unsqueeze(-1).expand(tok.size()).float()

@@ -345,3 +345,61 @@ def test_strided_rows_and_views(ops):
         ops.search_topk(qbig_d[:, 1:257], big_d[:, 1:257], 10, mode="tensor")
     s3, i3 = ops.search_topk(qbig_d[:, 1:257], big_d[:, 1:257], 10, mode="auto")
     assert torch.equal(i3.cpu(), O.search_exact(qbig[:, 1:257], big[:, 1:257], 10)[1])
+
+
+# ------------------------------------------------------------------------------------ K1 streaming variant
+@pytest.mark.parametrize("B,L,D,in_dt", [
+    (300, 600, 64, torch.float32),        # L > 512: every sentence is split over >= 2 items
+    (5000, 7, 384, torch.bfloat16),       # many short sentences: persistent CTAs loop over ~11 items each
+    (1024, 128, 768, torch.bfloat16),     # the bench shape (all CTAs stream full chunks)
+    (37, 200, 1024, torch.float16),       # rpi = 2, chunk of 8 tokens
+    (3, 40, 2048, torch.bfloat16),        # 256 vector columns: rpi = 1
+    (5, 300, 4096, torch.float32),        # row = 16 KB: one token per chunk is NOT streamable (> 256 columns) -> v1
+])
+def test_pool_stream_shapes(ops, B, L, D, in_dt):
+    g = torch.Generator().manual_seed(B + L + D)
+    emb = torch.randn(B, L, D, generator=g).to(in_dt)
+    lens = torch.randint(0, L + 1, (B,), generator=g)
+    lens[0], lens[B - 1] = L, 0                      # a full row and an all-masked row
+    mask = (torch.arange(L)[None] < lens[:, None])
+    mask = mask & (torch.rand(B, L, generator=g) > 0.1)      # interior holes
+    rows, inv = ops.pool_norm(emb.cuda(), mask.cuda(), normalize=False)
+    exp = O.mean_pool_exact(emb, mask.to(torch.int64))
+    np.testing.assert_allclose(rows.cpu().double().numpy(), exp.numpy(), rtol=0, atol=4 * TOL_F32)
+    assert (rows[B - 1] == 0).all()                  # all-masked sentence -> zero vector (reference behaviour)
+    rows_n, inv = ops.pool_norm(emb.cuda(), mask.cuda(), out_dtype=torch.bfloat16, normalize=True)
+    expn = O.l2_normalize_exact(exp)
+    np.testing.assert_allclose(rows_n.cpu().double().numpy(), expn.numpy(), rtol=0, atol=2 ** -8)
+    n = rows_n.cpu().double().norm(dim=-1).clamp_min(1e-8)
+    np.testing.assert_allclose(inv.cpu().double().numpy() * n.numpy(), 1.0, atol=1e-5)
+
+
+def test_pool_stream_weights_scatter_and_masked_garbage(ops):
+    g = torch.Generator().manual_seed(99)
+    B, L, D = 200, 90, 256
+    emb = torch.randn(B, L, D, generator=g)
+    w = torch.rand(B, L, generator=g)                # real-valued weights
+    w[w < 0.3] = 0.0
+    w[:, 70:] = 0.0
+    exp = O.mean_pool_exact(emb, w)
+    dirty = emb.clone()
+    dirty[w == 0] = float("nan")                     # masked positions hold garbage: must never reach the sum
+    big = torch.full((B + 50, D + 32), 7.0, device="cuda")
+    rows = torch.randperm(B + 50, generator=g)[:B]
+    view = big[:, :D]                                # out rows with stride D + 32
+    ops.pool_norm(dirty.cuda(), w.cuda(), normalize=False, out=view, out_rows=rows.cuda())
+    np.testing.assert_allclose(big.cpu()[rows, :D].double().numpy(), exp.numpy(), rtol=0, atol=4 * TOL_F32)
+    assert (big[:, D:] == 7.0).all()                 # nothing written outside the rows
+    untouched = torch.ones(B + 50, dtype=torch.bool)
+    untouched[rows] = False
+    assert (big.cpu()[untouched] == 7.0).all()
+    # batch / token strides: a [B, L, D] window of a larger tensor (token rows NOT contiguous -> register-staged kernel)
+    wide = torch.randn(B, L, D + 64, generator=g).cuda()
+    out, _ = ops.pool_norm(wide[:, :, :D], w.cuda(), normalize=False)
+    np.testing.assert_allclose(out.cpu().double().numpy(), O.mean_pool_exact(wide[:, :, :D].cpu(), w).numpy(),
+                               rtol=0, atol=4 * TOL_F32)
+    # batch stride only (token rows contiguous within a sentence -> streaming kernel)
+    tall = torch.randn(B, L + 10, D, generator=g).cuda()
+    out, _ = ops.pool_norm(tall[:, :L], w.cuda(), normalize=False)
+    np.testing.assert_allclose(out.cpu().double().numpy(), O.mean_pool_exact(tall[:, :L].cpu(), w).numpy(),
+                               rtol=0, atol=4 * TOL_F32)

@@ -8,6 +8,8 @@
 // all and masked tokens never enter the sum.  Grid = B * S CTAs (S = splits of the token axis) sized to >= 2 CTAs per SM;
 // split partial sums go through a small fp32 workspace and the last CTA to finish a row
 // (ticket counter) adds them in a fixed order, so results are deterministic.
+#include <stdlib.h>
+
 #include "tsim_common.cuh"
 
 namespace tsim {
@@ -220,6 +222,276 @@ __global__ void __launch_bounds__(256) pool_norm_kernel(PoolArgs a) {
   if (a.out_inv && tid == 0) a.out_inv[orow] = 1.f / fmaxf(sqrtf(ss2), (float)kCosEps);
 }
 
+// ---- K1, streaming variant ---------------------------------------------------------------------
+// Persistent CTAs (3 per SM), one producer warp + 8 consumer warps.  The producer walks this CTA's
+// (sentence, token-split) items: it reads the item's mask weights (one item AHEAD, so the latency
+// hides behind the copies in flight), skips chunks whose tokens are all masked (trailing padding is
+// never read) and moves each remaining chunk of up to 32 tokens -- one contiguous run of the token
+// tensor -- into a 4-stage shared-memory ring with ONE 1-D bulk async copy (TMA, UBLKCP) that
+// completes on the stage's mbarrier.  Consumers (thread = 16-byte column x token sub-row) wait on
+// the barrier, accumulate weight * token from shared memory in fp32 and hand the stage back; an
+// END marker stage closes an item, whose mean / L2 norm / cast / inverse norm the consumers then
+// finish among themselves (named barrier) while the producer is already streaming the next item.
+// HBM-bound: ~64 KB of copies in flight per CTA independent of register pressure.
+constexpr int kPsStages = 4;
+constexpr int kPsStageBytes = 16 * 1024;
+constexpr int kPsConsumers = 256;
+constexpr int kPsThreads = kPsConsumers + 32;
+constexpr int kPsMaxTL = 512;    // tokens per item (the launcher raises the split count to keep this)
+
+struct PsHdr { float w[32]; int ntok; int kind; float cnt; int pad; };   // kind 0: data, 1: end of item
+
+__device__ __forceinline__ uint32_t ps_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ps_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ps_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void ps_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ps_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void ps_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void ps_cbar() { asm volatile("bar.sync 1, %0;" ::"n"(kPsConsumers) : "memory"); }
+
+// deterministic sum / max over the 256 consumer threads (all get the result); red32 = 8 floats
+__device__ __forceinline__ float ps_sum(float v, float* red32) {
+  v = warp_sum_f32(v);
+  ps_cbar();
+  if ((threadIdx.x & 31) == 0) red32[threadIdx.x >> 5] = v;
+  ps_cbar();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < kPsConsumers / 32; ++i) t += red32[i];
+  return t;
+}
+__device__ __forceinline__ float ps_max(float v, float* red32) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  ps_cbar();
+  if ((threadIdx.x & 31) == 0) red32[threadIdx.x >> 5] = v;
+  ps_cbar();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < kPsConsumers / 32; ++i) t = fmaxf(t, red32[i]);
+  return t;
+}
+
+template <int DT> struct SmemVec;   // 16 bytes of tokens in shared memory -> floats
+template <> struct SmemVec<TSIM_F32> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void cvt(const uint4& v, float* o) {
+    o[0] = __uint_as_float(v.x); o[1] = __uint_as_float(v.y); o[2] = __uint_as_float(v.z); o[3] = __uint_as_float(v.w);
+  }
+};
+template <> struct SmemVec<TSIM_F16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void cvt(const uint4& v, float* o) {
+    const __half2* h = (const __half2*)&v;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { float2 f = __half22float2(h[j]); o[2 * j] = f.x; o[2 * j + 1] = f.y; }
+  }
+};
+template <> struct SmemVec<TSIM_BF16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void cvt(const uint4& v, float* o) {
+    // bf16 -> fp32 is a 16-bit shift: two integer ops per pair
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { o[2 * j] = __uint_as_float(w[j] << 16); o[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u); }
+  }
+};
+
+template <int DT>
+__global__ void __launch_bounds__(kPsThreads) pool_norm_stream_kernel(PoolArgs a, int64_t nitems, int CT) {
+  extern __shared__ __align__(128) unsigned char ps_raw[];
+  constexpr int VEC = SmemVec<DT>::N;
+  constexpr int ESZ = 16 / VEC;
+  unsigned char* data = ps_raw;                                        // [stages][16 KB]
+  PsHdr* hdr = (PsHdr*)(ps_raw + kPsStages * kPsStageBytes);           // [stages]
+  float* wbuf = (float*)(hdr + kPsStages);                             // [kPsMaxTL] producer-private weights
+  float* red = wbuf + kPsMaxTL;                                        // [rpi * D] (then pooled[D])
+  const int nvec = (int)(a.D / VEC);
+  const int rpi = kPsConsumers / nvec;                                 // token sub-rows per pass (>= 1)
+  float* red32 = red + (size_t)rpi * a.D;                              // [8]
+  uint64_t* bars = (uint64_t*)(red32 + 8);                             // full[stages], empty[stages]
+  __shared__ int s_last;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < kPsStages; ++s) {
+      ps_mbar_init(ps_smem(&bars[s]), 1);
+      ps_mbar_init(ps_smem(&bars[kPsStages + s]), kPsConsumers / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == kPsConsumers / 32) {
+    // ===================== producer warp =====================
+    int stage = 0; uint32_t phase = 0;
+    float wn[kPsMaxTL / 32];
+    auto load_mask = [&](int64_t item) {
+      const int64_t b = item / a.S; const int sp = (int)(item % a.S);
+      const int l0 = sp * a.TL, tl = min((int)a.L, l0 + a.TL) - l0;
+#pragma unroll
+      for (int j = 0; j < kPsMaxTL / 32; ++j)
+        wn[j] = (lane + 32 * j < tl) ? mask_value(a.mask, a.mask_dt, b * a.msb + l0 + lane + 32 * j) : 0.f;
+    };
+    if ((int64_t)blockIdx.x < nitems) load_mask(blockIdx.x);
+    for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const int64_t b = item / a.S; const int sp = (int)(item % a.S);
+      const int l0 = sp * a.TL, tl = min((int)a.L, l0 + a.TL) - l0;
+      float cnt = 0.f;
+#pragma unroll
+      for (int j = 0; j < kPsMaxTL / 32; ++j) {
+        if (lane + 32 * j < tl) wbuf[lane + 32 * j] = wn[j];
+        cnt += wn[j];
+      }
+      cnt = warp_sum_f32(cnt);
+      __syncwarp();
+      if (item + gridDim.x < nitems) load_mask(item + gridDim.x);    // in flight during this item's copies
+      for (int lc = 0; lc < tl; lc += CT) {
+        const int nt = min(CT, tl - lc);
+        const float w = lane < nt ? wbuf[lc + lane] : 0.f;
+        const unsigned nz = __ballot_sync(0xffffffffu, w != 0.f);
+        if (!nz) continue;                                            // all masked: not read at all
+        const int nte = 32 - __clz(nz);                               // up to the chunk's last real token
+        ps_mbar_wait(ps_smem(&bars[kPsStages + stage]), phase ^ 1);
+        hdr[stage].w[lane] = w;
+        if (lane == 0) { hdr[stage].ntok = nte; hdr[stage].kind = 0; }
+        __syncwarp();
+        if (lane == 0) {
+          const uint32_t bytes = (uint32_t)nte * (uint32_t)a.D * ESZ;
+          const uint32_t fb = ps_smem(&bars[stage]);
+          ps_mbar_expect_tx(fb, bytes);
+          ps_bulk_load(ps_smem(data + (size_t)stage * kPsStageBytes),
+                       (const unsigned char*)a.tok + (b * a.sb + (int64_t)(l0 + lc) * a.D) * ESZ, bytes, fb);
+        }
+        if (++stage == kPsStages) { stage = 0; phase ^= 1; }
+      }
+      ps_mbar_wait(ps_smem(&bars[kPsStages + stage]), phase ^ 1);
+      if (lane == 0) {
+        hdr[stage].kind = 1; hdr[stage].cnt = cnt;
+        ps_mbar_arrive(ps_smem(&bars[stage]));
+      }
+      __syncwarp();
+      if (++stage == kPsStages) { stage = 0; phase ^= 1; }
+    }
+    return;
+  }
+
+  // ===================== consumers =====================
+  const bool active = tid < rpi * nvec;
+  const int r = tid / nvec, v = tid - r * nvec;
+  int stage = 0; uint32_t phase = 0;
+  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int64_t b = item / a.S; const int sp = (int)(item % a.S);
+    float acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+    float cnt = 0.f;
+    for (;;) {
+      ps_mbar_wait(ps_smem(&bars[stage]), phase);
+      const PsHdr* h = hdr + stage;
+      const int kind = h->kind;
+      if (kind == 0 && active) {
+        const int ntok = h->ntok;
+        const uint4* src = (const uint4*)(data + (size_t)stage * kPsStageBytes) + v;
+#pragma unroll 4
+        for (int t = r; t < ntok; t += rpi) {
+          const float w = h->w[t];
+          if (w != 0.f) {     // a masked token's values must not reach the sum (they may be Inf/NaN)
+            const uint4 raw = src[(size_t)t * nvec];
+            float x[VEC];
+            SmemVec<DT>::cvt(raw, x);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) acc[j] = fmaf(w, x[j], acc[j]);
+          }
+        }
+      }
+      if (kind == 1) cnt = h->cnt;
+      __syncwarp();
+      if (lane == 0) ps_mbar_arrive(ps_smem(&bars[kPsStages + stage]));
+      if (++stage == kPsStages) { stage = 0; phase ^= 1; }
+      if (kind == 1) break;
+    }
+    // ---- item done: fold the token sub-rows in a fixed order ----
+    ps_cbar();    // the previous item's readers of red[] are done
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) red[(size_t)r * a.D + (size_t)v * VEC + j] = acc[j];
+    }
+    ps_cbar();
+    for (int d = tid; d < a.D; d += kPsConsumers) {
+      float t = red[d];
+      for (int rr = 1; rr < rpi; ++rr) t += red[(size_t)rr * a.D + d];
+      if (a.S > 1) a.partial[((int64_t)b * a.S + sp) * a.D + d] = t;
+      else red[d] = t;
+    }
+    if (a.S > 1) {
+      // the last CTA to finish a split of row b adds the partial sums in a fixed order
+      __threadfence();
+      ps_cbar();
+      if (tid == 0) s_last = (atomicAdd(&a.ticket[b], 1) == a.S - 1);
+      ps_cbar();
+      if (!s_last) continue;
+      __threadfence();
+      for (int d = tid; d < a.D; d += kPsConsumers) {
+        float t = 0.f;
+        for (int s = 0; s < a.S; ++s) t += __ldcg(&a.partial[((int64_t)b * a.S + s) * a.D + d]);
+        red[d] = t;
+      }
+      float c = 0.f;
+      for (int l = tid; l < a.L; l += kPsConsumers) c += mask_value(a.mask, a.mask_dt, b * a.msb + l);
+      cnt = ps_sum(c, red32);
+    }
+    ps_cbar();
+    const float denom = fmaxf(cnt, kPoolEps);  // modules.py:168
+    float ss = 0.f, amax = 0.f;
+    for (int d = tid; d < a.D; d += kPsConsumers) {
+      const float m = red[d] / denom;  // modules.py:170
+      red[d] = m;
+      ss = fmaf(m, m, ss);
+      amax = fmaxf(amax, fabsf(m));
+    }
+    float scale = 1.f;
+    if (a.normalize) scale = 1.f / fmaxf(sqrtf(ps_sum(ss, red32)), (float)kCosEps);
+    if (a.out_dt == TSIM_E4M3) {
+      // per-row power-of-two scale: largest |element| lands in [64, 128) (e4m3 max is 448)
+      const float bm = ps_max(amax, red32) * scale;
+      if (bm > 0.f) {
+        int e;
+        frexpf(bm, &e);  // bm = f * 2^e, f in [0.5, 1)
+        scale *= exp2f((float)(7 - e));
+      }
+    }
+    const int64_t orow = a.out_rows ? a.out_rows[b] : b;
+    float ss2 = 0.f;
+    for (int d = tid; d < a.D; d += kPsConsumers) {
+      const float st = round_store(a.out, a.out_dt, orow * a.out_stride + d, red[d] * scale);
+      ss2 = fmaf(st, st, ss2);
+    }
+    if (a.out_inv) {
+      ss2 = ps_sum(ss2, red32);
+      if (tid == 0) a.out_inv[orow] = 1.f / fmaxf(sqrtf(ss2), (float)kCosEps);
+    }
+  }
+}
+
 // Sum of squares of one 16-byte vector of a stored row.
 template <int DT> struct SqVec;
 template <> struct SqVec<TSIM_F32> {
@@ -333,8 +605,38 @@ int pool_splits(int64_t B, int64_t L) {
   int64_t maxs = (L + 7) / 8;                           // >= 8 tokens per CTA
   int64_t S = want < 1 ? 1 : want;
   if (S > maxs) S = maxs;
+  const int64_t mins = (L + kPsMaxTL - 1) / kPsMaxTL;   // <= kPsMaxTL tokens per item (streaming variant)
+  if (S < mins) S = mins;
   if (S < 1) S = 1;
   return (int)S;
+}
+
+// The streaming variant needs token rows that are contiguous within a sentence (one bulk copy per
+// chunk), 16-byte granularity, a row of at most one stage and at most 256 16-byte columns.
+bool pool_stream_ok(const PoolArgs& a, int esz, bool vec_ok) {
+  const char* v1 = getenv("TSIM_POOL_V1");   // experiment knob: force the register-staged kernel
+  if (v1 && v1[0] == '1') return false;
+  const int64_t rowb = a.D * esz;
+  return vec_ok && a.sl == a.D && rowb <= kPsStageBytes && rowb / 16 <= kPsConsumers && a.TL <= kPsMaxTL;
+}
+
+template <int DT>
+int launch_pool_stream(const PoolArgs& a, cudaStream_t st) {
+  constexpr int ESZ = 16 / SmemVec<DT>::N;
+  const int nvec = (int)(a.D * ESZ / 16);
+  const int rpi = kPsConsumers / nvec;
+  int CT = (int)(kPsStageBytes / (a.D * ESZ));
+  if (CT > 32) CT = 32;
+  const size_t smem = (size_t)kPsStages * kPsStageBytes + kPsStages * sizeof(PsHdr) + kPsMaxTL * sizeof(float) +
+                      (size_t)rpi * a.D * sizeof(float) + 8 * sizeof(float) + 2 * kPsStages * sizeof(uint64_t) + 128;
+  TSIM_CUDA(cudaFuncSetAttribute(pool_norm_stream_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t nitems = a.B * a.S;
+  const int64_t cap = 3 * (int64_t)device_sm_count();
+  const unsigned grid = (unsigned)(nitems < cap ? nitems : cap);
+  pool_norm_stream_kernel<DT><<<grid, kPsThreads, smem, st>>>(a, nitems, CT);
+  TSIM_CUDA(cudaGetLastError());
+  count_launch();
+  return TSIM_OK;
 }
 
 }  // namespace
@@ -407,6 +709,13 @@ extern "C" int tsim_pool_norm(const void* tok, int tok_dt, const void* mask, int
   const int vec = 16 / esz;
   const bool vec_ok = (D % vec == 0) && (tok_stride_b % vec == 0) && (tok_stride_l % vec == 0) &&
                       (((uintptr_t)tok & 15) == 0);
+  if (pool_stream_ok(a, esz, vec_ok)) {
+    switch (tok_dt) {
+      case TSIM_F32: return launch_pool_stream<TSIM_F32>(a, st);
+      case TSIM_F16: return launch_pool_stream<TSIM_F16>(a, st);
+      default: return launch_pool_stream<TSIM_BF16>(a, st);
+    }
+  }
   switch (tok_dt) {
     case TSIM_F32: return vec_ok ? launch_pool<TSIM_F32, 4>(a, st) : launch_pool<TSIM_F32, 1>(a, st);
     case TSIM_F16: return vec_ok ? launch_pool<TSIM_F16, 8>(a, st) : launch_pool<TSIM_F16, 1>(a, st);

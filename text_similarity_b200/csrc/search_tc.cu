@@ -188,8 +188,10 @@ struct TcArgs {
   int kblocks;          // ceil(D * element size / 128)
   int QB;               // query blocks (128 queries; 256 when CTA pairs are used)
   int64_t T;            // corpus tiles (of 256 rows) THIS launch scans (see tile_mode)
-  int tile_mode;        // 0: tiles 0..T-1; 1: the sample tiles i * tile_stride; 2: every tile that is not a sample tile
-  int64_t tile_stride;  // distance between sample tiles (modes 1, 2)
+  int tile_mode;        // 0: tiles 0..T-1; 1: the tiles i * tile_stride; 2: every tile that is not a multiple of
+                        // tile_stride; 3: the multiples of tile_stride that are not multiples of tile_stride * tile_mult
+  int64_t tile_stride;  // distance between sample tiles (modes 1, 2, 3)
+  int64_t tile_mult;    // mode 3: every tile_mult-th sample tile belongs to the mini sample
   int64_t slot_base;    // first candidate-list slot this launch writes
   int sticky;           // 1: CTA <-> (query block, tile residue class), one list per CTA lifetime
   int Gq;               // sticky: CTAs per query block
@@ -199,6 +201,7 @@ struct TcArgs {
   int self_on; int64_t self_off;
   uint64_t* cand;       // [Q][NC][KP] packed keys
   uint32_t* thr;        // [Q] ordered-float global thresholds (0 = none yet)
+  uint32_t* ladder;     // [Q][2 * kLadder] threshold ladder (main launch after a bootstrap), or null
   int dbg;              // TSIM_DEBUG bits (diagnosis only): 1 skip A loads, 2 skip MMAs, 4 skip epilogue math
 };
 
@@ -207,6 +210,7 @@ struct TcArgs {
 __device__ __forceinline__ int64_t actual_tile(const TcArgs& a, int64_t u) {
   if (a.tile_mode == 1) return u * a.tile_stride;
   if (a.tile_mode == 2) return u + u / (a.tile_stride - 1) + 1;
+  if (a.tile_mode == 3) return (u + u / (a.tile_mult - 1) + 1) * a.tile_stride;
   return u;
 }
 
@@ -236,6 +240,40 @@ __device__ __forceinline__ bool get_unit(const TcArgs& a, int it, int wid, int n
   return true;
 }
 
+// Threshold ladder.  lad[0..16) = ascending ordered-float score levels (written by tighten_kernel from
+// the bootstrap sample, immutable during this launch), lad[16..32) = how many candidate rows of this
+// query were seen so far, by ANY CTA, in [level i, level i+1).  A thread that has just inserted `n`
+// rows, all with score >= s, adds them to s's bin and raises its threshold to the highest level that
+// has >= KP rows at or above it.  Why that is a valid bound on the query's final KP-th best: every
+// counted row sits in a candidate list, or was evicted from a full list whose KP entries are all at
+// least as good -- either way >= KP candidates at or above the level reach select_rescore.
+// (Counts are read slightly stale and rows below the caller's own threshold are never counted:
+// both only delay a raise.)  Without this, after the bootstrap a query's threshold rises only when
+// one unit's own list fills, i.e. almost never with short units.
+__device__ __forceinline__ float ladder_update(uint32_t* lad, float s, uint32_t n, uint32_t KP, float thr) {
+  const uint32_t o = f32_to_ord(s);
+  uint32_t lev[kLadder], bin[kLadder];
+#pragma unroll
+  for (int i = 0; i < kLadder / 4; ++i) {
+    const uint4 l = __ldg((const uint4*)lad + i);
+    const uint4 b = __ldcg((const uint4*)lad + kLadder / 4 + i);
+    lev[4 * i] = l.x; lev[4 * i + 1] = l.y; lev[4 * i + 2] = l.z; lev[4 * i + 3] = l.w;
+    bin[4 * i] = b.x; bin[4 * i + 1] = b.y; bin[4 * i + 2] = b.z; bin[4 * i + 3] = b.w;
+  }
+  int j = -1;
+#pragma unroll
+  for (int i = 0; i < kLadder; ++i) j += (lev[i] <= o) ? 1 : 0;   // levels ascend: the last one <= o
+  if (j < 0) return thr;
+  atomicAdd(lad + kLadder + j, n);
+  uint32_t c = 0, best = 0;
+#pragma unroll
+  for (int i = kLadder - 1; i >= 0; --i) {
+    c += bin[i] + (i == j ? n : 0u);
+    if (best == 0 && c >= KP) best = lev[i];
+  }
+  return best ? fmaxf(thr, ord_to_f32(best)) : thr;
+}
+
 // ---- per-query candidate lists -----------------------------------------------------------------
 // Each epilogue thread owns the running top-KP (approx score, row) list of its query, sorted
 // descending, empty slots = (-inf, 0xffffffff).  The hot loop never touches the list: it takes the
@@ -248,6 +286,7 @@ __device__ __forceinline__ bool get_unit(const TcArgs& a, int it, int wid, int n
 // A full list's minimum is a valid lower bound of the query's KP-th best anywhere in the corpus,
 // so it is published with atomicMax for every other CTA to filter with.
 struct RegList16 {
+  static constexpr bool kFromRegs = false;  // slow() re-reads the flagged 8-column groups from TMEM
   float a[16]; uint32_t r[16];
   __device__ __forceinline__ RegList16(float*, uint32_t*, int*) {}
   __device__ __forceinline__ void reset() {
@@ -257,9 +296,11 @@ struct RegList16 {
   // gm0..gm3: this lane's maxima over the chunk's four 8-column groups; a group is re-read only if
   // some lane of the warp has a candidate in it (warp-uniform test: tcgen05.ld is .sync.aligned)
   __device__ __forceinline__ float slow(uint32_t taddr, const float* cnp, float thr, int64_t row_base,
-                                        int64_t self_row, int lim, uint32_t* thr_g, float gm0, float gm1,
-                                        float gm2, float gm3) {
+                                        int64_t self_row, int lim, uint32_t* thr_g, uint32_t* lad, float gm0,
+                                        float gm1, float gm2, float gm3) {
     const float thr_in = thr;
+    float ins_min = INFINITY;   // rows inserted by this call: how many, and their lowest score
+    uint32_t ins_n = 0;
 #pragma unroll 1
     for (int g = 0; g < 4; ++g) {
       const float gm = g == 0 ? gm0 : g == 1 ? gm1 : g == 2 ? gm2 : gm3;
@@ -273,6 +314,8 @@ struct RegList16 {
         const float s = __uint_as_float(w[jj]) * cnp[j];
         const int64_t row = row_base + j;
         if (s > thr && j < lim && row != self_row) {
+          ins_min = fminf(ins_min, s);
+          ++ins_n;
           // a[] is sorted descending, so (s > a[i]) is monotone in i: entry i becomes the newcomer
           // where the predicate first turns true, the old a[i-1] after that, and stays otherwise.
           // Strict '>' puts the newcomer after equal scores (it has the larger row).
@@ -287,6 +330,7 @@ struct RegList16 {
         }
       }
     }
+    if (lad && ins_n) thr = ladder_update(lad, ins_min, ins_n, 16u, thr);
     if (thr > thr_in) atomicMax(thr_g, f32_to_ord(thr));
     return thr;
   }
@@ -301,53 +345,22 @@ struct RegList16 {
 // shift would be a chain of ~KP/2 dependent load/store steps).  *statep packs the fill count (low 16
 // bits) and the slot of the minimum (high 16 bits).  Which of several equal minima is evicted does
 // not matter: every dropped row still has approx <= the final KP-th best (see select_merge.cu).
+// Position and value of the minimum of a full list: one pipelined scan of KP independent loads.
 template <int KP>
-__device__ __noinline__ float smem_list_slow(float* ls, uint32_t* li, int* statep, uint32_t taddr, const float* cnp, float thr,
-                                             int64_t row_base, int64_t self_row, int lim, uint32_t* thr_g,
-                                             float gm0, float gm1, float gm2, float gm3) {
-  const float thr_in = thr;
-  int cnt = *statep & 0xffff, minpos = *statep >> 16;
-#pragma unroll 1
-  for (int g = 0; g < 4; ++g) {
-    const float gm = g == 0 ? gm0 : g == 1 ? gm1 : g == 2 ? gm2 : gm3;
-    if (!__any_sync(0xffffffffu, gm > thr)) continue;
-    uint32_t w[8];
-    tc_ld8(taddr + g * 8, w);
-    tc_ld_wait();
-#pragma unroll 1
-    for (int jj = 0; jj < 8; ++jj) {
-      const int j = g * 8 + jj;
-      uint32_t wj = w[0];
-#pragma unroll
-      for (int x = 1; x < 8; ++x) wj = (jj == x) ? w[x] : wj;
-      const float s = __uint_as_float(wj) * cnp[j];
-      const int64_t row = row_base + j;
-      if (s > thr && j < lim && row != self_row) {
-        const int pos = cnt < KP ? cnt : minpos;
-        ls[pos * kEpiThreads] = s;
-        li[pos * kEpiThreads] = (uint32_t)row;
-        if (cnt < KP) ++cnt;
-        if (cnt == KP) {                        // full: locate the new minimum
-          float m = ls[0];
-          int mp = 0;
+__device__ __noinline__ uint64_t smem_list_min(const float* ls) {
+  float m = ls[0];
+  int mp = 0;
 #pragma unroll 8
-          for (int i = 1; i < KP; ++i) {
-            const float v = ls[i * kEpiThreads];
-            if (v < m) { m = v; mp = i; }
-          }
-          minpos = mp;
-          thr = fmaxf(thr, m);
-        }
-      }
-    }
+  for (int i = 1; i < KP; ++i) {
+    const float v = ls[i * kEpiThreads];
+    if (v < m) { m = v; mp = i; }
   }
-  *statep = cnt | (minpos << 16);
-  if (thr > thr_in) atomicMax(thr_g, f32_to_ord(thr));
-  return thr;
+  return ((uint64_t)(uint32_t)mp << 32) | __float_as_uint(m);
 }
 
 template <int KP>
 struct SmemList {
+  static constexpr bool kFromRegs = true;   // slow() takes the chunk's scaled scores from registers
   float* ls; uint32_t* li; int* cntp;
   __device__ __forceinline__ SmemList(float* s, uint32_t* i, int* n) : ls(s), li(i), cntp(n) {}
   __device__ __forceinline__ void reset() {
@@ -355,10 +368,36 @@ struct SmemList {
     for (int j = 0; j < KP; ++j) { ls[j * kEpiThreads] = -INFINITY; li[j * kEpiThreads] = 0xffffffffu; }
     *cntp = 0;
   }
-  __device__ __forceinline__ float slow(uint32_t taddr, const float* cnp, float thr, int64_t row_base,
-                                        int64_t self_row, int lim, uint32_t* thr_g, float gm0, float gm1,
-                                        float gm2, float gm3) {
-    return smem_list_slow<KP>(ls, li, cntp, taddr, cnp, thr, row_base, self_row, lim, thr_g, gm0, gm1, gm2, gm3);
+  // sc[0..32) = this lane's scaled scores of the chunk.  One predicated branch per column: a column
+  // costs two instructions unless some lane of the warp has a candidate in it, so the cost follows
+  // the number of candidates, not the number of chunks that have one.
+  __device__ __forceinline__ float slow(const float* sc, float thr, int64_t row_base, int64_t self_row, int lim,
+                                        uint32_t* thr_g, uint32_t* lad) {
+    const float thr_in = thr;
+    float ins_min = INFINITY;
+    uint32_t ins_n = 0;
+    int cnt = *cntp & 0xffff, minpos = *cntp >> 16;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float v = sc[j];
+      if (v > thr && j < lim && row_base + j != self_row) {
+        ins_min = fminf(ins_min, v);
+        ++ins_n;
+        const int pos = cnt < KP ? cnt : minpos;
+        ls[pos * kEpiThreads] = v;
+        li[pos * kEpiThreads] = (uint32_t)(row_base + j);
+        if (cnt < KP) ++cnt;
+        if (cnt == KP) {                        // full: locate the new minimum
+          const uint64_t r = smem_list_min<KP>(ls);
+          minpos = (int)(r >> 32);
+          thr = fmaxf(thr, __uint_as_float((uint32_t)r));
+        }
+      }
+    }
+    *cntp = cnt | (minpos << 16);
+    if (lad && ins_n) thr = ladder_update(lad, ins_min, ins_n, (uint32_t)KP, thr);
+    if (thr > thr_in) atomicMax(thr_g, f32_to_ord(thr));
+    return thr;
   }
   __device__ __forceinline__ void flush(uint64_t* dst) {
 #pragma unroll 4
@@ -501,6 +540,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       const bool qvalid = qg < a.Q;
       const int64_t self_row = a.self_on ? a.self_off + qg : -1;
       uint32_t* thr_g = a.thr + (qvalid ? qg : 0);
+      uint32_t* lad = (a.ladder && qvalid) ? a.ladder + (size_t)qg * (2 * kLadder) : nullptr;
       list.reset();
       float thr = qvalid ? -INFINITY : INFINITY;   // padded query lanes never insert
       // Tile metadata (the 256 inverse norms, 8 per lane, and the query's shared threshold) is
@@ -536,22 +576,27 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           tc_ld_wait();
           // hot path: 32 FMUL + FMNMX3 tree (kept per 8-column group) + one compare
           const float4* cn4 = (const float4*)(cn + c * 32);
-          float gm[4];
+          float sc[32], gm[4];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const float4 w0 = cn4[2 * g], w1 = cn4[2 * g + 1];
-            const float a0 = __uint_as_float(v[g * 8 + 0]) * w0.x, a1 = __uint_as_float(v[g * 8 + 1]) * w0.y;
-            const float a2 = __uint_as_float(v[g * 8 + 2]) * w0.z, a3 = __uint_as_float(v[g * 8 + 3]) * w0.w;
-            const float a4 = __uint_as_float(v[g * 8 + 4]) * w1.x, a5 = __uint_as_float(v[g * 8 + 5]) * w1.y;
-            const float a6 = __uint_as_float(v[g * 8 + 6]) * w1.z, a7 = __uint_as_float(v[g * 8 + 7]) * w1.w;
-            gm[g] = fmaxf(fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)), fmaxf(fmaxf(a4, a5), fmaxf(a6, a7)));
+            float* x = sc + g * 8;
+            x[0] = __uint_as_float(v[g * 8 + 0]) * w0.x; x[1] = __uint_as_float(v[g * 8 + 1]) * w0.y;
+            x[2] = __uint_as_float(v[g * 8 + 2]) * w0.z; x[3] = __uint_as_float(v[g * 8 + 3]) * w0.w;
+            x[4] = __uint_as_float(v[g * 8 + 4]) * w1.x; x[5] = __uint_as_float(v[g * 8 + 5]) * w1.y;
+            x[6] = __uint_as_float(v[g * 8 + 6]) * w1.z; x[7] = __uint_as_float(v[g * 8 + 7]) * w1.w;
+            gm[g] = fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7])));
           }
           const float mx = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
           // Cold path, taken by the WHOLE warp when any lane has a candidate (tcgen05.ld is
           // .sync.aligned: it must not run under divergence); rare once the lists are warm.
-          if (__any_sync(0xffffffffu, mx > thr))
-            thr = list.slow(tbase + c * 32, cn + c * 32, thr, trow0 + c * 32, self_row, ncols - c * 32, thr_g,
-                            gm[0], gm[1], gm[2], gm[3]);
+          if (__any_sync(0xffffffffu, mx > thr)) {
+            if constexpr (ListFor<KP>::type::kFromRegs)
+              thr = list.slow(sc, thr, trow0 + c * 32, self_row, ncols - c * 32, thr_g, lad);
+            else
+              thr = list.slow(tbase + c * 32, cn + c * 32, thr, trow0 + c * 32, self_row, ncols - c * 32, thr_g, lad,
+                              gm[0], gm[1], gm[2], gm[3]);
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -639,7 +684,7 @@ int launch_cfg(const CUtensorMap& mq, const CUtensorMap& mc, const TcArgs& a, cu
 
 int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_t c_stride, int dt,
                      const float* c_inv, int64_t Q, int64_t N, int64_t D, int self_on, int64_t self_off,
-                     const SearchPlan& p, int pass, uint64_t* cand, uint32_t* thr, cudaStream_t st) {
+                     const SearchPlan& p, int pass, uint64_t* cand, uint32_t* thr, uint32_t* ladder, cudaStream_t st) {
   CUtensorMap mq, mc;
   const int qrows = p.pair ? 2 * BM : BM;
   // q holds QB * qrows rows (the API pads the last query block with zero rows)
@@ -654,12 +699,28 @@ int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_
   const int64_t T = (N + BN - 1) / BN;
   a.QB = p.QB; a.sticky = p.sticky; a.Gq = p.Gq; a.tpc = p.R / BN;
   a.NC = p.NC;
-  // pass 0: the whole corpus in one launch; pass 1: bootstrap sample; pass 2: everything else
-  a.tile_mode = pass; a.tile_stride = p.boot_stride; a.slot_base = pass == 2 ? p.boot_slots : 0;
-  a.T = pass == 1 ? p.boot_tiles : pass == 2 ? T - p.boot_tiles : T;
+  a.tile_mode = 0; a.tile_stride = 1; a.tile_mult = 2; a.slot_base = 0; a.T = T;
+  switch (pass) {
+    case TC_PASS_SAMPLE:        // the whole sample, cold
+      a.tile_mode = 1; a.tile_stride = p.boot_stride; a.T = p.boot_tiles;
+      if (!p.sticky) a.tpc = p.boot_tpc;
+      break;
+    case TC_PASS_MINI:          // every mini_mult-th sample tile, one-tile units, cold
+      a.tile_mode = 1; a.tile_stride = p.boot_stride * p.mini_mult; a.T = p.mini_tiles; a.tpc = 1;
+      break;
+    case TC_PASS_SAMPLE_REST:   // the other sample tiles
+      a.tile_mode = 3; a.tile_stride = p.boot_stride; a.tile_mult = p.mini_mult; a.T = p.boot_tiles - p.mini_tiles;
+      a.tpc = p.boot_tpc; a.slot_base = p.mini_slots;
+      break;
+    case TC_PASS_MAIN:          // everything that is not a sample tile
+      a.tile_mode = 2; a.tile_stride = p.boot_stride; a.T = T - p.boot_tiles;
+      a.slot_base = p.mini_slots + p.boot_slots;
+      break;
+    default: break;
+  }
   a.n_units = (int64_t)p.QB * ((a.T + a.tpc - 1) / (a.tpc > 0 ? a.tpc : 1));
   a.self_on = self_on; a.self_off = self_off;
-  a.cand = cand; a.thr = thr;
+  a.cand = cand; a.thr = thr; a.ladder = ladder;
   const char* dbg = getenv("TSIM_DEBUG");
   a.dbg = dbg ? atoi(dbg) : 0;
 #define TSIM_DISPATCH(FP8)                                                       \

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(kSelThreads) select_rescore_kernel(SelArgs a) 
 // Between the bootstrap launch and the main launch: the KP-th best key of the union of a query's
 // bootstrap lists (slots 0..Gq-1) is a lower bound of its KP-th best over the whole corpus.
 __global__ void __launch_bounds__(kSelThreads) tighten_kernel(const uint64_t* cand, uint32_t* thr, int64_t NC, int KP,
-                                                              int nslots) {
+                                                              int nslots, uint32_t* ladder) {
   __shared__ uint64_t keys[kKeyCap];
   __shared__ int n_sh;
   const int64_t q = blockIdx.x;
@@ -264,6 +264,46 @@ __global__ void __launch_bounds__(kSelThreads) tighten_kernel(const uint64_t* ca
   __syncthreads();
   sort_keys_desc(keys, np);
   if (tid == 0 && n >= KP) atomicMax(thr + q, (uint32_t)(keys[KP - 1] >> 32));
+  if (!ladder) return;
+  // Threshold ladder for the main launch: levels 0..12 are the sample's own order statistics at
+  // geometrically spaced ranks KP .. 1 (each step cuts the pass rate by the same factor), levels
+  // 13..15 extrapolate above the sample's best (the full corpus's KP-th best usually ends up near
+  // it); counts start from the sample's top-KP rows.  Any ascending levels are VALID -- they only
+  // decide how fast the threshold can follow the data (see search_tc.cu, ladder_update).
+  __shared__ uint32_t lev[kLadder];
+  __shared__ uint32_t cum[kLadder + 1];
+  uint32_t* lad = ladder + (size_t)q * 2 * kLadder;
+  if (n < KP) {   // no threshold was set: a ladder that never fires
+    if (tid < kLadder) { lad[tid] = 0xffffffffu; lad[kLadder + tid] = 0u; }
+    return;
+  }
+  if (tid < kLadder) {
+    uint32_t o;
+    if (tid <= 12) {
+      int rank = (int)(powf((float)KP, 1.f - (float)tid / 12.f) + 0.5f);
+      rank = max(1, min(KP, rank));
+      o = (uint32_t)(keys[rank - 1] >> 32);
+    } else {
+      const float a1 = key_score(keys[0]), akp = key_score(keys[KP - 1]);
+      const float f = tid == 13 ? 0.25f : tid == 14 ? 0.5f : 1.f;
+      float v = a1 + (a1 - akp) * f;
+      if (!(v >= a1)) v = a1;
+      o = f32_to_ord(v);
+    }
+    lev[tid] = o;
+  }
+  if (tid == 0) cum[kLadder] = 0;
+  __syncthreads();
+  if (tid < kLadder) {
+    uint32_t c = 0;
+    for (int i = 0; i < KP; ++i) c += ((uint32_t)(keys[i] >> 32) >= lev[tid]) ? 1u : 0u;
+    cum[tid] = c;
+  }
+  __syncthreads();
+  if (tid < kLadder) {
+    lad[tid] = lev[tid];
+    lad[kLadder + tid] = cum[tid] - cum[tid + 1];   // rows in [lev[tid], lev[tid + 1])
+  }
 }
 
 struct ExMergeArgs {
@@ -348,8 +388,9 @@ int launch_select_rescore(const void* q, int q_dt, int64_t q_stride, const void*
   return TSIM_OK;
 }
 
-int launch_tighten(int64_t Q, const SearchPlan& p, const uint64_t* cand, uint32_t* thr, cudaStream_t st) {
-  tighten_kernel<<<(unsigned)Q, kSelThreads, 0, st>>>(cand, thr, p.NC, p.KP, (int)p.boot_slots);
+int launch_tighten(int64_t Q, const SearchPlan& p, int nslots, const uint64_t* cand, uint32_t* thr,
+                   uint32_t* ladder, cudaStream_t st) {
+  tighten_kernel<<<(unsigned)Q, kSelThreads, 0, st>>>(cand, thr, p.NC, p.KP, nslots, ladder);
   TSIM_CUDA(cudaGetLastError());
   count_launch();
   return TSIM_OK;

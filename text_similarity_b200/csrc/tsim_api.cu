@@ -78,17 +78,20 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
       // their union's KP-th best into every query's starting threshold.
       const char* noboot = getenv("TSIM_NO_BOOT");
       if (Q >= 16 && T >= 32 * (int64_t)p->Gq && !(noboot && noboot[0] == '1')) {
-        p->boot_stride = T / (2 * (int64_t)p->Gq);                      // >= 16
+        int64_t tpw = 2;                                                // sample tiles per worker
+        if (const char* e = getenv("TSIM_BOOT_TPW")) { int64_t v = atoll(e); if (v >= 1 && v <= 16) tpw = v; }
+        p->boot_stride = T / (tpw * (int64_t)p->Gq);                    // >= 2
         p->boot_tiles = (T + p->boot_stride - 1) / p->boot_stride;      // every multiple of the stride below T
         p->boot_slots = p->Gq;
       }
     }
     if (!p->sticky) {
-      // Round-robin units (many query blocks).  Every unit starts its lists cold, so a ~3 % strided
-      // sample is scanned first (bootstrap launch) and its KP-th best becomes every unit's starting
-      // threshold; with warm thresholds short units (16K rows) win: the units that share a corpus chunk
-      // drift less, so the chunk is re-read from DRAM less often (measured +2.5 % at k = 10, +14 % at
-      // k = 100 over 64K-row units).  Small corpora keep one launch and long units.
+      // Round-robin units (many query blocks).  A unit's list starts empty, so what it filters with is
+      // the query's GLOBAL threshold: a strided sample (~1/64 of the tiles) is scanned first and leaves
+      // every query a threshold and a threshold ladder (rank counters) that the main launch keeps
+      // raising.  With thresholds global, short units (16K rows) win: the units that share a corpus
+      // chunk drift less, so the chunk is re-read from DRAM less often.  Small corpora keep one launch
+      // and long units.
       const char* noboot = getenv("TSIM_NO_BOOT");
       const bool boot = T >= 24 * 64 && !(noboot && noboot[0] == '1');
       int64_t nct = (8 * (int64_t)workers + p->QB - 1) / p->QB;  // aim at >= ~8 units per worker
@@ -107,13 +110,35 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
       p->R = R;
       const int64_t tpc = R / 256;
       if (boot && T >= 24 * tpc) {
-        int64_t want = T / 32;
-        want = (want + tpc - 1) / tpc * tpc;                             // whole chunks of sample tiles
-        p->boot_stride = T / want;                                       // >= 16
+        // Sample = every boot_stride-th tile, ~1/64 of the corpus.  Its first launch (every
+        // mini_mult-th sample tile, about 4 tiles, one-tile units) is the only one that runs with
+        // cold lists; the rest of the sample and the main launch start from thresholds + a ladder.
+        int64_t div = 64;                                               // sample = 1 / div of the tiles
+        if (const char* e = getenv("TSIM_BOOT_DIV")) { int64_t v = atoll(e); if (v >= 4 && v <= 1024) div = v; }
+        int64_t want = T / div;
+        if (want < 8) want = 8;
+        p->boot_stride = T / want;                                       // >= 2
         p->boot_tiles = (T + p->boot_stride - 1) / p->boot_stride;
-        p->boot_slots = (p->boot_tiles + tpc - 1) / tpc;
+        const char* nomini = getenv("TSIM_NO_MINI");                     // experiment knob: one cold sample launch
+        if (!(nomini && nomini[0] == '1')) {
+          p->mini_mult = (p->boot_tiles + 3) / 4;
+          if (p->mini_mult < 2) p->mini_mult = 2;
+          p->mini_tiles = (p->boot_tiles + p->mini_mult - 1) / p->mini_mult;
+          p->mini_slots = p->mini_tiles;                                 // one-tile units
+        }
+        // the rest of the sample in short units (lists rarely fill, thresholds come from the ladder):
+        // the unit length in [8, 48] tiles with the smallest makespan = waves x tiles per unit
+        const int64_t rest = p->boot_tiles - p->mini_tiles;
+        int64_t best_tpc = 8, best_span = -1;
+        for (int64_t t = 8; t <= 48; ++t) {
+          const int64_t units = (int64_t)p->QB * ((rest + t - 1) / t);
+          const int64_t span = ((units + workers - 1) / workers) * t;
+          if (best_span < 0 || span < best_span) { best_span = span; best_tpc = t; }
+        }
+        p->boot_tpc = best_tpc;
+        p->boot_slots = (rest + p->boot_tpc - 1) / p->boot_tpc;
       }
-      p->NC = p->boot_tiles ? p->boot_slots + (T - p->boot_tiles + tpc - 1) / tpc : (T + tpc - 1) / tpc;
+      p->NC = p->boot_tiles ? p->mini_slots + p->boot_slots + (T - p->boot_tiles + tpc - 1) / tpc : (T + tpc - 1) / tpc;
     } else {
       p->R = 256;
       p->NC = p->boot_tiles ? 2 * p->Gq : p->Gq;
@@ -134,6 +159,9 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
   p->off_thr = off; off = align_up(off + (size_t)Q * sizeof(uint32_t), 256);
   p->off_flagcnt = off; off += 256;
   p->off_flaglist = off; off = align_up(off + (size_t)Q * sizeof(int32_t), 256);
+  if (p->use_tensor && p->boot_tiles) {
+    p->off_ladder = off; off = align_up(off + (size_t)Q * 2 * kLadder * sizeof(uint32_t), 256);
+  }
   if (p->use_tensor && Q % (p->pair ? 256 : 128) != 0) {  // zero-padded copy of the queries (TMA OOB fill is slow)
     p->off_qpad = off; off = align_up(off + (size_t)p->QB * (p->pair ? 256 : 128) * D * dtype_size(q_dt), 256);
   }
@@ -238,14 +266,27 @@ extern "C" int tsim_search_topk(const void* q, int q_dt, int64_t q_stride, const
     const bool timed = g_ev_start && g_ev_stop;
     if (timed) TSIM_CUDA(cudaEventRecord(g_ev_start, st));
     uint64_t* cand = (uint64_t*)(w + p.off_cand);
+    uint32_t* ladder = nullptr;
     if (p.boot_tiles) {
-      rc = launch_search_tc(qt, qt_stride, corpus, c_stride, c_dt, c_inv, Q, N, D, self_on, self_off, p, 1, cand, thr, st);
+      const char* nolad = getenv("TSIM_NO_LADDER");   // experiment knob
+      uint32_t* lad = (nolad && nolad[0] == '1') ? nullptr : (uint32_t*)(w + p.off_ladder);
+      if (p.mini_mult) {
+        rc = launch_search_tc(qt, qt_stride, corpus, c_stride, c_dt, c_inv, Q, N, D, self_on, self_off, p,
+                              TC_PASS_MINI, cand, thr, nullptr, st);
+        if (rc) return rc;
+        rc = launch_tighten(Q, p, (int)p.mini_slots, cand, thr, lad, st);
+        if (rc) return rc;
+        ladder = lad;
+      }
+      rc = launch_search_tc(qt, qt_stride, corpus, c_stride, c_dt, c_inv, Q, N, D, self_on, self_off, p,
+                            p.mini_mult ? TC_PASS_SAMPLE_REST : TC_PASS_SAMPLE, cand, thr, ladder, st);
       if (rc) return rc;
-      rc = launch_tighten(Q, p, cand, thr, st);
+      rc = launch_tighten(Q, p, (int)(p.mini_slots + p.boot_slots), cand, thr, lad, st);   // re-levels the ladder
       if (rc) return rc;
+      ladder = lad;
     }
     rc = launch_search_tc(qt, qt_stride, corpus, c_stride, c_dt, c_inv, Q, N, D, self_on, self_off, p,
-                          p.boot_tiles ? 2 : 0, cand, thr, st);
+                          p.boot_tiles ? TC_PASS_MAIN : TC_PASS_ALL, cand, thr, ladder, st);
     if (rc) return rc;
     if (timed) TSIM_CUDA(cudaEventRecord(g_ev_stop, st));
     rc = launch_select_rescore(q, q_dt, q_stride, corpus, c_dt, c_stride, Q, N, D, k, idx_base, p,

@@ -19,6 +19,12 @@ constexpr float kPoolEps = 1e-9f;  // clamp in AvgPoolingStrategy, reference mod
 // differ by more than 2 * kApproxEps (see select_merge.cu); tests measure the real error.
 constexpr float kApproxEps = 5e-5f;
 
+// Threshold ladder (search_tc.cu / select_merge.cu): per query, kLadder ascending score levels and
+// the number of candidate rows seen so far at or above each; once >= KP rows sit at or above a level
+// that level is a valid global threshold.  Lets every CTA filter with (nearly) the threshold a single
+// sequential top-KP scan of everything seen so far would have.
+constexpr int kLadder = 16;
+
 void set_error(const char* fmt, ...);
 
 #define TSIM_CHECK_ARG(cond, ...)          \
@@ -153,6 +159,12 @@ struct SearchPlan {
   int64_t boot_tiles;  // > 0: a bootstrap launch scans this many strided sample tiles first
   int64_t boot_stride; //      distance between sample tiles
   int64_t boot_slots;  //      candidate-list slots written by the bootstrap launch (the main launch follows)
+  int64_t boot_tpc;    //      round-robin: tiles per unit of the bootstrap launch
+  // round-robin only, > 0: the sample itself is scanned in two launches -- first every mini_mult-th
+  // sample tile (mini_tiles of them, one-tile units, cold lists), then the rest of the sample with
+  // thresholds and a ladder from the first.  Cold lists are expensive (every early row is inserted),
+  // so only a handful of tiles ever see them.
+  int64_t mini_mult, mini_tiles, mini_slots;
   int64_t R;           // round-robin: corpus rows per unit (multiple of 256)
   int64_t NC;          // candidate lists per query: chunks ceil(N / R), or Gq when sticky
   // exact path
@@ -160,6 +172,7 @@ struct SearchPlan {
   int64_t slice_rows;  // rows per slice
   // workspace offsets (bytes)
   size_t off_cand, off_thr, off_flagcnt, off_flaglist, off_invnorm, off_qpad, off_ex_score, off_ex_idx;
+  size_t off_ladder;   // [Q][2 * kLadder] u32: per-query threshold ladder (levels | counts), bootstrap plans only
   size_t total;
 };
 
@@ -167,11 +180,15 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
                      bool need_invnorm, SearchPlan* plan);
 
 // kernels' host launchers (defined in the .cu files)
+// pass: 0 = the whole corpus in one launch; 1 = bootstrap sample (all of it); 2 = main (everything
+// that is not a sample tile); 3 = mini sample (first of two sample launches); 4 = rest of the sample
+enum { TC_PASS_ALL = 0, TC_PASS_SAMPLE = 1, TC_PASS_MAIN = 2, TC_PASS_MINI = 3, TC_PASS_SAMPLE_REST = 4 };
 int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_t c_stride, int dt,
                      const float* c_inv, int64_t Q, int64_t N, int64_t D,
                      int self_on, int64_t self_off, const SearchPlan& p, int pass, uint64_t* cand,
-                     uint32_t* thr, cudaStream_t st);
-int launch_tighten(int64_t Q, const SearchPlan& p, const uint64_t* cand, uint32_t* thr, cudaStream_t st);
+                     uint32_t* thr, uint32_t* ladder, cudaStream_t st);
+int launch_tighten(int64_t Q, const SearchPlan& p, int nslots, const uint64_t* cand, uint32_t* thr,
+                   uint32_t* ladder, cudaStream_t st);
 int launch_select_rescore(const void* q, int q_dt, int64_t q_stride, const void* corpus, int c_dt,
                           int64_t c_stride, int64_t Q, int64_t N, int64_t D, int k,
                           int64_t idx_base, const SearchPlan& p, const uint64_t* cand,
