@@ -88,6 +88,8 @@ struct PoolArgs {
   int* ticket;            // [B]
   void* out; int out_dt; int64_t out_stride; const int64_t* out_rows;
   float* out_inv; int normalize;
+  int dbg;                // TSIM_POOL_DEBUG bits (diagnosis only): 1 = consumers skip the accumulation,
+                          // 2 = static round-robin items, 4 = finisher skips its work
 };
 
 template <int DT, int VEC>
@@ -223,23 +225,30 @@ __global__ void __launch_bounds__(256) pool_norm_kernel(PoolArgs a) {
 }
 
 // ---- K1, streaming variant ---------------------------------------------------------------------
-// Persistent CTAs (3 per SM), one producer warp + 8 consumer warps.  The producer walks this CTA's
-// (sentence, token-split) items: it reads the item's mask weights (one item AHEAD, so the latency
-// hides behind the copies in flight), skips chunks whose tokens are all masked (trailing padding is
-// never read) and moves each remaining chunk of up to 32 tokens -- one contiguous run of the token
-// tensor -- into a 4-stage shared-memory ring with ONE 1-D bulk async copy (TMA, UBLKCP) that
-// completes on the stage's mbarrier.  Consumers (thread = 16-byte column x token sub-row) wait on
-// the barrier, accumulate weight * token from shared memory in fp32 and hand the stage back; an
-// END marker stage closes an item, whose mean / L2 norm / cast / inverse norm the consumers then
-// finish among themselves (named barrier) while the producer is already streaming the next item.
-// HBM-bound: ~64 KB of copies in flight per CTA independent of register pressure.
-constexpr int kPsStages = 4;
-constexpr int kPsStageBytes = 16 * 1024;
+// Persistent CTAs, two per SM, three warp roles around a shared-memory ring of up to 8 stages (a stage =
+// one chunk of whole token rows, <= 16 KB; ~90 KB per CTA):
+//  * producer warp: takes (sentence, token-split) items from a global counter (CTAs that drew short
+//    sentences simply take more), reads an item's mask weights one item AHEAD (the latency hides
+//    behind the copies in flight), skips chunks whose tokens are all masked (trailing padding is
+//    never read) and moves each remaining chunk of up to 32 tokens -- one contiguous run of the
+//    token tensor -- into a ring stage with ONE 1-D bulk async copy (TMA, UBLKCP) that completes on
+//    the stage's mbarrier;
+//  * 8 consumer warps (thread = 16-byte column x token sub-row): wait on the barrier, accumulate
+//    weight * token from shared memory in fp32, hand the stage back; at an item's END stage they
+//    drop their partial sums into one of two fold buffers and go straight on to the next item;
+//  * finisher warp: folds the sub-rows in a fixed order, divides by the token count, L2-normalises,
+//    casts, stores the row and its inverse norm -- with warp shuffles only, off the streaming path.
+// HBM-bound: ~180 KB of copies in flight per SM, independent of register pressure.
+constexpr int kPsMaxStages = 8;          // ring depth: as many stages as fit in half an SM's shared memory
+constexpr int kPsStageBytes = 16 * 1024;  // upper bound of a stage (a chunk = up to 32 whole token rows)
 constexpr int kPsConsumers = 256;
-constexpr int kPsThreads = kPsConsumers + 32;
+constexpr int kPsThreads = kPsConsumers + 64;   // + producer warp + finisher warp
 constexpr int kPsMaxTL = 512;    // tokens per item (the launcher raises the split count to keep this)
 
-struct PsHdr { float w[32]; int ntok; int kind; float cnt; int pad; };   // kind 0: data, 1: end of item
+// kind 0: data chunk; 1: data chunk (ntok may be 0) that also ends item `item` (cnt = sum of its weights);
+// 2: no more items
+struct PsHdr { float w[32]; int ntok; int kind; float cnt; int pad; long long item; long long pad2; };
+struct PsMail { long long item; float cnt; int pad; };   // consumers -> finisher, one per fold buffer
 
 __device__ __forceinline__ uint32_t ps_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ps_mbar_init(uint32_t bar, uint32_t count) {
@@ -265,29 +274,10 @@ __device__ __forceinline__ void ps_bulk_load(uint32_t dst, const void* src, uint
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void ps_cbar() { asm volatile("bar.sync 1, %0;" ::"n"(kPsConsumers) : "memory"); }
-
-// deterministic sum / max over the 256 consumer threads (all get the result); red32 = 8 floats
-__device__ __forceinline__ float ps_sum(float v, float* red32) {
-  v = warp_sum_f32(v);
-  ps_cbar();
-  if ((threadIdx.x & 31) == 0) red32[threadIdx.x >> 5] = v;
-  ps_cbar();
-  float t = 0.f;
-#pragma unroll
-  for (int i = 0; i < kPsConsumers / 32; ++i) t += red32[i];
-  return t;
-}
-__device__ __forceinline__ float ps_max(float v, float* red32) {
+__device__ __forceinline__ float warp_max_f32(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  ps_cbar();
-  if ((threadIdx.x & 31) == 0) red32[threadIdx.x >> 5] = v;
-  ps_cbar();
-  float t = 0.f;
-#pragma unroll
-  for (int i = 0; i < kPsConsumers / 32; ++i) t = fmaxf(t, red32[i]);
-  return t;
+  return v;
 }
 
 template <int DT> struct SmemVec;   // 16 bytes of tokens in shared memory -> floats
@@ -316,34 +306,43 @@ template <> struct SmemVec<TSIM_BF16> {
 };
 
 template <int DT>
-__global__ void __launch_bounds__(kPsThreads) pool_norm_stream_kernel(PoolArgs a, int64_t nitems, int CT) {
+__global__ void __launch_bounds__(kPsThreads, 2) pool_norm_stream_kernel(PoolArgs a, int64_t nitems, int CT, int nst, int stage_bytes, int* counter) {
   extern __shared__ __align__(128) unsigned char ps_raw[];
   constexpr int VEC = SmemVec<DT>::N;
   constexpr int ESZ = 16 / VEC;
-  unsigned char* data = ps_raw;                                        // [stages][16 KB]
-  PsHdr* hdr = (PsHdr*)(ps_raw + kPsStages * kPsStageBytes);           // [stages]
-  float* wbuf = (float*)(hdr + kPsStages);                             // [kPsMaxTL] producer-private weights
-  float* red = wbuf + kPsMaxTL;                                        // [rpi * D] (then pooled[D])
+  constexpr int NCW = kPsConsumers / 32;                               // consumer warps
+  unsigned char* data = ps_raw;                                        // [nst][stage_bytes]
+  PsHdr* hdr = (PsHdr*)(ps_raw + (size_t)nst * stage_bytes);           // [nst]
+  float* wbuf = (float*)(hdr + nst);                             // [kPsMaxTL] producer-private weights
   const int nvec = (int)(a.D / VEC);
   const int rpi = kPsConsumers / nvec;                                 // token sub-rows per pass (>= 1)
-  float* red32 = red + (size_t)rpi * a.D;                              // [8]
-  uint64_t* bars = (uint64_t*)(red32 + 8);                             // full[stages], empty[stages]
-  __shared__ int s_last;
+  float* fold = wbuf + kPsMaxTL;                                       // [2][rpi * D] fold buffers
+  PsMail* mail = (PsMail*)(fold + 2 * (size_t)rpi * a.D);              // [2]
+  uint64_t* bars = (uint64_t*)(mail + 2);                              // full[nst], empty[nst], fold_full[2], fold_empty[2]
+  uint64_t* fold_full = bars + 2 * nst;
+  uint64_t* fold_empty = fold_full + 2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < kPsStages; ++s) {
+    for (int s = 0; s < nst; ++s) {
       ps_mbar_init(ps_smem(&bars[s]), 1);
-      ps_mbar_init(ps_smem(&bars[kPsStages + s]), kPsConsumers / 32);
+      ps_mbar_init(ps_smem(&bars[nst + s]), NCW);
     }
+    for (int s = 0; s < 2; ++s) { ps_mbar_init(ps_smem(&fold_full[s]), NCW); ps_mbar_init(ps_smem(&fold_empty[s]), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
 
-  if (warp == kPsConsumers / 32) {
+  if (warp == NCW) {
     // ===================== producer warp =====================
     int stage = 0; uint32_t phase = 0;
     float wn[kPsMaxTL / 32];
+    auto next_item = [&]() -> int64_t {     // CTA c starts with item c; further items come from the counter
+      int v = 0;
+      if (lane == 0) v = atomicAdd(counter, 1);
+      return (int64_t)__shfl_sync(0xffffffffu, v, 0) + gridDim.x;
+    };
+    int64_t static_next = (int64_t)blockIdx.x + gridDim.x;   // dbg bit 2: static round-robin items
     auto load_mask = [&](int64_t item) {
       const int64_t b = item / a.S; const int sp = (int)(item % a.S);
       const int l0 = sp * a.TL, tl = min((int)a.L, l0 + a.TL) - l0;
@@ -351,45 +350,151 @@ __global__ void __launch_bounds__(kPsThreads) pool_norm_stream_kernel(PoolArgs a
       for (int j = 0; j < kPsMaxTL / 32; ++j)
         wn[j] = (lane + 32 * j < tl) ? mask_value(a.mask, a.mask_dt, b * a.msb + l0 + lane + 32 * j) : 0.f;
     };
-    if ((int64_t)blockIdx.x < nitems) load_mask(blockIdx.x);
-    for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+    int64_t item = blockIdx.x;
+    if (item < nitems) load_mask(item);
+    while (item < nitems) {
       const int64_t b = item / a.S; const int sp = (int)(item % a.S);
       const int l0 = sp * a.TL, tl = min((int)a.L, l0 + a.TL) - l0;
       float cnt = 0.f;
+      int lend = 0;                                                   // one past the item's last real token
 #pragma unroll
       for (int j = 0; j < kPsMaxTL / 32; ++j) {
         if (lane + 32 * j < tl) wbuf[lane + 32 * j] = wn[j];
         cnt += wn[j];
+        if (wn[j] != 0.f) lend = lane + 32 * j + 1;
       }
       cnt = warp_sum_f32(cnt);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) lend = max(lend, __shfl_xor_sync(0xffffffffu, lend, o));
       __syncwarp();
-      if (item + gridDim.x < nitems) load_mask(item + gridDim.x);    // in flight during this item's copies
-      for (int lc = 0; lc < tl; lc += CT) {
-        const int nt = min(CT, tl - lc);
+      int64_t nxt;
+      if (a.dbg & 2) { nxt = static_next; static_next += gridDim.x; } else nxt = next_item();
+      if (nxt < nitems) load_mask(nxt);                               // in flight during this item's copies
+      // chunks up to the last real token (trailing padding is never read); the chunk that holds it
+      // also closes the item (kind 1); an item without any real token is a bare END stage
+      for (int lc = 0; lc < lend || lc == 0; lc += CT) {
+        const int nt = max(0, min(CT, lend - lc));
+        const bool last = lc + CT >= lend;
         const float w = lane < nt ? wbuf[lc + lane] : 0.f;
         const unsigned nz = __ballot_sync(0xffffffffu, w != 0.f);
-        if (!nz) continue;                                            // all masked: not read at all
-        const int nte = 32 - __clz(nz);                               // up to the chunk's last real token
-        ps_mbar_wait(ps_smem(&bars[kPsStages + stage]), phase ^ 1);
+        if (!nz && !last) continue;                                   // all masked: not read at all
+        ps_mbar_wait(ps_smem(&bars[nst + stage]), phase ^ 1);
         hdr[stage].w[lane] = w;
-        if (lane == 0) { hdr[stage].ntok = nte; hdr[stage].kind = 0; }
+        if (lane == 0) {
+          hdr[stage].ntok = nt; hdr[stage].kind = last ? 1 : 0;
+          hdr[stage].cnt = cnt; hdr[stage].item = item;
+        }
         __syncwarp();
         if (lane == 0) {
-          const uint32_t bytes = (uint32_t)nte * (uint32_t)a.D * ESZ;
+          const uint32_t bytes = (uint32_t)nt * (uint32_t)a.D * ESZ;
           const uint32_t fb = ps_smem(&bars[stage]);
-          ps_mbar_expect_tx(fb, bytes);
-          ps_bulk_load(ps_smem(data + (size_t)stage * kPsStageBytes),
-                       (const unsigned char*)a.tok + (b * a.sb + (int64_t)(l0 + lc) * a.D) * ESZ, bytes, fb);
+          if (bytes) {
+            ps_mbar_expect_tx(fb, bytes);
+            ps_bulk_load(ps_smem(data + (size_t)stage * stage_bytes),
+                         (const unsigned char*)a.tok + (b * a.sb + (int64_t)(l0 + lc) * a.D) * ESZ, bytes, fb);
+          } else {
+            ps_mbar_arrive(fb);
+          }
         }
-        if (++stage == kPsStages) { stage = 0; phase ^= 1; }
+        if (++stage == nst) { stage = 0; phase ^= 1; }
       }
-      ps_mbar_wait(ps_smem(&bars[kPsStages + stage]), phase ^ 1);
-      if (lane == 0) {
-        hdr[stage].kind = 1; hdr[stage].cnt = cnt;
-        ps_mbar_arrive(ps_smem(&bars[stage]));
+      item = nxt;
+    }
+    ps_mbar_wait(ps_smem(&bars[nst + stage]), phase ^ 1);
+    if (lane == 0) {
+      hdr[stage].kind = 2;
+      ps_mbar_arrive(ps_smem(&bars[stage]));
+    }
+    return;
+  }
+
+  if (warp == NCW + 1) {
+    // ===================== finisher warp =====================
+    int fb = 0; uint32_t fphase = 0;   // bit fb = phase of fold_full[fb]
+    for (;;) {
+      ps_mbar_wait(ps_smem(&fold_full[fb]), (fphase >> fb) & 1u);
+      fphase ^= 1u << fb;
+      const int64_t item = mail[fb].item;
+      float cnt = mail[fb].cnt;
+      if (item < 0) break;
+      if (a.dbg & 4) { __syncwarp(); if (lane == 0) ps_mbar_arrive(ps_smem(&fold_empty[fb])); fb ^= 1; continue; }
+      const int64_t b = item / a.S; const int sp = (int)(item % a.S);
+      float* rb = fold + (size_t)fb * rpi * a.D;
+      // fold the token sub-rows in a fixed order; pooled sums land in row 0 of the buffer
+      for (int d = lane * 4; d < a.D; d += 128) {
+        float4 t = *(const float4*)(rb + d);
+        for (int rr = 1; rr < rpi; ++rr) {
+          const float4 u = *(const float4*)(rb + (size_t)rr * a.D + d);
+          t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+        }
+        if (a.S > 1) *(float4*)(a.partial + ((int64_t)b * a.S + sp) * a.D + d) = t;
+        else *(float4*)(rb + d) = t;
+      }
+      bool finish = true;
+      if (a.S > 1) {
+        // the last CTA to finish a split of row b adds the partial sums in a fixed order
+        __threadfence();
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) last = (atomicAdd(&a.ticket[b], 1) == a.S - 1);
+        last = __shfl_sync(0xffffffffu, last, 0);
+        finish = last != 0;
+        if (finish) {
+          __threadfence();
+          for (int d = lane * 4; d < a.D; d += 128) {
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int s2 = 0; s2 < a.S; ++s2) {
+              const float4 u = __ldcg((const float4*)(a.partial + ((int64_t)b * a.S + s2) * a.D + d));
+              t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+            }
+            *(float4*)(rb + d) = t;
+          }
+          float c = 0.f;
+          for (int l = lane; l < a.L; l += 32) c += mask_value(a.mask, a.mask_dt, b * a.msb + l);
+          cnt = warp_sum_f32(c);
+        }
+      }
+      if (finish) {
+        __syncwarp();
+        const float denom = fmaxf(cnt, kPoolEps);  // modules.py:168
+        float ss = 0.f, amax = 0.f;
+        for (int d = lane * 4; d < a.D; d += 128) {
+          float4 t = *(const float4*)(rb + d);
+          t.x /= denom; t.y /= denom; t.z /= denom; t.w /= denom;  // modules.py:170
+          *(float4*)(rb + d) = t;
+          ss = fmaf(t.x, t.x, ss); ss = fmaf(t.y, t.y, ss); ss = fmaf(t.z, t.z, ss); ss = fmaf(t.w, t.w, ss);
+          amax = fmaxf(fmaxf(amax, fmaxf(fabsf(t.x), fabsf(t.y))), fmaxf(fabsf(t.z), fabsf(t.w)));
+        }
+        float scale = 1.f;
+        if (a.normalize) scale = 1.f / fmaxf(sqrtf(warp_sum_f32(ss)), (float)kCosEps);
+        if (a.out_dt == TSIM_E4M3) {
+          // per-row power-of-two scale: largest |element| lands in [64, 128) (e4m3 max is 448)
+          const float bm = warp_max_f32(amax) * scale;
+          if (bm > 0.f) {
+            int e;
+            frexpf(bm, &e);  // bm = f * 2^e, f in [0.5, 1)
+            scale *= exp2f((float)(7 - e));
+          }
+        }
+        const int64_t orow = a.out_rows ? a.out_rows[b] : b;
+        float ss2 = 0.f;
+        for (int d = lane * 4; d < a.D; d += 128) {
+          const float4 t = *(const float4*)(rb + d);
+          const float v4[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float st = round_store(a.out, a.out_dt, orow * a.out_stride + d + j, v4[j] * scale);
+            ss2 = fmaf(st, st, ss2);
+          }
+        }
+        if (a.out_inv) {
+          ss2 = warp_sum_f32(ss2);
+          if (lane == 0) a.out_inv[orow] = 1.f / fmaxf(sqrtf(ss2), (float)kCosEps);
+        }
       }
       __syncwarp();
-      if (++stage == kPsStages) { stage = 0; phase ^= 1; }
+      if (lane == 0) ps_mbar_arrive(ps_smem(&fold_empty[fb]));
+      fb ^= 1;
     }
     return;
   }
@@ -398,97 +503,61 @@ __global__ void __launch_bounds__(kPsThreads) pool_norm_stream_kernel(PoolArgs a
   const bool active = tid < rpi * nvec;
   const int r = tid / nvec, v = tid - r * nvec;
   int stage = 0; uint32_t phase = 0;
-  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
-    const int64_t b = item / a.S; const int sp = (int)(item % a.S);
+  int fb = 0; uint32_t ephase = 0;     // fold buffer to fill next; bit fb = phase of fold_empty[fb]
+  for (;;) {
     float acc[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
     float cnt = 0.f;
+    int64_t item = -1;
+    int kind;
     for (;;) {
       ps_mbar_wait(ps_smem(&bars[stage]), phase);
       const PsHdr* h = hdr + stage;
-      const int kind = h->kind;
-      if (kind == 0 && active) {
+      kind = h->kind;
+      if (kind != 2 && active && !(a.dbg & 1)) {
         const int ntok = h->ntok;
-        const uint4* src = (const uint4*)(data + (size_t)stage * kPsStageBytes) + v;
-#pragma unroll 4
-        for (int t = r; t < ntok; t += rpi) {
-          const float w = h->w[t];
-          if (w != 0.f) {     // a masked token's values must not reach the sum (they may be Inf/NaN)
-            const uint4 raw = src[(size_t)t * nvec];
-            float x[VEC];
-            SmemVec<DT>::cvt(raw, x);
+        const uint4* src = (const uint4*)(data + (size_t)stage * stage_bytes) + v;
+        for (int t = r; t < ntok; t += 2 * rpi) {
+          // two tokens per step, loads first; a masked token's values must not reach the sum (they may be Inf/NaN)
+          const int t1 = t + rpi;
+          const bool ok1 = t1 < ntok;
+          const float w0 = h->w[t], w1 = ok1 ? h->w[t1] : 0.f;
+          const uint4 raw0 = src[(size_t)t * nvec];
+          const uint4 raw1 = src[(size_t)(ok1 ? t1 : t) * nvec];
+          float x0[VEC], x1[VEC];
+          SmemVec<DT>::cvt(raw0, x0);
+          SmemVec<DT>::cvt(raw1, x1);
+          if (w0 != 0.f) {
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) acc[j] = fmaf(w, x[j], acc[j]);
+            for (int j = 0; j < VEC; ++j) acc[j] = fmaf(w0, x0[j], acc[j]);
+          }
+          if (w1 != 0.f) {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) acc[j] = fmaf(w1, x1[j], acc[j]);
           }
         }
       }
-      if (kind == 1) cnt = h->cnt;
+      if (kind == 1) { cnt = h->cnt; item = h->item; }
       __syncwarp();
-      if (lane == 0) ps_mbar_arrive(ps_smem(&bars[kPsStages + stage]));
-      if (++stage == kPsStages) { stage = 0; phase ^= 1; }
-      if (kind == 1) break;
+      if (lane == 0) ps_mbar_arrive(ps_smem(&bars[nst + stage]));
+      if (++stage == nst) { stage = 0; phase ^= 1; }
+      if (kind != 0) break;
     }
-    // ---- item done: fold the token sub-rows in a fixed order ----
-    ps_cbar();    // the previous item's readers of red[] are done
-    if (active) {
+    // ---- item done (or no more items: item = -1): hand the partial sums to the finisher ----
+    // wait until the finisher has released this fold buffer (the first use of each is free)
+    ps_mbar_wait(ps_smem(&fold_empty[fb]), ((ephase >> fb) & 1u) ^ 1u);
+    ephase ^= 1u << fb;
+    if (active && kind == 1) {
+      float* rb = fold + (size_t)fb * rpi * a.D + (size_t)r * a.D + (size_t)v * VEC;
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) red[(size_t)r * a.D + (size_t)v * VEC + j] = acc[j];
+      for (int j = 0; j < VEC; j += 4) *(float4*)(rb + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
     }
-    ps_cbar();
-    for (int d = tid; d < a.D; d += kPsConsumers) {
-      float t = red[d];
-      for (int rr = 1; rr < rpi; ++rr) t += red[(size_t)rr * a.D + d];
-      if (a.S > 1) a.partial[((int64_t)b * a.S + sp) * a.D + d] = t;
-      else red[d] = t;
-    }
-    if (a.S > 1) {
-      // the last CTA to finish a split of row b adds the partial sums in a fixed order
-      __threadfence();
-      ps_cbar();
-      if (tid == 0) s_last = (atomicAdd(&a.ticket[b], 1) == a.S - 1);
-      ps_cbar();
-      if (!s_last) continue;
-      __threadfence();
-      for (int d = tid; d < a.D; d += kPsConsumers) {
-        float t = 0.f;
-        for (int s = 0; s < a.S; ++s) t += __ldcg(&a.partial[((int64_t)b * a.S + s) * a.D + d]);
-        red[d] = t;
-      }
-      float c = 0.f;
-      for (int l = tid; l < a.L; l += kPsConsumers) c += mask_value(a.mask, a.mask_dt, b * a.msb + l);
-      cnt = ps_sum(c, red32);
-    }
-    ps_cbar();
-    const float denom = fmaxf(cnt, kPoolEps);  // modules.py:168
-    float ss = 0.f, amax = 0.f;
-    for (int d = tid; d < a.D; d += kPsConsumers) {
-      const float m = red[d] / denom;  // modules.py:170
-      red[d] = m;
-      ss = fmaf(m, m, ss);
-      amax = fmaxf(amax, fabsf(m));
-    }
-    float scale = 1.f;
-    if (a.normalize) scale = 1.f / fmaxf(sqrtf(ps_sum(ss, red32)), (float)kCosEps);
-    if (a.out_dt == TSIM_E4M3) {
-      // per-row power-of-two scale: largest |element| lands in [64, 128) (e4m3 max is 448)
-      const float bm = ps_max(amax, red32) * scale;
-      if (bm > 0.f) {
-        int e;
-        frexpf(bm, &e);  // bm = f * 2^e, f in [0.5, 1)
-        scale *= exp2f((float)(7 - e));
-      }
-    }
-    const int64_t orow = a.out_rows ? a.out_rows[b] : b;
-    float ss2 = 0.f;
-    for (int d = tid; d < a.D; d += kPsConsumers) {
-      const float st = round_store(a.out, a.out_dt, orow * a.out_stride + d, red[d] * scale);
-      ss2 = fmaf(st, st, ss2);
-    }
-    if (a.out_inv) {
-      ss2 = ps_sum(ss2, red32);
-      if (tid == 0) a.out_inv[orow] = 1.f / fmaxf(sqrtf(ss2), (float)kCosEps);
-    }
+    if (tid == 0) { mail[fb].item = item; mail[fb].cnt = cnt; }
+    __syncwarp();
+    if (lane == 0) ps_mbar_arrive(ps_smem(&fold_full[fb]));
+    fb ^= 1;
+    if (kind == 2) break;
   }
 }
 
@@ -621,19 +690,25 @@ bool pool_stream_ok(const PoolArgs& a, int esz, bool vec_ok) {
 }
 
 template <int DT>
-int launch_pool_stream(const PoolArgs& a, cudaStream_t st) {
+int launch_pool_stream(const PoolArgs& a, int* counter, cudaStream_t st) {
   constexpr int ESZ = 16 / SmemVec<DT>::N;
   const int nvec = (int)(a.D * ESZ / 16);
   const int rpi = kPsConsumers / nvec;
   int CT = (int)(kPsStageBytes / (a.D * ESZ));
   if (CT > 32) CT = 32;
-  const size_t smem = (size_t)kPsStages * kPsStageBytes + kPsStages * sizeof(PsHdr) + kPsMaxTL * sizeof(float) +
-                      (size_t)rpi * a.D * sizeof(float) + 8 * sizeof(float) + 2 * kPsStages * sizeof(uint64_t) + 128;
+  const int stage_bytes = (int)((CT * a.D * ESZ + 127) / 128 * 128);
+  const size_t fixed = kPsMaxTL * sizeof(float) + 2 * (size_t)rpi * a.D * sizeof(float) + 2 * sizeof(PsMail) +
+                       (2 * kPsMaxStages + 4) * sizeof(uint64_t) + 256;
+  const size_t budget = 113 * 1024;        // two CTAs per SM
+  int nst = (int)((budget - fixed) / (stage_bytes + sizeof(PsHdr)));
+  if (nst > kPsMaxStages) nst = kPsMaxStages;
+  if (nst < 2) nst = 2;
+  const size_t smem = (size_t)nst * (stage_bytes + sizeof(PsHdr)) + fixed;
   TSIM_CUDA(cudaFuncSetAttribute(pool_norm_stream_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t nitems = a.B * a.S;
-  const int64_t cap = 3 * (int64_t)device_sm_count();
+  const int64_t cap = 2 * (int64_t)device_sm_count();
   const unsigned grid = (unsigned)(nitems < cap ? nitems : cap);
-  pool_norm_stream_kernel<DT><<<grid, kPsThreads, smem, st>>>(a, nitems, CT);
+  pool_norm_stream_kernel<DT><<<grid, kPsThreads, smem, st>>>(a, nitems, CT, nst, stage_bytes, counter);
   TSIM_CUDA(cudaGetLastError());
   count_launch();
   return TSIM_OK;
@@ -667,12 +742,13 @@ int launch_row_inv_norm(const void* x, int dt, int64_t N, int64_t D, int64_t str
 
 using namespace tsim;
 
+// workspace layout: [item counter, 256 B][ticket, B ints][partial sums, B * S * D floats]
 extern "C" size_t tsim_pool_workspace_bytes(int64_t B, int64_t L, int64_t D) {
-  if (B <= 0 || L <= 0 || D <= 0) return 256;
+  if (B <= 0 || L <= 0 || D <= 0) return 512;
   int S = pool_splits(B, L);
   size_t partial = (S > 1) ? (size_t)B * S * D * sizeof(float) : 0;
   size_t ticket = (size_t)B * sizeof(int);
-  return ((partial + 255) / 256) * 256 + ((ticket + 255) / 256) * 256 + 256;
+  return 256 + ((ticket + 255) / 256) * 256 + ((partial + 255) / 256) * 256 + 256;
 }
 
 extern "C" int tsim_pool_norm(const void* tok, int tok_dt, const void* mask, int mask_dt,
@@ -697,23 +773,26 @@ extern "C" int tsim_pool_norm(const void* tok, int tok_dt, const void* mask, int
   a.out = out; a.out_dt = out_dt; a.out_stride = out_stride; a.out_rows = out_rows;
   a.out_inv = out_inv_norm; a.normalize = normalize;
   a.partial = nullptr; a.ticket = nullptr;
+  { const char* d = getenv("TSIM_POOL_DEBUG"); a.dbg = d ? atoi(d) : 0; }
+  const size_t ticket_al = (((size_t)B * sizeof(int) + 255) / 256) * 256;
+  const size_t need = 256 + (a.S > 1 ? ticket_al + (size_t)B * a.S * D * sizeof(float) : 0);
+  if (!ws || ws_bytes < need) { set_error("pool_norm: workspace too small (%zu < %zu)", ws_bytes, need); return TSIM_ERR_WORKSPACE; }
+  int* counter = (int*)ws;
   if (a.S > 1) {
-    size_t partial = (((size_t)B * a.S * D * sizeof(float) + 255) / 256) * 256;
-    size_t need = partial + (size_t)B * sizeof(int);
-    if (!ws || ws_bytes < need) { set_error("pool_norm: workspace too small (%zu < %zu)", ws_bytes, need); return TSIM_ERR_WORKSPACE; }
-    a.partial = (float*)ws;
-    a.ticket = (int*)((char*)ws + partial);
-    TSIM_CUDA(cudaMemsetAsync(a.ticket, 0, (size_t)B * sizeof(int), st));
+    a.ticket = (int*)((char*)ws + 256);
+    a.partial = (float*)((char*)ws + 256 + ticket_al);
   }
+  // the item counter and the tickets are adjacent: one memset
+  TSIM_CUDA(cudaMemsetAsync(ws, 0, 256 + (a.S > 1 ? (size_t)B * sizeof(int) : 0), st));
   const int esz = dtype_size(tok_dt);
   const int vec = 16 / esz;
   const bool vec_ok = (D % vec == 0) && (tok_stride_b % vec == 0) && (tok_stride_l % vec == 0) &&
                       (((uintptr_t)tok & 15) == 0);
   if (pool_stream_ok(a, esz, vec_ok)) {
     switch (tok_dt) {
-      case TSIM_F32: return launch_pool_stream<TSIM_F32>(a, st);
-      case TSIM_F16: return launch_pool_stream<TSIM_F16>(a, st);
-      default: return launch_pool_stream<TSIM_BF16>(a, st);
+      case TSIM_F32: return launch_pool_stream<TSIM_F32>(a, counter, st);
+      case TSIM_F16: return launch_pool_stream<TSIM_F16>(a, counter, st);
+      default: return launch_pool_stream<TSIM_BF16>(a, counter, st);
     }
   }
   switch (tok_dt) {

@@ -181,6 +181,31 @@ class SentenceTransformerWrapper(BaseEncoderModel):
             inv = torch.empty(0, dtype=torch.float32, device=dev)
         return out, inv
 
+    def encode_text_into(self, documents: List[str], store) -> List[int]:
+        """Text -> rows appended to an :class:`~text_similarity_b200.store.EmbeddingStore`, in document
+        order: every length-sorted batch is pooled, normalised, cast and written by ONE K1 launch
+        straight into the store's tail at its un-sorted positions (replaces the
+        per-row ``extend`` + ``stack`` of reference sentence_encoder.py:167-173).  Returns the labels."""
+        if not (isinstance(self.pooler, AvgPoolingStrategy) and isinstance(self.projection, nn.Identity)):
+            rows, inv = self.encode_text_normalized(documents, store.dtype)
+            return store.add(rows, inv).tolist()
+        self.to(self.params.device)
+        self.eval()
+        n = len(documents)
+        if n == 0:
+            return []
+        from . import ops
+        base = len(store)
+        labels = store._take_ids(n, None)
+        store._reserve(n)
+        with torch.no_grad():
+            for rows, feats in self._batches(documents):
+                tokens = self.context_embedder(**feats.to_dict())[0]
+                ops.pool_norm(tokens, feats.attention_mask, normalize=True, out=store.rows,
+                              out_rows=rows.to(tokens.device) + base, out_inv_norm=store.inv_norm)
+        store._register(labels)
+        return labels.tolist()
+
     def get_sentence_embedding_dimension(self):
         return self.context_embedder.config.hidden_size  # :175-176
 

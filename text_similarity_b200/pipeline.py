@@ -8,6 +8,7 @@ k is clamped by the corpus size (A6); results are best first, ties by lower inde
 """
 from __future__ import annotations
 
+import json
 import os
 import time
 from typing import Dict, List, Optional, Tuple, Union
@@ -172,56 +173,70 @@ class SemanticSearchPipeline(SentenceMiningPipeline):
     ``_search`` returning ``Dict[int, List[str]]`` best first, ``add_to_index`` /
     ``remove_from_index`` / ``num_indexed`` -- served by the EXACT engine: there is no ANN backend
     in this build (north_star), so ``ef`` / ``ef_construction`` / ``M`` are accepted and unused.
-    The encoded corpus is persisted at ``index_path/index.pt`` (the reference persists index.bin)."""
+    The "index" is an :class:`~text_similarity_b200.store.EmbeddingStore` (rows + inverse norms + ids
+    resident in HBM, dense under removal), persisted under ``index_path`` (the reference persists
+    ``index.bin``, :106-109,122) together with the texts."""
 
     def __init__(self, index_path, *args, **kwargs):
         super().__init__(kwargs.pop("corpus_chunk_size", 1 << 30), *args, **kwargs)
+        from .store import EmbeddingStore
         self.index_path = index_path
-        self._removed = set()
-        self._rows = self._inv = None
-        saved = os.path.join(self.index_path, "index.pt")
-        if os.path.exists(saved):
-            blob = torch.load(saved, map_location=self.params.device)
-            self._rows, self._inv = blob["rows"], blob["inv_norm"]
-            self._removed = set(blob.get("removed", []))
+        self.store: Optional[EmbeddingStore] = None
+        self._texts: Dict[int, str] = {}
+        if os.path.exists(os.path.join(self.index_path, "meta.json")):
+            self.store = EmbeddingStore.load(self.index_path, self.params.device, spare=1024)
+            with open(os.path.join(self.index_path, "texts.json")) as f:
+                self._texts = {int(k): v for k, v in json.load(f).items()}
         elif self.corpus is not None:
             self._index(self.corpus)
 
+    def _encode_into_store(self, texts: List[str]) -> List[int]:
+        from .store import EmbeddingStore
+        if hasattr(self.model, "encode_text_into"):
+            if self.store is None:
+                self.store = EmbeddingStore(self.model.get_sentence_embedding_dimension(), self._dtype(),
+                                            self.params.device, capacity=max(1024, len(texts)))
+            labels = self.model.encode_text_into(texts, self.store)
+        else:
+            rows = self.encode_corpus(texts)
+            if self.store is None:
+                self.store = EmbeddingStore(rows.shape[1], self._dtype(), self.params.device, capacity=max(1024, len(texts)))
+            labels = self.store.add(rows).tolist()
+        for lab, t in zip(labels, texts):
+            self._texts[int(lab)] = t
+        return labels
+
     def _index(self, corpus: List[str]):
-        os.makedirs(self.index_path, exist_ok=True)
-        self._rows, self._inv = self.model.encode_text_normalized(list(corpus), self._dtype())
+        self.store = None
+        self._texts = {}
+        self._encode_into_store(list(corpus))
         self._save()
 
     def _save(self):
-        torch.save({"rows": self._rows, "inv_norm": self._inv, "removed": sorted(self._removed)},
-                   os.path.join(self.index_path, "index.pt"))
+        os.makedirs(self.index_path, exist_ok=True)
+        self.store.save(self.index_path)
+        with open(os.path.join(self.index_path, "texts.json"), "w") as f:
+            json.dump({str(k): v for k, v in self._texts.items()}, f)
 
     def _search(self, queries: TextOrTensor, max_num_results: int) -> Dict[int, List[str]]:
         q = self._encode_queries(queries)
-        k = int(max_num_results)
-        fetch = min(self._rows.shape[0], k + len(self._removed))  # over-fetch past tombstones
-        _, idx = ops.search_topk(q.to(self._rows.dtype), self._rows, max(fetch, 1), corpus_inv_norm=self._inv)
-        out: Dict[int, List[str]] = {}
-        for qi, rows in enumerate(idx.cpu().tolist()):
-            hits = [r for r in rows if r >= 0 and r not in self._removed][:k]
-            out[qi] = [self.corpus[r] for r in hits]
-        return out
+        _, labels = self.store.search(q, int(max_num_results), mode=getattr(self.params, "search_mode", "auto"))
+        return {qi: [self._texts[lab] for lab in row if lab >= 0] for qi, row in enumerate(labels.cpu().tolist())}
 
     def __call__(self, queries: TextOrTensor, max_num_results: int):
         return self._search(queries, max_num_results)
 
     def add_to_index(self, text: Union[str, List[str]]):
         text = [text] if isinstance(text, str) else list(text)
-        rows, inv = self.model.encode_text_normalized(text, self._dtype())
-        self._rows = torch.cat([self._rows, rows]) if self._rows is not None else rows
-        self._inv = torch.cat([self._inv, inv]) if self._inv is not None else inv
+        labels = self._encode_into_store(text)
         self.corpus = list(self.corpus or []) + text
+        return labels
 
     def remove_from_index(self, ids):
-        n = 0 if self._rows is None else self._rows.shape[0]
-        for i in ids:
-            if 0 <= int(i) < n:  # unknown ids are skipped, like the reference's try/except (:164-169)
-                self._removed.add(int(i))
+        # unknown ids are skipped, like the reference's try/except (:164-169)
+        for lab in ids:
+            if self.store is not None and self.store.remove([int(lab)]):
+                self._texts.pop(int(lab), None)
 
     def num_indexed(self):
-        return (0 if self._rows is None else self._rows.shape[0]) - len(self._removed)
+        return 0 if self.store is None else len(self.store)
