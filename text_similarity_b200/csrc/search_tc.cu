@@ -240,39 +240,64 @@ __device__ __forceinline__ bool get_unit(const TcArgs& a, int it, int wid, int n
   return true;
 }
 
-// Threshold ladder.  lad[0..16) = ascending ordered-float score levels (written by tighten_kernel from
-// the bootstrap sample, immutable during this launch), lad[16..32) = how many candidate rows of this
-// query were seen so far, by ANY CTA, in [level i, level i+1).  A thread that has just inserted `n`
-// rows, all with score >= s, adds them to s's bin and raises its threshold to the highest level that
-// has >= KP rows at or above it.  Why that is a valid bound on the query's final KP-th best: every
-// counted row sits in a candidate list, or was evicted from a full list whose KP entries are all at
-// least as good -- either way >= KP candidates at or above the level reach select_rescore.
-// (Counts are read slightly stale and rows below the caller's own threshold are never counted:
-// both only delay a raise.)  Without this, after the bootstrap a query's threshold rises only when
-// one unit's own list fills, i.e. almost never with short units.
-__device__ __forceinline__ float ladder_update(uint32_t* lad, float s, uint32_t n, uint32_t KP, float thr) {
-  const uint32_t o = f32_to_ord(s);
-  uint32_t lev[kLadder], bin[kLadder];
+// Threshold ladder (layout and level function: tsim_common.cuh; levels and initial counts: tighten_kernel).
+// Each epilogue thread bins the rows it inserts into a private histogram (16 x 16-bit counters in
+// registers) and, at the end of a tile in which it inserted anything, adds the histogram to its query's
+// global counters (fire-and-forget atomics), reads them back once and raises its threshold to the
+// highest level that has >= KP rows at or above it.  Why that is a valid bound on the query's final
+// KP-th best: every counted row sits in a candidate list, or was evicted from a full list whose KP
+// entries are all at least as good -- either way >= KP candidates at or above the level reach
+// select_rescore.  (Counts are read slightly stale and rows that are not inserted are never counted:
+// both only delay a raise.)  Without this, after the bootstrap a query's threshold rises only when one
+// unit's own list fills, i.e. almost never with short units.
+struct Ladder {
+  float base, step, inv;
+  uint32_t hist[kLadder / 2];
+  uint32_t* g;
+  __device__ __forceinline__ void init(uint32_t* lad) {
+    g = lad;
+    base = INFINITY; step = 0.f; inv = 0.f;
+    if (g) {
+      const uint4 h = __ldg((const uint4*)g);
+      base = __uint_as_float(h.x); step = __uint_as_float(h.y); inv = __uint_as_float(h.z);
+    }
 #pragma unroll
-  for (int i = 0; i < kLadder / 4; ++i) {
-    const uint4 l = __ldg((const uint4*)lad + i);
-    const uint4 b = __ldcg((const uint4*)lad + kLadder / 4 + i);
-    lev[4 * i] = l.x; lev[4 * i + 1] = l.y; lev[4 * i + 2] = l.z; lev[4 * i + 3] = l.w;
-    bin[4 * i] = b.x; bin[4 * i + 1] = b.y; bin[4 * i + 2] = b.z; bin[4 * i + 3] = b.w;
+    for (int i = 0; i < kLadder / 2; ++i) hist[i] = 0;
   }
-  int j = -1;
+  __device__ __forceinline__ void count(float s) {
+    const int j = ladder_level(base, step, inv, s);     // base = +inf without a ladder: j = -1
+    if (j < 0) return;
+    const uint32_t inc = 1u << ((j & 1) * 16);
+    const int w = j >> 1;
 #pragma unroll
-  for (int i = 0; i < kLadder; ++i) j += (lev[i] <= o) ? 1 : 0;   // levels ascend: the last one <= o
-  if (j < 0) return thr;
-  atomicAdd(lad + kLadder + j, n);
-  uint32_t c = 0, best = 0;
-#pragma unroll
-  for (int i = kLadder - 1; i >= 0; --i) {
-    c += bin[i] + (i == j ? n : 0u);
-    if (best == 0 && c >= KP) best = lev[i];
+    for (int i = 0; i < kLadder / 2; ++i) hist[i] += (i == w) ? inc : 0u;
   }
-  return best ? fmaxf(thr, ord_to_f32(best)) : thr;
-}
+  // at most 256 rows are counted between two flushes (one tile), so the 16-bit counters cannot overflow
+  __device__ __forceinline__ float flush(float thr, uint32_t KP) {
+    uint32_t any = 0;
+#pragma unroll
+    for (int i = 0; i < kLadder / 2; ++i) any |= hist[i];
+    if (!g || !any) return thr;
+    uint32_t bin[kLadder];
+#pragma unroll
+    for (int i = 0; i < kLadder / 4; ++i) {
+      const uint4 b = __ldcg((const uint4*)g + kLadder / 4 + i);
+      bin[4 * i] = b.x; bin[4 * i + 1] = b.y; bin[4 * i + 2] = b.z; bin[4 * i + 3] = b.w;
+    }
+    uint32_t c = 0;
+    int best = -1;
+#pragma unroll
+    for (int i = kLadder - 1; i >= 0; --i) {
+      const uint32_t own = (hist[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
+      if (own) atomicAdd(g + kLadder + i, own);
+      c += bin[i] + own;
+      if (best < 0 && c >= KP) best = i;
+    }
+#pragma unroll
+    for (int i = 0; i < kLadder / 2; ++i) hist[i] = 0;
+    return best >= 0 ? fmaxf(thr, ladder_value(base, step, best)) : thr;
+  }
+};
 
 // ---- per-query candidate lists -----------------------------------------------------------------
 // Each epilogue thread owns the running top-KP (approx score, row) list of its query, sorted
@@ -296,11 +321,9 @@ struct RegList16 {
   // gm0..gm3: this lane's maxima over the chunk's four 8-column groups; a group is re-read only if
   // some lane of the warp has a candidate in it (warp-uniform test: tcgen05.ld is .sync.aligned)
   __device__ __forceinline__ float slow(uint32_t taddr, const float* cnp, float thr, int64_t row_base,
-                                        int64_t self_row, int lim, uint32_t* thr_g, uint32_t* lad, float gm0,
+                                        int64_t self_row, int lim, uint32_t* thr_g, Ladder& lad, float gm0,
                                         float gm1, float gm2, float gm3) {
     const float thr_in = thr;
-    float ins_min = INFINITY;   // rows inserted by this call: how many, and their lowest score
-    uint32_t ins_n = 0;
 #pragma unroll 1
     for (int g = 0; g < 4; ++g) {
       const float gm = g == 0 ? gm0 : g == 1 ? gm1 : g == 2 ? gm2 : gm3;
@@ -314,8 +337,7 @@ struct RegList16 {
         const float s = __uint_as_float(w[jj]) * cnp[j];
         const int64_t row = row_base + j;
         if (s > thr && j < lim && row != self_row) {
-          ins_min = fminf(ins_min, s);
-          ++ins_n;
+          lad.count(s);
           // a[] is sorted descending, so (s > a[i]) is monotone in i: entry i becomes the newcomer
           // where the predicate first turns true, the old a[i-1] after that, and stays otherwise.
           // Strict '>' puts the newcomer after equal scores (it has the larger row).
@@ -330,7 +352,6 @@ struct RegList16 {
         }
       }
     }
-    if (lad && ins_n) thr = ladder_update(lad, ins_min, ins_n, 16u, thr);
     if (thr > thr_in) atomicMax(thr_g, f32_to_ord(thr));
     return thr;
   }
@@ -372,17 +393,14 @@ struct SmemList {
   // costs two instructions unless some lane of the warp has a candidate in it, so the cost follows
   // the number of candidates, not the number of chunks that have one.
   __device__ __forceinline__ float slow(const float* sc, float thr, int64_t row_base, int64_t self_row, int lim,
-                                        uint32_t* thr_g, uint32_t* lad) {
+                                        uint32_t* thr_g, Ladder& lad) {
     const float thr_in = thr;
-    float ins_min = INFINITY;
-    uint32_t ins_n = 0;
     int cnt = *cntp & 0xffff, minpos = *cntp >> 16;
+    const int cnt0 = cnt;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const float v = sc[j];
       if (v > thr && j < lim && row_base + j != self_row) {
-        ins_min = fminf(ins_min, v);
-        ++ins_n;
         const int pos = cnt < KP ? cnt : minpos;
         ls[pos * kEpiThreads] = v;
         li[pos * kEpiThreads] = (uint32_t)(row_base + j);
@@ -395,7 +413,10 @@ struct SmemList {
       }
     }
     *cntp = cnt | (minpos << 16);
-    if (lad && ins_n) thr = ladder_update(lad, ins_min, ins_n, (uint32_t)KP, thr);
+    // ladder: the rows appended while the list was not full sit at [cnt0, cnt) (replacements of a full
+    // list's minimum are not counted: that list's own minimum is the threshold then)
+#pragma unroll 1
+    for (int pos = cnt0; pos < cnt; ++pos) lad.count(ls[pos * kEpiThreads]);
     if (thr > thr_in) atomicMax(thr_g, f32_to_ord(thr));
     return thr;
   }
@@ -540,7 +561,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       const bool qvalid = qg < a.Q;
       const int64_t self_row = a.self_on ? a.self_off + qg : -1;
       uint32_t* thr_g = a.thr + (qvalid ? qg : 0);
-      uint32_t* lad = (a.ladder && qvalid) ? a.ladder + (size_t)qg * (2 * kLadder) : nullptr;
+      Ladder lad;
+      lad.init((a.ladder && qvalid) ? a.ladder + (size_t)qg * (2 * kLadder) : nullptr);
       list.reset();
       float thr = qvalid ? -INFINITY : INFINITY;   // padded query lanes never insert
       // Tile metadata (the 256 inverse norms, 8 per lane, and the query's shared threshold) is
@@ -605,6 +627,13 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           else mbar_arrive(smem_u32(&tempty_bar[acc]));
         }
         if (++acc == 2) { acc = 0; aphase ^= 1; }
+        // ladder: publish this tile's insertions, pick up everybody else's (after the accumulator
+        // stage has been handed back: the MMA of the tile after next does not wait for this)
+        {
+          const float t0 = thr;
+          thr = lad.flush(thr, (uint32_t)KP);
+          if (thr > t0) atomicMax(thr_g, f32_to_ord(thr));
+        }
       }
       // flush this unit's list
       if (qvalid) list.flush(a.cand + ((size_t)qg * a.NC + a.slot_base + un.slot) * KP);

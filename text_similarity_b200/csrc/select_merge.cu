@@ -236,15 +236,37 @@ __global__ void __launch_bounds__(kSelThreads) tighten_kernel(const uint64_t* ca
   const uint64_t* src = cand + (size_t)q * NC * KP;
   const int64_t total = (int64_t)nslots * KP;
   const uint32_t thr_ord = thr[q];
-  if (tid == 0) n_sh = 0;
+  // A full list's minimum is a lower bound of the union's KP-th best: only keys at or above the best
+  // such bound can matter (at least KP of them exist), which leaves a few dozen keys to sort instead of
+  // nslots * KP.  One warp per list.
+  __shared__ unsigned long long bound_sh;
+  if (tid == 0) { n_sh = 0; bound_sh = 0ull; }
   __syncthreads();
+  for (int slot = tid >> 5; slot < nslots; slot += kSelThreads / 32) {
+    const uint64_t* sp = src + (size_t)slot * KP;
+    uint64_t mn = ~0ull;
+    int c = 0;
+    for (int i = tid & 31; i < KP; i += 32) {
+      const uint64_t key = __ldcg(sp + i);
+      if (key != 0) { ++c; mn = key < mn ? key : mn; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+      const uint64_t other = __shfl_xor_sync(0xffffffffu, mn, o);
+      mn = other < mn ? other : mn;
+    }
+    if ((tid & 31) == 0 && c == KP) atomicMax(&bound_sh, (unsigned long long)mn);
+  }
+  __syncthreads();
+  const uint64_t bound = bound_sh;
   int64_t cursor = 0;
   int n = 0;
   while (cursor < total) {
     int64_t take = min((int64_t)(kKeyCap - n), total - cursor);
     for (int64_t i = tid; i < take; i += blockDim.x) {
       uint64_t key = __ldcg(src + cursor + i);
-      if (key != 0 && (uint32_t)(key >> 32) >= thr_ord) keys[atomicAdd(&n_sh, 1)] = key;
+      if (key != 0 && key >= bound && (uint32_t)(key >> 32) >= thr_ord) keys[atomicAdd(&n_sh, 1)] = key;
     }
     cursor += take;
     __syncthreads();
@@ -265,44 +287,31 @@ __global__ void __launch_bounds__(kSelThreads) tighten_kernel(const uint64_t* ca
   sort_keys_desc(keys, np);
   if (tid == 0 && n >= KP) atomicMax(thr + q, (uint32_t)(keys[KP - 1] >> 32));
   if (!ladder) return;
-  // Threshold ladder for the main launch: levels 0..12 are the sample's own order statistics at
-  // geometrically spaced ranks KP .. 1 (each step cuts the pass rate by the same factor), levels
-  // 13..15 extrapolate above the sample's best (the full corpus's KP-th best usually ends up near
-  // it); counts start from the sample's top-KP rows.  Any ascending levels are VALID -- they only
-  // decide how fast the threshold can follow the data (see search_tc.cu, ladder_update).
-  __shared__ uint32_t lev[kLadder];
-  __shared__ uint32_t cum[kLadder + 1];
+  // Threshold ladder for the following launches: 16 evenly spaced levels from the sample's KP-th best
+  // (level 0 = the threshold just set) through its best (level 8) to as far again above it -- for
+  // Gaussian-like tails even steps in score are roughly geometric steps in rank, and the full corpus's
+  // KP-th best usually ends up near the sample's best.  ANY ascending levels are valid; they only decide
+  // how closely the threshold can follow the data (search_tc.cu, struct Ladder).  Counts start from the
+  // sample's own top-KP rows.
+  __shared__ uint32_t cnt[kLadder];
   uint32_t* lad = ladder + (size_t)q * 2 * kLadder;
-  if (n < KP) {   // no threshold was set: a ladder that never fires
-    if (tid < kLadder) { lad[tid] = 0xffffffffu; lad[kLadder + tid] = 0u; }
-    return;
-  }
-  if (tid < kLadder) {
-    uint32_t o;
-    if (tid <= 12) {
-      int rank = (int)(powf((float)KP, 1.f - (float)tid / 12.f) + 0.5f);
-      rank = max(1, min(KP, rank));
-      o = (uint32_t)(keys[rank - 1] >> 32);
-    } else {
-      const float a1 = key_score(keys[0]), akp = key_score(keys[KP - 1]);
-      const float f = tid == 13 ? 0.25f : tid == 14 ? 0.5f : 1.f;
-      float v = a1 + (a1 - akp) * f;
-      if (!(v >= a1)) v = a1;
-      o = f32_to_ord(v);
+  if (tid < kLadder) cnt[tid] = 0;
+  __syncthreads();
+  float base = INFINITY, step = 0.f, inv = 0.f;      // n < KP: no threshold was set -> a ladder that never fires
+  if (n >= KP) {
+    base = key_score(keys[KP - 1]);
+    step = (key_score(keys[0]) - base) * (1.f / 8.f);
+    if (!(step > 0.f) || !(step < INFINITY)) step = 0.f;
+    inv = step > 0.f ? 1.f / step : 0.f;
+    for (int i = tid; i < KP; i += blockDim.x) {
+      const int j = ladder_level(base, step, inv, key_score(keys[i]));
+      if (j >= 0) atomicAdd(&cnt[j], 1u);
     }
-    lev[tid] = o;
-  }
-  if (tid == 0) cum[kLadder] = 0;
-  __syncthreads();
-  if (tid < kLadder) {
-    uint32_t c = 0;
-    for (int i = 0; i < KP; ++i) c += ((uint32_t)(keys[i] >> 32) >= lev[tid]) ? 1u : 0u;
-    cum[tid] = c;
   }
   __syncthreads();
   if (tid < kLadder) {
-    lad[tid] = lev[tid];
-    lad[kLadder + tid] = cum[tid] - cum[tid + 1];   // rows in [lev[tid], lev[tid + 1])
+    lad[kLadder + tid] = cnt[tid];
+    lad[tid] = tid == 0 ? __float_as_uint(base) : tid == 1 ? __float_as_uint(step) : tid == 2 ? __float_as_uint(inv) : 0u;
   }
 }
 

@@ -73,12 +73,14 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
       p->Gq = workers / p->QB;
       if (p->Gq > T) p->Gq = (int)T;
       if (p->Gq < 1) p->Gq = 1;
-      // Bootstrap: with >= 16 queries the per-CTA lists' warm-up (every early score is a candidate)
-      // costs more than two extra launches; scan 2 strided sample tiles per worker first and turn
+      // Bootstrap: with >= 2 queries the per-CTA lists' warm-up (every early score is a candidate)
+      // costs more than two extra launches (measured on the fp8 12.5M x 384 shard: Q = 8 1.23 -> 1.02 ms); scan 1 strided sample tile per worker first and turn
       // their union's KP-th best into every query's starting threshold.
       const char* noboot = getenv("TSIM_NO_BOOT");
-      if (Q >= 16 && T >= 32 * (int64_t)p->Gq && !(noboot && noboot[0] == '1')) {
-        int64_t tpw = 2;                                                // sample tiles per worker
+      int64_t minq = 2;
+      if (const char* e = getenv("TSIM_BOOT_MINQ")) { int64_t v = atoll(e); if (v >= 1) minq = v; }   // experiment knob
+      if (Q >= minq && T >= 32 * (int64_t)p->Gq && !(noboot && noboot[0] == '1')) {
+        int64_t tpw = 1;                                                // sample tiles per worker
         if (const char* e = getenv("TSIM_BOOT_TPW")) { int64_t v = atoll(e); if (v >= 1 && v <= 16) tpw = v; }
         p->boot_stride = T / (tpw * (int64_t)p->Gq);                    // >= 2
         p->boot_tiles = (T + p->boot_stride - 1) / p->boot_stride;      // every multiple of the stride below T

@@ -19,10 +19,11 @@ constexpr float kPoolEps = 1e-9f;  // clamp in AvgPoolingStrategy, reference mod
 // differ by more than 2 * kApproxEps (see select_merge.cu); tests measure the real error.
 constexpr float kApproxEps = 5e-5f;
 
-// Threshold ladder (search_tc.cu / select_merge.cu): per query, kLadder ascending score levels and
-// the number of candidate rows seen so far at or above each; once >= KP rows sit at or above a level
-// that level is a valid global threshold.  Lets every CTA filter with (nearly) the threshold a single
-// sequential top-KP scan of everything seen so far would have.
+// Threshold ladder (search_tc.cu / select_merge.cu): per query, kLadder ascending score levels
+// level(i) = base + i * step and the number of candidate rows seen so far in [level(i), level(i+1));
+// once >= KP rows sit at or above a level, that level is a valid global threshold.  Lets every CTA
+// filter with (nearly) the threshold a single sequential top-KP scan of everything seen so far would
+// have.  Per-query record: 2 * kLadder words = { base, step, 1/step, pad..., counts[kLadder] }.
 constexpr int kLadder = 16;
 
 void set_error(const char* fmt, ...);
@@ -110,6 +111,17 @@ __device__ __forceinline__ uint64_t pack_key(float s, uint32_t idx) {
 }
 __device__ __forceinline__ float key_score(uint64_t k) { return ord_to_f32((uint32_t)(k >> 32)); }
 __device__ __forceinline__ uint32_t key_idx(uint64_t k) { return 0xffffffffu - (uint32_t)k; }
+
+// ---- threshold ladder ---------------------------------------------------------------------
+__device__ __forceinline__ float ladder_value(float base, float step, int i) { return fmaf((float)i, step, base); }
+// Highest level whose VALUE is <= s (-1: s is below the ladder).  The value test makes the answer
+// safe against rounding in the division-free index estimate: a row is never credited above its score.
+__device__ __forceinline__ int ladder_level(float base, float step, float inv, float s) {
+  const float t = (s - base) * inv;
+  int j = t >= (float)(kLadder - 1) ? kLadder - 1 : (t > 0.f ? (int)t : 0);
+  if (ladder_value(base, step, j) > s) --j;
+  return j;
+}
 
 // ---- warp helpers ------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum_f64(double v) {
