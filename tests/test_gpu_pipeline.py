@@ -180,3 +180,43 @@ def test_ranking_pipeline_and_helpers(stack):
     x[2500] = x[5]
     dup = near_duplicates(x.cuda(), threshold=0.99, k=3)
     assert dup == {5: [2000, 2500], 2000: [5, 2500], 2500: [5, 2000]}
+
+
+def test_cuda_graph_replay_equals_eager_search():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from text_similarity_b200.sharded import ShardedCorpus
+    g = torch.Generator(device="cuda").manual_seed(11)
+    c = torch.randn(1_300_000, 64, generator=g, device="cuda")
+    c = (c / c.norm(dim=-1, keepdim=True)).to(torch.bfloat16)
+    corpus = ShardedCorpus(c, idx_base=1000)
+    for Q in (1, 24):                                   # no bootstrap / bootstrap + ladder plans
+        for rep in range(3):                            # first call captures, the others replay
+            q = torch.randn(Q, 64, generator=g, device="cuda")
+            q = (q / q.norm(dim=-1, keepdim=True)).to(torch.bfloat16)
+            es, ei = corpus.search(q, 10)
+            gs, gi = corpus.search_graphed(q, 10)
+            assert torch.equal(gi, ei) and torch.equal(gs, es)
+    hs = torch.empty(24, 10, dtype=torch.float32).pin_memory()
+    hi = torch.empty(24, 10, dtype=torch.int64).pin_memory()
+    corpus.search_host(q.cpu().pin_memory(), 10, hs, hi, graphed=True)
+    torch.cuda.synchronize()
+    assert torch.equal(hi, ei.cpu()) and torch.equal(hs, es.cpu())
+
+
+def test_retrieval_accuracy_meter_matches_dense_argmax():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from src.utils.metrics import RetrievalAccuracyMeter
+    g = torch.Generator().manual_seed(5)
+    src = torch.randn(700, 96, generator=g)
+    tgt = src + 0.9 * torch.randn(700, 96, generator=g)        # noisy "translations": some retrievals fail
+    meter = RetrievalAccuracyMeter(print_wrong_matches=True)
+    meter.update(src.cuda(), tgt.cuda(), [f"s{i}" for i in range(700)], [f"t{i}" for i in range(700)])
+    dense = O.cosine_scores_exact(src, tgt)                      # what the reference's cos_sim + np.argmax computes
+    exp_fwd = (dense.argmax(1) == torch.arange(700)).double().mean().item()
+    exp_bwd = (dense.argmax(0) == torch.arange(700)).double().mean().item()
+    assert 0.2 < exp_fwd < 1.0
+    assert abs(meter.src2tgt - exp_fwd) < 1e-6 and abs(meter.tgt2src - exp_bwd) < 1e-6
+    assert abs(meter.avg - (exp_fwd + exp_bwd) / 2) < 1e-6
+    assert len(meter.lines) == int(round((1 - exp_fwd) * 700)) and "INCORRECT" in str(meter)

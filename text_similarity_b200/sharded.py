@@ -65,6 +65,53 @@ class ShardedCorpus:
         self.inv_norm = inv_norm if inv_norm is not None else (
             ops.row_inv_norm(shard) if shard.shape[0] and shard.is_cuda else None)
         self._gather_buf = {}
+        self._graphs = {}
+
+    # -- CUDA-graph replay of the local search -------------------------------------------------------
+    # One search is ~8 dependent stream operations (threshold memset, sample pass, tighten, main pass,
+    # select / re-score, two fallback kernels); replaying them as one captured graph removes the launch
+    # gaps and the host-side planning, which matters for the ~1 ms small-batch (HBM-bound) searches.
+    def _graph(self, Q: int, k: int, dtype: torch.dtype, exclude_self_base: int, mode: str):
+        key = (Q, k, dtype, exclude_self_base, mode)
+        g = self._graphs.get(key)
+        if g is not None:
+            return g
+        dev = self.shard.device
+        q_static = torch.zeros(Q, self.shard.shape[1], dtype=dtype, device=dev)
+        s64 = torch.empty(Q, k, dtype=torch.float64, device=dev)
+        idx = torch.empty(Q, k, dtype=torch.int64, device=dev)
+        scores = torch.empty(Q, k, dtype=torch.float32, device=dev)
+
+        def run():
+            ops.search_topk(q_static, self.shard, k, corpus_inv_norm=self.inv_norm, idx_base=self.idx_base,
+                            exclude_self_base=exclude_self_base, mode=mode, out_scores=scores,
+                            out_score64=s64, out_idx=idx)
+
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            run()                      # warm-up on the capture stream: sizes that stream's workspace
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            run()
+        g = self._graphs[key] = (graph, q_static, scores, s64, idx)
+        return g
+
+    def search_graphed(self, queries: torch.Tensor, k: int, exclude_self_base: int = -1, mode: str = "auto"
+                       ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """`search` with the local search replayed from a CUDA graph captured on first use of this
+        (batch size, k, dtype).  The returned tensors are the graph's static outputs: consume them
+        before the next call with the same shape (or clone)."""
+        graph, q_static, scores, s64, idx = self._graph(queries.shape[0], k, queries.dtype, exclude_self_base, mode)
+        q_static.copy_(queries, non_blocking=True)
+        graph.replay()
+        if self.world == 1:
+            return scores, idx
+        g64, gidx = gather_shard_results(s64, idx, self.group)
+        merged, _, rows = ops.merge_topk(g64, gidx, k, self.world)
+        return merged, rows
 
     def search_local(self, queries: torch.Tensor, k: int, **kw):
         return ops.search_topk(queries, self.shard, k, corpus_inv_norm=self.inv_norm,
@@ -92,9 +139,12 @@ class ShardedCorpus:
         return scores, rows
 
     def search_host(self, host_queries: torch.Tensor, k: int, host_scores: torch.Tensor,
-                    host_idx: torch.Tensor) -> None:
+                    host_idx: torch.Tensor, graphed: bool = False) -> None:
         """End-to-end step: pinned host queries -> device, search, results -> pinned host."""
-        q = host_queries.to(self.shard.device, non_blocking=True)
-        scores, rows = self.search(q, k)
+        if graphed:
+            scores, rows = self.search_graphed(host_queries, k)       # H2D straight into the graph's input
+        else:
+            q = host_queries.to(self.shard.device, non_blocking=True)
+            scores, rows = self.search(q, k)
         host_scores.copy_(scores, non_blocking=True)
         host_idx.copy_(rows, non_blocking=True)
