@@ -35,6 +35,10 @@ for (N, Q, D, k) in [(300_001, 257, 768, 10), (200_000, 64, 384, 100), (50_000, 
     s2, i2 = sc.search(qs, 5, exclude_self_base=1000)
     fs2, fi2 = ops.search_topk(qs, full, 5, exclude_self_base=1000)
     same = same and torch.equal(i2, fi2) and torch.equal(s2, fs2)
+    # local search replayed from a CUDA graph, then the same all-gather + merge
+    for _ in range(2):
+        s3, i3 = sc.search_graphed(q, k)
+        same = same and torch.equal(i3, fi) and torch.equal(s3, fs)
     t = torch.tensor([int(same)], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     ok = ok and bool(t.item())

@@ -210,7 +210,7 @@ def test_retrieval_accuracy_meter_matches_dense_argmax():
     from src.utils.metrics import RetrievalAccuracyMeter
     g = torch.Generator().manual_seed(5)
     src = torch.randn(700, 96, generator=g)
-    tgt = src + 0.9 * torch.randn(700, 96, generator=g)        # noisy "translations": some retrievals fail
+    tgt = src + 2.5 * torch.randn(700, 96, generator=g)        # noisy "translations": ~1 in 4 retrievals fails
     meter = RetrievalAccuracyMeter(print_wrong_matches=True)
     meter.update(src.cuda(), tgt.cuda(), [f"s{i}" for i in range(700)], [f"t{i}" for i in range(700)])
     dense = O.cosine_scores_exact(src, tgt)                      # what the reference's cos_sim + np.argmax computes

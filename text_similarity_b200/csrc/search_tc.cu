@@ -397,20 +397,28 @@ struct SmemList {
     const float thr_in = thr;
     int cnt = *cntp & 0xffff, minpos = *cntp >> 16;
     const int cnt0 = cnt;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float v = sc[j];
-      if (v > thr && j < lim && row_base + j != self_row) {
-        const int pos = cnt < KP ? cnt : minpos;
-        ls[pos * kEpiThreads] = v;
-        li[pos * kEpiThreads] = (uint32_t)(row_base + j);
-        if (cnt < KP) ++cnt;
-        if (cnt == KP) {                        // full: locate the new minimum
-          const uint64_t r = smem_list_min<KP>(ls);
-          minpos = (int)(r >> 32);
-          thr = fmaxf(thr, __uint_as_float((uint32_t)r));
-        }
+    auto put = [&](float v, int j) {
+      const int pos = cnt < KP ? cnt : minpos;
+      ls[pos * kEpiThreads] = v;
+      li[pos * kEpiThreads] = (uint32_t)(row_base + j);
+      if (cnt < KP) ++cnt;
+      if (cnt == KP) {                        // full: locate the new minimum
+        const uint64_t r = smem_list_min<KP>(ls);
+        minpos = (int)(r >> 32);
+        thr = fmaxf(thr, __uint_as_float((uint32_t)r));
       }
+    };
+    // whole chunk inside the corpus and no query of this warp has its own row in it (the usual case):
+    // one compare per column
+    const bool plain = lim >= 32 && (self_row < row_base || self_row >= row_base + 32);
+    if (__all_sync(0xffffffffu, plain)) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (sc[j] > thr) put(sc[j], j);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (sc[j] > thr && j < lim && row_base + j != self_row) put(sc[j], j);
     }
     *cntp = cnt | (minpos << 16);
     // ladder: the rows appended while the list was not full sit at [cnt0, cnt) (replacements of a full
