@@ -218,7 +218,7 @@ class EmbeddingStore:
                 s = i & 1
                 if events[s] is not None:
                     events[s].synchronize()          # the previous copy out of this buffer has finished
-                stages[s][:e - b].copy_(torch.from_numpy(src[b:e]))
+                stages[s][:e - b].numpy()[:] = src[b:e]     # page cache -> pinned staging buffer
                 with torch.cuda.stream(copy_stream):
                     dst[b:e].copy_(stages[s][:e - b], non_blocking=True)
                     events[s] = torch.cuda.Event()
