@@ -88,8 +88,7 @@ struct PoolArgs {
   int* ticket;            // [B]
   void* out; int out_dt; int64_t out_stride; const int64_t* out_rows;
   float* out_inv; int normalize;
-  int dbg;                // TSIM_POOL_DEBUG bits (diagnosis only): 1 = consumers skip the accumulation,
-                          // 2 = static round-robin items, 4 = finisher skips its work
+  int dbg;                // TSIM_POOL_DEBUG bits (diagnosis only): 1 = skip the accumulation
 };
 
 template <int DT, int VEC>
@@ -224,31 +223,8 @@ __global__ void __launch_bounds__(256) pool_norm_kernel(PoolArgs a) {
   if (a.out_inv && tid == 0) a.out_inv[orow] = 1.f / fmaxf(sqrtf(ss2), (float)kCosEps);
 }
 
-// ---- K1, streaming variant ---------------------------------------------------------------------
-// Persistent CTAs, two per SM, three warp roles around a shared-memory ring of up to 8 stages (a stage =
-// one chunk of whole token rows, <= 16 KB; ~90 KB per CTA):
-//  * producer warp: takes (sentence, token-split) items from a global counter (CTAs that drew short
-//    sentences simply take more), reads an item's mask weights one item AHEAD (the latency hides
-//    behind the copies in flight), skips chunks whose tokens are all masked (trailing padding is
-//    never read) and moves each remaining chunk of up to 32 tokens -- one contiguous run of the
-//    token tensor -- into a ring stage with ONE 1-D bulk async copy (TMA, UBLKCP) that completes on
-//    the stage's mbarrier;
-//  * 8 consumer warps (thread = 16-byte column x token sub-row): wait on the barrier, accumulate
-//    weight * token from shared memory in fp32, hand the stage back; at an item's END stage they
-//    drop their partial sums into one of two fold buffers and go straight on to the next item;
-//  * finisher warp: folds the sub-rows in a fixed order, divides by the token count, L2-normalises,
-//    casts, stores the row and its inverse norm -- with warp shuffles only, off the streaming path.
-// HBM-bound: ~180 KB of copies in flight per SM, independent of register pressure.
-constexpr int kPsMaxStages = 8;          // ring depth: as many stages as fit in half an SM's shared memory
-constexpr int kPsStageBytes = 16 * 1024;  // upper bound of a stage (a chunk = up to 32 whole token rows)
-constexpr int kPsConsumers = 256;
-constexpr int kPsThreads = kPsConsumers + 64;   // + producer warp + finisher warp
-constexpr int kPsMaxTL = 512;    // tokens per item (the launcher raises the split count to keep this)
-
-// kind 0: data chunk; 1: data chunk (ntok may be 0) that also ends item `item` (cnt = sum of its weights);
-// 2: no more items
-struct PsHdr { float w[32]; int ntok; int kind; float cnt; int pad; long long item; long long pad2; };
-struct PsMail { long long item; float cnt; int pad; };   // consumers -> finisher, one per fold buffer
+// ---- helpers of the streaming kernel: mbarrier / bulk-copy PTX, shared-memory vector decode ------
+constexpr int kPsStageBytes = 16 * 1024;  // upper bound of a ring stage (a chunk = up to 32 whole token rows)
 
 __device__ __forceinline__ uint32_t ps_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ps_mbar_init(uint32_t bar, uint32_t count) {
@@ -305,259 +281,271 @@ template <> struct SmemVec<TSIM_BF16> {
   }
 };
 
-template <int DT>
-__global__ void __launch_bounds__(kPsThreads, 2) pool_norm_stream_kernel(PoolArgs a, int64_t nitems, int CT, int nst, int stage_bytes, int* counter) {
-  extern __shared__ __align__(128) unsigned char ps_raw[];
+// ---- K1, streaming kernel -------------------------------------------------------------------------
+// One persistent CTA per SM; every warp is a self-contained streaming reducer with its OWN two-stage
+// shared-memory ring, so there is no hand-off between warps anywhere:
+//   * it draws (sentence, token-split) items from a global counter and reads an item's mask weights one
+//     item ahead;
+//   * lane 0 moves each chunk of up to 32 whole token rows (one contiguous run of the token tensor,
+//     fully masked chunks skipped, trailing padding never read) with ONE 1-D bulk async copy (TMA,
+//     UBLKCP) that completes on the stage's mbarrier -- always two chunks in flight per warp, across
+//     item boundaries;
+//   * the warp accumulates weight * token from its stage into registers (lane = 16-byte columns
+//     lane, lane + 32, ...), and at an item's last chunk finishes the row itself: token count, mean
+//     (modules.py:168-170), L2 norm, cast, store at out_rows[b], inverse norm -- warp shuffles only.
+// ~14 chunks (210 KB) in flight per SM; no block-level barrier after start-up.
+constexpr int kPwStages = 2;          // ring stages per warp
+constexpr int kPwMaxWarps = 8;
+constexpr int kPwMaxTL = 256;         // tokens per item (the launcher raises the split count to keep this)
+struct PwHdr { float w[32]; int ntok; int last; float cnt; int pad; long long item; long long pad2; };
+
+template <int DT, int NV>
+__global__ void __launch_bounds__(kPwMaxWarps * 32, 1)
+pool_norm_warp_kernel(PoolArgs a, int64_t nitems, int CT, int stage_bytes, int* counter) {
+  extern __shared__ __align__(128) unsigned char pw_raw[];
   constexpr int VEC = SmemVec<DT>::N;
   constexpr int ESZ = 16 / VEC;
-  constexpr int NCW = kPsConsumers / 32;                               // consumer warps
-  unsigned char* data = ps_raw;                                        // [nst][stage_bytes]
-  PsHdr* hdr = (PsHdr*)(ps_raw + (size_t)nst * stage_bytes);           // [nst]
-  float* wbuf = (float*)(hdr + nst);                             // [kPsMaxTL] producer-private weights
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  // per warp: [stages][stage_bytes] data | hdr[stages] | wbuf[kPwMaxTL] | full[stages]
+  const size_t per_warp = (size_t)kPwStages * stage_bytes + kPwStages * sizeof(PwHdr) + kPwMaxTL * sizeof(float) + 64;
+  unsigned char* base = pw_raw + (size_t)warp * per_warp;
+  unsigned char* data = base;
+  PwHdr* hdr = (PwHdr*)(base + (size_t)kPwStages * stage_bytes);
+  float* wbuf = (float*)(hdr + kPwStages);
+  uint64_t* full = (uint64_t*)(wbuf + kPwMaxTL);
   const int nvec = (int)(a.D / VEC);
-  const int rpi = kPsConsumers / nvec;                                 // token sub-rows per pass (>= 1)
-  float* fold = wbuf + kPsMaxTL;                                       // [2][rpi * D] fold buffers
-  PsMail* mail = (PsMail*)(fold + 2 * (size_t)rpi * a.D);              // [2]
-  uint64_t* bars = (uint64_t*)(mail + 2);                              // full[nst], empty[nst], fold_full[2], fold_empty[2]
-  uint64_t* fold_full = bars + 2 * nst;
-  uint64_t* fold_empty = fold_full + 2;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) {
-    for (int s = 0; s < nst; ++s) {
-      ps_mbar_init(ps_smem(&bars[s]), 1);
-      ps_mbar_init(ps_smem(&bars[nst + s]), NCW);
-    }
-    for (int s = 0; s < 2; ++s) { ps_mbar_init(ps_smem(&fold_full[s]), NCW); ps_mbar_init(ps_smem(&fold_empty[s]), 1); }
+  if (lane == 0) {
+    for (int s = 0; s < kPwStages; ++s) ps_mbar_init(ps_smem(&full[s]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  __syncthreads();
+  __syncwarp();
 
-  if (warp == NCW) {
-    // ===================== producer warp =====================
-    int stage = 0; uint32_t phase = 0;
-    float wn[kPsMaxTL / 32];
-    auto next_item = [&]() -> int64_t {     // CTA c starts with item c; further items come from the counter
-      int v = 0;
-      if (lane == 0) v = atomicAdd(counter, 1);
-      return (int64_t)__shfl_sync(0xffffffffu, v, 0) + gridDim.x;
-    };
-    int64_t static_next = (int64_t)blockIdx.x + gridDim.x;   // dbg bit 2: static round-robin items
-    auto load_mask = [&](int64_t item) {
-      const int64_t b = item / a.S; const int sp = (int)(item % a.S);
-      const int l0 = sp * a.TL, tl = min((int)a.L, l0 + a.TL) - l0;
+  const int64_t stride_items = (int64_t)gridDim.x * nwarps;
+  auto next_item = [&]() -> int64_t {       // warp g starts with item g; further items come from the counter
+    int v = 0;
+    if (lane == 0) v = atomicAdd(counter, 1);
+    return (int64_t)__shfl_sync(0xffffffffu, v, 0) + stride_items;
+  };
+  float wn[kPwMaxTL / 32];
+  auto load_mask = [&](int64_t item) {
+    const int64_t b = item / a.S; const int sp = (int)(item % a.S);
+    const int l0 = sp * a.TL, tl = min((int)a.L, l0 + a.TL) - l0;
 #pragma unroll
-      for (int j = 0; j < kPsMaxTL / 32; ++j)
-        wn[j] = (lane + 32 * j < tl) ? mask_value(a.mask, a.mask_dt, b * a.msb + l0 + lane + 32 * j) : 0.f;
-    };
-    int64_t item = blockIdx.x;
-    if (item < nitems) load_mask(item);
-    while (item < nitems) {
-      const int64_t b = item / a.S; const int sp = (int)(item % a.S);
-      const int l0 = sp * a.TL, tl = min((int)a.L, l0 + a.TL) - l0;
-      float cnt = 0.f;
-      int lend = 0;                                                   // one past the item's last real token
+    for (int j = 0; j < kPwMaxTL / 32; ++j)
+      wn[j] = (lane + 32 * j < tl) ? mask_value(a.mask, a.mask_dt, b * a.msb + l0 + lane + 32 * j) : 0.f;
+  };
+
+  // ---- issue side: the (item, chunk) cursor ----
+  int64_t p_item = (int64_t)blockIdx.x * nwarps + warp, p_next = -1;
+  int p_lend = 0, p_lc = 0, p_l0 = 0;
+  float p_cnt = 0.f;
+  bool p_open = false;                    // wbuf / p_lend describe p_item
+  if (p_item < nitems) load_mask(p_item);
+  uint32_t issued = 0, consumed = 0;
+  auto open_item = [&]() {                // wn holds p_item's mask: publish it, prefetch the next one's
+    const int sp = (int)(p_item % a.S);
+    p_l0 = sp * a.TL;
+    const int tl = min((int)a.L, p_l0 + a.TL) - p_l0;
+    float cnt = 0.f;
+    int lend = 0;
 #pragma unroll
-      for (int j = 0; j < kPsMaxTL / 32; ++j) {
-        if (lane + 32 * j < tl) wbuf[lane + 32 * j] = wn[j];
-        cnt += wn[j];
-        if (wn[j] != 0.f) lend = lane + 32 * j + 1;
-      }
-      cnt = warp_sum_f32(cnt);
+    for (int j = 0; j < kPwMaxTL / 32; ++j) {
+      if (lane + 32 * j < tl) wbuf[lane + 32 * j] = wn[j];
+      cnt += wn[j];
+      if (wn[j] != 0.f) lend = lane + 32 * j + 1;
+    }
+    p_cnt = warp_sum_f32(cnt);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) lend = max(lend, __shfl_xor_sync(0xffffffffu, lend, o));
-      __syncwarp();
-      int64_t nxt;
-      if (a.dbg & 2) { nxt = static_next; static_next += gridDim.x; } else nxt = next_item();
-      if (nxt < nitems) load_mask(nxt);                               // in flight during this item's copies
-      // chunks up to the last real token (trailing padding is never read); the chunk that holds it
-      // also closes the item (kind 1); an item without any real token is a bare END stage
-      for (int lc = 0; lc < lend || lc == 0; lc += CT) {
-        const int nt = max(0, min(CT, lend - lc));
-        const bool last = lc + CT >= lend;
+    for (int o = 16; o > 0; o >>= 1) lend = max(lend, __shfl_xor_sync(0xffffffffu, lend, o));
+    p_lend = lend; p_lc = 0; p_open = true;
+    __syncwarp();
+    p_next = next_item();
+    if (p_next < nitems) load_mask(p_next);
+  };
+  // issue the next chunk into stage issued % kPwStages; false when there is nothing left to issue
+  auto issue_one = [&]() -> bool {
+    for (;;) {
+      if (p_item >= nitems) return false;
+      if (!p_open) open_item();
+      // chunks up to the item's last real token; the chunk that holds it closes the item; an item
+      // without any real token is a bare closing stage
+      while (p_lc < p_lend || p_lc == 0) {
+        const int lc = p_lc;
+        p_lc += CT;
+        const int nt = max(0, min(CT, p_lend - lc));
+        const bool last = lc + CT >= p_lend;
         const float w = lane < nt ? wbuf[lc + lane] : 0.f;
         const unsigned nz = __ballot_sync(0xffffffffu, w != 0.f);
-        if (!nz && !last) continue;                                   // all masked: not read at all
-        ps_mbar_wait(ps_smem(&bars[nst + stage]), phase ^ 1);
-        hdr[stage].w[lane] = w;
-        if (lane == 0) {
-          hdr[stage].ntok = nt; hdr[stage].kind = last ? 1 : 0;
-          hdr[stage].cnt = cnt; hdr[stage].item = item;
-        }
+        if (!nz && !last) continue;                                     // all masked: not read at all
+        const int st = (int)(issued % kPwStages);
+        hdr[st].w[lane] = w;
+        if (lane == 0) { hdr[st].ntok = nt; hdr[st].last = last ? 1 : 0; hdr[st].cnt = p_cnt; hdr[st].item = p_item; }
         __syncwarp();
         if (lane == 0) {
           const uint32_t bytes = (uint32_t)nt * (uint32_t)a.D * ESZ;
-          const uint32_t fb = ps_smem(&bars[stage]);
+          const uint32_t fb = ps_smem(&full[st]);
           if (bytes) {
+            // the stage was read by this warp's generic loads: order them before the async-proxy write
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             ps_mbar_expect_tx(fb, bytes);
-            ps_bulk_load(ps_smem(data + (size_t)stage * stage_bytes),
-                         (const unsigned char*)a.tok + (b * a.sb + (int64_t)(l0 + lc) * a.D) * ESZ, bytes, fb);
+            const int64_t b = p_item / a.S;
+            ps_bulk_load(ps_smem(data + (size_t)st * stage_bytes),
+                         (const unsigned char*)a.tok + (b * a.sb + (int64_t)(p_l0 + lc) * a.D) * ESZ, bytes, fb);
           } else {
             ps_mbar_arrive(fb);
           }
         }
-        if (++stage == nst) { stage = 0; phase ^= 1; }
+        ++issued;
+        if (last) { p_item = p_next; p_open = false; }
+        return true;
       }
-      item = nxt;
+      p_item = p_next; p_open = false;      // not reached: the loop above always ends with a closing chunk
     }
-    ps_mbar_wait(ps_smem(&bars[nst + stage]), phase ^ 1);
-    if (lane == 0) {
-      hdr[stage].kind = 2;
-      ps_mbar_arrive(ps_smem(&bars[stage]));
-    }
-    return;
-  }
+  };
 
-  if (warp == NCW + 1) {
-    // ===================== finisher warp =====================
-    int fb = 0; uint32_t fphase = 0;   // bit fb = phase of fold_full[fb]
-    for (;;) {
-      ps_mbar_wait(ps_smem(&fold_full[fb]), (fphase >> fb) & 1u);
-      fphase ^= 1u << fb;
-      const int64_t item = mail[fb].item;
-      float cnt = mail[fb].cnt;
-      if (item < 0) break;
-      if (a.dbg & 4) { __syncwarp(); if (lane == 0) ps_mbar_arrive(ps_smem(&fold_empty[fb])); fb ^= 1; continue; }
-      const int64_t b = item / a.S; const int sp = (int)(item % a.S);
-      float* rb = fold + (size_t)fb * rpi * a.D;
-      // fold the token sub-rows in a fixed order; pooled sums land in row 0 of the buffer
-      for (int d = lane * 4; d < a.D; d += 128) {
-        float4 t = *(const float4*)(rb + d);
-        for (int rr = 1; rr < rpi; ++rr) {
-          const float4 u = *(const float4*)(rb + (size_t)rr * a.D + d);
-          t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
-        }
-        if (a.S > 1) *(float4*)(a.partial + ((int64_t)b * a.S + sp) * a.D + d) = t;
-        else *(float4*)(rb + d) = t;
-      }
-      bool finish = true;
-      if (a.S > 1) {
-        // the last CTA to finish a split of row b adds the partial sums in a fixed order
-        __threadfence();
-        __syncwarp();
-        int last = 0;
-        if (lane == 0) last = (atomicAdd(&a.ticket[b], 1) == a.S - 1);
-        last = __shfl_sync(0xffffffffu, last, 0);
-        finish = last != 0;
-        if (finish) {
-          __threadfence();
-          for (int d = lane * 4; d < a.D; d += 128) {
-            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int s2 = 0; s2 < a.S; ++s2) {
-              const float4 u = __ldcg((const float4*)(a.partial + ((int64_t)b * a.S + s2) * a.D + d));
-              t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
-            }
-            *(float4*)(rb + d) = t;
-          }
-          float c = 0.f;
-          for (int l = lane; l < a.L; l += 32) c += mask_value(a.mask, a.mask_dt, b * a.msb + l);
-          cnt = warp_sum_f32(c);
-        }
-      }
-      if (finish) {
-        __syncwarp();
-        const float denom = fmaxf(cnt, kPoolEps);  // modules.py:168
-        float ss = 0.f, amax = 0.f;
-        for (int d = lane * 4; d < a.D; d += 128) {
-          float4 t = *(const float4*)(rb + d);
-          t.x /= denom; t.y /= denom; t.z /= denom; t.w /= denom;  // modules.py:170
-          *(float4*)(rb + d) = t;
-          ss = fmaf(t.x, t.x, ss); ss = fmaf(t.y, t.y, ss); ss = fmaf(t.z, t.z, ss); ss = fmaf(t.w, t.w, ss);
-          amax = fmaxf(fmaxf(amax, fmaxf(fabsf(t.x), fabsf(t.y))), fmaxf(fabsf(t.z), fabsf(t.w)));
-        }
-        float scale = 1.f;
-        if (a.normalize) scale = 1.f / fmaxf(sqrtf(warp_sum_f32(ss)), (float)kCosEps);
-        if (a.out_dt == TSIM_E4M3) {
-          // per-row power-of-two scale: largest |element| lands in [64, 128) (e4m3 max is 448)
-          const float bm = warp_max_f32(amax) * scale;
-          if (bm > 0.f) {
-            int e;
-            frexpf(bm, &e);  // bm = f * 2^e, f in [0.5, 1)
-            scale *= exp2f((float)(7 - e));
-          }
-        }
-        const int64_t orow = a.out_rows ? a.out_rows[b] : b;
-        float ss2 = 0.f;
-        for (int d = lane * 4; d < a.D; d += 128) {
-          const float4 t = *(const float4*)(rb + d);
-          const float v4[4] = {t.x, t.y, t.z, t.w};
+  float acc[NV][VEC];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float st = round_store(a.out, a.out_dt, orow * a.out_stride + d + j, v4[j] * scale);
-            ss2 = fmaf(st, st, ss2);
-          }
-        }
-        if (a.out_inv) {
-          ss2 = warp_sum_f32(ss2);
-          if (lane == 0) a.out_inv[orow] = 1.f / fmaxf(sqrtf(ss2), (float)kCosEps);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) ps_mbar_arrive(ps_smem(&fold_empty[fb]));
-      fb ^= 1;
-    }
-    return;
-  }
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[i][j] = 0.f;
 
-  // ===================== consumers =====================
-  const bool active = tid < rpi * nvec;
-  const int r = tid / nvec, v = tid - r * nvec;
-  int stage = 0; uint32_t phase = 0;
-  int fb = 0; uint32_t ephase = 0;     // fold buffer to fill next; bit fb = phase of fold_empty[fb]
   for (;;) {
-    float acc[VEC];
+    while (issued - consumed < (uint32_t)kPwStages && issue_one()) {}
+    if (issued == consumed) break;
+    const int st = (int)(consumed % kPwStages);
+    ps_mbar_wait(ps_smem(&full[st]), (consumed / kPwStages) & 1u);
+    const PwHdr* h = hdr + st;
+    const int ntok = h->ntok;
+    const uint4* src = (const uint4*)(data + (size_t)st * stage_bytes);
+    if (!(a.dbg & 1)) {
+      for (int t = 0; t < ntok; t += 2) {
+        // two tokens per step, loads first; a masked token's values must not reach the sum (they may be Inf/NaN)
+        const bool ok1 = t + 1 < ntok;
+        const float w0 = h->w[t], w1 = ok1 ? h->w[t + 1] : 0.f;
+        uint4 r0[NV], r1[NV];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
-    float cnt = 0.f;
-    int64_t item = -1;
-    int kind;
-    for (;;) {
-      ps_mbar_wait(ps_smem(&bars[stage]), phase);
-      const PsHdr* h = hdr + stage;
-      kind = h->kind;
-      if (kind != 2 && active && !(a.dbg & 1)) {
-        const int ntok = h->ntok;
-        const uint4* src = (const uint4*)(data + (size_t)stage * stage_bytes) + v;
-        for (int t = r; t < ntok; t += 2 * rpi) {
-          // two tokens per step, loads first; a masked token's values must not reach the sum (they may be Inf/NaN)
-          const int t1 = t + rpi;
-          const bool ok1 = t1 < ntok;
-          const float w0 = h->w[t], w1 = ok1 ? h->w[t1] : 0.f;
-          const uint4 raw0 = src[(size_t)t * nvec];
-          const uint4 raw1 = src[(size_t)(ok1 ? t1 : t) * nvec];
-          float x0[VEC], x1[VEC];
-          SmemVec<DT>::cvt(raw0, x0);
-          SmemVec<DT>::cvt(raw1, x1);
-          if (w0 != 0.f) {
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) acc[j] = fmaf(w0, x0[j], acc[j]);
+        for (int i = 0; i < NV; ++i) {
+          const int v = lane + 32 * i;
+          if (v < nvec) {
+            r0[i] = src[(size_t)t * nvec + v];
+            r1[i] = src[(size_t)(ok1 ? t + 1 : t) * nvec + v];
           }
-          if (w1 != 0.f) {
+        }
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) acc[j] = fmaf(w1, x1[j], acc[j]);
+        for (int i = 0; i < NV; ++i) {
+          if (lane + 32 * i < nvec) {
+            float x0[VEC], x1[VEC];
+            SmemVec<DT>::cvt(r0[i], x0);
+            SmemVec<DT>::cvt(r1[i], x1);
+            if (w0 != 0.f) {
+#pragma unroll
+              for (int j = 0; j < VEC; ++j) acc[i][j] = fmaf(w0, x0[j], acc[i][j]);
+            }
+            if (w1 != 0.f) {
+#pragma unroll
+              for (int j = 0; j < VEC; ++j) acc[i][j] = fmaf(w1, x1[j], acc[i][j]);
+            }
           }
         }
       }
-      if (kind == 1) { cnt = h->cnt; item = h->item; }
-      __syncwarp();
-      if (lane == 0) ps_mbar_arrive(ps_smem(&bars[nst + stage]));
-      if (++stage == nst) { stage = 0; phase ^= 1; }
-      if (kind != 0) break;
     }
-    // ---- item done (or no more items: item = -1): hand the partial sums to the finisher ----
-    // wait until the finisher has released this fold buffer (the first use of each is free)
-    ps_mbar_wait(ps_smem(&fold_empty[fb]), ((ephase >> fb) & 1u) ^ 1u);
-    ephase ^= 1u << fb;
-    if (active && kind == 1) {
-      float* rb = fold + (size_t)fb * rpi * a.D + (size_t)r * a.D + (size_t)v * VEC;
+    const int last = h->last;
+    float cnt = h->cnt;
+    const int64_t item = h->item;
+    __syncwarp();                 // every lane is done with the stage (and its header) before it is refilled
+    ++consumed;
+    if (!last) continue;
+
+    // ---- the item is complete: finish the row in registers ----
+    const int64_t b = item / a.S; const int sp = (int)(item % a.S);
+    bool finish = true;
+    if (a.S > 1) {
+      float* pr = a.partial + ((int64_t)b * a.S + sp) * a.D;
 #pragma unroll
-      for (int j = 0; j < VEC; j += 4) *(float4*)(rb + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+      for (int i = 0; i < NV; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nvec) {
+#pragma unroll
+          for (int j = 0; j < VEC; j += 4)
+            *(float4*)(pr + (size_t)v * VEC + j) = make_float4(acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]);
+        }
+      }
+      // the last warp to finish a split of row b adds the partial sums in a fixed order
+      __threadfence();
+      __syncwarp();
+      int lastw = 0;
+      if (lane == 0) lastw = (atomicAdd(&a.ticket[b], 1) == a.S - 1);
+      lastw = __shfl_sync(0xffffffffu, lastw, 0);
+      finish = lastw != 0;
+      if (finish) {
+        __threadfence();
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int v = lane + 32 * i;
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) acc[i][j] = 0.f;
+          if (v < nvec) {
+            for (int s2 = 0; s2 < a.S; ++s2) {
+              const float* ps = a.partial + ((int64_t)b * a.S + s2) * a.D + (size_t)v * VEC;
+#pragma unroll
+              for (int j = 0; j < VEC; j += 4) {
+                const float4 u = __ldcg((const float4*)(ps + j));
+                acc[i][j] += u.x; acc[i][j + 1] += u.y; acc[i][j + 2] += u.z; acc[i][j + 3] += u.w;
+              }
+            }
+          }
+        }
+        float c = 0.f;
+        for (int l = lane; l < a.L; l += 32) c += mask_value(a.mask, a.mask_dt, b * a.msb + l);
+        cnt = warp_sum_f32(c);
+      }
     }
-    if (tid == 0) { mail[fb].item = item; mail[fb].cnt = cnt; }
-    __syncwarp();
-    if (lane == 0) ps_mbar_arrive(ps_smem(&fold_full[fb]));
-    fb ^= 1;
-    if (kind == 2) break;
+    if (finish) {
+      const float denom = fmaxf(cnt, kPoolEps);  // modules.py:168
+      float ss = 0.f, amax = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const float m = acc[i][j] / denom;     // modules.py:170 (lanes past the row hold zeros)
+          acc[i][j] = m;
+          ss = fmaf(m, m, ss);
+          amax = fmaxf(amax, fabsf(m));
+        }
+      float scale = 1.f;
+      if (a.normalize) scale = 1.f / fmaxf(sqrtf(warp_sum_f32(ss)), (float)kCosEps);
+      if (a.out_dt == TSIM_E4M3) {
+        // per-row power-of-two scale: largest |element| lands in [64, 128) (e4m3 max is 448)
+        const float bm = warp_max_f32(amax) * scale;
+        if (bm > 0.f) {
+          int e;
+          frexpf(bm, &e);  // bm = f * 2^e, f in [0.5, 1)
+          scale *= exp2f((float)(7 - e));
+        }
+      }
+      const int64_t orow = a.out_rows ? a.out_rows[b] : b;
+      float ss2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nvec) {
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) {
+            const float stv = round_store(a.out, a.out_dt, orow * a.out_stride + (int64_t)v * VEC + j, acc[i][j] * scale);
+            ss2 = fmaf(stv, stv, ss2);
+          }
+        }
+      }
+      if (a.out_inv) {
+        ss2 = warp_sum_f32(ss2);
+        if (lane == 0) a.out_inv[orow] = 1.f / fmaxf(sqrtf(ss2), (float)kCosEps);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) acc[i][j] = 0.f;
   }
 }
 
@@ -674,44 +662,61 @@ int pool_splits(int64_t B, int64_t L) {
   int64_t maxs = (L + 7) / 8;                           // >= 8 tokens per CTA
   int64_t S = want < 1 ? 1 : want;
   if (S > maxs) S = maxs;
-  const int64_t mins = (L + kPsMaxTL - 1) / kPsMaxTL;   // <= kPsMaxTL tokens per item (streaming variant)
+  const int64_t mins = (L + kPwMaxTL - 1) / kPwMaxTL;   // <= kPwMaxTL tokens per item (streaming kernel)
   if (S < mins) S = mins;
   if (S < 1) S = 1;
   return (int)S;
 }
 
-// The streaming variant needs token rows that are contiguous within a sentence (one bulk copy per
-// chunk), 16-byte granularity, a row of at most one stage and at most 256 16-byte columns.
-bool pool_stream_ok(const PoolArgs& a, int esz, bool vec_ok) {
-  const char* v1 = getenv("TSIM_POOL_V1");   // experiment knob: force the register-staged kernel
-  if (v1 && v1[0] == '1') return false;
+// The streaming kernel needs token rows that are contiguous within a sentence (one bulk copy per
+// chunk) and 16-byte granularity.  TSIM_POOL_MODE=1 (experiment knob) forces the register-staged kernel.
+int pool_mode() {
+  const char* m = getenv("TSIM_POOL_MODE");
+  const char* v1 = getenv("TSIM_POOL_V1");
+  if (v1 && v1[0] == '1') return 1;
+  return m ? atoi(m) : 0;
+}
+// warp-autonomous variant: at most 8 sixteen-byte columns per lane (row <= 4 KB), items of <= 256 tokens
+bool pool_warp_ok(const PoolArgs& a, int esz, bool vec_ok) {
   const int64_t rowb = a.D * esz;
-  return vec_ok && a.sl == a.D && rowb <= kPsStageBytes && rowb / 16 <= kPsConsumers && a.TL <= kPsMaxTL;
+  return vec_ok && a.sl == a.D && rowb <= 4096 && a.TL <= kPwMaxTL;
 }
 
-template <int DT>
-int launch_pool_stream(const PoolArgs& a, int* counter, cudaStream_t st) {
+template <int DT, int NV>
+int launch_pool_warp_nv(const PoolArgs& a, int* counter, cudaStream_t st) {
   constexpr int ESZ = 16 / SmemVec<DT>::N;
-  const int nvec = (int)(a.D * ESZ / 16);
-  const int rpi = kPsConsumers / nvec;
-  int CT = (int)(kPsStageBytes / (a.D * ESZ));
+  const int64_t rowb = a.D * ESZ;
+  int CT = (int)(kPsStageBytes / rowb);
   if (CT > 32) CT = 32;
-  const int stage_bytes = (int)((CT * a.D * ESZ + 127) / 128 * 128);
-  const size_t fixed = kPsMaxTL * sizeof(float) + 2 * (size_t)rpi * a.D * sizeof(float) + 2 * sizeof(PsMail) +
-                       (2 * kPsMaxStages + 4) * sizeof(uint64_t) + 256;
-  const size_t budget = 113 * 1024;        // two CTAs per SM
-  int nst = (int)((budget - fixed) / (stage_bytes + sizeof(PsHdr)));
-  if (nst > kPsMaxStages) nst = kPsMaxStages;
-  if (nst < 2) nst = 2;
-  const size_t smem = (size_t)nst * (stage_bytes + sizeof(PsHdr)) + fixed;
-  TSIM_CUDA(cudaFuncSetAttribute(pool_norm_stream_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int stage_bytes = (int)((CT * rowb + 127) / 128 * 128);
+  const size_t per_warp = (size_t)kPwStages * stage_bytes + kPwStages * sizeof(PwHdr) + kPwMaxTL * sizeof(float) + 64;
+  int nw = (int)((size_t)(225 * 1024) / per_warp);
+  if (nw > kPwMaxWarps) nw = kPwMaxWarps;
+  if (nw < 1) nw = 1;
+  const size_t smem = (size_t)nw * per_warp + 128;
+  auto kern = pool_norm_warp_kernel<DT, NV>;
+  TSIM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t nitems = a.B * a.S;
-  const int64_t cap = 2 * (int64_t)device_sm_count();
-  const unsigned grid = (unsigned)(nitems < cap ? nitems : cap);
-  pool_norm_stream_kernel<DT><<<grid, kPsThreads, smem, st>>>(a, nitems, CT, nst, stage_bytes, counter);
+  int64_t ctas = (nitems + nw - 1) / nw;
+  const int64_t cap = device_sm_count();
+  if (ctas > cap) ctas = cap;
+  kern<<<(unsigned)ctas, nw * 32, smem, st>>>(a, nitems, CT, stage_bytes, counter);
   TSIM_CUDA(cudaGetLastError());
   count_launch();
   return TSIM_OK;
+}
+template <int DT>
+int launch_pool_warp(const PoolArgs& a, int* counter, cudaStream_t st) {
+  const int nvec = (int)(a.D / SmemVec<DT>::N);
+  const int nv = (nvec + 31) / 32;
+  switch (nv) {
+    case 1: return launch_pool_warp_nv<DT, 1>(a, counter, st);
+    case 2: return launch_pool_warp_nv<DT, 2>(a, counter, st);
+    case 3: return launch_pool_warp_nv<DT, 3>(a, counter, st);
+    case 4: return launch_pool_warp_nv<DT, 4>(a, counter, st);
+    case 5: case 6: return launch_pool_warp_nv<DT, 6>(a, counter, st);
+    default: return launch_pool_warp_nv<DT, 8>(a, counter, st);
+  }
 }
 
 }  // namespace
@@ -788,11 +793,12 @@ extern "C" int tsim_pool_norm(const void* tok, int tok_dt, const void* mask, int
   const int vec = 16 / esz;
   const bool vec_ok = (D % vec == 0) && (tok_stride_b % vec == 0) && (tok_stride_l % vec == 0) &&
                       (((uintptr_t)tok & 15) == 0);
-  if (pool_stream_ok(a, esz, vec_ok)) {
+  const int mode = pool_mode();
+  if (mode != 1 && pool_warp_ok(a, esz, vec_ok)) {
     switch (tok_dt) {
-      case TSIM_F32: return launch_pool_stream<TSIM_F32>(a, counter, st);
-      case TSIM_F16: return launch_pool_stream<TSIM_F16>(a, counter, st);
-      default: return launch_pool_stream<TSIM_BF16>(a, counter, st);
+      case TSIM_F32: return launch_pool_warp<TSIM_F32>(a, counter, st);
+      case TSIM_F16: return launch_pool_warp<TSIM_F16>(a, counter, st);
+      default: return launch_pool_warp<TSIM_BF16>(a, counter, st);
     }
   }
   switch (tok_dt) {
