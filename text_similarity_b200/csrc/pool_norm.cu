@@ -581,10 +581,16 @@ template <> struct SqVec<TSIM_BF16> {
 template <> struct SqVec<TSIM_E4M3> {
   static constexpr int N = 16;
   static __device__ __forceinline__ float sq(const uint4& raw) {
-    const __nv_fp8_e4m3* e = (const __nv_fp8_e4m3*)&raw;
+    // two e4m3 values per conversion (cvt.rn.f16x2.e4m3x2); the squares are exact in fp32
+    const __nv_fp8x2_storage_t* e = (const __nv_fp8x2_storage_t*)&raw;
     float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { const float v = float(e[j]); s = fmaf(v, v, s); }
+    for (int j = 0; j < 8; ++j) {
+      const __half2_raw h = __nv_cvt_fp8x2_to_halfraw2(e[j], __NV_E4M3);
+      const float2 f = __half22float2(*(const __half2*)&h);
+      s = fmaf(f.x, f.x, s);
+      s = fmaf(f.y, f.y, s);
+    }
     return s;
   }
 };

@@ -140,16 +140,46 @@ __device__ __forceinline__ float warp_sum_f32(float v) {
 // row, so equal stored rows always yield bit-identical scores (ties -> lower index).
 // Products of bf16/fp16/fp8/fp32 values are exact in float64; lane l sums elements
 // l, l+32, ... sequentially, then a fixed xor-butterfly adds the 32 partials.
+template <int QDT, int CDT>
+__device__ __forceinline__ void exact_cosine_sums(const void* q, const void* c, int64_t D, double& dot, double& qq,
+                                                  double& cc) {
+  int64_t d = threadIdx.x & 31;
+  // eight elements per lane per step, loads first (16 in flight), FMAs in the canonical order
+  for (; d + 32 * 7 < D; d += 32 * 8) {
+    float a[8], b[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { a[u] = Elem<QDT>::ld(q, d + 32 * u); b[u] = Elem<CDT>::ld(c, d + 32 * u); }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const double x = (double)a[u], y = (double)b[u];
+      dot = fma(x, y, dot);
+      qq = fma(x, x, qq);
+      cc = fma(y, y, cc);
+    }
+  }
+  for (; d < D; d += 32) {
+    const double x = (double)Elem<QDT>::ld(q, d), y = (double)Elem<CDT>::ld(c, d);
+    dot = fma(x, y, dot);
+    qq = fma(x, x, qq);
+    cc = fma(y, y, cc);
+  }
+}
+
 __device__ __forceinline__ double warp_exact_cosine(const void* q, int q_dt, const void* c, int c_dt,
                                                     int64_t D) {
   const int lane = threadIdx.x & 31;
   double dot = 0.0, qq = 0.0, cc = 0.0;
-  for (int64_t d = lane; d < D; d += 32) {
-    double a = (double)load_elem(q, q_dt, d);
-    double b = (double)load_elem(c, c_dt, d);
-    dot = fma(a, b, dot);
-    qq = fma(a, a, qq);
-    cc = fma(b, b, cc);
+  if (q_dt == TSIM_BF16 && c_dt == TSIM_BF16) exact_cosine_sums<TSIM_BF16, TSIM_BF16>(q, c, D, dot, qq, cc);
+  else if (q_dt == TSIM_E4M3 && c_dt == TSIM_E4M3) exact_cosine_sums<TSIM_E4M3, TSIM_E4M3>(q, c, D, dot, qq, cc);
+  else if (q_dt == TSIM_F32 && c_dt == TSIM_F32) exact_cosine_sums<TSIM_F32, TSIM_F32>(q, c, D, dot, qq, cc);
+  else {
+    for (int64_t d = lane; d < D; d += 32) {
+      double a = (double)load_elem(q, q_dt, d);
+      double b = (double)load_elem(c, c_dt, d);
+      dot = fma(a, b, dot);
+      qq = fma(a, a, qq);
+      cc = fma(b, b, cc);
+    }
   }
   dot = warp_sum_f64(dot);
   qq = warp_sum_f64(qq);
