@@ -166,12 +166,6 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t* v) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-               : "r"(taddr)
-               : "memory");
-}
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B, 128-byte rows:
@@ -187,17 +181,17 @@ struct TcArgs {
   int64_t Q, N;
   int kblocks;          // ceil(D * element size / 128)
   int QB;               // query blocks (128 queries; 256 when CTA pairs are used)
-  int64_t T;            // corpus tiles (of 256 rows) THIS launch scans (see tile_mode)
+  int T;                // corpus tiles (of 256 rows) THIS launch scans (see tile_mode); all tile arithmetic is 32-bit
   int tile_mode;        // 0: tiles 0..T-1; 1: the tiles i * tile_stride; 2: every tile that is not a multiple of
                         // tile_stride; 3: the multiples of tile_stride that are not multiples of tile_stride * tile_mult
-  int64_t tile_stride;  // distance between sample tiles (modes 1, 2, 3)
-  int64_t tile_mult;    // mode 3: every tile_mult-th sample tile belongs to the mini sample
-  int64_t slot_base;    // first candidate-list slot this launch writes
+  int tile_stride;      // distance between sample tiles (modes 1, 2, 3)
+  int tile_mult;        // mode 3: every tile_mult-th sample tile belongs to the mini sample
+  int slot_base;        // first candidate-list slot this launch writes
   int sticky;           // 1: CTA <-> (query block, tile residue class), one list per CTA lifetime
   int Gq;               // sticky: CTAs per query block
-  int64_t tpc;          // round-robin: tiles per corpus chunk
+  int tpc;              // round-robin: tiles per corpus chunk
   int64_t NC;           // candidate lists per query (chunks, or Gq when sticky)
-  int64_t n_units;      // round-robin: QB * NC
+  int n_units;          // round-robin: QB * chunks of this launch
   int self_on; int64_t self_off;
   uint64_t* cand;       // [Q][NC][KP] packed keys
   uint32_t* thr;        // [Q] ordered-float global thresholds (0 = none yet)
@@ -207,7 +201,7 @@ struct TcArgs {
 
 // Logical tile number of this launch -> tile of the corpus.  A bootstrap launch (mode 1) scans a
 // strided sample so every query gets a good threshold before the main launch (mode 2) scans the rest.
-__device__ __forceinline__ int64_t actual_tile(const TcArgs& a, int64_t u) {
+__device__ __forceinline__ int actual_tile(const TcArgs& a, int u) {
   if (a.tile_mode == 1) return u * a.tile_stride;
   if (a.tile_mode == 2) return u + u / (a.tile_stride - 1) + 1;
   if (a.tile_mode == 3) return (u + u / (a.tile_mult - 1) + 1) * a.tile_stride;
@@ -215,7 +209,7 @@ __device__ __forceinline__ int64_t actual_tile(const TcArgs& a, int64_t u) {
 }
 
 // A unit = one candidate list: a query block and the sequence of corpus tiles scanned into it.
-struct Unit { int qb; int64_t slot; int64_t tile0; int64_t tstride; int ntiles; };
+struct Unit { int qb; int slot; int tile0; int tstride; int ntiles; };
 
 // Sticky schedule (few query blocks, the HBM-bound regime): CTA c keeps query block c % QB for its
 // whole life and takes tiles j, j+Gq, ... (j = c / QB): perfect tile balance, neighbouring CTAs
@@ -229,14 +223,14 @@ __device__ __forceinline__ bool get_unit(const TcArgs& a, int it, int wid, int n
     if (it > 0 || wid >= a.Gq * a.QB) return false;
     const int j = wid / a.QB;
     un.qb = wid % a.QB; un.slot = j; un.tile0 = j; un.tstride = a.Gq;
-    un.ntiles = j < a.T ? (int)((a.T - j + a.Gq - 1) / a.Gq) : 0;
+    un.ntiles = j < a.T ? (a.T - j + a.Gq - 1) / a.Gq : 0;
     return true;
   }
-  const int64_t u = wid + (int64_t)it * nw;
+  const int u = wid + it * nw;
   if (u >= a.n_units) return false;
-  const int64_t chunk = u / a.QB;
-  un.qb = (int)(u % a.QB); un.slot = chunk; un.tile0 = chunk * a.tpc; un.tstride = 1;
-  un.ntiles = (int)min(a.tpc, a.T - un.tile0);
+  const int chunk = u / a.QB;
+  un.qb = u - chunk * a.QB; un.slot = chunk; un.tile0 = chunk * a.tpc; un.tstride = 1;
+  un.ntiles = min(a.tpc, a.T - un.tile0);
   return true;
 }
 
@@ -310,46 +304,64 @@ struct Ladder {
 //    and the cold path is one non-inlined sorted shift-insertion.
 // A full list's minimum is a valid lower bound of the query's KP-th best anywhere in the corpus,
 // so it is published with atomicMax for every other CTA to filter with.
+// Cold-path helpers shared by both list types.  The chunk's 32 scaled scores are in registers (the
+// hot path just produced them): the columns that beat the threshold become a bit mask (branch-free)
+// and ONE rolled loop walks the set bits, fetching sc[j] through a 5-level select tree (registers
+// cannot be indexed dynamically).  The cold path stays a few hundred bytes of code; 32 (or 8) inlined
+// insertions overflowed the instruction cache and cost ~4000 cycles per triggered chunk.
+__device__ __forceinline__ uint32_t candidate_mask(const float* sc, float thr, int64_t row_base, int64_t self_row,
+                                                   int lim) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) m |= (sc[j] > thr) ? (1u << j) : 0u;
+  if (lim < 32) m &= (1u << lim) - 1u;
+  const int64_t ds = self_row - row_base;
+  if (ds >= 0 && ds < 32) m &= ~(1u << (int)ds);
+  return m;
+}
+__device__ __forceinline__ float select32(const float* sc, int j) {
+  float t16[16], t8[8], t4[4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) t16[i] = (j & 16) ? sc[16 + i] : sc[i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t8[i] = (j & 8) ? t16[8 + i] : t16[i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) t4[i] = (j & 4) ? t8[4 + i] : t8[i];
+  const float u0 = (j & 2) ? t4[2] : t4[0], u1 = (j & 2) ? t4[3] : t4[1];
+  return (j & 1) ? u1 : u0;
+}
+
 struct RegList16 {
-  static constexpr bool kFromRegs = false;  // slow() re-reads the flagged 8-column groups from TMEM
   float a[16]; uint32_t r[16];
   __device__ __forceinline__ RegList16(float*, uint32_t*, int*) {}
   __device__ __forceinline__ void reset() {
 #pragma unroll
     for (int i = 0; i < 16; ++i) { a[i] = -INFINITY; r[i] = 0xffffffffu; }
   }
-  // gm0..gm3: this lane's maxima over the chunk's four 8-column groups; a group is re-read only if
-  // some lane of the warp has a candidate in it (warp-uniform test: tcgen05.ld is .sync.aligned)
-  __device__ __forceinline__ float slow(uint32_t taddr, const float* cnp, float thr, int64_t row_base,
-                                        int64_t self_row, int lim, uint32_t* thr_g, Ladder& lad, float gm0,
-                                        float gm1, float gm2, float gm3) {
+  // sc[0..32) = this lane's scaled scores of the chunk
+  __device__ __forceinline__ float slow(const float* sc, float thr, int64_t row_base, int64_t self_row, int lim,
+                                        uint32_t* thr_g, Ladder& lad) {
     const float thr_in = thr;
+    uint32_t m = candidate_mask(sc, thr, row_base, self_row, lim);
 #pragma unroll 1
-    for (int g = 0; g < 4; ++g) {
-      const float gm = g == 0 ? gm0 : g == 1 ? gm1 : g == 2 ? gm2 : gm3;
-      if (!__any_sync(0xffffffffu, gm > thr)) continue;
-      uint32_t w[8];
-      tc_ld8(taddr + g * 8, w);
-      tc_ld_wait();
+    while (m) {
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      const float s = select32(sc, j);
+      if (s > thr) {              // thr may have risen since the mask was built
+        const uint32_t row = (uint32_t)(row_base + j);
+        lad.count(s);
+        // a[] is sorted descending, so (s > a[i]) is monotone in i: entry i becomes the newcomer
+        // where the predicate first turns true, the old a[i-1] after that, and stays otherwise.
+        // Strict '>' puts the newcomer after equal scores (it has the larger row).
 #pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        const int j = g * 8 + jj;
-        const float s = __uint_as_float(w[jj]) * cnp[j];
-        const int64_t row = row_base + j;
-        if (s > thr && j < lim && row != self_row) {
-          lad.count(s);
-          // a[] is sorted descending, so (s > a[i]) is monotone in i: entry i becomes the newcomer
-          // where the predicate first turns true, the old a[i-1] after that, and stays otherwise.
-          // Strict '>' puts the newcomer after equal scores (it has the larger row).
-#pragma unroll
-          for (int i = 15; i > 0; --i) {
-            const bool gt = s > a[i], gtp = s > a[i - 1];
-            a[i] = gt ? (gtp ? a[i - 1] : s) : a[i];
-            r[i] = gt ? (gtp ? r[i - 1] : (uint32_t)row) : r[i];
-          }
-          if (s > a[0]) { a[0] = s; r[0] = (uint32_t)row; }
-          thr = fmaxf(thr, a[15]);
+        for (int i = 15; i > 0; --i) {
+          const bool gt = s > a[i], gtp = s > a[i - 1];
+          a[i] = gt ? (gtp ? a[i - 1] : s) : a[i];
+          r[i] = gt ? (gtp ? r[i - 1] : row) : r[i];
         }
+        if (s > a[0]) { a[0] = s; r[0] = row; }
+        thr = fmaxf(thr, a[15]);
       }
     }
     if (thr > thr_in) atomicMax(thr_g, f32_to_ord(thr));
@@ -381,7 +393,6 @@ __device__ __noinline__ uint64_t smem_list_min(const float* ls) {
 
 template <int KP>
 struct SmemList {
-  static constexpr bool kFromRegs = true;   // slow() takes the chunk's scaled scores from registers
   float* ls; uint32_t* li; int* cntp;
   __device__ __forceinline__ SmemList(float* s, uint32_t* i, int* n) : ls(s), li(i), cntp(n) {}
   __device__ __forceinline__ void reset() {
@@ -408,17 +419,13 @@ struct SmemList {
         thr = fmaxf(thr, __uint_as_float((uint32_t)r));
       }
     };
-    // whole chunk inside the corpus and no query of this warp has its own row in it (the usual case):
-    // one compare per column
-    const bool plain = lim >= 32 && (self_row < row_base || self_row >= row_base + 32);
-    if (__all_sync(0xffffffffu, plain)) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (sc[j] > thr) put(sc[j], j);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (sc[j] > thr && j < lim && row_base + j != self_row) put(sc[j], j);
+    uint32_t m = candidate_mask(sc, thr, row_base, self_row, lim);
+#pragma unroll 1
+    while (m) {
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      const float v = select32(sc, j);
+      if (v > thr) put(v, j);     // thr may have risen since the mask was built (the list filled up)
     }
     *cntp = cnt | (minpos << 16);
     // ladder: the rows appended while the list was not full sit at [cnt0, cnt) (replacements of a full
@@ -502,7 +509,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       Unit un;
       for (int it = 0; get_unit(a, it, wid, nw, un); ++it) {
         for (int t = 0; t < un.ntiles; ++t) {
-          const int row0 = (int)(actual_tile(a, un.tile0 + (int64_t)t * un.tstride) * BN);
+          const int row0 = actual_tile(a, un.tile0 + t * un.tstride) * BN;
           for (int kb = 0; kb < a.kblocks; ++kb) {
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
             const uint32_t sa = smem_u32(tiles + (size_t)stage * STAGE_BYTES);
@@ -578,7 +585,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       float nreg[8];
       uint32_t gthr = 0;
       auto fetch_meta = [&](int t) {
-        const int64_t r0 = actual_tile(a, un.tile0 + (int64_t)t * un.tstride) * BN;
+        const int64_t r0 = (int64_t)actual_tile(a, un.tile0 + t * un.tstride) * BN;
         const int nc = (int)min((int64_t)BN, a.N - r0);
 #pragma unroll
         for (int i = 0; i < 8; ++i) nreg[i] = (lane + 32 * i < nc) ? __ldg(a.c_inv + r0 + lane + 32 * i) : 0.f;
@@ -586,7 +593,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       };
       if (un.ntiles > 0) fetch_meta(0);
       for (int t = 0; t < un.ntiles; ++t) {
-        const int64_t trow0 = actual_tile(a, un.tile0 + (int64_t)t * un.tstride) * BN;
+        const int64_t trow0 = (int64_t)actual_tile(a, un.tile0 + t * un.tstride) * BN;
         const int ncols = (int)min((int64_t)BN, a.N - trow0);
         // each epilogue warp keeps a private copy of the tile's inverse norms: no cross-warp barrier
         float* cn = cnorm + (acc * 4 + (warp & 3)) * BN;
@@ -618,15 +625,9 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             gm[g] = fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7])));
           }
           const float mx = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
-          // Cold path, taken by the WHOLE warp when any lane has a candidate (tcgen05.ld is
-          // .sync.aligned: it must not run under divergence); rare once the lists are warm.
-          if (__any_sync(0xffffffffu, mx > thr)) {
-            if constexpr (ListFor<KP>::type::kFromRegs)
-              thr = list.slow(sc, thr, trow0 + c * 32, self_row, ncols - c * 32, thr_g, lad);
-            else
-              thr = list.slow(tbase + c * 32, cn + c * 32, thr, trow0 + c * 32, self_row, ncols - c * 32, thr_g, lad,
-                              gm[0], gm[1], gm[2], gm[3]);
-          }
+          // Cold path, entered by the whole warp when any lane has a candidate; rare once the lists are warm.
+          if (__any_sync(0xffffffffu, mx > thr))
+            thr = list.slow(sc, thr, trow0 + c * 32, self_row, ncols - c * 32, thr_g, lad);
         }
         tc_fence_before();
         __syncwarp();
@@ -734,28 +735,28 @@ int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_
   a.c_inv = c_inv; a.Q = Q; a.N = N;
   a.kblocks = (int)((D * esz + BK_BYTES - 1) / BK_BYTES);
   const int64_t T = (N + BN - 1) / BN;
-  a.QB = p.QB; a.sticky = p.sticky; a.Gq = p.Gq; a.tpc = p.R / BN;
+  a.QB = p.QB; a.sticky = p.sticky; a.Gq = p.Gq; a.tpc = (int)(p.R / BN);
   a.NC = p.NC;
-  a.tile_mode = 0; a.tile_stride = 1; a.tile_mult = 2; a.slot_base = 0; a.T = T;
+  a.tile_mode = 0; a.tile_stride = 1; a.tile_mult = 2; a.slot_base = 0; a.T = (int)T;
   switch (pass) {
     case TC_PASS_SAMPLE:        // the whole sample, cold
-      a.tile_mode = 1; a.tile_stride = p.boot_stride; a.T = p.boot_tiles;
-      if (!p.sticky) a.tpc = p.boot_tpc;
+      a.tile_mode = 1; a.tile_stride = (int)p.boot_stride; a.T = (int)p.boot_tiles;
+      if (!p.sticky) a.tpc = (int)p.boot_tpc;
       break;
     case TC_PASS_MINI:          // every mini_mult-th sample tile, one-tile units, cold
-      a.tile_mode = 1; a.tile_stride = p.boot_stride * p.mini_mult; a.T = p.mini_tiles; a.tpc = 1;
+      a.tile_mode = 1; a.tile_stride = (int)(p.boot_stride * p.mini_mult); a.T = (int)p.mini_tiles; a.tpc = 1;
       break;
     case TC_PASS_SAMPLE_REST:   // the other sample tiles
-      a.tile_mode = 3; a.tile_stride = p.boot_stride; a.tile_mult = p.mini_mult; a.T = p.boot_tiles - p.mini_tiles;
-      a.tpc = p.boot_tpc; a.slot_base = p.mini_slots;
+      a.tile_mode = 3; a.tile_stride = (int)p.boot_stride; a.tile_mult = (int)p.mini_mult; a.T = (int)(p.boot_tiles - p.mini_tiles);
+      a.tpc = (int)p.boot_tpc; a.slot_base = (int)p.mini_slots;
       break;
     case TC_PASS_MAIN:          // everything that is not a sample tile
-      a.tile_mode = 2; a.tile_stride = p.boot_stride; a.T = T - p.boot_tiles;
-      a.slot_base = p.mini_slots + p.boot_slots;
+      a.tile_mode = 2; a.tile_stride = (int)p.boot_stride; a.T = (int)(T - p.boot_tiles);
+      a.slot_base = (int)(p.mini_slots + p.boot_slots);
       break;
     default: break;
   }
-  a.n_units = (int64_t)p.QB * ((a.T + a.tpc - 1) / (a.tpc > 0 ? a.tpc : 1));
+  a.n_units = p.QB * ((a.T + a.tpc - 1) / (a.tpc > 0 ? a.tpc : 1));
   a.self_on = self_on; a.self_off = self_off;
   a.cand = cand; a.thr = thr; a.ladder = ladder;
   const char* dbg = getenv("TSIM_DEBUG");
