@@ -42,6 +42,71 @@ __device__ void sort_keys_desc(uint64_t* a, int n) {
   }
 }
 
+// Keep only the keys whose approximate SCORE (upper 32 bits) is at least the `keep`-th best score:
+// MSB-first radix select over the 32 score bits (4 passes of 8 bits, shared-memory histogram, one
+// warp picks the bucket), then a compaction through `out` (kSelOut entries).  Returns the new count
+// m (>= keep, ties at the cut included; keys[0..m) in arbitrary order), or n unchanged when the
+// survivors would not fit `out` (massive ties: the caller's full sort handles that).  Replaces a
+// 2048-element bitonic sort (66 barrier stages) whenever only the best few dozen of ~2000 keys matter.
+constexpr int kSelOut = 512;
+__device__ int keep_top_scores(uint64_t* keys, int n, int keep, uint64_t* out, uint32_t* hist, int* sh) {
+  if (n <= keep) return n;
+  const int tid = threadIdx.x;
+  uint32_t prefix = 0;   // score bits decided so far (upper bits)
+  int need = keep;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const uint32_t hi_mask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+    for (int i = tid; i < n; i += blockDim.x) {
+      const uint32_t sc = (uint32_t)(keys[i] >> 32);
+      if ((sc & hi_mask) == prefix) atomicAdd(&hist[(sc >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid < 32) {
+      // lane l owns buckets 255 - 8l .. 248 - 8l (descending); find where the running count reaches `need`
+      uint32_t c[8], tot = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { c[j] = hist[255 - 8 * tid - j]; tot += c[j]; }
+      uint32_t incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (tid >= o) incl += v;
+      }
+      const uint32_t before = incl - tot;
+      if (before < (uint32_t)need && incl >= (uint32_t)need) {
+        uint32_t run = before;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (run < (uint32_t)need && run + c[j] >= (uint32_t)need) { sh[0] = 255 - 8 * tid - j; sh[1] = need - (int)run; }
+          run += c[j];
+        }
+      }
+    }
+    __syncthreads();
+    prefix |= (uint32_t)sh[0] << shift;
+    need = sh[1];
+    __syncthreads();
+  }
+  // prefix = the keep-th best score; everything at or above it survives
+  if (tid == 0) sh[2] = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += blockDim.x) {
+    const uint64_t key = keys[i];
+    if ((uint32_t)(key >> 32) >= prefix) {
+      const int p = atomicAdd(&sh[2], 1);
+      if (p < kSelOut) out[p] = key;
+    }
+  }
+  __syncthreads();
+  const int m = sh[2];
+  if (m > kSelOut) return n;
+  for (int i = tid; i < m; i += blockDim.x) keys[i] = out[i];
+  __syncthreads();
+  return m;
+}
+
 // (score desc, index asc) order on pairs; idx < 0 (padding) ranks last
 __device__ __forceinline__ bool pair_before(double s1, int64_t i1, double s2, int64_t i2) {
   bool p1 = i1 < 0, p2 = i2 < 0;
@@ -162,9 +227,16 @@ __global__ void __launch_bounds__(kSelThreads) select_rescore_kernel(SelArgs a) 
   int n = 0;
   while (cursor < total) {
     int64_t take = min((int64_t)(kKeyCap - n), total - cursor);
-    for (int64_t i = tid; i < take; i += blockDim.x) {
-      uint64_t key = __ldcg(src + cursor + i);
-      if (key != 0 && (uint32_t)(key >> 32) >= thr_ord) keys[atomicAdd(&n_sh, 1)] = key;
+    for (int64_t i0 = tid; i0 < take; i0 += (int64_t)blockDim.x * 8) {   // eight independent loads in flight
+      uint64_t key[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int64_t i = i0 + (int64_t)u * blockDim.x;
+        key[u] = i < take ? __ldcg(src + cursor + i) : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (key[u] != 0 && (uint32_t)(key[u] >> 32) >= thr_ord) keys[atomicAdd(&n_sh, 1)] = key[u];
     }
     cursor += take;
     __syncthreads();
@@ -230,6 +302,9 @@ __global__ void __launch_bounds__(kSelThreads) select_rescore_kernel(SelArgs a) 
 __global__ void __launch_bounds__(kSelThreads) tighten_kernel(const uint64_t* cand, uint32_t* thr, int64_t NC, int KP,
                                                               int nslots, uint32_t* ladder) {
   __shared__ uint64_t keys[kKeyCap];
+  __shared__ uint64_t sel_out[kSelOut];
+  __shared__ uint32_t sel_hist[256];
+  __shared__ int sel_sh[4];
   __shared__ int n_sh;
   const int64_t q = blockIdx.x;
   const int tid = threadIdx.x;
@@ -238,25 +313,36 @@ __global__ void __launch_bounds__(kSelThreads) tighten_kernel(const uint64_t* ca
   const uint32_t thr_ord = thr[q];
   // A full list's minimum is a lower bound of the union's KP-th best: only keys at or above the best
   // such bound can matter (at least KP of them exist), which leaves a few dozen keys to sort instead of
-  // nslots * KP.  One warp per list.
+  // nslots * KP.  Thread per key, eight independent loads in flight; per-list minimum and fill count
+  // through shared-memory atomics.
+  constexpr int kMaxSlots = 1024;
+  __shared__ unsigned long long slot_min[kMaxSlots];
+  __shared__ int slot_cnt[kMaxSlots];
   __shared__ unsigned long long bound_sh;
+  const bool use_bound = nslots <= kMaxSlots;
   if (tid == 0) { n_sh = 0; bound_sh = 0ull; }
-  __syncthreads();
-  for (int slot = tid >> 5; slot < nslots; slot += kSelThreads / 32) {
-    const uint64_t* sp = src + (size_t)slot * KP;
-    uint64_t mn = ~0ull;
-    int c = 0;
-    for (int i = tid & 31; i < KP; i += 32) {
-      const uint64_t key = __ldcg(sp + i);
-      if (key != 0) { ++c; mn = key < mn ? key : mn; }
-    }
+  if (use_bound) {
+    for (int sl = tid; sl < nslots; sl += blockDim.x) { slot_min[sl] = ~0ull; slot_cnt[sl] = 0; }
+    __syncthreads();
+    for (int64_t i0 = tid; i0 < total; i0 += (int64_t)blockDim.x * 8) {
+      uint64_t key[8];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      c += __shfl_xor_sync(0xffffffffu, c, o);
-      const uint64_t other = __shfl_xor_sync(0xffffffffu, mn, o);
-      mn = other < mn ? other : mn;
+      for (int u = 0; u < 8; ++u) {
+        const int64_t i = i0 + (int64_t)u * blockDim.x;
+        key[u] = i < total ? __ldcg(src + i) : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (key[u] != 0) {
+          const int sl = (int)((i0 + (int64_t)u * blockDim.x) / KP);
+          atomicMin(&slot_min[sl], (unsigned long long)key[u]);
+          atomicAdd(&slot_cnt[sl], 1);
+        }
+      }
     }
-    if ((tid & 31) == 0 && c == KP) atomicMax(&bound_sh, (unsigned long long)mn);
+    __syncthreads();
+    for (int sl = tid; sl < nslots; sl += blockDim.x)
+      if (slot_cnt[sl] == KP) atomicMax(&bound_sh, slot_min[sl]);
   }
   __syncthreads();
   const uint64_t bound = bound_sh;
@@ -264,23 +350,36 @@ __global__ void __launch_bounds__(kSelThreads) tighten_kernel(const uint64_t* ca
   int n = 0;
   while (cursor < total) {
     int64_t take = min((int64_t)(kKeyCap - n), total - cursor);
-    for (int64_t i = tid; i < take; i += blockDim.x) {
-      uint64_t key = __ldcg(src + cursor + i);
-      if (key != 0 && key >= bound && (uint32_t)(key >> 32) >= thr_ord) keys[atomicAdd(&n_sh, 1)] = key;
+    for (int64_t i0 = tid; i0 < take; i0 += (int64_t)blockDim.x * 4) {
+      uint64_t key[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t i = i0 + (int64_t)u * blockDim.x;
+        key[u] = i < take ? __ldcg(src + cursor + i) : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (key[u] != 0 && key[u] >= bound && (uint32_t)(key[u] >> 32) >= thr_ord) keys[atomicAdd(&n_sh, 1)] = key[u];
     }
     cursor += take;
     __syncthreads();
     n = n_sh;
     if (cursor < total && n > kKeyCap / 2) {
-      int np = next_pow2(n);
-      for (int i = n + tid; i < np; i += blockDim.x) keys[i] = 0;
-      __syncthreads();
-      sort_keys_desc(keys, np);
-      n = min(n, KP);
+      const int m = keep_top_scores(keys, n, KP, sel_out, sel_hist, sel_sh);
+      if (m == n) {                 // massive ties: sort and truncate
+        int np = next_pow2(n);
+        for (int i = n + tid; i < np; i += blockDim.x) keys[i] = 0;
+        __syncthreads();
+        sort_keys_desc(keys, np);
+        n = min(n, KP);
+      } else {
+        n = m;
+      }
       if (tid == 0) n_sh = n;
       __syncthreads();
     }
   }
+  n = keep_top_scores(keys, n, KP, sel_out, sel_hist, sel_sh);
   int np = next_pow2(max(n, 1));
   for (int i = n + tid; i < np; i += blockDim.x) keys[i] = 0;
   __syncthreads();
