@@ -128,6 +128,28 @@ int tsim_search_topk(const void* q, int q_dt, int64_t q_stride,
                      int32_t* out_flags,
                      void* ws, size_t ws_bytes, void* stream);
 
+/* The same search for fp32 / fp16 rows at tensor-core speed: the candidate pass reads bf16 SHADOWS of the
+ * queries and the corpus (plain element-wise casts, made once per corpus by the caller; any norm),
+ * 112 candidates per query are nominated, and the survivors are re-scored in float64 on the ORIGINAL rows,
+ * so the result is the one tsim_search_topk defines on (q, corpus) -- same indices, same score bits.  The
+ * completeness proof uses the rounding bound of the shadows (6e-3 instead of 5e-5); queries it cannot cover
+ * (many rows within ~1e-2 of the k-th best) are answered by the float64 scan, as usual.  Needs D % 8 == 0,
+ * 16-byte aligned shadow rows and k <= 24; otherwise the whole call runs the exact scan.
+ *   q_shadow [Q, D], corpus_shadow [N, D]  shadow_dt = TSIM_BF16, row strides in elements
+ *   shadow_inv_norm [N] float = tsim_row_inv_norm(corpus_shadow), may be NULL (computed per call)
+ *   ws     tsim_search_shadow_workspace_bytes(Q, N, D, k, shadow_dt) bytes. */
+size_t tsim_search_shadow_workspace_bytes(int64_t Q, int64_t N, int64_t D, int k, int shadow_dt);
+int tsim_search_topk_shadow(const void* q, int q_dt, int64_t q_stride,
+                            const void* corpus, int c_dt, int64_t c_stride,
+                            const void* q_shadow, int64_t qs_stride,
+                            const void* corpus_shadow, int64_t cs_stride, int shadow_dt,
+                            const float* shadow_inv_norm,
+                            int64_t Q, int64_t N, int64_t D, int k,
+                            int64_t idx_base, int64_t exclude_self_base,
+                            float* out_score, double* out_score64, int64_t* out_idx,
+                            int32_t* out_flags,
+                            void* ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * K3 (second pass): merge n_lists candidate lists per query into the top k_out, ranked by
  * (score descending, index ascending); entries with index < 0 are padding.

@@ -31,6 +31,11 @@ SIGNATURES = {
     "tsim_search_topk": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p,
                                  c_int64, c_int64, c_int64, c_int, c_int64, c_int64, c_int,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tsim_search_shadow_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int, c_int]),
+    "tsim_search_topk_shadow": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64,
+                                        c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p,
+                                        c_int64, c_int64, c_int64, c_int, c_int64, c_int64,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tsim_set_timing_events": (c_int, [c_void_p, c_void_p]),
     "tsim_launch_count": (ctypes.c_uint64, []),
     "tsim_merge_topk": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,

@@ -202,7 +202,7 @@ struct SelArgs {
   const void* q; int q_dt; int64_t q_stride;
   const void* corpus; int c_dt; int64_t c_stride;
   int64_t Q, N, D; int k; int64_t idx_base;
-  int KP; int64_t NC;
+  int KP; int64_t NC; float eps;
   const uint64_t* cand; const uint32_t* thr;
   int32_t* flag_cnt; int32_t* flag_list;
   float* out_score; double* out_score64; int64_t* out_idx; int32_t* out_flags;
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(kSelThreads) select_rescore_kernel(SelArgs a) 
     int kk = min(a.k, m);
     float a_k = key_score(keys[kk - 1]);
     float a_kp = key_score(keys[m - 1]);
-    flagged = !((double)a_k - (double)a_kp > 2.0 * (double)kApproxEps * qn) || (m < a.KP);
+    flagged = !((double)a_k - (double)a_kp > 2.0 * (double)a.eps * qn) || (m < a.KP);
   }
 
   for (int j = tid; j < m; j += blockDim.x) { ei[j] = (int64_t)key_idx(keys[j]); es[j] = 0.0; }
@@ -487,7 +487,7 @@ int launch_select_rescore(const void* q, int q_dt, int64_t q_stride, const void*
   a.q = q; a.q_dt = q_dt; a.q_stride = q_stride;
   a.corpus = corpus; a.c_dt = c_dt; a.c_stride = c_stride;
   a.Q = Q; a.N = N; a.D = D; a.k = k; a.idx_base = idx_base;
-  a.KP = p.KP; a.NC = p.NC; a.cand = cand; a.thr = thr;
+  a.KP = p.KP; a.NC = p.NC; a.eps = p.eps; a.cand = cand; a.thr = thr;
   a.flag_cnt = flag_cnt; a.flag_list = flag_list;
   a.out_score = out_score; a.out_score64 = out_score64; a.out_idx = out_idx; a.out_flags = out_flags;
   select_rescore_kernel<<<(unsigned)Q, kSelThreads, 0, st>>>(a);

@@ -47,10 +47,12 @@ static bool tensor_shape_ok(int64_t Q, int64_t N, int64_t D, int k, int q_dt, in
 }
 
 int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt, int mode,
-                     bool need_invnorm, SearchPlan* p) {
+                     bool need_invnorm, bool shadow, SearchPlan* p) {
   memset(p, 0, sizeof(*p));
   const int sms = device_sm_count();
-  const bool ok = tensor_shape_ok(Q, N, D, k, q_dt, c_dt);
+  // a shadow pass needs the widest lists: the candidates must reach 2 * kShadowEps below the k-th best
+  const bool ok = tensor_shape_ok(Q, N, D, k, q_dt, c_dt) && (!shadow || k <= 24);
+  p->eps = shadow ? kShadowEps : kApproxEps;
   if (mode == TSIM_MODE_TENSOR && !ok) {
     set_error("search: TSIM_MODE_TENSOR needs bf16 (D %% 8 == 0) or e4m3 (D %% 16 == 0) queries AND corpus, k <= 100 "
               "(got q_dt=%d c_dt=%d D=%lld k=%d)", q_dt, c_dt, (long long)D, k);
@@ -59,7 +61,7 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
   p->use_tensor = (mode != TSIM_MODE_EXACT) && ok;
   size_t off = 0;
   if (p->use_tensor) {
-    p->KP = k <= 10 ? 16 : k <= 24 ? 32 : k <= 52 ? 64 : 112;
+    p->KP = shadow ? 112 : k <= 10 ? 16 : k <= 24 ? 32 : k <= 52 ? 64 : 112;
     // more than one 128-query block: CTA pairs (cta_group::2) share each corpus tile between two SMs
     const char* nopair = getenv("TSIM_NO_PAIR");
     p->pair = (Q > 128 && !(nopair && nopair[0] == '1')) ? 1 : 0;
@@ -200,15 +202,25 @@ extern "C" size_t tsim_search_workspace_bytes(int64_t Q, int64_t N, int64_t D, i
                                               int mode) {
   if (check_search_args(Q, N, D, k, q_dt, c_dt, mode) != TSIM_OK) return 0;
   SearchPlan p;
-  if (make_search_plan(Q, N, D, k, q_dt, c_dt, mode, /*need_invnorm=*/true, &p) != TSIM_OK) return 0;
+  if (make_search_plan(Q, N, D, k, q_dt, c_dt, mode, /*need_invnorm=*/true, /*shadow=*/false, &p) != TSIM_OK) return 0;
   return p.total;
 }
 
-extern "C" int tsim_search_topk(const void* q, int q_dt, int64_t q_stride, const void* corpus, int c_dt,
-                                int64_t c_stride, const float* corpus_inv_norm, int64_t Q, int64_t N,
-                                int64_t D, int k, int64_t idx_base, int64_t exclude_self_base, int mode,
-                                float* out_score, double* out_score64, int64_t* out_idx,
-                                int32_t* out_flags, void* ws, size_t ws_bytes, void* stream) {
+extern "C" size_t tsim_search_shadow_workspace_bytes(int64_t Q, int64_t N, int64_t D, int k, int shadow_dt) {
+  if (check_search_args(Q, N, D, k, shadow_dt, shadow_dt, TSIM_MODE_AUTO) != TSIM_OK) return 0;
+  SearchPlan p;
+  if (make_search_plan(Q, N, D, k, shadow_dt, shadow_dt, TSIM_MODE_AUTO, true, /*shadow=*/true, &p) != TSIM_OK) return 0;
+  return p.total;
+}
+
+// q / corpus: the rows results are defined on (re-score, exact scan).  tq / tcorpus (dtype t_dt): what the
+// tensor pass reads -- the same arrays, or bf16 shadows of fp32 / fp16 rows (`shadow`).
+static int search_impl(const void* q, int q_dt, int64_t q_stride, const void* corpus, int c_dt, int64_t c_stride,
+                       const void* tq, int64_t tq_stride, const void* tcorpus, int64_t tc_stride, int t_dt, bool shadow,
+                       const float* corpus_inv_norm, int64_t Q, int64_t N,
+                       int64_t D, int k, int64_t idx_base, int64_t exclude_self_base, int mode,
+                       float* out_score, double* out_score64, int64_t* out_idx,
+                       int32_t* out_flags, void* ws, size_t ws_bytes, void* stream) {
   int rc = check_search_args(Q, N, D, k, q_dt, c_dt, mode);
   if (rc) return rc;
   if (Q == 0) return TSIM_OK;
@@ -217,16 +229,16 @@ extern "C" int tsim_search_topk(const void* q, int q_dt, int64_t q_stride, const
   TSIM_CHECK_ARG(q_stride >= D && c_stride >= D, "search: row stride smaller than D");
   cudaStream_t st = (cudaStream_t)stream;
   SearchPlan p;
-  rc = make_search_plan(Q, N, D, k, q_dt, c_dt, mode, true, &p);
+  rc = make_search_plan(Q, N, D, k, shadow ? t_dt : q_dt, shadow ? t_dt : c_dt, mode, true, shadow, &p);
   if (rc) return rc;
   if (!ws || ws_bytes < p.total) {
     set_error("search: workspace too small (%zu < %zu bytes)", ws_bytes, p.total);
     return TSIM_ERR_WORKSPACE;
   }
   if (p.use_tensor) {
-    const int per16 = 16 / dtype_size(c_dt);
-    const bool aligned = (((uintptr_t)q & 15) == 0) && (((uintptr_t)corpus & 15) == 0) &&
-                         (q_stride % per16 == 0) && (c_stride % per16 == 0);
+    const int per16 = 16 / dtype_size(t_dt);
+    const bool aligned = (((uintptr_t)tq & 15) == 0) && (((uintptr_t)tcorpus & 15) == 0) &&
+                         (tq_stride % per16 == 0) && (tc_stride % per16 == 0);
     if (!aligned) {
       if (mode == TSIM_MODE_TENSOR) {
         set_error("search: TMA needs 16-byte aligned bases and row strides");
@@ -250,18 +262,18 @@ extern "C" int tsim_search_topk(const void* q, int q_dt, int64_t q_stride, const
     const float* c_inv = corpus_inv_norm;
     if (!c_inv) {
       float* tmp = (float*)(w + p.off_invnorm);
-      rc = launch_row_inv_norm(corpus, c_dt, N, D, c_stride, tmp, st);
+      rc = launch_row_inv_norm(tcorpus, t_dt, N, D, tc_stride, tmp, st);
       if (rc) return rc;
       c_inv = tmp;
     }
-    const void* qt = q;
-    int64_t qt_stride = q_stride;
+    const void* qt = tq;
+    int64_t qt_stride = tq_stride;
     const int qrows = p.pair ? 256 : 128;
     if (Q % qrows != 0) {
       char* qp = w + p.off_qpad;
-      const size_t rowb = (size_t)D * dtype_size(q_dt);
+      const size_t rowb = (size_t)D * dtype_size(t_dt);
       TSIM_CUDA(cudaMemsetAsync(qp + (size_t)Q * rowb, 0, ((size_t)p.QB * qrows - Q) * rowb, st));
-      TSIM_CUDA(cudaMemcpy2DAsync(qp, rowb, q, (size_t)q_stride * dtype_size(q_dt), rowb, (size_t)Q, cudaMemcpyDeviceToDevice, st));
+      TSIM_CUDA(cudaMemcpy2DAsync(qp, rowb, tq, (size_t)tq_stride * dtype_size(t_dt), rowb, (size_t)Q, cudaMemcpyDeviceToDevice, st));
       qt = qp;
       qt_stride = D;
     }
@@ -273,21 +285,21 @@ extern "C" int tsim_search_topk(const void* q, int q_dt, int64_t q_stride, const
       const char* nolad = getenv("TSIM_NO_LADDER");   // experiment knob
       uint32_t* lad = (nolad && nolad[0] == '1') ? nullptr : (uint32_t*)(w + p.off_ladder);
       if (p.mini_mult) {
-        rc = launch_search_tc(qt, qt_stride, corpus, c_stride, c_dt, c_inv, Q, N, D, self_on, self_off, p,
+        rc = launch_search_tc(qt, qt_stride, tcorpus, tc_stride, t_dt, c_inv, Q, N, D, self_on, self_off, p,
                               TC_PASS_MINI, cand, thr, nullptr, st);
         if (rc) return rc;
         rc = launch_tighten(Q, p, (int)p.mini_slots, cand, thr, lad, st);
         if (rc) return rc;
         ladder = lad;
       }
-      rc = launch_search_tc(qt, qt_stride, corpus, c_stride, c_dt, c_inv, Q, N, D, self_on, self_off, p,
+      rc = launch_search_tc(qt, qt_stride, tcorpus, tc_stride, t_dt, c_inv, Q, N, D, self_on, self_off, p,
                             p.mini_mult ? TC_PASS_SAMPLE_REST : TC_PASS_SAMPLE, cand, thr, ladder, st);
       if (rc) return rc;
       rc = launch_tighten(Q, p, (int)(p.mini_slots + p.boot_slots), cand, thr, lad, st);   // re-levels the ladder
       if (rc) return rc;
       ladder = lad;
     }
-    rc = launch_search_tc(qt, qt_stride, corpus, c_stride, c_dt, c_inv, Q, N, D, self_on, self_off, p,
+    rc = launch_search_tc(qt, qt_stride, tcorpus, tc_stride, t_dt, c_inv, Q, N, D, self_on, self_off, p,
                           p.boot_tiles ? TC_PASS_MAIN : TC_PASS_ALL, cand, thr, ladder, st);
     if (rc) return rc;
     if (timed) TSIM_CUDA(cudaEventRecord(g_ev_stop, st));
@@ -312,6 +324,31 @@ extern "C" int tsim_search_topk(const void* q, int q_dt, int64_t q_stride, const
   return launch_merge_exact_lists(q, q_dt, q_stride, corpus, c_dt, c_stride, Q, D, k, idx_base, p,
                                   nullptr, nullptr, ex_score, ex_idx, out_score, out_score64, out_idx,
                                   out_flags, st);
+}
+
+extern "C" int tsim_search_topk(const void* q, int q_dt, int64_t q_stride, const void* corpus, int c_dt,
+                                int64_t c_stride, const float* corpus_inv_norm, int64_t Q, int64_t N,
+                                int64_t D, int k, int64_t idx_base, int64_t exclude_self_base, int mode,
+                                float* out_score, double* out_score64, int64_t* out_idx,
+                                int32_t* out_flags, void* ws, size_t ws_bytes, void* stream) {
+  return search_impl(q, q_dt, q_stride, corpus, c_dt, c_stride, q, q_stride, corpus, c_stride, c_dt, false,
+                     corpus_inv_norm, Q, N, D, k, idx_base, exclude_self_base, mode, out_score, out_score64, out_idx,
+                     out_flags, ws, ws_bytes, stream);
+}
+
+extern "C" int tsim_search_topk_shadow(const void* q, int q_dt, int64_t q_stride, const void* corpus, int c_dt,
+                                       int64_t c_stride, const void* q_shadow, int64_t qs_stride,
+                                       const void* corpus_shadow, int64_t cs_stride, int shadow_dt,
+                                       const float* shadow_inv_norm, int64_t Q, int64_t N, int64_t D, int k,
+                                       int64_t idx_base, int64_t exclude_self_base,
+                                       float* out_score, double* out_score64, int64_t* out_idx,
+                                       int32_t* out_flags, void* ws, size_t ws_bytes, void* stream) {
+  TSIM_CHECK_ARG(q_shadow && (N == 0 || corpus_shadow), "search_shadow: null shadow pointer");
+  TSIM_CHECK_ARG(shadow_dt == TSIM_BF16, "search_shadow: the shadow must be bf16 (got dtype %d)", shadow_dt);
+  TSIM_CHECK_ARG(qs_stride >= D && cs_stride >= D, "search_shadow: row stride smaller than D");
+  return search_impl(q, q_dt, q_stride, corpus, c_dt, c_stride, q_shadow, qs_stride, corpus_shadow, cs_stride,
+                     shadow_dt, true, shadow_inv_norm, Q, N, D, k, idx_base, exclude_self_base, TSIM_MODE_AUTO,
+                     out_score, out_score64, out_idx, out_flags, ws, ws_bytes, stream);
 }
 
 extern "C" int tsim_merge_topk(const double* sc, const int64_t* ix, int64_t Q, int64_t n_lists, int k_in,

@@ -18,6 +18,11 @@ constexpr float kPoolEps = 1e-9f;  // clamp in AvgPoolingStrategy, reference mod
 // ||q|| * ||c||.  Candidates are proven complete when the approximate k-th and KP-th best
 // differ by more than 2 * kApproxEps (see select_merge.cu); tests measure the real error.
 constexpr float kApproxEps = 5e-5f;
+// The same bound when the tensor pass runs on a bf16 SHADOW of fp32 / fp16 rows (both operands rounded
+// to 8 mantissa bits): |cos_shadow - cos| <= 2 * 2^-9 * 1.002 = 3.92e-3 (each unit vector moves by at most
+// its relative rounding error), the shadow query's norm is off by <= 2^-9 (1.95e-3 of a score <= 1), plus
+// the tensor-core term: 5.93e-3, rounded up.
+constexpr float kShadowEps = 6e-3f;
 
 // Threshold ladder (search_tc.cu / select_merge.cu): per query, kLadder ascending score levels
 // level(i) = base + i * step and the number of candidate rows seen so far in [level(i), level(i+1));
@@ -193,6 +198,7 @@ __device__ __forceinline__ double warp_exact_cosine(const void* q, int q_dt, con
 struct SearchPlan {
   // tensor path
   int use_tensor;      // 1: tcgen05 candidate pass + select/rescore
+  float eps;           // bound of |approx - exact| in units of ||q|| used by the completeness proof
   int KP;              // per-unit candidate list capacity (16/32/64/128)
   int pair;            // 1: CTA pairs (cta_group::2), query blocks of 256
   int QB;              // query blocks of 128 (256 when pair)
@@ -218,8 +224,9 @@ struct SearchPlan {
   size_t total;
 };
 
+// q_dt / c_dt: the dtypes the tensor pass reads (the shadow's when `shadow`)
 int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt, int mode,
-                     bool need_invnorm, SearchPlan* plan);
+                     bool need_invnorm, bool shadow, SearchPlan* plan);
 
 // kernels' host launchers (defined in the .cu files)
 // pass: 0 = the whole corpus in one launch; 1 = bootstrap sample (all of it); 2 = main (everything

@@ -127,12 +127,21 @@ def row_inv_norm(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def make_shadow(rows: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """bf16 shadow of fp32 / fp16 rows plus the shadow rows' inverse norms: what ``search_topk`` needs
+    (``corpus_shadow=``, ``shadow_inv_norm=``) to search such rows at tensor-core speed, still exactly."""
+    _require_cuda(rows)
+    shadow = rows.to(torch.bfloat16).contiguous()
+    return shadow, row_inv_norm(shadow)
+
+
 def search_topk(queries: torch.Tensor, corpus: torch.Tensor, k: int, *,
                 corpus_inv_norm: Optional[torch.Tensor] = None, idx_base: int = 0,
                 exclude_self_base: int = -1, mode: str = "auto",
                 return_score64: bool = False, return_flags: bool = False,
                 out_scores: Optional[torch.Tensor] = None, out_idx: Optional[torch.Tensor] = None,
-                out_score64: Optional[torch.Tensor] = None):
+                out_score64: Optional[torch.Tensor] = None,
+                corpus_shadow: Optional[torch.Tensor] = None, shadow_inv_norm: Optional[torch.Tensor] = None):
     """K2 + K3 -- exact cosine top-k of every query row against every corpus row.
 
     Returns (scores float32 [Q, k], idx int64 [Q, k]) best first, ties by lower index, idx -1 /
@@ -167,6 +176,31 @@ def search_topk(queries: torch.Tensor, corpus: torch.Tensor, k: int, *,
     idx = _out(out_idx, torch.int64)
     s64 = _out(out_score64, torch.float64) if (return_score64 or out_score64 is not None) else None
     flags = torch.empty(Q, dtype=torch.int32, device=dev) if return_flags else None
+    if corpus_shadow is not None and mode == "auto" and N > 0:
+        # fp32 / fp16 rows: candidates from the bf16 shadows on the tensor cores, float64 re-score on the originals
+        _require_cuda(corpus_shadow, shadow_inv_norm)
+        if corpus_shadow.shape != corpus.shape or corpus_shadow.dtype != torch.bfloat16 or corpus_shadow.stride(1) != 1:
+            raise ValueError("corpus_shadow must be a bfloat16 [N, D] tensor with contiguous rows")
+        q_shadow = queries.to(torch.bfloat16).contiguous()
+        nbytes = lib.tsim_search_shadow_workspace_bytes(Q, N, D, k, _lib.BF16)
+        if nbytes == 0:
+            _lib.check(_lib.ERR_INVALID_ARG, "tsim_search_shadow_workspace_bytes")
+        ws = _workspace(dev, nbytes, "search")
+        with torch.cuda.device(dev):
+            rc = lib.tsim_search_topk_shadow(queries.data_ptr(), _dt(queries), queries.stride(0),
+                                             corpus.data_ptr(), _dt(corpus), corpus.stride(0),
+                                             q_shadow.data_ptr(), q_shadow.stride(0),
+                                             corpus_shadow.data_ptr(), corpus_shadow.stride(0), _lib.BF16,
+                                             _ptr(shadow_inv_norm), Q, N, D, k, int(idx_base), int(exclude_self_base),
+                                             scores.data_ptr(), _ptr(s64), idx.data_ptr(), _ptr(flags),
+                                             ws.data_ptr(), ws.numel(), _stream(dev))
+        _lib.check(rc, "tsim_search_topk_shadow")
+        res = [scores, idx]
+        if return_score64 or out_score64 is not None:
+            res.append(s64)
+        if return_flags:
+            res.append(flags)
+        return tuple(res)
     nbytes = lib.tsim_search_workspace_bytes(Q, N, D, k, _dt(queries), _dt(corpus), _MODES[mode])
     if nbytes == 0:
         _lib.check(_lib.ERR_INVALID_ARG if mode != "tensor" else _lib.ERR_UNSUPPORTED,

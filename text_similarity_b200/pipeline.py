@@ -55,6 +55,11 @@ class _EncodedCorpus:
 
     def __init__(self, rows: torch.Tensor, inv_norm: torch.Tensor):
         self.rows, self.inv_norm = rows, inv_norm
+        # fp32 / fp16 tensors: bf16 shadow for the tensor-core candidate pass (results stay exact on `rows`)
+        self.shadow_kw = {}
+        if rows.dtype in (torch.float32, torch.float16) and rows.shape[0] and rows.shape[1] % 8 == 0:
+            shadow, shadow_inv = ops.make_shadow(rows)
+            self.shadow_kw = {"corpus_shadow": shadow, "shadow_inv_norm": shadow_inv}
 
 
 class SentenceMiningPipeline(SearchPipeline):
@@ -122,12 +127,13 @@ class SentenceMiningPipeline(SearchPipeline):
         if len(chunks) == 1:
             begin, enc = chunks[0]
             qq = q if q.dtype == enc.rows.dtype or enc.rows.dtype == torch.float32 else q.to(enc.rows.dtype)
-            return ops.search_topk(qq, enc.rows, k, corpus_inv_norm=enc.inv_norm, idx_base=begin, mode=mode)
+            return ops.search_topk(qq, enc.rows, k, corpus_inv_norm=enc.inv_norm, idx_base=begin, mode=mode,
+                                   **enc.shadow_kw)
         s64_parts, idx_parts = [], []
         for begin, enc in chunks:
             qq = q if q.dtype == enc.rows.dtype or enc.rows.dtype == torch.float32 else q.to(enc.rows.dtype)
             _, idx, s64 = ops.search_topk(qq, enc.rows, k, corpus_inv_norm=enc.inv_norm, idx_base=begin,
-                                          mode=mode, return_score64=True)
+                                          mode=mode, return_score64=True, **enc.shadow_kw)
             s64_parts.append(s64)
             idx_parts.append(idx)
         # cross-chunk merge, absent in the reference (:83,88 overwrite): K3 second pass

@@ -50,7 +50,7 @@ class ShardedCorpus:
     """One rank's block of the corpus embedding matrix plus what the search needs with it."""
 
     def __init__(self, shard: torch.Tensor, idx_base: int = 0, group=None,
-                 inv_norm: Optional[torch.Tensor] = None):
+                 inv_norm: Optional[torch.Tensor] = None, bf16_shadow: bool = True):
         if shard.dim() != 2:
             raise ValueError("shard must be [rows, D]")
         self.shard = shard
@@ -64,8 +64,17 @@ class ShardedCorpus:
         # norms for every query: F.cosine_similarity at search_pipeline.py:77)
         self.inv_norm = inv_norm if inv_norm is not None else (
             ops.row_inv_norm(shard) if shard.shape[0] and shard.is_cuda else None)
+        # fp32 / fp16 rows: a bf16 shadow (+50 % / +100 % memory) lets the tensor cores nominate candidates;
+        # results are still defined on -- and re-scored in float64 from -- the original rows
+        self.shadow = self.shadow_inv = None
+        if (bf16_shadow and shard.is_cuda and shard.shape[0] and shard.dtype in (torch.float32, torch.float16)
+                and shard.shape[1] % 8 == 0):
+            self.shadow, self.shadow_inv = ops.make_shadow(shard)
         self._gather_buf = {}
         self._graphs = {}
+
+    def _shadow_kw(self):
+        return {} if self.shadow is None else {"corpus_shadow": self.shadow, "shadow_inv_norm": self.shadow_inv}
 
     # -- CUDA-graph replay of the local search -------------------------------------------------------
     # One search is ~8 dependent stream operations (threshold memset, sample pass, tighten, main pass,
@@ -85,7 +94,7 @@ class ShardedCorpus:
         def run():
             ops.search_topk(q_static, self.shard, k, corpus_inv_norm=self.inv_norm, idx_base=self.idx_base,
                             exclude_self_base=exclude_self_base, mode=mode, out_scores=scores,
-                            out_score64=s64, out_idx=idx)
+                            out_score64=s64, out_idx=idx, **self._shadow_kw())
 
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -115,7 +124,7 @@ class ShardedCorpus:
 
     def search_local(self, queries: torch.Tensor, k: int, **kw):
         return ops.search_topk(queries, self.shard, k, corpus_inv_norm=self.inv_norm,
-                               idx_base=self.idx_base, **kw)
+                               idx_base=self.idx_base, **self._shadow_kw(), **kw)
 
     def search(self, queries: torch.Tensor, k: int, exclude_self_base: int = -1, mode: str = "auto"
                ) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -133,7 +142,7 @@ class ShardedCorpus:
         # the search kernels write their float64 scores and int64 rows straight into the send buffer
         ops.search_topk(queries, self.shard, k, corpus_inv_norm=self.inv_norm, idx_base=self.idx_base,
                         exclude_self_base=exclude_self_base, mode=mode,
-                        out_score64=send[0].view(torch.float64), out_idx=send[1])
+                        out_score64=send[0].view(torch.float64), out_idx=send[1], **self._shadow_kw())
         s64, idx = gather_shard_results(send[0].view(torch.float64), send[1], self.group, bufs)
         scores, _, rows = ops.merge_topk(s64, idx, k, self.world)
         return scores, rows
