@@ -114,3 +114,33 @@ def test_two_rank_gather_and_merge_equals_single_search():
     ret = mgr.dict()
     mp.spawn(_gloo_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+def test_store_meter_and_shadow_refuse_the_cpu():
+    from src.utils.metrics import RetrievalAccuracyMeter
+    from text_similarity_b200 import ops
+    from text_similarity_b200.sharded import ShardedCorpus
+    from text_similarity_b200.store import EmbeddingStore
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        EmbeddingStore(64, torch.bfloat16, "cpu")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        RetrievalAccuracyMeter().update(torch.randn(4, 8), torch.randn(4, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.make_shadow(torch.randn(4, 8))
+    sc = ShardedCorpus(torch.randn(16, 8), idx_base=3)       # a CPU shard is only a description (gloo tests)
+    assert sc.shadow is None and sc.inv_norm is None and sc.idx_base == 3
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sc.search(torch.randn(2, 8), 3)
+
+
+def test_abi_shadow_entry_validates_arguments_before_touching_the_gpu():
+    from text_similarity_b200 import _lib
+    lib = _lib.load()
+    assert lib.tsim_search_shadow_workspace_bytes(100, 10_000, 384, 10, _lib.BF16) > 0
+    assert lib.tsim_search_shadow_workspace_bytes(100, 10_000, 384, 0, _lib.BF16) == 0
+    rc = lib.tsim_search_topk_shadow(None, _lib.F32, 8, None, _lib.F32, 8, None, 8, None, 8, _lib.BF16, None,
+                                     4, 10, 8, 3, 0, -1, None, None, None, None, None, 0, None)
+    assert rc == _lib.ERR_INVALID_ARG and b"shadow" in lib.tsim_last_error()
+    rc = lib.tsim_search_topk_shadow(1, _lib.F32, 8, 1, _lib.F32, 8, 1, 8, 1, 8, _lib.E4M3, None,
+                                     4, 10, 8, 3, 0, -1, None, None, None, None, None, 0, None)
+    assert rc == _lib.ERR_INVALID_ARG and b"bf16" in lib.tsim_last_error()
