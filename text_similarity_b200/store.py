@@ -56,7 +56,8 @@ class EmbeddingStore:
         self.rows = torch.empty(cap, self.dim, dtype=dtype, device=self.device)
         self.inv_norm = torch.empty(cap, dtype=torch.float32, device=self.device)
         self.ids = torch.empty(cap, dtype=torch.int64, device=self.device)
-        self._pos = {}          # label -> row position (host side; removal needs it)
+        self._pos = {}          # label -> row position (host side; built lazily: only removal and explicit ids need it)
+        self._pos_valid = True
 
     # -- size -------------------------------------------------------------------------------------
     def __len__(self) -> int:
@@ -79,24 +80,32 @@ class EmbeddingStore:
             new[:self.n] = old[:self.n]
             setattr(self, name, new)
 
+    def _positions(self) -> dict:
+        """label -> row position; rebuilt from the device-side ids after bulk appends (a Python dict entry per
+        row is too slow to maintain eagerly for 10M-row stores that never remove anything)."""
+        if not self._pos_valid:
+            self._pos = {int(lab): i for i, lab in enumerate(self.ids[:self.n].tolist())}
+            self._pos_valid = True
+        return self._pos
+
     def _take_ids(self, count: int, ids: Optional[Sequence[int]]) -> torch.Tensor:
         if ids is None:
-            out = torch.arange(self._next_id, self._next_id + count, dtype=torch.int64)
+            out = torch.arange(self._next_id, self._next_id + count, dtype=torch.int64)   # fresh labels: no clash possible
         else:
             out = torch.as_tensor(list(ids) if not isinstance(ids, torch.Tensor) else ids.cpu(), dtype=torch.int64)
             if out.numel() != count:
                 raise ValueError("one id per row")
-            if len(set(out.tolist())) != count or any(int(i) in self._pos for i in out.tolist()):
+            pos = self._positions()
+            if len(set(out.tolist())) != count or any(int(i) in pos for i in out.tolist()):
                 raise ValueError("ids must be unique and not already in the store")
         if count:
             self._next_id = max(self._next_id, int(out.max()) + 1)
         return out
 
     def _register(self, ids: torch.Tensor) -> None:
-        for off, lab in enumerate(ids.tolist()):
-            self._pos[lab] = self.n + off
         self.ids[self.n:self.n + ids.numel()] = ids.to(self.device)
         self.n += ids.numel()
+        self._pos_valid = False
 
     # -- add --------------------------------------------------------------------------------------
     def add(self, rows: torch.Tensor, inv_norm: Optional[torch.Tensor] = None,
@@ -136,9 +145,10 @@ class EmbeddingStore:
         """Delete rows by label; unknown labels are skipped like the reference's try/except
         (search_pipeline.py:164-169).  The last live row moves into each hole.  Returns the count."""
         done = 0
+        pos = self._positions()
         for lab in ids:
             lab = int(lab)
-            p = self._pos.pop(lab, None)
+            p = pos.pop(lab, None)
             if p is None:
                 continue
             last = self.n - 1
@@ -147,7 +157,7 @@ class EmbeddingStore:
                 self.inv_norm[p] = self.inv_norm[last]
                 moved = int(self.ids[last])
                 self.ids[p] = moved
-                self._pos[moved] = p
+                pos[moved] = p
             self.n -= 1
             done += 1
         return done
@@ -227,5 +237,5 @@ class EmbeddingStore:
             del src
         st.n = n
         st._next_id = meta["next_id"]
-        st._pos = {int(lab): i for i, lab in enumerate(st.ids[:n].tolist())}
+        st._pos_valid = False
         return st
