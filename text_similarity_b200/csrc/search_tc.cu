@@ -198,6 +198,8 @@ struct TcArgs {
   uint64_t* cand;       // [Q][NC][KP] packed keys
   uint32_t* thr;        // [Q] ordered-float global thresholds (0 = none yet)
   uint32_t* ladder;     // [Q][2 * kLadder] threshold ladder (main launch after a bootstrap), or null
+  uint64_t* sched;      // round-robin: this launch's claim area (zeroed per call), or null = static dealing:
+                        // [0] next-unit counter, then per worker a ring of kSchedRing claim records
   int roles_low;        // experiment knob (TSIM_ROLES_LOW=1): TMA / MMA / alloc on warps 0-2, epilogue on warps 4-7
   int dbg;              // TSIM_DEBUG bits (diagnosis only): 1 skip A loads, 2 skip MMAs, 4 skip epilogue math
 };
@@ -219,9 +221,24 @@ struct Unit { int qb; int slot; int tile0; int tstride; int ntiles; };
 // stream neighbouring tiles, the QB CTAs that share a tile run side by side (L2), and each query's
 // list -- hence its threshold -- persists over everything the CTA sees.
 // Round-robin schedule (many query blocks, the tensor-bound regime): unit u = (chunk u / QB,
-// query block u % QB) dealt to CTA u % grid; the QB units of one chunk run side by side.
+// query block u % QB); the QB units of one chunk are handed out back to back so that the workers
+// scanning a chunk run side by side and the chunk comes from HBM once and from L2 for the rest.
+//  * claimed (a.sched): a worker takes the next unit from a global counter when it has issued the
+//    loads of its previous one.  The QB units of a chunk then start within QB / workers of a unit's
+//    duration of each other, whatever the workers' history: with static dealing every worker's
+//    cold-path time random-walks away from its neighbours' over ~130 units, the 16 readers of a chunk
+//    end up further apart than L2 holds, and the corpus came from DRAM 3.1 times.
+//    One thread per worker claims (the TMA thread; the leader CTA's for a pair) and publishes
+//    (iteration, unit) in the worker's ring in global memory; the MMA thread, the epilogue threads and
+//    the peer CTA poll that record -- the claimer runs a pipeline depth ahead, so they rarely spin.
+//    The ring cannot wrap onto a record still needed: the TMA thread is never more than
+//    STAGES k-blocks + 2 accumulator tiles (< 10 one-tile units) ahead of the slowest reader.
+//  * static (a.sched == null, TSIM_STATIC_UNITS=1): unit u -> worker u % nw.
 // `wid` / `nw` = this worker's index and the number of workers (CTAs, or CTA pairs).
-__device__ __forceinline__ bool get_unit(const TcArgs& a, int it, int wid, int nw, Unit& un) {
+constexpr int kSchedRing = 32;
+constexpr uint32_t kNoUnit = 0xffffffffu;
+
+__device__ __forceinline__ bool get_unit(const TcArgs& a, int it, int wid, int nw, bool claimer, Unit& un) {
   if (a.sticky) {
     if (it > 0 || wid >= a.Gq * a.QB) return false;
     const int j = wid / a.QB;
@@ -229,8 +246,28 @@ __device__ __forceinline__ bool get_unit(const TcArgs& a, int it, int wid, int n
     un.ntiles = j < a.T ? (a.T - j + a.Gq - 1) / a.Gq : 0;
     return true;
   }
-  const int u = wid + it * nw;
-  if (u >= a.n_units) return false;
+  int u;
+  if (a.sched) {
+    uint64_t* rec = a.sched + 32 + (size_t)wid * kSchedRing + (it & (kSchedRing - 1));
+    uint32_t got;
+    if (claimer) {
+      got = atomicAdd((unsigned int*)a.sched, 1u);
+      if (got >= (uint32_t)a.n_units) got = kNoUnit;
+      const uint64_t v = ((uint64_t)(uint32_t)(it + 1) << 32) | got;
+      asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(rec), "l"(v) : "memory");
+    } else {
+      uint64_t v;
+      do {
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(rec) : "memory");
+      } while ((uint32_t)(v >> 32) != (uint32_t)(it + 1));
+      got = (uint32_t)v;
+    }
+    if (got == kNoUnit) return false;
+    u = (int)got;
+  } else {
+    u = wid + it * nw;
+    if (u >= a.n_units) return false;
+  }
   const int chunk = u / a.QB;
   un.qb = u - chunk * a.QB; un.slot = chunk; un.tile0 = chunk * a.tpc; un.tstride = 1;
   un.ntiles = min(a.tpc, a.T - un.tile0);
@@ -512,7 +549,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       Unit un;
-      for (int it = 0; get_unit(a, it, wid, nw, un); ++it) {
+      for (int it = 0; get_unit(a, it, wid, nw, rank == 0, un); ++it) {
         for (int t = 0; t < un.ntiles; ++t) {
           const int row0 = actual_tile(a, un.tile0 + t * un.tstride) * BN;
           for (int kb = 0; kb < a.kblocks; ++kb) {
@@ -541,7 +578,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t aphase = 0;
       Unit un;
-      for (int it = 0; get_unit(a, it, wid, nw, un); ++it) {
+      for (int it = 0; get_unit(a, it, wid, nw, false, un); ++it) {
         for (int t = 0; t < un.ntiles; ++t) {
           mbar_wait(smem_u32(&tempty_bar[acc]), aphase ^ 1);
           tc_fence_after();
@@ -576,7 +613,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     typename ListFor<KP>::type list(list_s + et, list_i + et, list_n + et);
     int acc = 0; uint32_t aphase = 0;
     Unit un;
-    for (int it = 0; get_unit(a, it, wid, nw, un); ++it) {
+    for (int it = 0; get_unit(a, it, wid, nw, false, un); ++it) {
       const int64_t qg = PAIR ? (int64_t)un.qb * (2 * BM) + rank * BM + et : (int64_t)un.qb * BM + et;
       const bool qvalid = qg < a.Q;
       const int64_t self_row = a.self_on ? a.self_off + qg : -1;
@@ -727,7 +764,8 @@ int launch_cfg(const CUtensorMap& mq, const CUtensorMap& mc, const TcArgs& a, cu
 
 int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_t c_stride, int dt,
                      const float* c_inv, int64_t Q, int64_t N, int64_t D, int self_on, int64_t self_off,
-                     const SearchPlan& p, int pass, uint64_t* cand, uint32_t* thr, uint32_t* ladder, cudaStream_t st) {
+                     const SearchPlan& p, int pass, uint64_t* cand, uint32_t* thr, uint32_t* ladder, uint64_t* sched,
+                     cudaStream_t st) {
   CUtensorMap mq, mc;
   const int qrows = p.pair ? 2 * BM : BM;
   // q holds QB * qrows rows (the API pads the last query block with zero rows)
@@ -764,6 +802,10 @@ int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_
   a.n_units = p.QB * ((a.T + a.tpc - 1) / (a.tpc > 0 ? a.tpc : 1));
   a.self_on = self_on; a.self_off = self_off;
   a.cand = cand; a.thr = thr; a.ladder = ladder;
+  // every tcgen05 launch of a call claims from its own zeroed area (mini sample | sample | main)
+  const int area = pass == TC_PASS_MINI ? 0 : (pass == TC_PASS_SAMPLE || pass == TC_PASS_SAMPLE_REST) ? 1 : 2;
+  const char* su = getenv("TSIM_STATIC_UNITS");   // experiment knob: static round-robin dealing
+  a.sched = (sched && !p.sticky && !(su && su[0] == '1')) ? sched + (size_t)area * (p.sched_area / 8) : nullptr;
   const char* dbg = getenv("TSIM_DEBUG");
   a.dbg = dbg ? atoi(dbg) : 0;
   const char* rl = getenv("TSIM_ROLES_LOW");

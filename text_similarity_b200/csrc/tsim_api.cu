@@ -162,6 +162,10 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
   if (p->S < 1) p->S = 1;
   p->off_thr = off; off = align_up(off + (size_t)Q * sizeof(uint32_t), 256);
   p->off_flagcnt = off; off += 256;
+  // unit-claim areas of the round-robin schedule (search_tc.cu), zeroed by the same memset as thr / flag count
+  p->off_sched = off;
+  p->sched_area = (p->use_tensor && !p->sticky) ? 256 + (size_t)sms * 32 * sizeof(uint64_t) : 0;
+  off += 3 * p->sched_area;
   p->off_flaglist = off; off = align_up(off + (size_t)Q * sizeof(int32_t), 256);
   if (p->use_tensor && p->boot_tiles) {
     p->off_ladder = off; off = align_up(off + (size_t)Q * 2 * kLadder * sizeof(uint32_t), 256);
@@ -257,8 +261,9 @@ static int search_impl(const void* q, int q_dt, int64_t q_stride, const void* co
   const int64_t self_off = exclude_self_base - idx_base;  // local corpus row of query 0's own row
 
   if (p.use_tensor) {
-    // thr and flag_cnt are adjacent: one memset
-    TSIM_CUDA(cudaMemsetAsync(thr, 0, (p.off_flagcnt + 256) - p.off_thr, st));
+    // thr, flag_cnt and the unit-claim areas are adjacent: one memset
+    TSIM_CUDA(cudaMemsetAsync(thr, 0, (p.off_sched + 3 * p.sched_area) - p.off_thr, st));
+    uint64_t* sched = p.sched_area ? (uint64_t*)(w + p.off_sched) : nullptr;
     const float* c_inv = corpus_inv_norm;
     if (!c_inv) {
       float* tmp = (float*)(w + p.off_invnorm);
@@ -286,21 +291,21 @@ static int search_impl(const void* q, int q_dt, int64_t q_stride, const void* co
       uint32_t* lad = (nolad && nolad[0] == '1') ? nullptr : (uint32_t*)(w + p.off_ladder);
       if (p.mini_mult) {
         rc = launch_search_tc(qt, qt_stride, tcorpus, tc_stride, t_dt, c_inv, Q, N, D, self_on, self_off, p,
-                              TC_PASS_MINI, cand, thr, nullptr, st);
+                              TC_PASS_MINI, cand, thr, nullptr, sched, st);
         if (rc) return rc;
         rc = launch_tighten(Q, p, (int)p.mini_slots, cand, thr, lad, st);
         if (rc) return rc;
         ladder = lad;
       }
       rc = launch_search_tc(qt, qt_stride, tcorpus, tc_stride, t_dt, c_inv, Q, N, D, self_on, self_off, p,
-                            p.mini_mult ? TC_PASS_SAMPLE_REST : TC_PASS_SAMPLE, cand, thr, ladder, st);
+                            p.mini_mult ? TC_PASS_SAMPLE_REST : TC_PASS_SAMPLE, cand, thr, ladder, sched, st);
       if (rc) return rc;
       rc = launch_tighten(Q, p, (int)(p.mini_slots + p.boot_slots), cand, thr, lad, st);   // re-levels the ladder
       if (rc) return rc;
       ladder = lad;
     }
     rc = launch_search_tc(qt, qt_stride, tcorpus, tc_stride, t_dt, c_inv, Q, N, D, self_on, self_off, p,
-                          p.boot_tiles ? TC_PASS_MAIN : TC_PASS_ALL, cand, thr, ladder, st);
+                          p.boot_tiles ? TC_PASS_MAIN : TC_PASS_ALL, cand, thr, ladder, sched, st);
     if (rc) return rc;
     if (timed) TSIM_CUDA(cudaEventRecord(g_ev_stop, st));
     rc = launch_select_rescore(q, q_dt, q_stride, corpus, c_dt, c_stride, Q, N, D, k, idx_base, p,

@@ -221,6 +221,8 @@ struct SearchPlan {
   // workspace offsets (bytes)
   size_t off_cand, off_thr, off_flagcnt, off_flaglist, off_invnorm, off_qpad, off_ex_score, off_ex_idx;
   size_t off_ladder;   // [Q][2 * kLadder] u32: per-query threshold ladder (levels | counts), bootstrap plans only
+  size_t off_sched;    // round-robin: 3 unit-claim areas (one per tcgen05 launch of a call), zeroed with thr
+  size_t sched_area;   // bytes per claim area: 256 (counter) + workers * 32 records * 8
   size_t total;
 };
 
@@ -235,7 +237,7 @@ enum { TC_PASS_ALL = 0, TC_PASS_SAMPLE = 1, TC_PASS_MAIN = 2, TC_PASS_MINI = 3, 
 int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_t c_stride, int dt,
                      const float* c_inv, int64_t Q, int64_t N, int64_t D,
                      int self_on, int64_t self_off, const SearchPlan& p, int pass, uint64_t* cand,
-                     uint32_t* thr, uint32_t* ladder, cudaStream_t st);
+                     uint32_t* thr, uint32_t* ladder, uint64_t* sched, cudaStream_t st);
 int launch_tighten(int64_t Q, const SearchPlan& p, int nslots, const uint64_t* cand, uint32_t* thr,
                    uint32_t* ladder, cudaStream_t st);
 int launch_select_rescore(const void* q, int q_dt, int64_t q_stride, const void* corpus, int c_dt,
