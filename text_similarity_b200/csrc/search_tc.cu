@@ -13,9 +13,9 @@
 // insertion into that query's private sorted list in shared memory.  Two 256-column
 // accumulator stages (all 512 TMEM columns) let the epilogue of tile t overlap the MMAs of t+1.
 //
-// Work unit = (128-query block, R-row corpus chunk); units are dealt round-robin to one
-// persistent CTA per SM with the query block fastest, so the CTAs that share a corpus chunk
-// run side by side and the chunk is read from HBM once and from L2 by the rest.
+// Work unit = (128-query block, R-row corpus chunk); one persistent CTA per SM claims units from a
+// global counter, query block fastest, so the CTAs that share a corpus chunk run side by side and
+// the chunk is read from HBM once and from L2 by the rest (get_unit below).
 // Each unit leaves its KP best (approx score, row) keys in cand[q][chunk][KP]; full lists raise
 // thr[q] (atomicMax) so later units start with a tight threshold.  select_merge.cu finishes.
 //
