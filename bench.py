@@ -159,6 +159,8 @@ def run_reference(args, out_fd):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "corpus_rows": N, "dim": D, "queries_per_step": Q, "k": k,
+                   "rows_per_gpu": N, "sharding": "none (host CPU)", "cache": "n/a (CPU)",
+                   "scores": "fp32 cos_sim + torch.topk, as the reference computes them",
                    "note": "CPU arm: oracle port of the reference's cos_sim+topk search on host cores"},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -94,3 +94,24 @@ def test_ladder_can_be_switched_off_and_results_do_not_change(ops, monkeypatch):
     monkeypatch.setenv("TSIM_NO_LADDER", "1")
     b = ops.search_topk(q, c, k, mode="tensor", return_score64=True)
     assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+
+
+@pytest.mark.parametrize("Q,N,D,k", [(1280, 500_000, 64, 10), (4096, 150_000, 128, 100), (300, 40_000, 768, 10)])
+def test_claimed_units_equal_static_dealing(ops, monkeypatch, Q, N, D, k):
+    # Round-robin plans hand units to workers through a global counter (search_tc.cu get_unit); which
+    # worker scans a unit must not change the result: identical indices and float64 score bits with the
+    # static dealing (TSIM_STATIC_UNITS=1, read per call), and both equal to the exact scan.
+    c = _rows(N, D, 808, torch.bfloat16)
+    c[N // 2:N // 2 + 50] = c[100:150]
+    q = _rows(Q, D, 909 + k, torch.bfloat16)
+    a = _agree(ops, q, c, k, oracle_queries=2)
+    monkeypatch.setenv("TSIM_STATIC_UNITS", "1")
+    b = ops.search_topk(q, c, k, mode="tensor", return_score64=True, return_flags=True)
+    torch.cuda.synchronize()
+    assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    # back-to-back calls reuse the workspace: the claim areas are re-zeroed by every call
+    monkeypatch.delenv("TSIM_STATIC_UNITS")
+    for _ in range(3):
+        d = ops.search_topk(q, c, k, mode="tensor", return_score64=True)
+    torch.cuda.synchronize()
+    assert torch.equal(a[1], d[1]) and torch.equal(a[2], d[2])
