@@ -106,8 +106,8 @@ int tsim_row_inv_norm(const void* x, int dt, int64_t N, int64_t D, int64_t strid
  *   out_score64 [Q, k] double  nullable; the float64 value out_score was rounded from
  *                      (carry it through shard merges so ranking stays exact)
  *   out_idx     [Q, k] int64   idx_base + row; ties by lower index; -1 past the last row
- *   out_flags   [Q]    int32   nullable; 1 where the query was answered by the exact-scan
- *                      fallback (diagnostic)
+ *   out_flags   [Q]    int32   nullable; diagnostic: which stage answered the query -- 0 the first
+ *                      tensor pass, 2 the wide (112-candidate) retry pass, 1 the float64 scan
  *
  * Result definition (what is "exact"): rows are ranked by the float64 cosine of the
  * STORED values, dot / (max(||q||,1e-8) * max(||c||,1e-8)), descending, ties by ascending

@@ -200,6 +200,8 @@ struct TcArgs {
   uint32_t* ladder;     // [Q][2 * kLadder] threshold ladder (main launch after a bootstrap), or null
   uint64_t* sched;      // round-robin: this launch's claim area (zeroed per call), or null = static dealing:
                         // [0] next-unit counter, then per worker a ring of kSchedRing claim records
+  const int32_t* q_count;  // retry pass: device-side number of live queries (<= Q), or null = Q
+  const int32_t* q_map;    // retry pass: compact query -> query of the call (self-exclusion), or null
   int roles_low;        // experiment knob (TSIM_ROLES_LOW=1): TMA / MMA / alloc on warps 0-2, epilogue on warps 4-7
   int dbg;              // TSIM_DEBUG bits (diagnosis only): 1 skip A loads, 2 skip MMAs, 4 skip epilogue math
 };
@@ -511,6 +513,13 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   uint64_t* tempty_bar = tfull_bar + 2;      // [2]       epilogue -> MMA
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
 
+  // retry pass: the number of live queries is only known on the device; usually none -> leave at once
+  int64_t q_live = a.Q;
+  if (a.q_count) {
+    const int64_t c = *a.q_count;
+    q_live = c < a.Q ? c : a.Q;
+    if (q_live <= 0) return;
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kWarpTma = a.roles_low ? 0 : 4, kWarpMma = a.roles_low ? 1 : 5, kWarpAlloc = a.roles_low ? 2 : 6;
   const bool is_epi = a.roles_low ? warp >= 4 : warp < 4;
@@ -615,8 +624,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     Unit un;
     for (int it = 0; get_unit(a, it, wid, nw, false, un); ++it) {
       const int64_t qg = PAIR ? (int64_t)un.qb * (2 * BM) + rank * BM + et : (int64_t)un.qb * BM + et;
-      const bool qvalid = qg < a.Q;
-      const int64_t self_row = a.self_on ? a.self_off + qg : -1;
+      const bool qvalid = qg < q_live;
+      const int64_t self_row = a.self_on ? a.self_off + ((a.q_map && qvalid) ? (int64_t)a.q_map[qg] : qg) : -1;
       uint32_t* thr_g = a.thr + (qvalid ? qg : 0);
       Ladder lad;
       lad.init((a.ladder && qvalid) ? a.ladder + (size_t)qg * (2 * kLadder) : nullptr);
@@ -765,7 +774,7 @@ int launch_cfg(const CUtensorMap& mq, const CUtensorMap& mc, const TcArgs& a, cu
 int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_t c_stride, int dt,
                      const float* c_inv, int64_t Q, int64_t N, int64_t D, int self_on, int64_t self_off,
                      const SearchPlan& p, int pass, uint64_t* cand, uint32_t* thr, uint32_t* ladder, uint64_t* sched,
-                     cudaStream_t st) {
+                     cudaStream_t st, const int32_t* q_count, const int32_t* q_map) {
   CUtensorMap mq, mc;
   const int qrows = p.pair ? 2 * BM : BM;
   // q holds QB * qrows rows (the API pads the last query block with zero rows)
@@ -802,6 +811,7 @@ int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_
   a.n_units = p.QB * ((a.T + a.tpc - 1) / (a.tpc > 0 ? a.tpc : 1));
   a.self_on = self_on; a.self_off = self_off;
   a.cand = cand; a.thr = thr; a.ladder = ladder;
+  a.q_count = q_count; a.q_map = q_map;
   // every tcgen05 launch of a call claims from its own zeroed area (mini sample | sample | main)
   const int area = pass == TC_PASS_MINI ? 0 : (pass == TC_PASS_SAMPLE || pass == TC_PASS_SAMPLE_REST) ? 1 : 2;
   const char* su = getenv("TSIM_STATIC_UNITS");   // experiment knob: static round-robin dealing

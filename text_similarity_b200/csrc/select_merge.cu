@@ -206,6 +206,9 @@ struct SelArgs {
   const uint64_t* cand; const uint32_t* thr;
   int32_t* flag_cnt; int32_t* flag_list;
   float* out_score; double* out_score64; int64_t* out_idx; int32_t* out_flags;
+  // retry stage (SelRetry, tsim_common.cuh): r_in_list != null -> this launch IS the retry pass
+  const int32_t* r_in_cnt; const int32_t* r_in_list; int r_cap;
+  void* r_q; int64_t r_q_stride;
 };
 
 __global__ void __launch_bounds__(kSelThreads) select_rescore_kernel(SelArgs a) {
@@ -214,10 +217,19 @@ __global__ void __launch_bounds__(kSelThreads) select_rescore_kernel(SelArgs a) 
   __shared__ int64_t ei[128];
   __shared__ int n_sh;
   __shared__ double red[kSelThreads / 32];
-  const int64_t q = blockIdx.x;
   const int tid = threadIdx.x;
-  const uint32_t thr_ord = a.thr[q];  // 0: no unit list ever filled -> nothing was dropped
-  const uint64_t* src = a.cand + (size_t)q * a.NC * a.KP;
+  const int64_t slot = blockIdx.x;   // position of this query's lists and threshold in the workspace
+  int64_t q = slot;                  // query of the call
+  if (a.r_in_list) {
+    // retry pass: compact slot b <-> query in_list[b]; the overflow goes straight to the float64 scan
+    const int n_in = *a.r_in_cnt;
+    if (slot == 0)
+      for (int i = a.r_cap + tid; i < n_in; i += blockDim.x) a.flag_list[atomicAdd(a.flag_cnt, 1)] = a.r_in_list[i];
+    if (slot >= n_in || slot >= a.r_cap) return;
+    q = a.r_in_list[slot];
+  }
+  const uint32_t thr_ord = a.thr[slot];  // 0: no unit list ever filled -> nothing was dropped
+  const uint64_t* src = a.cand + (size_t)slot * a.NC * a.KP;
   const int64_t total = a.NC * a.KP;
   if (tid == 0) n_sh = 0;
   __syncthreads();
@@ -291,9 +303,22 @@ __global__ void __launch_bounds__(kSelThreads) select_rescore_kernel(SelArgs a) 
   rescore_and_emit(es, ei, m, qrow, a.q_dt, a.corpus, a.c_dt, a.c_stride, a.D, a.k, a.idx_base,
                    a.out_score + q * a.k, a.out_score64 ? a.out_score64 + q * a.k : nullptr,
                    a.out_idx + q * a.k);
+  // out_flags: 0 answered by the first tensor pass, 2 by the wide retry pass, 1 by the float64 scan
+  // (a flagged query keeps / gets 1 here; whichever later stage answers it overwrites that)
   if (tid == 0) {
-    if (a.out_flags) a.out_flags[q] = flagged ? 1 : 0;
-    if (flagged) a.flag_list[atomicAdd(a.flag_cnt, 1)] = (int32_t)q;
+    if (a.out_flags) a.out_flags[q] = flagged ? 1 : (a.r_in_list ? 2 : 0);
+    if (flagged) n_sh = atomicAdd(a.flag_cnt, 1);
+  }
+  if (!flagged) return;               // block-uniform
+  __syncthreads();
+  const int pos = n_sh;
+  if (tid == 0) a.flag_list[pos] = (int32_t)q;
+  if (a.r_q && !a.r_in_list && pos < a.r_cap) {
+    // first pass with a retry stage behind it: leave the query row where the wide pass reads it
+    const int esz = dtype_size(a.q_dt);
+    const uint4* s4 = (const uint4*)qrow;   // tensor-path rows: 16-byte aligned, D * esz % 16 == 0
+    uint4* d4 = (uint4*)((char*)a.r_q + (size_t)pos * a.r_q_stride * esz);
+    for (int64_t i = tid; i < a.D * esz / 16; i += blockDim.x) d4[i] = s4[i];
   }
 }
 
@@ -482,7 +507,7 @@ int launch_select_rescore(const void* q, int q_dt, int64_t q_stride, const void*
                           int64_t idx_base, const SearchPlan& p, const uint64_t* cand,
                           const uint32_t* thr, int32_t* flag_cnt, int32_t* flag_list,
                           float* out_score, double* out_score64, int64_t* out_idx,
-                          int32_t* out_flags, cudaStream_t st) {
+                          int32_t* out_flags, cudaStream_t st, const SelRetry* retry) {
   SelArgs a;
   a.q = q; a.q_dt = q_dt; a.q_stride = q_stride;
   a.corpus = corpus; a.c_dt = c_dt; a.c_stride = c_stride;
@@ -490,6 +515,9 @@ int launch_select_rescore(const void* q, int q_dt, int64_t q_stride, const void*
   a.KP = p.KP; a.NC = p.NC; a.eps = p.eps; a.cand = cand; a.thr = thr;
   a.flag_cnt = flag_cnt; a.flag_list = flag_list;
   a.out_score = out_score; a.out_score64 = out_score64; a.out_idx = out_idx; a.out_flags = out_flags;
+  a.r_in_cnt = retry ? retry->in_cnt : nullptr; a.r_in_list = retry ? retry->in_list : nullptr;
+  a.r_cap = retry ? retry->cap : 0; a.r_q = retry ? retry->r_q : nullptr; a.r_q_stride = retry ? retry->r_q_stride : 0;
+  // a retry pass launches one block per compact slot: Q = the slot capacity there
   select_rescore_kernel<<<(unsigned)Q, kSelThreads, 0, st>>>(a);
   TSIM_CUDA(cudaGetLastError());
   count_launch();

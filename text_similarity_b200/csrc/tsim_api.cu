@@ -166,6 +166,13 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
   p->off_sched = off;
   p->sched_area = (p->use_tensor && !p->sticky) ? 256 + (size_t)sms * 32 * sizeof(uint64_t) : 0;
   off += 3 * p->sched_area;
+  // retry stage: its thresholds and level-2 flag count sit in the same zeroed span
+  const char* noretry = getenv("TSIM_NO_RETRY");   // experiment knob: flagged queries go straight to the float64 scan
+  p->retry = (p->use_tensor && !shadow && p->KP < kRetryKP && !(noretry && noretry[0] == '1')) ? 1 : 0;
+  if (p->retry) {
+    p->off_r_thr = off; off += align_up((size_t)kRetryQ * sizeof(uint32_t), 256);
+    p->off_r_flagcnt = off; off += 256;
+  }
   p->off_flaglist = off; off = align_up(off + (size_t)Q * sizeof(int32_t), 256);
   if (p->use_tensor && p->boot_tiles) {
     p->off_ladder = off; off = align_up(off + (size_t)Q * 2 * kLadder * sizeof(uint32_t), 256);
@@ -174,6 +181,13 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
     p->off_qpad = off; off = align_up(off + (size_t)p->QB * (p->pair ? 256 : 128) * D * dtype_size(q_dt), 256);
   }
   if (need_invnorm && p->use_tensor) { p->off_invnorm = off; off = align_up(off + (size_t)N * sizeof(float), 256); }
+  if (p->retry) {
+    const int64_t T = (N + 255) / 256;
+    p->r_Gq = (int)(T < sms ? T : sms);
+    p->off_r_flaglist = off; off = align_up(off + (size_t)Q * sizeof(int32_t), 256);
+    p->off_r_q = off; off = align_up(off + (size_t)kRetryQ * D * dtype_size(q_dt), 256);
+    p->off_r_cand = off; off = align_up(off + (size_t)kRetryQ * p->r_Gq * kRetryKP * sizeof(uint64_t), 256);
+  }
   p->off_ex_score = off; off = align_up(off + (size_t)Q * p->S * k * sizeof(double), 256);
   p->off_ex_idx = off; off = align_up(off + (size_t)Q * p->S * k * sizeof(uint32_t), 256);
   p->total = off + 256;
@@ -261,8 +275,9 @@ static int search_impl(const void* q, int q_dt, int64_t q_stride, const void* co
   const int64_t self_off = exclude_self_base - idx_base;  // local corpus row of query 0's own row
 
   if (p.use_tensor) {
-    // thr, flag_cnt and the unit-claim areas are adjacent: one memset
-    TSIM_CUDA(cudaMemsetAsync(thr, 0, (p.off_sched + 3 * p.sched_area) - p.off_thr, st));
+    // thr, flag_cnt, the unit-claim areas and the retry stage's thr / flag_cnt are adjacent: one memset
+    const size_t zero_end = p.retry ? p.off_r_flagcnt + 256 : p.off_sched + 3 * p.sched_area;
+    TSIM_CUDA(cudaMemsetAsync(thr, 0, zero_end - p.off_thr, st));
     uint64_t* sched = p.sched_area ? (uint64_t*)(w + p.off_sched) : nullptr;
     const float* c_inv = corpus_inv_norm;
     if (!c_inv) {
@@ -308,10 +323,34 @@ static int search_impl(const void* q, int q_dt, int64_t q_stride, const void* co
                           p.boot_tiles ? TC_PASS_MAIN : TC_PASS_ALL, cand, thr, ladder, sched, st);
     if (rc) return rc;
     if (timed) TSIM_CUDA(cudaEventRecord(g_ev_stop, st));
+    SelRetry first = {nullptr, nullptr, kRetryQ, w + p.off_r_q, D};
     rc = launch_select_rescore(q, q_dt, q_stride, corpus, c_dt, c_stride, Q, N, D, k, idx_base, p,
                                (const uint64_t*)(w + p.off_cand), thr, flag_cnt, flag_list,
-                               out_score, out_score64, out_idx, out_flags, st);
+                               out_score, out_score64, out_idx, out_flags, st, p.retry ? &first : nullptr);
     if (rc) return rc;
+    if (p.retry) {
+      // Queries whose KP candidates could not be proven complete (ties straddling ranks k..KP) are re-run
+      // as ONE compact block with KP = 112 lists: sticky single-launch plan, every kernel of the stage
+      // reads the flagged count on the device and leaves at once when it is zero (the usual case).
+      SearchPlan pr;
+      memset(&pr, 0, sizeof(pr));
+      pr.use_tensor = 1; pr.eps = p.eps; pr.KP = kRetryKP; pr.pair = 0; pr.QB = 1; pr.sticky = 1;
+      pr.Gq = p.r_Gq; pr.R = 256; pr.NC = p.r_Gq;
+      uint32_t* r_thr = (uint32_t*)(w + p.off_r_thr);
+      int32_t* r_flag_cnt = (int32_t*)(w + p.off_r_flagcnt);
+      int32_t* r_flag_list = (int32_t*)(w + p.off_r_flaglist);
+      uint64_t* r_cand = (uint64_t*)(w + p.off_r_cand);
+      rc = launch_search_tc(w + p.off_r_q, D, tcorpus, tc_stride, t_dt, c_inv, kRetryQ, N, D, self_on, self_off, pr,
+                            TC_PASS_ALL, r_cand, r_thr, nullptr, nullptr, st, flag_cnt, flag_list);
+      if (rc) return rc;
+      SelRetry second = {flag_cnt, flag_list, kRetryQ, nullptr, 0};
+      rc = launch_select_rescore(q, q_dt, q_stride, corpus, c_dt, c_stride, kRetryQ, N, D, k, idx_base, pr,
+                                 r_cand, r_thr, r_flag_cnt, r_flag_list, out_score, out_score64, out_idx,
+                                 out_flags, st, &second);
+      if (rc) return rc;
+      flag_cnt = r_flag_cnt;      // the float64 scan answers what is left
+      flag_list = r_flag_list;
+    }
     // queries whose candidate set could not be proven complete: float64 scan (usually none)
     rc = launch_search_exact(q, q_dt, q_stride, corpus, c_dt, c_stride, Q, N, D, k, self_on, self_off, p,
                              flag_cnt, flag_list, ex_score, ex_idx, st);

@@ -223,12 +223,34 @@ struct SearchPlan {
   size_t off_ladder;   // [Q][2 * kLadder] u32: per-query threshold ladder (levels | counts), bootstrap plans only
   size_t off_sched;    // round-robin: 3 unit-claim areas (one per tcgen05 launch of a call), zeroed with thr
   size_t sched_area;   // bytes per claim area: 256 (counter) + workers * 32 records * 8
+  // Wide second tensor pass for queries whose first-pass candidate set could not be proven complete
+  // (ties straddling ranks k..KP, e.g. a sentence duplicated more than KP - k times): up to kRetryQ of
+  // them are re-run with KP = kRetryKP lists before anything falls back to the float64 scan.
+  int retry;           // 1: plan has a retry stage (tensor path, KP < kRetryKP, no shadow)
+  int r_Gq;            // retry: workers (= candidate lists per retried query)
+  size_t off_r_thr, off_r_flagcnt;   // [kRetryQ] thresholds, level-2 flag count (zeroed with thr)
+  size_t off_r_flaglist;             // [Q] level-2 flag list (queries the float64 scan answers)
+  size_t off_r_q;                    // [kRetryQ][D] compact copy of the flagged queries
+  size_t off_r_cand;                 // [kRetryQ][r_Gq][kRetryKP] keys
   size_t total;
 };
+constexpr int kRetryQ = 128;
+constexpr int kRetryKP = 112;
 
 // q_dt / c_dt: the dtypes the tensor pass reads (the shadow's when `shadow`)
 int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt, int mode,
                      bool need_invnorm, bool shadow, SearchPlan* plan);
+
+// How select_rescore takes part in the retry stage (null: plain call, flagged queries go to flag_list).
+//  * first pass (in_list == null): a flagged query also copies its row into r_q[position in flag_list]
+//    (positions < cap) so that the wide pass can read the flagged queries as one compact block;
+//  * retry pass (in_list != null): block b handles query in_list[b] (b < min(*in_cnt, cap)) with the
+//    compact slot b; queries it still cannot prove -- and the overflow in_list[cap..*in_cnt) -- go to
+//    flag_list (the level-2 list the float64 scan reads).
+struct SelRetry {
+  const int32_t* in_cnt; const int32_t* in_list; int cap;
+  void* r_q; int64_t r_q_stride;   // first pass only: compact query buffer (elements of q_dt)
+};
 
 // kernels' host launchers (defined in the .cu files)
 // pass: 0 = the whole corpus in one launch; 1 = bootstrap sample (all of it); 2 = main (everything
@@ -237,7 +259,8 @@ enum { TC_PASS_ALL = 0, TC_PASS_SAMPLE = 1, TC_PASS_MAIN = 2, TC_PASS_MINI = 3, 
 int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_t c_stride, int dt,
                      const float* c_inv, int64_t Q, int64_t N, int64_t D,
                      int self_on, int64_t self_off, const SearchPlan& p, int pass, uint64_t* cand,
-                     uint32_t* thr, uint32_t* ladder, uint64_t* sched, cudaStream_t st);
+                     uint32_t* thr, uint32_t* ladder, uint64_t* sched, cudaStream_t st,
+                     const int32_t* q_count = nullptr, const int32_t* q_map = nullptr);
 int launch_tighten(int64_t Q, const SearchPlan& p, int nslots, const uint64_t* cand, uint32_t* thr,
                    uint32_t* ladder, cudaStream_t st);
 int launch_select_rescore(const void* q, int q_dt, int64_t q_stride, const void* corpus, int c_dt,
@@ -245,7 +268,7 @@ int launch_select_rescore(const void* q, int q_dt, int64_t q_stride, const void*
                           int64_t idx_base, const SearchPlan& p, const uint64_t* cand,
                           const uint32_t* thr, int32_t* flag_cnt, int32_t* flag_list,
                           float* out_score, double* out_score64, int64_t* out_idx,
-                          int32_t* out_flags, cudaStream_t st);
+                          int32_t* out_flags, cudaStream_t st, const SelRetry* retry = nullptr);
 int launch_search_exact(const void* q, int q_dt, int64_t q_stride, const void* corpus, int c_dt,
                         int64_t c_stride, int64_t Q, int64_t N, int64_t D, int k,
                         int self_on, int64_t self_off, const SearchPlan& p, const int32_t* flag_cnt,

@@ -146,7 +146,7 @@ def search_topk(queries: torch.Tensor, corpus: torch.Tensor, k: int, *,
 
     Returns (scores float32 [Q, k], idx int64 [Q, k]) best first, ties by lower index, idx -1 /
     score -inf past the last available row; optionally the float64 scores and the per-query
-    fallback flags.  Replaces the loop at reference src/pipeline/search_pipeline.py:73-79.
+    stage flags (0: first tensor pass, 2: wide retry pass, 1: float64 scan).  Replaces the loop at reference src/pipeline/search_pipeline.py:73-79.
     """
     lib = _lib.load()
     dev = _require_cuda(queries, corpus, corpus_inv_norm)
