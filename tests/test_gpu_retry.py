@@ -75,14 +75,16 @@ def test_retry_then_float64_scan(ops):
     assert fl[5] == 1 and fl[6] == 2 and int((fl == 0).sum()) == 38
 
 
-def test_retry_overflow_goes_to_scan(ops):
-    # more flagged queries than the retry block holds (128): the overflow is answered by the float64 scan
+@pytest.mark.parametrize("Q,n_retry,n_scan", [(100, 100, 0), (200, 200, 0), (700, 512, 188)])
+def test_retry_rounds_and_overflow(ops, Q, n_retry, n_scan):
+    # every query is flagged; the retry stage runs one round of 128 per 128 queries of the call, at most 4:
+    # what overflows is answered by the float64 scan
     N, D, k = 120_000, 64, 10
     c = _dup_corpus(N, D, [(i, 20) for i in range(8)], 55)
-    q = c[torch.arange(200, device="cuda") % 8].clone()
+    q = c[torch.arange(Q, device="cuda") % 8].clone()
     a = _check(ops, q, c, k)
     fl = a[3].cpu()
-    assert int((fl == 2).sum()) == 128 and int((fl == 1).sum()) == 72
+    assert int((fl == 2).sum()) == n_retry and int((fl == 1).sum()) == n_scan
 
 
 def test_retry_with_self_exclusion_and_idx_base(ops):

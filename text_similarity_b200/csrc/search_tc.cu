@@ -202,6 +202,7 @@ struct TcArgs {
                         // [0] next-unit counter, then per worker a ring of kSchedRing claim records
   const int32_t* q_count;  // retry pass: device-side number of live queries (<= Q), or null = Q
   const int32_t* q_map;    // retry pass: compact query -> query of the call (self-exclusion), or null
+  int q_skip;              // retry pass: live queries = clamp(*q_count - q_skip, 0, Q)
   int roles_low;        // experiment knob (TSIM_ROLES_LOW=1): TMA / MMA / alloc on warps 0-2, epilogue on warps 4-7
   int dbg;              // TSIM_DEBUG bits (diagnosis only): 1 skip A loads, 2 skip MMAs, 4 skip epilogue math
 };
@@ -516,7 +517,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   // retry pass: the number of live queries is only known on the device; usually none -> leave at once
   int64_t q_live = a.Q;
   if (a.q_count) {
-    const int64_t c = *a.q_count;
+    const int64_t c = (int64_t)*a.q_count - a.q_skip;
     q_live = c < a.Q ? c : a.Q;
     if (q_live <= 0) return;
   }
@@ -774,7 +775,7 @@ int launch_cfg(const CUtensorMap& mq, const CUtensorMap& mc, const TcArgs& a, cu
 int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_t c_stride, int dt,
                      const float* c_inv, int64_t Q, int64_t N, int64_t D, int self_on, int64_t self_off,
                      const SearchPlan& p, int pass, uint64_t* cand, uint32_t* thr, uint32_t* ladder, uint64_t* sched,
-                     cudaStream_t st, const int32_t* q_count, const int32_t* q_map) {
+                     cudaStream_t st, const int32_t* q_count, const int32_t* q_map, int q_skip) {
   CUtensorMap mq, mc;
   const int qrows = p.pair ? 2 * BM : BM;
   // q holds QB * qrows rows (the API pads the last query block with zero rows)
@@ -811,7 +812,7 @@ int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_
   a.n_units = p.QB * ((a.T + a.tpc - 1) / (a.tpc > 0 ? a.tpc : 1));
   a.self_on = self_on; a.self_off = self_off;
   a.cand = cand; a.thr = thr; a.ladder = ladder;
-  a.q_count = q_count; a.q_map = q_map;
+  a.q_count = q_count; a.q_map = q_map; a.q_skip = q_skip;
   // every tcgen05 launch of a call claims from its own zeroed area (mini sample | sample | main)
   const int area = pass == TC_PASS_MINI ? 0 : (pass == TC_PASS_SAMPLE || pass == TC_PASS_SAMPLE_REST) ? 1 : 2;
   const char* su = getenv("TSIM_STATIC_UNITS");   // experiment knob: static round-robin dealing

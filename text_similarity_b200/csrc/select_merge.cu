@@ -207,7 +207,7 @@ struct SelArgs {
   int32_t* flag_cnt; int32_t* flag_list;
   float* out_score; double* out_score64; int64_t* out_idx; int32_t* out_flags;
   // retry stage (SelRetry, tsim_common.cuh): r_in_list != null -> this launch IS the retry pass
-  const int32_t* r_in_cnt; const int32_t* r_in_list; int r_cap;
+  const int32_t* r_in_cnt; const int32_t* r_in_list; int r_cap; int r_skip; int r_forward;
   void* r_q; int64_t r_q_stride;
 };
 
@@ -223,10 +223,10 @@ __global__ void __launch_bounds__(kSelThreads) select_rescore_kernel(SelArgs a) 
   if (a.r_in_list) {
     // retry pass: compact slot b <-> query in_list[b]; the overflow goes straight to the float64 scan
     const int n_in = *a.r_in_cnt;
-    if (slot == 0)
+    if (slot == 0 && a.r_forward)
       for (int i = a.r_cap + tid; i < n_in; i += blockDim.x) a.flag_list[atomicAdd(a.flag_cnt, 1)] = a.r_in_list[i];
-    if (slot >= n_in || slot >= a.r_cap) return;
-    q = a.r_in_list[slot];
+    if (a.r_skip + slot >= n_in || a.r_skip + slot >= a.r_cap) return;
+    q = a.r_in_list[a.r_skip + slot];
   }
   const uint32_t thr_ord = a.thr[slot];  // 0: no unit list ever filled -> nothing was dropped
   const uint64_t* src = a.cand + (size_t)slot * a.NC * a.KP;
@@ -517,6 +517,7 @@ int launch_select_rescore(const void* q, int q_dt, int64_t q_stride, const void*
   a.out_score = out_score; a.out_score64 = out_score64; a.out_idx = out_idx; a.out_flags = out_flags;
   a.r_in_cnt = retry ? retry->in_cnt : nullptr; a.r_in_list = retry ? retry->in_list : nullptr;
   a.r_cap = retry ? retry->cap : 0; a.r_q = retry ? retry->r_q : nullptr; a.r_q_stride = retry ? retry->r_q_stride : 0;
+  a.r_skip = retry ? retry->skip : 0; a.r_forward = retry ? retry->forward : 0;
   // a retry pass launches one block per compact slot: Q = the slot capacity there
   select_rescore_kernel<<<(unsigned)Q, kSelThreads, 0, st>>>(a);
   TSIM_CUDA(cudaGetLastError());

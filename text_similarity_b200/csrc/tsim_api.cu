@@ -168,9 +168,13 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
   off += 3 * p->sched_area;
   // retry stage: its thresholds and level-2 flag count sit in the same zeroed span
   const char* noretry = getenv("TSIM_NO_RETRY");   // experiment knob: flagged queries go straight to the float64 scan
-  p->retry = (p->use_tensor && !shadow && p->KP < kRetryKP && !(noretry && noretry[0] == '1')) ? 1 : 0;
+  p->retry = 0;
+  if (p->use_tensor && !shadow && p->KP < kRetryKP && !(noretry && noretry[0] == '1')) {
+    const int64_t rounds = (Q + kRetryQ - 1) / kRetryQ;
+    p->retry = (int)(rounds < kRetryMaxRounds ? rounds : kRetryMaxRounds);
+  }
   if (p->retry) {
-    p->off_r_thr = off; off += align_up((size_t)kRetryQ * sizeof(uint32_t), 256);
+    p->off_r_thr = off; off += align_up((size_t)p->retry * kRetryQ * sizeof(uint32_t), 256);
     p->off_r_flagcnt = off; off += 256;
   }
   p->off_flaglist = off; off = align_up(off + (size_t)Q * sizeof(int32_t), 256);
@@ -185,7 +189,7 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
     const int64_t T = (N + 255) / 256;
     p->r_Gq = (int)(T < sms ? T : sms);
     p->off_r_flaglist = off; off = align_up(off + (size_t)Q * sizeof(int32_t), 256);
-    p->off_r_q = off; off = align_up(off + (size_t)kRetryQ * D * dtype_size(q_dt), 256);
+    p->off_r_q = off; off = align_up(off + (size_t)p->retry * kRetryQ * D * dtype_size(q_dt), 256);
     p->off_r_cand = off; off = align_up(off + (size_t)kRetryQ * p->r_Gq * kRetryKP * sizeof(uint64_t), 256);
   }
   p->off_ex_score = off; off = align_up(off + (size_t)Q * p->S * k * sizeof(double), 256);
@@ -323,31 +327,36 @@ static int search_impl(const void* q, int q_dt, int64_t q_stride, const void* co
                           p.boot_tiles ? TC_PASS_MAIN : TC_PASS_ALL, cand, thr, ladder, sched, st);
     if (rc) return rc;
     if (timed) TSIM_CUDA(cudaEventRecord(g_ev_stop, st));
-    SelRetry first = {nullptr, nullptr, kRetryQ, w + p.off_r_q, D};
+    SelRetry first = {nullptr, nullptr, p.retry * kRetryQ, 0, 0, w + p.off_r_q, D};
     rc = launch_select_rescore(q, q_dt, q_stride, corpus, c_dt, c_stride, Q, N, D, k, idx_base, p,
                                (const uint64_t*)(w + p.off_cand), thr, flag_cnt, flag_list,
                                out_score, out_score64, out_idx, out_flags, st, p.retry ? &first : nullptr);
     if (rc) return rc;
     if (p.retry) {
       // Queries whose KP candidates could not be proven complete (ties straddling ranks k..KP) are re-run
-      // as ONE compact block with KP = 112 lists: sticky single-launch plan, every kernel of the stage
-      // reads the flagged count on the device and leaves at once when it is zero (the usual case).
+      // in compact blocks of 128 with KP = 112 lists: per round one sticky single-launch pass over the
+      // corpus and a second select_rescore; every kernel of the stage reads the flagged count on the
+      // device and leaves at once when its round has nothing to do (the usual case).
       SearchPlan pr;
       memset(&pr, 0, sizeof(pr));
       pr.use_tensor = 1; pr.eps = p.eps; pr.KP = kRetryKP; pr.pair = 0; pr.QB = 1; pr.sticky = 1;
       pr.Gq = p.r_Gq; pr.R = 256; pr.NC = p.r_Gq;
-      uint32_t* r_thr = (uint32_t*)(w + p.off_r_thr);
       int32_t* r_flag_cnt = (int32_t*)(w + p.off_r_flagcnt);
       int32_t* r_flag_list = (int32_t*)(w + p.off_r_flaglist);
       uint64_t* r_cand = (uint64_t*)(w + p.off_r_cand);
-      rc = launch_search_tc(w + p.off_r_q, D, tcorpus, tc_stride, t_dt, c_inv, kRetryQ, N, D, self_on, self_off, pr,
-                            TC_PASS_ALL, r_cand, r_thr, nullptr, nullptr, st, flag_cnt, flag_list);
-      if (rc) return rc;
-      SelRetry second = {flag_cnt, flag_list, kRetryQ, nullptr, 0};
-      rc = launch_select_rescore(q, q_dt, q_stride, corpus, c_dt, c_stride, kRetryQ, N, D, k, idx_base, pr,
-                                 r_cand, r_thr, r_flag_cnt, r_flag_list, out_score, out_score64, out_idx,
-                                 out_flags, st, &second);
-      if (rc) return rc;
+      const size_t rowb = (size_t)D * dtype_size(t_dt);
+      for (int r = 0; r < p.retry; ++r) {
+        uint32_t* r_thr = (uint32_t*)(w + p.off_r_thr) + (size_t)r * kRetryQ;
+        rc = launch_search_tc(w + p.off_r_q + (size_t)r * kRetryQ * rowb, D, tcorpus, tc_stride, t_dt, c_inv, kRetryQ, N, D,
+                              self_on, self_off, pr, TC_PASS_ALL, r_cand, r_thr, nullptr, nullptr, st,
+                              flag_cnt, flag_list + (size_t)r * kRetryQ, r * kRetryQ);
+        if (rc) return rc;
+        SelRetry again = {flag_cnt, flag_list, p.retry * kRetryQ, r * kRetryQ, r == p.retry - 1, nullptr, 0};
+        rc = launch_select_rescore(q, q_dt, q_stride, corpus, c_dt, c_stride, kRetryQ, N, D, k, idx_base, pr,
+                                   r_cand, r_thr, r_flag_cnt, r_flag_list, out_score, out_score64, out_idx,
+                                   out_flags, st, &again);
+        if (rc) return rc;
+      }
       flag_cnt = r_flag_cnt;      // the float64 scan answers what is left
       flag_list = r_flag_list;
     }

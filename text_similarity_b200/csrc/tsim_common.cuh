@@ -226,16 +226,18 @@ struct SearchPlan {
   // Wide second tensor pass for queries whose first-pass candidate set could not be proven complete
   // (ties straddling ranks k..KP, e.g. a sentence duplicated more than KP - k times): up to kRetryQ of
   // them are re-run with KP = kRetryKP lists before anything falls back to the float64 scan.
-  int retry;           // 1: plan has a retry stage (tensor path, KP < kRetryKP, no shadow)
+  int retry;           // > 0: rounds of the retry stage (tensor path, KP < kRetryKP, no shadow): round r re-runs
+                       // flagged queries [r * kRetryQ, (r + 1) * kRetryQ); 1 round per 128 queries of the call, <= 4
   int r_Gq;            // retry: workers (= candidate lists per retried query)
-  size_t off_r_thr, off_r_flagcnt;   // [kRetryQ] thresholds, level-2 flag count (zeroed with thr)
+  size_t off_r_thr, off_r_flagcnt;   // [rounds][kRetryQ] thresholds, level-2 flag count (zeroed with thr)
   size_t off_r_flaglist;             // [Q] level-2 flag list (queries the float64 scan answers)
-  size_t off_r_q;                    // [kRetryQ][D] compact copy of the flagged queries
-  size_t off_r_cand;                 // [kRetryQ][r_Gq][kRetryKP] keys
+  size_t off_r_q;                    // [rounds * kRetryQ][D] compact copy of the flagged queries
+  size_t off_r_cand;                 // [kRetryQ][r_Gq][kRetryKP] keys (reused by every round)
   size_t total;
 };
 constexpr int kRetryQ = 128;
 constexpr int kRetryKP = 112;
+constexpr int kRetryMaxRounds = 4;
 
 // q_dt / c_dt: the dtypes the tensor pass reads (the shadow's when `shadow`)
 int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt, int mode,
@@ -244,11 +246,11 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
 // How select_rescore takes part in the retry stage (null: plain call, flagged queries go to flag_list).
 //  * first pass (in_list == null): a flagged query also copies its row into r_q[position in flag_list]
 //    (positions < cap) so that the wide pass can read the flagged queries as one compact block;
-//  * retry pass (in_list != null): block b handles query in_list[b] (b < min(*in_cnt, cap)) with the
-//    compact slot b; queries it still cannot prove -- and the overflow in_list[cap..*in_cnt) -- go to
-//    flag_list (the level-2 list the float64 scan reads).
+//  * retry pass (in_list != null): block b handles query in_list[skip + b] (skip + b < min(*in_cnt, cap))
+//    with the compact slot b; queries it still cannot prove -- and, in the last round (`forward`), the
+//    overflow in_list[cap..*in_cnt) -- go to flag_list (the level-2 list the float64 scan reads).
 struct SelRetry {
-  const int32_t* in_cnt; const int32_t* in_list; int cap;
+  const int32_t* in_cnt; const int32_t* in_list; int cap; int skip; int forward;
   void* r_q; int64_t r_q_stride;   // first pass only: compact query buffer (elements of q_dt)
 };
 
@@ -260,7 +262,7 @@ int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_
                      const float* c_inv, int64_t Q, int64_t N, int64_t D,
                      int self_on, int64_t self_off, const SearchPlan& p, int pass, uint64_t* cand,
                      uint32_t* thr, uint32_t* ladder, uint64_t* sched, cudaStream_t st,
-                     const int32_t* q_count = nullptr, const int32_t* q_map = nullptr);
+                     const int32_t* q_count = nullptr, const int32_t* q_map = nullptr, int q_skip = 0);
 int launch_tighten(int64_t Q, const SearchPlan& p, int nslots, const uint64_t* cand, uint32_t* thr,
                    uint32_t* ladder, cudaStream_t st);
 int launch_select_rescore(const void* q, int q_dt, int64_t q_stride, const void* corpus, int c_dt,
