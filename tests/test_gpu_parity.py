@@ -280,6 +280,34 @@ def test_merge_topk_matches_oracle(ops):
     assert torch.equal(s64.cpu(), ev)
 
 
+@pytest.mark.parametrize("n_lists,k_in,k", [(8, 100, 100), (8, 10, 10), (3, 7, 5), (40, 100, 100), (2, 1, 1), (5, 33, 60)])
+def test_merge_topk_sorted_lists_rank_merge(ops, n_lists, k_in, k):
+    # lists that arrive best-first (what the search emits, padding last) take the rank-merge path of
+    # merge_topk_kernel: ragged fills, equal scores across lists, one list entirely padding
+    g = torch.Generator().manual_seed(62 + n_lists)
+    Q = 53
+    sc = torch.randn(Q, n_lists, k_in, generator=g, dtype=torch.float64)
+    sc = (sc * 4).round() / 4                         # many equal scores with different rows
+    ix = torch.stack([torch.randperm(100_000, generator=g)[:n_lists * k_in] for _ in range(Q)]).view(Q, n_lists, k_in)
+    fill = torch.randint(0, k_in + 1, (Q, n_lists), generator=g)
+    fill[:, 0] = k_in
+    if n_lists > 1:
+        fill[:, 1] = 0
+    pad = torch.arange(k_in)[None, None, :] >= fill[:, :, None]
+    ix[pad] = -1
+    # order every list by (score desc, row asc), padding last
+    key_s = torch.where(pad, torch.full_like(sc, -float("inf")), sc)
+    order = torch.argsort(ix, dim=-1, stable=True)
+    key_s, ix, sc = key_s.gather(-1, order), ix.gather(-1, order), sc.gather(-1, order)
+    order = torch.argsort(key_s, dim=-1, descending=True, stable=True)
+    ix, sc = ix.gather(-1, order), sc.gather(-1, order)
+    sc, ix = sc.reshape(Q, -1), ix.reshape(Q, -1)
+    s, s64, i = ops.merge_topk(sc.cuda(), ix.cuda(), k, n_lists)
+    ev, ei = O.merge_topk_exact(sc, ix, k)
+    assert torch.equal(i.cpu(), ei)
+    assert torch.equal(s64.cpu(), ev)
+
+
 @pytest.mark.parametrize("G", [2, 4, 8])
 def test_fake_shards_plus_merge_equal_single_search(ops, G):
     q, c = _make(24_000, 70, 384, torch.bfloat16, seed=71)

@@ -476,8 +476,14 @@ __global__ void __launch_bounds__(kSelThreads) merge_exact_lists_kernel(ExMergeA
   if (threadIdx.x == 0 && a.out_flags) a.out_flags[q] = 1;
 }
 
+// Lists that are already ordered best-first (what tsim_search_topk emits, padding last) are merged by
+// RANK: the final position of an element is the number of elements of every list that precede it, found
+// by one binary search per list -- no barriers, ~n_lists * log2(k_in) shared-memory probes per element
+// (8 lists of 100: 332 -> ~60 us at Q = 4096 against the 55-stage bitonic sort).  Equal (score, index)
+// pairs in two lists (overlapping shards; not expected) are ordered by list number so ranks stay unique.
+// Anything else (unsorted input) takes the bitonic sort.
 __global__ void __launch_bounds__(kSelThreads) merge_topk_kernel(const double* sc, const int64_t* ix_in,
-                                                                int64_t total, int k_out,
+                                                                int64_t total, int k_in, int k_out,
                                                                 float* out_score, double* out_score64,
                                                                 int64_t* out_idx) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -491,6 +497,54 @@ __global__ void __launch_bounds__(kSelThreads) merge_topk_kernel(const double* s
     ix[i] = ok ? ix_in[q * total + i] : -1;
   }
   __syncthreads();
+  int unsorted = 0, valid = 0;
+  for (int i = threadIdx.x; i < (int)total; i += blockDim.x) {
+    if (ix[i] >= 0) ++valid;
+    if ((i + 1) % k_in != 0 && pair_before(s[i + 1], ix[i + 1], s[i], ix[i])) unsorted = 1;
+  }
+  unsorted = __syncthreads_or(unsorted);
+  if (!unsorted) {
+    const int n_lists = (int)(total / k_in);
+    float* os = out_score + q * k_out;
+    double* os64 = out_score64 ? out_score64 + q * k_out : nullptr;
+    int64_t* oi = out_idx + q * k_out;
+    __shared__ int n_valid_sh;
+    if (threadIdx.x == 0) n_valid_sh = 0;
+    __syncthreads();
+    if (valid) atomicAdd(&n_valid_sh, valid);
+    for (int e = threadIdx.x; e < (int)total; e += blockDim.x) {
+      const double se = s[e];
+      const int64_t ie = ix[e];
+      if (ie < 0) continue;
+      const int le = e / k_in;
+      int rank = 0;
+      for (int l = 0; l < n_lists && rank < k_out; ++l) {
+        if (l == le) { rank += e - le * k_in; continue; }
+        // number of elements of list l that come before e (ties: the lower list number first)
+        const double* sl = s + l * k_in;
+        const int64_t* il = ix + l * k_in;
+        int lo = 0, hi = k_in;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          const bool before = l < le ? !pair_before(se, ie, sl[mid], il[mid]) : pair_before(sl[mid], il[mid], se, ie);
+          if (before) lo = mid + 1; else hi = mid;
+        }
+        rank += lo;
+      }
+      if (rank < k_out) {
+        os[rank] = (float)se;
+        if (os64) os64[rank] = se;
+        oi[rank] = ie;
+      }
+    }
+    __syncthreads();
+    for (int j = n_valid_sh + threadIdx.x; j < k_out; j += blockDim.x) {
+      os[j] = -INFINITY;
+      if (os64) os64[j] = -INFINITY;
+      oi[j] = -1;
+    }
+    return;
+  }
   sort_pairs(s, ix, np);
   for (int j = threadIdx.x; j < k_out; j += blockDim.x) {
     bool ok = j < total && ix[j] >= 0;
@@ -561,7 +615,7 @@ int launch_merge_topk(const double* sc, const int64_t* ix, int64_t Q, int64_t n_
   size_t smem = (size_t)np * (sizeof(double) + sizeof(int64_t));
   if (smem > 48 * 1024)
     TSIM_CUDA(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  merge_topk_kernel<<<(unsigned)Q, kSelThreads, smem, st>>>(sc, ix, total, k_out, out_score, out_score64, out_idx);
+  merge_topk_kernel<<<(unsigned)Q, kSelThreads, smem, st>>>(sc, ix, total, k_in, k_out, out_score, out_score64, out_idx);
   TSIM_CUDA(cudaGetLastError());
   count_launch();
   return TSIM_OK;
