@@ -364,6 +364,35 @@ def main():
         qps, cores, sample, _ = cpu_reference_qps(N, D, k, budget_s=12.0)
         cpu_baseline = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample}
 
+    # ---- stock PyTorch on the same GPU (rank 0, N = 1 only; SURVEY.md 8d's second baseline): cuBLAS
+    # `Q @ chunk.T` -> torch.topk per chunk -> topk of the concatenated lists.  bf16 scores, so its indices are
+    # not exact; reported for scale only, after both timed regions.
+    torch_gpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        def stock(qb):
+            vals, idxs = [], []
+            for s0 in range(0, rows, 500_000):
+                sc = qb @ shard[s0:s0 + 500_000].T
+                v, ix = torch.topk(sc, min(k, sc.shape[1]), dim=1)
+                vals.append(v)
+                idxs.append(ix + s0)
+            v, ix = torch.cat(vals, 1), torch.cat(idxs, 1)
+            top, pos = torch.topk(v.float(), min(k, v.shape[1]), dim=1)
+            return top, torch.gather(ix, 1, pos)
+        try:
+            stock(dev_batches[0])
+            e0.record()
+            for i in range(2):
+                stock(dev_batches[i % nbatch])
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 2
+            torch_gpu = {"value": Q / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms,
+                         "what": "torch bf16 matmul (cuBLAS) + torch.topk, 500k-row chunks, [Q, chunk] scores through HBM; "
+                                 "bf16 scores, indices not exact"}
+        except Exception as exc:  # noqa: BLE001  (informational leg: never fail the bench on it)
+            torch_gpu = {"value": None, "error": str(exc)[:200]}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": steps,
@@ -376,7 +405,8 @@ def main():
             "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": Q * D * 2,
                     "d2h_bytes_per_step": Q * k * 12, "ms_per_step": e2e_ms / steps},
             "gpu_launches": gpu_launches,
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "regimes": regimes,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "torch_gpu_baseline": torch_gpu, "clocks": clocks,
+            "regimes": regimes,
         }
         _emit(out_fd, line)
     if dist:
