@@ -154,18 +154,24 @@ def test_exact_scan_fp8_and_mixed(ops):
     (35_001, 200, 8, 5, torch.float32),         # one D chunk of 8, ragged last slice
 ])
 def test_exact_scan_register_blocked(ops, monkeypatch, N, Q, D, k, dtype):
-    """Whole-call scans of more than 32 queries over enough slices run search_exact_blocked_kernel (8 queries x
-    4 rows per thread): same answers as the oracle and, bit for bit, as the one-query-per-warp kernel."""
+    """Whole-call scans of more than 32 queries over enough slices run search_exact_mma_kernel (FP64 tensor
+    cores) or, with that switched off, search_exact_blocked_kernel (8 queries x 4 rows per thread): same answers
+    as the oracle and, bit for bit, as the one-query-per-warp kernel."""
     q, c = _make(N, Q, D, dtype, seed=N + Q, dup_frac=0.01)
     c[11] = 0
     _check(ops, q, c, k, TOL_F32 if dtype == torch.float32 else TOL_BF16, mode="exact")
     _check(ops, q, c, k, TOL_F32 if dtype == torch.float32 else TOL_BF16, mode="exact", idx_base=1000,
            exclude_self_base=1000 + 17)
     qd, cd = q.cuda(), c.cuda()
+    s2, i2, d2 = ops.search_topk(qd, cd, k, mode="exact", return_score64=True)
+    monkeypatch.setenv("TSIM_NO_MMA_SCAN", "1")
+    tol = TOL_F32 if dtype == torch.float32 else TOL_BF16
+    _check(ops, q, c, k, tol, mode="exact", idx_base=1000, exclude_self_base=1000 + 17)
     s1, i1, d1 = ops.search_topk(qd, cd, k, mode="exact", return_score64=True)
     monkeypatch.setenv("TSIM_NO_BLOCKED_SCAN", "1")
     s0, i0, d0 = ops.search_topk(qd, cd, k, mode="exact", return_score64=True)
     assert torch.equal(i0, i1) and torch.equal(d0, d1) and torch.equal(s0, s1)
+    assert torch.equal(i0, i2) and torch.equal(d0, d2) and torch.equal(s0, s2)
 
 
 def test_exact_scan_register_blocked_fp8(ops):

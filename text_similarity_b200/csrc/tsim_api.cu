@@ -154,6 +154,15 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
   if (S < 1) S = 1;
   if (S > 2 * sms) S = 2 * sms;
   while (S > 1 && (double)Q * (double)S * k * 12.0 > 5.0e8) S = (S + 1) / 2;
+  if (!p->use_tensor && Q > 32) {
+    // whole-call scan of many queries (64 per CTA, search_exact.cu): every slice starts its lists cold, so no more
+    // slices than it takes to fill the GPU a few times over (Q = 1024, k = 100: 296 slices cost 133K list
+    // insertions per query, 37 slices 24K)
+    int64_t cap = (4 * (int64_t)sms + (Q + 63) / 64 - 1) / ((Q + 63) / 64);
+    if (const char* e = getenv("TSIM_SCAN_SLICES")) { int64_t v = atoll(e); if (v >= 1) cap = v; }   // experiment knob
+    if (cap < 1) cap = 1;
+    if (S > cap) S = cap;
+  }
   int64_t sr = (N + S - 1) / S;
   sr = (sr + 31) / 32 * 32;
   if (sr < 32) sr = 32;
