@@ -1,5 +1,5 @@
-"""Float64 exact scan: FP64 tensor-core kernel (DMMA) against the register-blocked DFMA kernel (TSIM_NO_MMA_SCAN=1)
-and the one-query-per-warp kernel (+ TSIM_NO_BLOCKED_SCAN=1); same call, same results."""
+"""Float64 exact scan: FP64 tensor-core kernel (DMMA) against the one-query-per-warp DFMA kernel
+(TSIM_NO_MMA_SCAN=1); same call, same results."""
 import os
 import sys
 
@@ -28,17 +28,12 @@ for (N, Q, D, k, dt) in [(100_000, 100, 384, 10, torch.float32), (1_000_000, 64,
                          (1_000_000, 1024, 768, 128, torch.bfloat16), (250_000, 4096, 384, 50, torch.float32)]:
     c = torch.randn(N, D, device=dev).to(dt)
     q = torch.randn(Q, D, device=dev).to(dt)
-    for kn in ("TSIM_NO_BLOCKED_SCAN", "TSIM_NO_MMA_SCAN"):
-        os.environ.pop(kn, None)
-    ms2, (s2, i2) = timed(lambda: ops.search_topk(q, c, k, mode="exact"), 3)
-    os.environ["TSIM_NO_MMA_SCAN"] = "1"
+    os.environ.pop("TSIM_NO_MMA_SCAN", None)
     ms1, (s1, i1) = timed(lambda: ops.search_topk(q, c, k, mode="exact"), 3)
-    os.environ["TSIM_NO_BLOCKED_SCAN"] = "1"
+    os.environ["TSIM_NO_MMA_SCAN"] = "1"
     ms0, (s0, i0) = timed(lambda: ops.search_topk(q, c, k, mode="exact"), 2)
-    for kn in ("TSIM_NO_BLOCKED_SCAN", "TSIM_NO_MMA_SCAN"):
-        os.environ.pop(kn, None)
+    os.environ.pop("TSIM_NO_MMA_SCAN", None)
     tf = 2.0 * Q * N * D / 1e9
-    same = bool(torch.equal(i0, i1) and torch.equal(s0, s1) and torch.equal(i0, i2) and torch.equal(s0, s2))
-    print(f"exact scan {str(dt).split('.')[-1]} {N}x{D} Q={Q} k={k}: DMMA {ms2:.2f} ms ({tf / ms2:.2f} TFLOP/s f64)  "
-          f"blocked DFMA {ms1:.2f} ms ({tf / ms1:.2f})  one-query-per-warp {ms0:.2f} ms ({tf / ms0:.2f})  "
-          f"x{ms0 / ms2:.2f}  same: {same}", flush=True)
+    print(f"exact scan {str(dt).split('.')[-1]} {N}x{D} Q={Q} k={k}: DMMA {ms1:.2f} ms ({tf / ms1:.2f} TFLOP/s f64)  "
+          f"one-query-per-warp {ms0:.2f} ms ({tf / ms0:.2f})  x{ms0 / ms1:.2f}  "
+          f"same: {bool(torch.equal(i0, i1) and torch.equal(s0, s1))}", flush=True)

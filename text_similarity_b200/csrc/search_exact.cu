@@ -28,6 +28,7 @@ struct ExArgs {
   int S; int64_t slice_rows;
   const int32_t* flag_cnt; const int32_t* flag_list;
   double* ex_score; uint32_t* ex_idx;
+  const double* rinv;   // [N] 1 / max(||row||, eps), tensor-core scan only
 };
 
 // insert (s, r) into a descending list ls/li of length *cnt (capacity k); whole warp calls
@@ -150,223 +151,28 @@ __global__ void __launch_bounds__(kExThreads) search_exact_kernel(ExArgs a) {
 }
 
 
-// ---- register-blocked variant: whole-call scans of >= 33 queries ------------------------------
-// The kernel above issues two shared-memory loads per DFMA (3 wavefronts per warp-DFMA: the shared
-// memory port caps it at 1/6 of the DFMA rate).  Here a thread owns an 8-query x 4-row block of
-// accumulators: per d it loads 8 query values (4 broadcast LDS.128) and 4 row values for 32 DFMAs.
-// A CTA takes 64 queries (warp w: queries 8w..8w+7 of the group) against 128-row tiles (lane l:
-// rows l, l+32, l+64, l+96), so the corpus slice is also streamed once per 64 queries instead of
-// once per 8.  D is walked in chunks of 32 (lane <-> element while staging); the next chunk's rows
-// AND query values are fetched into registers while the current one is multiplied.  Staging stores
-// are bank-conflict free: rows with an odd stride (33 doubles), queries as 16-byte pairs with a
-// stride of 66 doubles (the first version wrote them 32-way conflicted: 36 % of all shared-memory
-// wavefronts, ncu).  Same per-warp lists, same insertion order (rows ascending), same output
-// layout as the kernel above; merge_exact_lists re-scores canonically.
-constexpr int kBQ = 8;           // queries per warp
-constexpr int kBR = 4;           // rows per lane
-constexpr int kBGroup = 8 * kBQ; // queries per CTA
-constexpr int kBRows = 32 * kBR; // rows per tile
-constexpr int kBDC = 32;         // D chunk: one element per lane while staging
-constexpr int kBOwn = kBRows / 8;  // tile rows staged by each warp
-constexpr int kBQStride = kBGroup + 2;  // doubles per d in the query stage (even: LDS.128 / STS.128 stay aligned)
-constexpr int kBTStride = kBDC + 1;     // doubles per row in the tile
-
-// rows warp + 8 i of the tile at r0, element d0 + lane, as floats (exact for every dtype)
-template <int DT>
-__device__ __forceinline__ void fetch_rows(float (&pre)[kBOwn], const ExArgs& a, int64_t r0, int64_t row_end,
-                                           int64_t d, int warp) {
-#pragma unroll
-  for (int i = 0; i < kBOwn; ++i) {
-    const int64_t row = r0 + warp + 8 * i;
-    const char* crow = (const char*)a.corpus + (size_t)row * a.c_stride * dtype_size(DT);
-    pre[i] = (row < row_end && d < a.D) ? Elem<DT>::ld(crow, d) : 0.f;
-  }
-}
-// element d of the warp's 8 queries
-template <int DT>
-__device__ __forceinline__ void fetch_queries(float (&qpre)[kBQ], const ExArgs& a, int64_t slot0, int64_t d) {
-#pragma unroll
-  for (int j = 0; j < kBQ; ++j) {
-    const int64_t qid = min(slot0 + j, a.Q - 1);
-    const char* qrow = (const char*)a.q + (size_t)qid * a.q_stride * dtype_size(DT);
-    qpre[j] = d < a.D ? Elem<DT>::ld(qrow, d) : 0.f;
-  }
-}
-
-// one copy of the insertion code for the 32 (query, row group) call sites of the blocked kernel
+// one copy of the insertion code for the many call sites of the tensor-core kernel
 __device__ __noinline__ void warp_list_insert_call(double* ls, uint32_t* li, int* cnt, int k, double s, uint32_t r) {
   int c = *cnt;
   warp_list_insert(ls, li, c, k, s, r);
   *cnt = c;
 }
 
-__global__ void __launch_bounds__(kExThreads) search_exact_blocked_kernel(ExArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* qs = (double*)smem_raw;                       // [kBDC][kBQStride]
-  double* tile = qs + kBDC * kBQStride;                 // [kBRows][kBTStride]
-  double* norm2 = tile + kBRows * kBTStride;            // [kBRows]
-  double* qn_s = norm2 + kBRows;                        // [kBGroup] 1 / query norm
-  double* ls_all = qn_s + kBGroup;                      // [kBGroup][k]
-  uint32_t* li_all = (uint32_t*)(ls_all + (size_t)kBGroup * a.k);  // [kBGroup][k]
-  int* cnt_s = (int*)(li_all + (size_t)kBGroup * a.k);  // [kBGroup] list lengths (warp-private)
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t ngroups = (a.Q + kBGroup - 1) / kBGroup;
-  const int slice = blockIdx.x;
-  const int64_t row_begin = (int64_t)slice * a.slice_rows;
-  const int64_t row_end = min(a.N, row_begin + a.slice_rows);
-  const int qsz = dtype_size(a.q_dt);
-  const int nchunks = (int)((a.D + kBDC - 1) / kBDC);
-  const int64_t ntiles = row_end > row_begin ? (row_end - row_begin + kBRows - 1) / kBRows : 0;
-  const int64_t total = ntiles * nchunks;
-
-  for (int64_t g = blockIdx.y; g < ngroups; g += gridDim.y) {
-    const int64_t slot0 = g * kBGroup + warp * kBQ;     // this warp's first query
-#pragma unroll 1
-    for (int j = 0; j < kBQ; ++j) {
-      const int64_t qid = min(slot0 + j, a.Q - 1);
-      const char* qrow = (const char*)a.q + (size_t)qid * a.q_stride * qsz;
-      double qq = 0.0;
-      for (int64_t d = lane; d < a.D; d += 32) {
-        double v = (double)load_elem(qrow, a.q_dt, d);
-        qq = fma(v, v, qq);
-      }
-      qq = warp_sum_f64(qq);
-      if (lane == 0) {
-        qn_s[warp * kBQ + j] = 1.0 / fmax(sqrt(qq), kCosEps);
-        cnt_s[warp * kBQ + j] = 0;
-      }
-    }
-    __syncwarp();
-
-    float pre[kBOwn];   // the next (tile, chunk): rows warp + 8 i, element lane
-    float qpre[kBQ];    // ... and element lane of this warp's queries
-    int fc = 0;                   // (tile, chunk) the next fetch reads -- counters, no 64-bit divisions per chunk
-    int64_t fr0 = row_begin;
-    auto fetch = [&]() {
-      const int64_t d = (int64_t)fc * kBDC + lane;
-      switch (a.c_dt) {
-        case TSIM_F32: fetch_rows<TSIM_F32>(pre, a, fr0, row_end, d, warp); break;
-        case TSIM_F16: fetch_rows<TSIM_F16>(pre, a, fr0, row_end, d, warp); break;
-        case TSIM_BF16: fetch_rows<TSIM_BF16>(pre, a, fr0, row_end, d, warp); break;
-        default: fetch_rows<TSIM_E4M3>(pre, a, fr0, row_end, d, warp); break;
-      }
-      switch (a.q_dt) {
-        case TSIM_F32: fetch_queries<TSIM_F32>(qpre, a, slot0, d); break;
-        case TSIM_F16: fetch_queries<TSIM_F16>(qpre, a, slot0, d); break;
-        case TSIM_BF16: fetch_queries<TSIM_BF16>(qpre, a, slot0, d); break;
-        default: fetch_queries<TSIM_E4M3>(qpre, a, slot0, d); break;
-      }
-      if (++fc == nchunks) { fc = 0; fr0 += kBRows; }
-    };
-    if (total) fetch();
-
-    double acc[kBQ][kBR];
-    int c = 0;                    // (tile, chunk) being multiplied
-    int64_t r0 = row_begin;
-    for (int64_t it = 0; it < total; ++it) {
-      const int dc = (int)min((int64_t)kBDC, a.D - (int64_t)c * kBDC);
-      __syncthreads();  // everyone is done reading the previous chunk
-      if (c == 0) {
-#pragma unroll
-        for (int j = 0; j < kBQ; ++j)
-#pragma unroll
-          for (int r = 0; r < kBR; ++r) acc[j][r] = 0.0;
-      }
-#pragma unroll
-      for (int i = 0; i < kBOwn; ++i) {
-        const int rr = warp + 8 * i;
-        const double v = (double)pre[i];
-        tile[rr * kBTStride + lane] = v;
-        const double sq = warp_sum_f64(v * v);
-        if (lane == 0) norm2[rr] = (c == 0 ? 0.0 : norm2[rr]) + sq;   // row rr belongs to this warp alone
-      }
-#pragma unroll
-      for (int j = 0; j < kBQ; j += 2)   // lane <-> d: 16-byte stores 528 bytes apart, conflict-free
-        *reinterpret_cast<double2*>(qs + lane * kBQStride + warp * kBQ + j) = make_double2((double)qpre[j], (double)qpre[j + 1]);
-      __syncthreads();
-      if (it + 1 < total) fetch();   // in flight while this chunk is multiplied
-
-      const double* qv = qs + warp * kBQ;
-      const double* tv = tile + lane * kBTStride;
-#pragma unroll 2
-      for (int d = 0; d < dc; ++d) {
-        double x[kBQ], y[kBR];
-#pragma unroll
-        for (int j = 0; j < kBQ; j += 2) {
-          const double2 t = *reinterpret_cast<const double2*>(qv + d * kBQStride + j);
-          x[j] = t.x; x[j + 1] = t.y;
-        }
-#pragma unroll
-        for (int r = 0; r < kBR; ++r) y[r] = tv[r * 32 * kBTStride + d];
-#pragma unroll
-        for (int j = 0; j < kBQ; ++j)
-#pragma unroll
-          for (int r = 0; r < kBR; ++r) acc[j][r] = fma(x[j], y[r], acc[j][r]);
-      }
-
-      if (c == nchunks - 1) {
-        // this tile is complete: lane <-> rows r0 + lane + 32 r; insert in ascending row order
-        double cn[kBR];   // 1 / row norm
-#pragma unroll
-        for (int r = 0; r < kBR; ++r) cn[r] = 1.0 / fmax(sqrt(norm2[lane + 32 * r]), kCosEps);
-#pragma unroll
-        for (int j = 0; j < kBQ; ++j) {
-          const int64_t qid = slot0 + j;
-          if (qid >= a.Q) break;    // warp-uniform
-          double* ls = ls_all + (size_t)(warp * kBQ + j) * a.k;
-          uint32_t* li = li_all + (size_t)(warp * kBQ + j) * a.k;
-          int* cnt = cnt_s + warp * kBQ + j;
-          const double qn = qn_s[warp * kBQ + j];   // 1 / query norm
-#pragma unroll
-          for (int r = 0; r < kBR; ++r) {
-            const int64_t row = r0 + lane + 32 * r;
-            // nomination only (merge_exact_lists re-scores canonically): reciprocals instead of 32 divisions
-            const double score = acc[j][r] * qn * cn[r];
-            bool want = row < row_end && !(a.self_on && row == a.self_off + qid);
-            want = want && !(score != score);  // NaN rows are never returned
-            want = want && (*cnt < a.k || score > ls[a.k - 1]);   // rows of one ballot are re-checked on insertion
-            unsigned mask = __ballot_sync(0xffffffffu, want);
-            while (mask) {
-              const int src = __ffs(mask) - 1;
-              mask &= mask - 1;
-              const double s = __shfl_sync(0xffffffffu, score, src);
-              warp_list_insert_call(ls, li, cnt, a.k, s, (uint32_t)(r0 + src + 32 * r));
-            }
-          }
-        }
-      }
-      if (++c == nchunks) { c = 0; r0 += kBRows; }
-    }
-    // write this warp's (slot, slice) lists
-#pragma unroll 1
-    for (int j = 0; j < kBQ; ++j) {
-      const int64_t slot = slot0 + j;
-      if (slot >= a.Q) break;
-      const double* ls = ls_all + (size_t)(warp * kBQ + j) * a.k;
-      const uint32_t* li = li_all + (size_t)(warp * kBQ + j) * a.k;
-      const int cnt = cnt_s[warp * kBQ + j];
-      double* os = a.ex_score + ((size_t)slot * a.S + slice) * a.k;
-      uint32_t* oi = a.ex_idx + ((size_t)slot * a.S + slice) * a.k;
-      for (int i = lane; i < a.k; i += 32) {
-        os[i] = i < cnt ? ls[i] : 0.0;
-        oi[i] = i < cnt ? li[i] : 0xffffffffu;
-      }
-    }
-    __syncwarp();
-  }
-}
-
-// ---- FP64 tensor-core variant (DMMA.8x8x4) ----------------------------------------------------
-// The register-blocked kernel above is bound by shared-memory wavefronts (16 per 32 DFMAs, ncu: LSU data
-// pipe and FP64 pipe co-limited at 33 %).  mma.sync.m8n8k4.f64 multiplies an 8-query x 4-d fragment by a
-// 4-d x 8-row fragment from ONE 8-byte load per lane each, so a warp tile of (8 MF) queries x 64 rows
-// costs MF + 8 loads per 8 MF DMMAs (64 MF DFMA-equivalents): 0.16-0.28 wavefronts per DFMA instead
-// of 0.5.  B200 keeps full-rate FP64 tensor cores (B300 does not), so this is where the exact float64
-// path belongs.  CTA = 8 warps x (8 MF) queries against 64-row tiles; queries and rows are staged as
-// [row][32 d + 4] doubles (fragment loads and staging stores both conflict-free); D in chunks of 32
-// with register prefetch as above.  C fragments: lane holds query (lane >> 2), rows 2 (lane & 3) + {0, 1}
-// of each 8 x 8 block; insertion walks them in ascending row order per query.
+// ---- FP64 tensor-core variant (DMMA.8x8x4): whole-call scans of more than 32 queries -----------
+// The kernel above issues two shared-memory loads per DFMA: the shared-memory port caps it at ~3 TFLOP/s.
+// A register-blocked DFMA version (8 queries x 4 rows per thread, removed) reached 11.3 TFLOP/s, still
+// bound by shared-memory wavefronts (16 per 32 DFMAs; ncu: LSU data pipe and FP64 pipe co-limited at 33 %).
+// mma.sync.m8n8k4.f64 multiplies an 8-query x 4-d fragment by a 4-d x 8-row fragment from ONE 8-byte
+// load per lane each, so a warp tile of (8 MF) queries x 64 rows costs MF + 8 loads per 8 MF DMMAs
+// (64 MF DFMA-equivalents): 0.16-0.28 wavefronts per DFMA instead of 0.5.  B200 keeps full-rate FP64
+// tensor cores (measured 37 TFLOP/s, scripts/dfma_peak.cu; B300 does not), so this is where the exact
+// float64 path belongs.  CTA = 8 warps x (8 MF) queries against 64-row tiles; queries and rows are staged
+// as [row][32 d + 4] doubles (fragment loads and staging stores both conflict-free); D in chunks of 32,
+// the next chunk's rows and query values fetched into registers while the current one is multiplied.
+// Inverse row norms come from one pre-pass per call (row_rinv_f64_kernel), not once per query group.
+// C fragments: lane holds query (lane >> 2), rows 2 (lane & 3) + {0, 1} of each 8 x 8 block; insertion
+// walks them in ascending row order per query.  Same per-warp lists and output layout as the kernel
+// above; merge_exact_lists re-scores canonically, so results are bit-identical.
 constexpr int kMRows = 64;             // corpus rows per tile
 constexpr int kMNF = kMRows / 8;       // row fragments per tile
 constexpr int kMDC = 32;               // D chunk
@@ -378,26 +184,42 @@ __device__ __forceinline__ void dmma_8x8x4(double (&c)[2], double a, double b) {
                : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
+// element `d` (already folded into p0) of NR rows `step_bytes` apart; rows i >= nvalid read as 0
 template <int DT, int NR>
-__device__ __forceinline__ void fetch_col(float (&pre)[NR], const void* base, int64_t stride, int64_t first, int step,
-                                          int64_t limit, bool clamp, int64_t d, int64_t D) {
+__device__ __forceinline__ void fetch_col(float (&pre)[NR], const char* p0, int64_t step_bytes, int nvalid) {
 #pragma unroll
-  for (int i = 0; i < NR; ++i) {
-    int64_t row = first + (int64_t)step * i;
-    const bool ok = clamp || row < limit;
-    if (clamp) row = min(row, limit - 1);
-    const char* p = (const char*)base + (size_t)row * stride * dtype_size(DT);
-    pre[i] = (ok && d < D) ? Elem<DT>::ld(p, d) : 0.f;
-  }
+  for (int i = 0; i < NR; ++i) pre[i] = i < nvalid ? Elem<DT>::ld(p0 + i * step_bytes, 0) : 0.f;
 }
 template <int NR>
 __device__ __forceinline__ void fetch_col_dt(float (&pre)[NR], int dt, const void* base, int64_t stride, int64_t first,
-                                             int step, int64_t limit, bool clamp, int64_t d, int64_t D) {
+                                             int step, int64_t limit, int64_t d, int64_t D) {
+  const int esz = dtype_size(dt);
+  const char* p0 = (const char*)base + ((size_t)first * stride + d) * esz;
+  const int64_t left = d < D ? (limit - first + step - 1) / step : 0;   // rows first + step i < limit
+  const int nvalid = (int)max((int64_t)0, min((int64_t)NR, left));
+  const int64_t sb = (int64_t)step * stride * esz;
   switch (dt) {
-    case TSIM_F32: fetch_col<TSIM_F32, NR>(pre, base, stride, first, step, limit, clamp, d, D); break;
-    case TSIM_F16: fetch_col<TSIM_F16, NR>(pre, base, stride, first, step, limit, clamp, d, D); break;
-    case TSIM_BF16: fetch_col<TSIM_BF16, NR>(pre, base, stride, first, step, limit, clamp, d, D); break;
-    default: fetch_col<TSIM_E4M3, NR>(pre, base, stride, first, step, limit, clamp, d, D); break;
+    case TSIM_F32: fetch_col<TSIM_F32, NR>(pre, p0, sb, nvalid); break;
+    case TSIM_F16: fetch_col<TSIM_F16, NR>(pre, p0, sb, nvalid); break;
+    case TSIM_BF16: fetch_col<TSIM_BF16, NR>(pre, p0, sb, nvalid); break;
+    default: fetch_col<TSIM_E4M3, NR>(pre, p0, sb, nvalid); break;
+  }
+}
+
+// 1 / max(||row||, eps) in float64, one warp per row (lane-strided sums, fixed butterfly)
+__global__ void __launch_bounds__(256) row_rinv_f64_kernel(const void* corpus, int c_dt, int64_t c_stride, int64_t N,
+                                                           int64_t D, double* rinv) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < N; row += warps) {
+    const char* crow = (const char*)corpus + (size_t)row * c_stride * dtype_size(c_dt);
+    double sq = 0.0;
+    for (int64_t d = lane; d < D; d += 32) {
+      const double v = (double)load_elem(crow, c_dt, d);
+      sq = fma(v, v, sq);
+    }
+    sq = warp_sum_f64(sq);
+    if (lane == 0) rinv[row] = 1.0 / fmax(sqrt(sq), kCosEps);
   }
 }
 
@@ -408,8 +230,7 @@ __global__ void __launch_bounds__(kExThreads, MINB) search_exact_mma_kernel(ExAr
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* qs = (double*)smem_raw;                       // [QG][kMStride]
   double* tile = qs + QG * kMStride;                    // [kMRows][kMStride]
-  double* norm2 = tile + kMRows * kMStride;             // [kMRows] running squared norms
-  double* rinv = norm2 + kMRows;                        // [kMRows] 1 / row norm of the finished tile
+  double* rinv = tile + kMRows * kMStride;              // [kMRows] 1 / row norm of the tile being finished
   double* qn_s = rinv + kMRows;                         // [QG] 1 / query norm
   double* ls_all = qn_s + QG;                           // [QG][k]
   uint32_t* li_all = (uint32_t*)(ls_all + (size_t)QG * a.k);  // [QG][k]
@@ -451,8 +272,8 @@ __global__ void __launch_bounds__(kExThreads, MINB) search_exact_mma_kernel(ExAr
     int64_t fr0 = row_begin;
     auto fetch = [&]() {
       const int64_t d = (int64_t)fc * kMDC + lane;
-      fetch_col_dt<kMOwn>(pre, a.c_dt, a.corpus, a.c_stride, fr0 + warp, 8, row_end, false, d, a.D);
-      fetch_col_dt<QW>(qpre, a.q_dt, a.q, a.q_stride, slot0, 1, a.Q, true, d, a.D);
+      fetch_col_dt<kMOwn>(pre, a.c_dt, a.corpus, a.c_stride, fr0 + warp, 8, row_end, d, a.D);
+      fetch_col_dt<QW>(qpre, a.q_dt, a.q, a.q_stride, slot0, 1, a.Q, d, a.D);
       if (++fc == nchunks) { fc = 0; fr0 += kMRows; }
     };
     if (total) fetch();
@@ -469,19 +290,10 @@ __global__ void __launch_bounds__(kExThreads, MINB) search_exact_mma_kernel(ExAr
           for (int ni = 0; ni < kMNF; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
       }
 #pragma unroll
-      for (int i = 0; i < kMOwn; ++i) {
-        const int rr = warp + 8 * i;
-        const double v = (double)pre[i];
-        tile[rr * kMStride + lane] = v;
-        const double sq = warp_sum_f64(v * v);
-        if (lane == 0) norm2[rr] = (c == 0 ? 0.0 : norm2[rr]) + sq;   // row rr belongs to this warp alone
-      }
+      for (int i = 0; i < kMOwn; ++i) tile[(warp + 8 * i) * kMStride + lane] = (double)pre[i];
 #pragma unroll
       for (int j = 0; j < QW; ++j) qs[(warp * QW + j) * kMStride + lane] = (double)qpre[j];
-      if (c == nchunks - 1) {
-        __syncwarp();
-        if (lane < kMOwn) rinv[warp + 8 * lane] = 1.0 / fmax(sqrt(norm2[warp + 8 * lane]), kCosEps);
-      }
+      if (c == nchunks - 1 && tid < kMRows) rinv[tid] = r0 + tid < row_end ? a.rinv[r0 + tid] : 0.0;
       __syncthreads();
       if (it + 1 < total) fetch();   // in flight while this chunk is multiplied
 
@@ -556,12 +368,7 @@ __global__ void __launch_bounds__(kExThreads, MINB) search_exact_mma_kernel(ExAr
 
 size_t mma_smem_bytes(int k, int MF) {
   const size_t QG = 64 * (size_t)MF;
-  return sizeof(double) * ((QG + kMRows) * kMStride + 2 * kMRows + QG + QG * k) + sizeof(uint32_t) * QG * k + sizeof(int) * QG;
-}
-
-size_t blocked_smem_bytes(int k) {
-  return sizeof(double) * ((size_t)kBDC * kBQStride + (size_t)kBRows * kBTStride + kBRows + kBGroup + (size_t)kBGroup * k) +
-         sizeof(uint32_t) * (size_t)kBGroup * k + sizeof(int) * kBGroup;
+  return sizeof(double) * ((QG + kMRows) * kMStride + kMRows + QG + QG * k) + sizeof(uint32_t) * QG * k + sizeof(int) * QG;
 }
 
 }  // namespace
@@ -570,19 +377,19 @@ int launch_search_exact(const void* q, int q_dt, int64_t q_stride, const void* c
                         int64_t c_stride, int64_t Q, int64_t N, int64_t D, int k,
                         int self_on, int64_t self_off, const SearchPlan& p, const int32_t* flag_cnt,
                         const int32_t* flag_list, double* ex_score, uint32_t* ex_idx,
-                        cudaStream_t st) {
+                        double* ex_rinv, cudaStream_t st) {
   ExArgs a;
   a.q = q; a.q_dt = q_dt; a.q_stride = q_stride;
   a.corpus = corpus; a.c_dt = c_dt; a.c_stride = c_stride;
   a.Q = Q; a.N = N; a.D = D; a.k = k; a.self_on = self_on; a.self_off = self_off;
   a.S = p.S; a.slice_rows = p.slice_rows;
-  a.flag_cnt = flag_cnt; a.flag_list = flag_list; a.ex_score = ex_score; a.ex_idx = ex_idx;
+  a.flag_cnt = flag_cnt; a.flag_list = flag_list; a.ex_score = ex_score; a.ex_idx = ex_idx; a.rinv = ex_rinv;
   // whole-call scans of more than a warp's worth of queries: FP64 tensor cores.  Default: 64 queries per CTA,
   // two CTAs per SM (one stages while the other multiplies).  Measured on 1M x 768 fp32 (scripts/ab_exact.py),
   // Q = 1024: k = 10 92.9 ms / k = 100 103.4 ms, against 90.7 / 111.3 ms with 128 queries per CTA and one CTA per
   // SM, 116.4 / 128.5 ms with 64 queries and one CTA; Q = 64: 6.4 ms against 7.9-12.4 ms.
   const char* nomma = getenv("TSIM_NO_MMA_SCAN");       // experiment knob
-  if (!flag_cnt && Q > 32 && !(nomma && nomma[0] == '1')) {
+  if (!flag_cnt && ex_rinv && Q > 32 && N > 0 && !(nomma && nomma[0] == '1')) {
     int MF = 1, minb = 2;
     if (const char* v = getenv("TSIM_MMA_VARIANT")) {   // experiment knob: "<8-query fragments per warp>x<CTAs per SM>"
       if (v[0] == '1' && v[1] && v[2] == '1') minb = 1;
@@ -591,6 +398,10 @@ int launch_search_exact(const void* q, int q_dt, int64_t q_stride, const void* c
     const size_t msmem = mma_smem_bytes(k, MF);
     const int64_t mgroups = (Q + 64 * MF - 1) / (64 * MF);
     if (msmem <= 227 * 1024 && (int64_t)p.S * mgroups >= 64) {
+      const int64_t nb = (N + 7) / 8;
+      row_rinv_f64_kernel<<<(unsigned)(nb < 8 * 148 ? nb : 8 * 148), 256, 0, st>>>(corpus, c_dt, c_stride, N, D, ex_rinv);
+      TSIM_CUDA(cudaGetLastError());
+      count_launch();
       dim3 mgrid((unsigned)p.S, (unsigned)(mgroups < 4096 ? mgroups : 4096));
       auto kern = MF == 2 ? search_exact_mma_kernel<2, 1> : minb == 2 ? search_exact_mma_kernel<1, 2> : search_exact_mma_kernel<1, 1>;
       TSIM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
@@ -599,18 +410,6 @@ int launch_search_exact(const void* q, int q_dt, int64_t q_stride, const void* c
       count_launch();
       return TSIM_OK;
     }
-  }
-  const char* noblk = getenv("TSIM_NO_BLOCKED_SCAN");   // experiment knob
-  const int64_t bgroups = (Q + kBGroup - 1) / kBGroup;
-  if (!flag_cnt && Q > 32 && (int64_t)p.S * bgroups >= 64 && blocked_smem_bytes(k) <= 227 * 1024 &&
-      !(noblk && noblk[0] == '1')) {
-    const size_t bsmem = blocked_smem_bytes(k);
-    TSIM_CUDA(cudaFuncSetAttribute(search_exact_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
-    dim3 bgrid((unsigned)p.S, (unsigned)(bgroups < 4096 ? bgroups : 4096));
-    search_exact_blocked_kernel<<<bgrid, kExThreads, bsmem, st>>>(a);
-    TSIM_CUDA(cudaGetLastError());
-    count_launch();
-    return TSIM_OK;
   }
   size_t smem = sizeof(double) * (8 * kDC + kRows * (kDC + 1) + kRows + 8 * (size_t)k) + sizeof(uint32_t) * 8 * (size_t)k;
   if (smem > 48 * 1024)

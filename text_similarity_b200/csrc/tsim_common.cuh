@@ -220,6 +220,8 @@ struct SearchPlan {
   int64_t slice_rows;  // rows per slice
   // workspace offsets (bytes)
   size_t off_cand, off_thr, off_flagcnt, off_flaglist, off_invnorm, off_qpad, off_ex_score, off_ex_idx;
+  int has_ex_rinv;     // 1: the workspace holds [N] float64 inverse row norms for the tensor-core exact scan
+  size_t off_ex_rinv;
   size_t off_ladder;   // [Q][2 * kLadder] u32: per-query threshold ladder (levels | counts), bootstrap plans only
   size_t off_sched;    // round-robin: 3 unit-claim areas (one per tcgen05 launch of a call), zeroed with thr
   size_t sched_area;   // bytes per claim area: 256 (counter) + workers * 32 records * 8
@@ -275,7 +277,7 @@ int launch_search_exact(const void* q, int q_dt, int64_t q_stride, const void* c
                         int64_t c_stride, int64_t Q, int64_t N, int64_t D, int k,
                         int self_on, int64_t self_off, const SearchPlan& p, const int32_t* flag_cnt,
                         const int32_t* flag_list, double* ex_score, uint32_t* ex_idx,
-                        cudaStream_t st);
+                        double* ex_rinv, cudaStream_t st);
 int launch_merge_exact_lists(const void* q, int q_dt, int64_t q_stride, const void* corpus,
                              int c_dt, int64_t c_stride, int64_t Q, int64_t D, int k,
                              int64_t idx_base, const SearchPlan& p, const int32_t* flag_cnt,
