@@ -257,11 +257,16 @@ __global__ void __launch_bounds__(kSelThreads) select_rescore_kernel(SelArgs a) 
     __syncthreads();
     n = n_sh;
     if (cursor < total && n > kKeyCap / 2) {
-      int np = next_pow2(n);
-      for (int i = n + tid; i < np; i += blockDim.x) keys[i] = 0;
-      __syncthreads();
-      sort_keys_desc(keys, np);
-      n = min(n, a.KP);
+      const int kept = keep_top_scores(keys, n, a.KP, sel_out, sel_hist, sel_sh);
+      if (kept == n) {              // massive ties: sort and truncate
+        int np = next_pow2(n);
+        for (int i = n + tid; i < np; i += blockDim.x) keys[i] = 0;
+        __syncthreads();
+        sort_keys_desc(keys, np);
+        n = min(n, a.KP);
+      } else {
+        n = kept;
+      }
       if (tid == 0) n_sh = n;
       __syncthreads();
     }
