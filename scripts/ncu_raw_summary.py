@@ -9,7 +9,8 @@ KEEP = re.compile(r"^(Kernel Name|Block Size|Grid Size|Device|CC|gpu__time_durat
                   r"dram__throughput|sm__pipe_tensor|sm__inst_executed_pipe_tensor|sm__warps_active|sm__throughput|sm__cycles_active|"
                   r"launch__|lts__t_sector_hit_rate|lts__t_bytes|lts__throughput|l1tex__m_xbar2l1tex_read_bytes|l1tex__throughput|"
                   r"l1tex__data_pipe_lsu_wavefronts_mem_shared|smsp__cycles_active|smsp__inst_executed\.sum|smsp__warp_issue_stalled.*_per_warp_active|"
-                  r"sm__sass_inst_executed_op_shared|smsp__pcsamp_warps_issue_stalled)")
+                  r"sm__sass_inst_executed_op_shared|smsp__pcsamp_warps_issue_stalled|sm__pipe_fp64_cycles_active|sm__inst_executed_pipe_fp64|"
+                  r"sm__inst_executed_pipe_lsu|l1tex__data_pipe_lsu_wavefronts|l1tex__data_bank_conflicts_pipe_lsu_mem_shared|smsp__issue_active)")
 rows = list(csv.reader(sys.stdin))
 hdr, units = rows[0], rows[1]
 for vals in rows[2:]:
