@@ -1,5 +1,6 @@
-// Measured float64 FMA peak of the CUDA cores (the roofline of the exact scan, search_exact.cu), and how it
-// depends on the warps resident per SM sub-partition: every thread runs ILP independent DFMA chains from registers.
+// Measured float64 peaks (the rooflines of the exact scan, search_exact.cu): DFMA on the CUDA cores, and how it
+// depends on the warps resident per SM sub-partition (every thread runs ILP independent chains from registers),
+// and DMMA.8x8x4 on the FP64 tensor cores.
 //   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o scripts/dfma_peak scripts/dfma_peak.cu && scripts/dfma_peak
 #include <cstdio>
 #include <cuda_runtime.h>
