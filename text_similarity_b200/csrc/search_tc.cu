@@ -30,6 +30,7 @@ namespace {
 
 constexpr int BM = 128;        // queries per CTA tile (TMEM lanes)
 constexpr int BN = 256;        // corpus rows per tile (TMEM columns per accumulator stage)
+constexpr int kCnStride = BN + 16;   // per-warp copy of a tile's inverse norms + (max, min) per 32-column chunk
 constexpr int BK_BYTES = 128;  // bytes per row per k-block = one 128-byte swizzle atom row (64 bf16 / 128 e4m3)
 constexpr int UMMA_K_BYTES = 32;  // one MMA consumes 32 bytes of K per row (K = 16 bf16 / 32 e4m3)
 constexpr int kThreads = 256;  // warps0-3 epilogue, warp4 TMA, warp5 MMA, warp6 TMEM alloc, warp7 idle (the issue
@@ -203,6 +204,7 @@ struct TcArgs {
   const int32_t* q_count;  // retry pass: device-side number of live queries (<= Q), or null = Q
   const int32_t* q_map;    // retry pass: compact query -> query of the call (self-exclusion), or null
   int q_skip;              // retry pass: live queries = clamp(*q_count - q_skip, 0, Q)
+  int hot_scaled;       // experiment knob (TSIM_HOT_SCALED=1): scale all 32 scores of a chunk before the filter (the old hot path)
   int roles_low;        // experiment knob (TSIM_ROLES_LOW=1): TMA / MMA / alloc on warps 0-2, epilogue on warps 4-7
   int dbg;              // TSIM_DEBUG bits (diagnosis only): 1 skip A loads, 2 skip MMAs, 4 skip epilogue math
 };
@@ -496,7 +498,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   extern __shared__ unsigned char smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment: round the dynamic window up (1 KB of slack is
   // requested by the launcher).
-  // [STAGES][A 16K | B 32K] | lists | cnorm[2 acc][4 warps][BN] | list fill counts | barriers | tmem ptr
+  // [STAGES][A 16K | B 32K] | lists | cnorm[2 acc][4 warps][BN + 16] | list fill counts | barriers | tmem ptr
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int B_BYTES = Cfg<PAIR>::B_BYTES;
   constexpr int STAGE_BYTES = Cfg<PAIR>::STAGE_BYTES;
@@ -506,7 +508,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   float* list_s = (float*)(smem + (size_t)STAGES * STAGE_BYTES);
   uint32_t* list_i = (uint32_t*)(list_s + KP * kEpiThreads);
   float* cnorm = (float*)(list_i + KP * kEpiThreads);
-  int* list_n = (int*)(cnorm + 2 * 4 * BN);
+  int* list_n = (int*)(cnorm + 2 * 4 * kCnStride);
   uint64_t* bars = (uint64_t*)(list_n + kEpiThreads);
   uint64_t* full_bar = bars;                 // [STAGES]  TMA -> MMA
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]  MMA -> TMA
@@ -648,9 +650,17 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const int64_t trow0 = (int64_t)actual_tile(a, un.tile0 + t * un.tstride) * BN;
         const int ncols = (int)min((int64_t)BN, a.N - trow0);
         // each epilogue warp keeps a private copy of the tile's inverse norms: no cross-warp barrier
-        float* cn = cnorm + (acc * 4 + (warp & 3)) * BN;
+        // ... followed by, per 32-column chunk, the largest and the smallest of its inverse norms (chunk i = nreg[i]
+        // across the lanes; inverse norms are >= 0, so their bit patterns order like the values; a NaN / Inf norm
+        // reads as "not finite" below and sends its chunk down the exact path)
+        float* cn = cnorm + (acc * 4 + (warp & 3)) * kCnStride;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) cn[lane + 32 * i] = nreg[i];
+        for (int i = 0; i < 8; ++i) {
+          cn[lane + 32 * i] = nreg[i];
+          const uint32_t hi = __reduce_max_sync(0xffffffffu, __float_as_uint(nreg[i]));
+          const uint32_t lo = __reduce_min_sync(0xffffffffu, __float_as_uint(nreg[i]));
+          if (lane == 0) { cn[BN + 2 * i] = __uint_as_float(hi); cn[BN + 2 * i + 1] = __uint_as_float(lo); }
+        }
         if (gthr) thr = fmaxf(thr, ord_to_f32(gthr));
         __syncwarp();
         if (t + 1 < un.ntiles) fetch_meta(t + 1);
@@ -663,23 +673,39 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           uint32_t v[32];
           tc_ld32(tbase + c * 32, v);
           tc_ld_wait();
-          // hot path: 32 FMUL + FMNMX3 tree (kept per 8-column group) + one compare
-          const float4* cn4 = (const float4*)(cn + c * 32);
-          float sc[32], gm[4];
+          // Hot path: FMNMX3 tree over the 32 RAW dot products, one FMUL, one compare.  A scaled score is
+          // s_j * inv_j with inv_lo <= inv_j <= inv_hi, so none can exceed  bound = mx * (mx >= 0 ? inv_hi : inv_lo)
+          // (float rounding is monotone): bound <= thr proves the chunk holds no candidate without scaling a
+          // single score or reading a norm.  With unit-norm rows inv_hi / inv_lo - 1 ~ 4e-3, i.e. ~8 % more chunks
+          // reach the exact path than with the exact maximum; the 32 FMULs + 8 LDS.128 per chunk move there.
+          float gm[4];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const float4 w0 = cn4[2 * g], w1 = cn4[2 * g + 1];
-            float* x = sc + g * 8;
-            x[0] = __uint_as_float(v[g * 8 + 0]) * w0.x; x[1] = __uint_as_float(v[g * 8 + 1]) * w0.y;
-            x[2] = __uint_as_float(v[g * 8 + 2]) * w0.z; x[3] = __uint_as_float(v[g * 8 + 3]) * w0.w;
-            x[4] = __uint_as_float(v[g * 8 + 4]) * w1.x; x[5] = __uint_as_float(v[g * 8 + 5]) * w1.y;
-            x[6] = __uint_as_float(v[g * 8 + 6]) * w1.z; x[7] = __uint_as_float(v[g * 8 + 7]) * w1.w;
-            gm[g] = fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7])));
+            const uint32_t* x = v + g * 8;
+            gm[g] = fmaxf(fmaxf(fmaxf(__uint_as_float(x[0]), __uint_as_float(x[1])), fmaxf(__uint_as_float(x[2]), __uint_as_float(x[3]))),
+                          fmaxf(fmaxf(__uint_as_float(x[4]), __uint_as_float(x[5])), fmaxf(__uint_as_float(x[6]), __uint_as_float(x[7]))));
           }
-          const float mx = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
-          // Cold path, entered by the whole warp when any lane has a candidate; rare once the lists are warm.
-          if (__any_sync(0xffffffffu, mx > thr))
-            thr = list.slow(sc, thr, trow0 + c * 32, self_row, ncols - c * 32, thr_g, lad);
+          const float mxr = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
+          const float2 mm = *reinterpret_cast<const float2*>(cn + BN + 2 * c);
+          const bool fire = mxr * (mxr >= 0.f ? mm.x : mm.y) > thr || !(mm.x < INFINITY) || a.hot_scaled;
+          // Exact path, entered by the whole warp when any lane may have a candidate; rare once the lists are warm.
+          if (__any_sync(0xffffffffu, fire)) {
+            const float4* cn4 = (const float4*)(cn + c * 32);
+            float sc[32];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float4 w0 = cn4[2 * g], w1 = cn4[2 * g + 1];
+              float* x = sc + g * 8;
+              x[0] = __uint_as_float(v[g * 8 + 0]) * w0.x; x[1] = __uint_as_float(v[g * 8 + 1]) * w0.y;
+              x[2] = __uint_as_float(v[g * 8 + 2]) * w0.z; x[3] = __uint_as_float(v[g * 8 + 3]) * w0.w;
+              x[4] = __uint_as_float(v[g * 8 + 4]) * w1.x; x[5] = __uint_as_float(v[g * 8 + 5]) * w1.y;
+              x[6] = __uint_as_float(v[g * 8 + 6]) * w1.z; x[7] = __uint_as_float(v[g * 8 + 7]) * w1.w;
+              mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7]))));
+            }
+            if (__any_sync(0xffffffffu, mx > thr))
+              thr = list.slow(sc, thr, trow0 + c * 32, self_row, ncols - c * 32, thr_g, lad);
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -746,7 +772,7 @@ int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t D, int64_t 
 
 template <int KP, int STAGES, bool PAIR, bool FP8>
 int launch_cfg(const CUtensorMap& mq, const CUtensorMap& mc, const TcArgs& a, cudaStream_t st) {
-  size_t smem = 1024 + (size_t)STAGES * Cfg<PAIR>::STAGE_BYTES + (size_t)KP * kEpiThreads * 8 + 2 * 4 * BN * 4 +
+  size_t smem = 1024 + (size_t)STAGES * Cfg<PAIR>::STAGE_BYTES + (size_t)KP * kEpiThreads * 8 + 2 * 4 * kCnStride * 4 +
                 kEpiThreads * 4 + (2 * STAGES + 4) * 8 + 16;
   auto kern = search_tc_kernel<KP, STAGES, PAIR, FP8>;
   TSIM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -821,6 +847,8 @@ int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_
   a.dbg = dbg ? atoi(dbg) : 0;
   const char* rl = getenv("TSIM_ROLES_LOW");
   a.roles_low = (rl && rl[0] == '1') ? 1 : 0;
+  const char* hs = getenv("TSIM_HOT_SCALED");
+  a.hot_scaled = (hs && hs[0] == '1') ? 1 : 0;
 #define TSIM_DISPATCH(FP8)                                                       \
   if (p.pair) {                                                                  \
     switch (p.KP) {                                                              \
