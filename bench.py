@@ -374,9 +374,9 @@ def main():
                     "frac": gbs / peaks["hbm_gbs"], "traffic": None}
     if world == 1 and args.workload == DEFAULT_WORKLOAD and Q == WORKLOADS[DEFAULT_WORKLOAD][2]:
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload, one ncu --set full
-        # capture (profiles/r01c_search_tc_bench_q4096.ncu_raw.txt)
-        roofline["traffic"] = 16.72e9 + 0.33e9   # main-pass launch (98.4 % of the rows; the sample passes are not in this figure)
-        roofline["traffic_source"] = "profiles/r01c_search_tc_bench_q4096.ncu_raw.txt"
+        # capture (profiles/r01i_search_tc_bench_q4096.ncu_raw.txt)
+        roofline["traffic"] = 16.87e9 + 0.33e9   # main-pass launch (98.4 % of the rows; the sample passes are not in this figure)
+        roofline["traffic_source"] = "profiles/r01i_search_tc_bench_q4096.ncu_raw.txt"
     roofline.update({"kernel": "search_tc_kernel", "kernel_ms": kern_ms, "peak_source": peaks["source"],
                      "algorithmic_flops": flops, "algorithmic_bytes": bytes_alg})
 
