@@ -206,9 +206,29 @@ __device__ __forceinline__ void fetch_col_dt(float (&pre)[NR], int dt, const voi
   }
 }
 
-// 1 / max(||row||, eps) in float64, one warp per row (lane-strided sums, fixed butterfly)
+// element `d` of NR query rows given by byte offsets (shared memory; a flagged-query launch scans scattered rows)
+template <int DT, int NR>
+__device__ __forceinline__ void fetch_rows_at(float (&pre)[NR], const char* base, const int64_t* off, int nvalid, int64_t d) {
+#pragma unroll
+  for (int i = 0; i < NR; ++i) pre[i] = i < nvalid ? Elem<DT>::ld(base + off[i], d) : 0.f;
+}
+template <int NR>
+__device__ __forceinline__ void fetch_rows_at_dt(float (&pre)[NR], int dt, const void* base, const int64_t* off, int nvalid,
+                                                 int64_t d, int64_t D) {
+  if (d >= D) nvalid = 0;
+  switch (dt) {
+    case TSIM_F32: fetch_rows_at<TSIM_F32, NR>(pre, (const char*)base, off, nvalid, d); break;
+    case TSIM_F16: fetch_rows_at<TSIM_F16, NR>(pre, (const char*)base, off, nvalid, d); break;
+    case TSIM_BF16: fetch_rows_at<TSIM_BF16, NR>(pre, (const char*)base, off, nvalid, d); break;
+    default: fetch_rows_at<TSIM_E4M3, NR>(pre, (const char*)base, off, nvalid, d); break;
+  }
+}
+
+// 1 / max(||row||, eps) in float64, one warp per row (lane-strided sums, fixed butterfly); a fallback launch
+// (flag_cnt given) leaves at once when no query is flagged
 __global__ void __launch_bounds__(256) row_rinv_f64_kernel(const void* corpus, int c_dt, int64_t c_stride, int64_t N,
-                                                           int64_t D, double* rinv) {
+                                                           int64_t D, const int32_t* flag_cnt, double* rinv) {
+  if (flag_cnt && *flag_cnt == 0) return;
   const int lane = threadIdx.x & 31;
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < N; row += warps) {
@@ -235,10 +255,14 @@ __global__ void __launch_bounds__(kExThreads, MINB) search_exact_mma_kernel(ExAr
   double* ls_all = qn_s + QG;                           // [QG][k]
   uint32_t* li_all = (uint32_t*)(ls_all + (size_t)QG * a.k);  // [QG][k]
   int* cnt_s = (int*)(li_all + (size_t)QG * a.k);       // [QG] list lengths (warp-private)
+  int64_t* qoff_s = (int64_t*)(cnt_s + QG);             // [QG] byte offset of the slot's query row
+  int64_t* qid_s = qoff_s + QG;                         // [QG] query number of the slot (self exclusion)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int fr = lane >> 2, fk = lane & 3;              // fragment row / k index of this lane
-  const int64_t ngroups = (a.Q + QG - 1) / QG;
+  // whole-call scan: slot = query.  Fallback launch: slot b = the b-th flagged query, count read on the device
+  const int64_t nq = a.flag_cnt ? (int64_t)*a.flag_cnt : a.Q;
+  const int64_t ngroups = (nq + QG - 1) / QG;
   const int slice = blockIdx.x;
   const int64_t row_begin = (int64_t)slice * a.slice_rows;
   const int64_t row_end = min(a.N, row_begin + a.slice_rows);
@@ -251,8 +275,10 @@ __global__ void __launch_bounds__(kExThreads, MINB) search_exact_mma_kernel(ExAr
     const int64_t slot0 = g * QG + warp * QW;           // this warp's first query
 #pragma unroll 1
     for (int j = 0; j < QW; ++j) {
-      const int64_t qid = min(slot0 + j, a.Q - 1);
-      const char* qrow = (const char*)a.q + (size_t)qid * a.q_stride * qsz;
+      const int64_t slot = min(slot0 + j, nq - 1);
+      const int64_t qid = a.flag_list ? (int64_t)a.flag_list[slot] : slot;
+      const int64_t qoff = qid * a.q_stride * qsz;
+      const char* qrow = (const char*)a.q + qoff;
       double qq = 0.0;
       for (int64_t d = lane; d < a.D; d += 32) {
         double v = (double)load_elem(qrow, a.q_dt, d);
@@ -262,9 +288,12 @@ __global__ void __launch_bounds__(kExThreads, MINB) search_exact_mma_kernel(ExAr
       if (lane == 0) {
         qn_s[warp * QW + j] = 1.0 / fmax(sqrt(qq), kCosEps);
         cnt_s[warp * QW + j] = 0;
+        qoff_s[warp * QW + j] = qoff;
+        qid_s[warp * QW + j] = qid;
       }
     }
     __syncwarp();
+    const int qlive = (int)max((int64_t)0, min((int64_t)QW, nq - slot0));   // live queries of this warp
 
     float pre[kMOwn];   // the next (tile, chunk): rows warp + 8 i, element lane
     float qpre[QW];     // ... and element lane of this warp's queries
@@ -273,7 +302,7 @@ __global__ void __launch_bounds__(kExThreads, MINB) search_exact_mma_kernel(ExAr
     auto fetch = [&]() {
       const int64_t d = (int64_t)fc * kMDC + lane;
       fetch_col_dt<kMOwn>(pre, a.c_dt, a.corpus, a.c_stride, fr0 + warp, 8, row_end, d, a.D);
-      fetch_col_dt<QW>(qpre, a.q_dt, a.q, a.q_stride, slot0, 1, a.Q, d, a.D);
+      fetch_rows_at_dt<QW>(qpre, a.q_dt, a.q, qoff_s + warp * QW, qlive, d, a.D);
       if (++fc == nchunks) { fc = 0; fr0 += kMRows; }
     };
     if (total) fetch();
@@ -317,8 +346,9 @@ __global__ void __launch_bounds__(kExThreads, MINB) search_exact_mma_kernel(ExAr
         // a block are walked by ascending (lane, element), i.e. ascending row for every query.
 #pragma unroll
         for (int mi = 0; mi < MF; ++mi) {
-          const int ql = warp * QW + mi * 8 + fr;          // this lane's query within the CTA
-          const int64_t qid = g * QG + ql;
+          const int ql = warp * QW + mi * 8 + fr;          // this lane's query slot within the CTA
+          const int64_t qid = qid_s[ql];
+          const bool live = g * QG + ql < nq;
           const double qn = qn_s[ql];
 #pragma unroll
           for (int ni = 0; ni < kMNF; ++ni) {
@@ -328,7 +358,6 @@ __global__ void __launch_bounds__(kExThreads, MINB) search_exact_mma_kernel(ExAr
             const double2 ri = *reinterpret_cast<const double2*>(rinv + col);
             const double s0 = acc[mi][ni][0] * qn * ri.x, s1 = acc[mi][ni][1] * qn * ri.y;
             const int64_t row = r0 + col;
-            const bool live = qid < a.Q;
             // NaN scores fail `>`: never returned.  Rows of one block are re-checked on insertion.
             const bool w0 = live && row < row_end && !(a.self_on && row == a.self_off + qid) && s0 > thr;
             const bool w1 = live && row + 1 < row_end && !(a.self_on && row + 1 == a.self_off + qid) && s1 > thr;
@@ -351,7 +380,7 @@ __global__ void __launch_bounds__(kExThreads, MINB) search_exact_mma_kernel(ExAr
 #pragma unroll 1
     for (int j = 0; j < QW; ++j) {
       const int64_t slot = slot0 + j;
-      if (slot >= a.Q) break;
+      if (slot >= nq) break;
       const double* ls = ls_all + (size_t)(warp * QW + j) * a.k;
       const uint32_t* li = li_all + (size_t)(warp * QW + j) * a.k;
       const int cnt = cnt_s[warp * QW + j];
@@ -368,7 +397,8 @@ __global__ void __launch_bounds__(kExThreads, MINB) search_exact_mma_kernel(ExAr
 
 size_t mma_smem_bytes(int k, int MF) {
   const size_t QG = 64 * (size_t)MF;
-  return sizeof(double) * ((QG + kMRows) * kMStride + kMRows + QG + QG * k) + sizeof(uint32_t) * QG * k + sizeof(int) * QG;
+  return sizeof(double) * ((QG + kMRows) * kMStride + kMRows + QG + QG * k) + sizeof(uint32_t) * QG * k + sizeof(int) * QG +
+         2 * sizeof(int64_t) * QG;
 }
 
 }  // namespace
@@ -389,17 +419,19 @@ int launch_search_exact(const void* q, int q_dt, int64_t q_stride, const void* c
   // Q = 1024: k = 10 92.9 ms / k = 100 103.4 ms, against 90.7 / 111.3 ms with 128 queries per CTA and one CTA per
   // SM, 116.4 / 128.5 ms with 64 queries and one CTA; Q = 64: 6.4 ms against 7.9-12.4 ms.
   const char* nomma = getenv("TSIM_NO_MMA_SCAN");       // experiment knob
-  if (!flag_cnt && ex_rinv && Q > 32 && N > 0 && !(nomma && nomma[0] == '1')) {
+  // (a fallback launch does not know how many queries are flagged: up to 8 group CTAs per slice stride over them)
+  if (ex_rinv && Q > 32 && N > 0 && !(nomma && nomma[0] == '1')) {
     int MF = 1, minb = 2;
     if (const char* v = getenv("TSIM_MMA_VARIANT")) {   // experiment knob: "<8-query fragments per warp>x<CTAs per SM>"
       if (v[0] == '1' && v[1] && v[2] == '1') minb = 1;
       if (v[0] == '2' && mma_smem_bytes(k, 2) <= 227 * 1024) { MF = 2; minb = 1; }
     }
     const size_t msmem = mma_smem_bytes(k, MF);
-    const int64_t mgroups = (Q + 64 * MF - 1) / (64 * MF);
+    int64_t mgroups = (Q + 64 * MF - 1) / (64 * MF);
+    if (flag_cnt && mgroups > 8) mgroups = 8;
     if (msmem <= 227 * 1024 && (int64_t)p.S * mgroups >= 64) {
       const int64_t nb = (N + 7) / 8;
-      row_rinv_f64_kernel<<<(unsigned)(nb < 8 * 148 ? nb : 8 * 148), 256, 0, st>>>(corpus, c_dt, c_stride, N, D, ex_rinv);
+      row_rinv_f64_kernel<<<(unsigned)(nb < 8 * 148 ? nb : 8 * 148), 256, 0, st>>>(corpus, c_dt, c_stride, N, D, flag_cnt, ex_rinv);
       TSIM_CUDA(cudaGetLastError());
       count_launch();
       dim3 mgrid((unsigned)p.S, (unsigned)(mgroups < 4096 ? mgroups : 4096));

@@ -201,7 +201,7 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
     p->off_r_q = off; off = align_up(off + (size_t)p->retry * kRetryQ * D * dtype_size(q_dt), 256);
     p->off_r_cand = off; off = align_up(off + (size_t)kRetryQ * p->r_Gq * kRetryKP * sizeof(uint64_t), 256);
   }
-  if (!p->use_tensor && Q > 32) {   // whole-call scan on the FP64 tensor cores: row norms once per call
+  if (Q > 32 && N > 0) {   // float64 scan on the FP64 tensor cores (whole call, or the flagged-query fallback): row norms once per call
     p->has_ex_rinv = 1;
     p->off_ex_rinv = off; off = align_up(off + (size_t)N * sizeof(double), 256);
   }
@@ -375,7 +375,7 @@ static int search_impl(const void* q, int q_dt, int64_t q_stride, const void* co
     }
     // queries whose candidate set could not be proven complete: float64 scan (usually none)
     rc = launch_search_exact(q, q_dt, q_stride, corpus, c_dt, c_stride, Q, N, D, k, self_on, self_off, p,
-                             flag_cnt, flag_list, ex_score, ex_idx, nullptr, st);
+                             flag_cnt, flag_list, ex_score, ex_idx, p.has_ex_rinv ? (double*)(w + p.off_ex_rinv) : nullptr, st);
     if (rc) return rc;
     return launch_merge_exact_lists(q, q_dt, q_stride, corpus, c_dt, c_stride, Q, D, k, idx_base, p,
                                     flag_cnt, flag_list, ex_score, ex_idx, out_score, out_score64,
