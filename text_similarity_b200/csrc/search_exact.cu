@@ -1,17 +1,20 @@
-// K2 (exact scan): float64 brute-force cosine + per-slice top-k on the CUDA cores.
+// K2x (exact scan): float64 brute-force cosine + per-slice top-k.
 //
-// This is the path for fp32 inputs (tolerance 1e-5 rules out TF32 tensor cores; the reference's
-// own CPU-runnable case, BASELINE config 1, is 10k x 384 fp32), for shapes the TMA path cannot
-// take, and the fallback for the few queries whose tensor-core candidates could not be proven
-// complete (select_merge.cu).  It restates, in float64, exactly what the reference computes per
-// query: F.cosine_similarity(q.expand_as(C), C, -1) (search_pipeline.py:76-77) then the k
-// largest (:78), with the north_star tie rule (lower index first).
+// This is the path for calls the tcgen05 kernel cannot take (k > 100, k > 24 on fp32 / fp16 rows,
+// odd widths, misaligned or mixed-dtype inputs; fp32 tolerance 1e-5 rules out TF32) and the
+// fallback for the few queries whose tensor-core candidates could not be proven complete
+// (select_merge.cu).  It restates, in float64, exactly what the reference computes per query:
+// F.cosine_similarity(q.expand_as(C), C, -1) (search_pipeline.py:76-77) then the k largest (:78),
+// with the north_star tie rule (lower index first).
 //
-// Layout: grid = (S corpus slices, query groups); one warp per query of a group of 8, one lane
-// per corpus row of a 32-row tile staged through shared memory as float64 (coalesced global
-// loads, conflict-free column reads).  Each warp keeps a sorted top-k list in shared memory and
-// inserts cooperatively.  Lists go to the workspace as [slot][slice][k]; merge_exact_lists
-// finishes.  Bytes: N*D*e per group of 8 queries -- this path is not the roofline path.
+// Two kernels share the layout grid = (S corpus slices, query groups), per-warp sorted top-k
+// lists in shared memory with cooperative insertion, and the output [slot][slice][k] that
+// merge_exact_lists (select_merge.cu) re-scores canonically and merges:
+//  * search_exact_mma_kernel -- FP64 tensor cores (DMMA.8x8x4), 64 queries per CTA; more than 32
+//    queries, k <= 251, >= 64 slices.  See the comment above it.
+//  * search_exact_kernel -- one warp per query of a group of 8, one lane per corpus row of a
+//    32-row tile staged through shared memory as float64 (DFMA); everything else.
+// Bytes: N*D*e per query group -- compute-bound on the FP64 pipes, not the HBM roofline path.
 #include "tsim_common.cuh"
 
 namespace tsim {
