@@ -209,21 +209,23 @@ __device__ __forceinline__ void fetch_col_dt(float (&pre)[NR], int dt, const voi
   }
 }
 
-// element `d` of NR query rows given by byte offsets (shared memory; a flagged-query launch scans scattered rows)
+// element `d` of NR query rows given by row numbers (shared memory; a flagged-query launch scans scattered rows)
 template <int DT, int NR>
-__device__ __forceinline__ void fetch_rows_at(float (&pre)[NR], const char* base, const int64_t* off, int nvalid, int64_t d) {
+__device__ __forceinline__ void fetch_rows_at(float (&pre)[NR], const char* base, int64_t row_bytes, const int32_t* rows,
+                                              int nvalid, int64_t d) {
 #pragma unroll
-  for (int i = 0; i < NR; ++i) pre[i] = i < nvalid ? Elem<DT>::ld(base + off[i], d) : 0.f;
+  for (int i = 0; i < NR; ++i) pre[i] = i < nvalid ? Elem<DT>::ld(base + rows[i] * row_bytes, d) : 0.f;
 }
 template <int NR>
-__device__ __forceinline__ void fetch_rows_at_dt(float (&pre)[NR], int dt, const void* base, const int64_t* off, int nvalid,
-                                                 int64_t d, int64_t D) {
+__device__ __forceinline__ void fetch_rows_at_dt(float (&pre)[NR], int dt, const void* base, int64_t stride, const int32_t* rows,
+                                                 int nvalid, int64_t d, int64_t D) {
   if (d >= D) nvalid = 0;
+  const int64_t rb = stride * dtype_size(dt);
   switch (dt) {
-    case TSIM_F32: fetch_rows_at<TSIM_F32, NR>(pre, (const char*)base, off, nvalid, d); break;
-    case TSIM_F16: fetch_rows_at<TSIM_F16, NR>(pre, (const char*)base, off, nvalid, d); break;
-    case TSIM_BF16: fetch_rows_at<TSIM_BF16, NR>(pre, (const char*)base, off, nvalid, d); break;
-    default: fetch_rows_at<TSIM_E4M3, NR>(pre, (const char*)base, off, nvalid, d); break;
+    case TSIM_F32: fetch_rows_at<TSIM_F32, NR>(pre, (const char*)base, rb, rows, nvalid, d); break;
+    case TSIM_F16: fetch_rows_at<TSIM_F16, NR>(pre, (const char*)base, rb, rows, nvalid, d); break;
+    case TSIM_BF16: fetch_rows_at<TSIM_BF16, NR>(pre, (const char*)base, rb, rows, nvalid, d); break;
+    default: fetch_rows_at<TSIM_E4M3, NR>(pre, (const char*)base, rb, rows, nvalid, d); break;
   }
 }
 
@@ -258,8 +260,7 @@ __global__ void __launch_bounds__(kExThreads, MINB) search_exact_mma_kernel(ExAr
   double* ls_all = qn_s + QG;                           // [QG][k]
   uint32_t* li_all = (uint32_t*)(ls_all + (size_t)QG * a.k);  // [QG][k]
   int* cnt_s = (int*)(li_all + (size_t)QG * a.k);       // [QG] list lengths (warp-private)
-  int64_t* qoff_s = (int64_t*)(cnt_s + QG);             // [QG] byte offset of the slot's query row
-  int64_t* qid_s = qoff_s + QG;                         // [QG] query number of the slot (self exclusion)
+  int32_t* qid_s = cnt_s + QG;                          // [QG] query number of the slot (its row, self exclusion)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int fr = lane >> 2, fk = lane & 3;              // fragment row / k index of this lane
@@ -280,8 +281,7 @@ __global__ void __launch_bounds__(kExThreads, MINB) search_exact_mma_kernel(ExAr
     for (int j = 0; j < QW; ++j) {
       const int64_t slot = min(slot0 + j, nq - 1);
       const int64_t qid = a.flag_list ? (int64_t)a.flag_list[slot] : slot;
-      const int64_t qoff = qid * a.q_stride * qsz;
-      const char* qrow = (const char*)a.q + qoff;
+      const char* qrow = (const char*)a.q + (size_t)qid * a.q_stride * qsz;
       double qq = 0.0;
       for (int64_t d = lane; d < a.D; d += 32) {
         double v = (double)load_elem(qrow, a.q_dt, d);
@@ -291,8 +291,7 @@ __global__ void __launch_bounds__(kExThreads, MINB) search_exact_mma_kernel(ExAr
       if (lane == 0) {
         qn_s[warp * QW + j] = 1.0 / fmax(sqrt(qq), kCosEps);
         cnt_s[warp * QW + j] = 0;
-        qoff_s[warp * QW + j] = qoff;
-        qid_s[warp * QW + j] = qid;
+        qid_s[warp * QW + j] = (int32_t)qid;
       }
     }
     __syncwarp();
@@ -305,7 +304,7 @@ __global__ void __launch_bounds__(kExThreads, MINB) search_exact_mma_kernel(ExAr
     auto fetch = [&]() {
       const int64_t d = (int64_t)fc * kMDC + lane;
       fetch_col_dt<kMOwn>(pre, a.c_dt, a.corpus, a.c_stride, fr0 + warp, 8, row_end, d, a.D);
-      fetch_rows_at_dt<QW>(qpre, a.q_dt, a.q, qoff_s + warp * QW, qlive, d, a.D);
+      fetch_rows_at_dt<QW>(qpre, a.q_dt, a.q, a.q_stride, qid_s + warp * QW, qlive, d, a.D);
       if (++fc == nchunks) { fc = 0; fr0 += kMRows; }
     };
     if (total) fetch();
@@ -331,7 +330,7 @@ __global__ void __launch_bounds__(kExThreads, MINB) search_exact_mma_kernel(ExAr
 
       const double* qf = qs + (warp * QW + fr) * kMStride + fk;
       const double* tf = tile + fr * kMStride + fk;
-#pragma unroll 2
+#pragma unroll 2   // deeper unrolling measured no faster (scripts/ab_exact.py)
       for (int ks = 0; ks < kMDC / 4; ++ks) {
         double af[MF], bf[kMNF];
 #pragma unroll
@@ -400,8 +399,7 @@ __global__ void __launch_bounds__(kExThreads, MINB) search_exact_mma_kernel(ExAr
 
 size_t mma_smem_bytes(int k, int MF) {
   const size_t QG = 64 * (size_t)MF;
-  return sizeof(double) * ((QG + kMRows) * kMStride + kMRows + QG + QG * k) + sizeof(uint32_t) * QG * k + sizeof(int) * QG +
-         2 * sizeof(int64_t) * QG;
+  return sizeof(double) * ((QG + kMRows) * kMStride + kMRows + QG + QG * k) + sizeof(uint32_t) * QG * k + 2 * sizeof(int) * QG;
 }
 
 }  // namespace

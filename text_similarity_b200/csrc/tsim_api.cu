@@ -230,6 +230,7 @@ static int check_search_args(int64_t Q, int64_t N, int64_t D, int k, int q_dt, i
   TSIM_CHECK_ARG(dtype_size(q_dt) && dtype_size(c_dt), "search: bad dtype q=%d c=%d", q_dt, c_dt);
   TSIM_CHECK_ARG(mode >= TSIM_MODE_AUTO && mode <= TSIM_MODE_TENSOR, "search: bad mode %d", mode);
   TSIM_CHECK_ARG(N < (int64_t)0xfffffff0, "search: N=%lld rows per shard exceeds 2^32", (long long)N);
+  TSIM_CHECK_ARG(Q < ((int64_t)1 << 31), "search: Q=%lld queries per call exceeds 2^31", (long long)Q);
   return TSIM_OK;
 }
 
