@@ -149,7 +149,7 @@ def test_exact_scan_fp8_and_mixed(ops):
 @pytest.mark.parametrize("N,Q,D,k,dtype", [
     (70_000, 100, 384, 10, torch.float32),      # 69 slices x 2 groups, second group ragged (36 of 64 queries)
     (40_000, 130, 50, 100, torch.bfloat16),     # D not a multiple of the 64-wide chunk, three groups
-    (33_000, 65, 100, 250, torch.float16),      # near the largest k the kernel takes (251); one query in the last warp
+    (33_000, 65, 100, 250, torch.float16),      # near the largest k the kernel takes (252); one query in the last warp
     (150_000, 33, 768, 24, torch.bfloat16),     # a single group with 31 idle query slots
     (35_001, 200, 8, 5, torch.float32),         # one D chunk of 8, ragged last slice
 ])

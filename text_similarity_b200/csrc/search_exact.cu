@@ -11,7 +11,7 @@
 // lists in shared memory with cooperative insertion, and the output [slot][slice][k] that
 // merge_exact_lists (select_merge.cu) re-scores canonically and merges:
 //  * search_exact_mma_kernel -- FP64 tensor cores (DMMA.8x8x4), 64 queries per CTA; more than 32
-//    queries, k <= 251, >= 64 slices.  See the comment above it.
+//    queries, k <= 252, >= 64 slices.  See the comment above it.
 //  * search_exact_kernel -- one warp per query of a group of 8, one lane per corpus row of a
 //    32-row tile staged through shared memory as float64 (DFMA); everything else.
 // Bytes: N*D*e per query group -- compute-bound on the FP64 pipes, not the HBM roofline path.
