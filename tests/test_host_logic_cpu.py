@@ -144,3 +144,35 @@ def test_abi_shadow_entry_validates_arguments_before_touching_the_gpu():
     rc = lib.tsim_search_topk_shadow(1, _lib.F32, 8, 1, _lib.F32, 8, 1, 8, 1, 8, _lib.E4M3, None,
                                      4, 10, 8, 3, 0, -1, None, None, None, None, None, 0, None)
     assert rc == _lib.ERR_INVALID_ARG and b"bf16" in lib.tsim_last_error()
+
+
+def test_bench_reference_arm_contract(monkeypatch):
+    """bench.py --impl reference: rank 0 prints ONE JSON line carrying the base contract's keys plus impl /
+    cpu_baseline / e2e; other ranks exit 0 without work (the CPU sample itself is shrunk here)."""
+    import json
+    import subprocess
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([_sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                         capture_output=True, text=True, env=env, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+    _sys.path.insert(0, root)
+    import bench
+    qps, cores, sample, spent = bench.cpu_reference_qps(20_000, 64, 10, budget_s=0.2)
+    assert qps > 0 and cores >= 1 and "scaled linearly" in sample
+
+    monkeypatch.setattr(bench, "cpu_reference_qps", lambda N, D, k, budget_s=12.0: (12.5, 4, "stub sample", 0.1))
+    lines = []
+    monkeypatch.setattr(bench, "_emit", lambda fd, line: lines.append(line))
+    args = type("A", (), {"workload": bench.DEFAULT_WORKLOAD, "steps": 2, "warmup": 1, "gpus": 1})()
+    monkeypatch.setenv("RANK", "0")
+    bench.run_reference(args, 1)
+    (line,) = lines
+    json.dumps(line)
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline", "impl"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["config"]["workload"] == bench.DEFAULT_WORKLOAD and line["vs_baseline"] is None
