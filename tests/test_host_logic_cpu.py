@@ -176,3 +176,23 @@ def test_bench_reference_arm_contract(monkeypatch):
         assert key in line, key
     assert line["impl"] == "reference" and line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["config"]["workload"] == bench.DEFAULT_WORKLOAD and line["vs_baseline"] is None
+
+
+def test_raw_maximum_bound_of_the_epilogue_filter_is_conservative():
+    """search_tc.cu's hot path skips a 32-column chunk when  max_j(raw_j) * (max >= 0 ? inv_hi : inv_lo) <= thr.
+    Property restated in float32 on the host: that product is never below any scaled score fl(raw_j * inv_j),
+    whatever the signs (float rounding is monotone), so a skipped chunk cannot hold a candidate."""
+    import numpy as np
+    rng = np.random.default_rng(7)
+    for trial in range(2000):
+        scale = np.float32(10.0 ** rng.uniform(-3, 3))
+        raw = (rng.standard_normal(32) * scale).astype(np.float32)
+        if trial % 3 == 0:
+            raw = -np.abs(raw)                      # an all-negative chunk takes the inv_lo branch
+        inv = (1.0 + rng.uniform(-0.3, 0.3, 32)).astype(np.float32) * np.float32(10.0 ** rng.uniform(-2, 2))
+        if trial % 7 == 0:
+            inv[rng.integers(0, 32)] = np.float32(0.0)   # out-of-range column of a ragged last tile
+        scaled = raw * inv                           # float32 products, as the exact path computes them
+        mx = raw.max()
+        bound = mx * (inv.max() if mx >= 0 else inv.min())
+        assert bound >= scaled.max(), (trial, bound, scaled.max())
