@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TSIM_ABI_VERSION 1
+#define TSIM_ABI_VERSION 2
 
 /* element types */
 #define TSIM_F32 0
@@ -151,6 +151,33 @@ int tsim_search_topk_shadow(const void* q, int q_dt, int64_t q_stride,
                             void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Plan handles ("Ownership": the C side may cache TMA descriptors keyed by (ptr, shape) in
+ * an opaque handle the Python side owns and destroys).  A handle fixes (Q, N, D, k, dtypes, mode) on the
+ * CURRENT device: the launch plan is made once, and the cuTensorMapEncodeTiled descriptors of every array
+ * it has seen (queries, corpus, shadows; up to 16, least recently used replaced) are kept, so a repeated
+ * tsim_plan_search over the same arrays does no planning and encodes nothing.  Same result, same
+ * workspace contract as tsim_search_topk / tsim_search_topk_shadow (reference lines replaced: the same,
+ * src/pipeline/search_pipeline.py:73-79).  A handle is not thread-safe: one search at a time per handle.
+ *   shadow_dt  TSIM_BF16: the plan of tsim_search_topk_shadow (q_dt / c_dt = dtypes of the ORIGINAL rows,
+ *              corpus_inv_norm = the shadow's, q_shadow / corpus_shadow required); -1: no shadow (the shadow
+ *              arguments of tsim_plan_search are ignored).
+ *   tsim_plan_create returns NULL on error (tsim_last_error() says why).
+ * ---------------------------------------------------------------------------------- */
+typedef struct tsim_plan tsim_plan_t;
+tsim_plan_t* tsim_plan_create(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt, int mode,
+                              int shadow_dt);
+void tsim_plan_destroy(tsim_plan_t* plan);
+size_t tsim_plan_workspace_bytes(const tsim_plan_t* plan);
+int tsim_plan_search(tsim_plan_t* plan,
+                     const void* q, int64_t q_stride, const void* corpus, int64_t c_stride,
+                     const float* corpus_inv_norm,
+                     const void* q_shadow, int64_t qs_stride,
+                     const void* corpus_shadow, int64_t cs_stride,
+                     int64_t idx_base, int64_t exclude_self_base,
+                     float* out_score, double* out_score64, int64_t* out_idx, int32_t* out_flags,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * K3 (second pass): merge n_lists candidate lists per query into the top k_out, ranked by
  * (score descending, index ascending); entries with index < 0 are padding.
  * The reference has no merge: its chunk loop overwrites earlier chunks' results
@@ -172,6 +199,13 @@ int tsim_set_timing_events(void* start, void* stop);
 /* Number of CUDA kernels this library has launched in the process so far (bench.py reports the
  * difference over its timed region as `gpu_launches`). */
 uint64_t tsim_launch_count(void);
+
+/* Process-wide counters for tests: out[0] kernels launched, out[1] cuTensorMapEncodeTiled calls, out[2]
+ * environment variables read (always 0 in the release library: it reads none), out[3] launch plans made. */
+void tsim_debug_counters(uint64_t out[4]);
+/* Bit 0: built with -DTSIM_EXPERIMENT (environment knobs and in-kernel diagnosis switches compiled in;
+ * never the library the package loads by default). */
+int tsim_build_flags(void);
 
 #ifdef __cplusplus
 }

@@ -1,4 +1,4 @@
-"""A/B the float64 scan's experiment knobs: python scripts/ab_exact.py "X=1" "TSIM_MMA_VARIANT=1x2" "TSIM_SCAN_SLICES=74" ...
+"""A/B the float64 scan's experiment knobs: python scripts/ab_exact.py "X=1" "TSIM_MMA_VARIANT=12" "TSIM_SCAN_SLICES=74" ...
 (every argument is a comma-separated set of VAR=value pairs applied for one timing)."""
 import os
 import sys
@@ -6,7 +6,10 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from text_similarity_b200 import ops  # noqa: E402
+from text_similarity_b200 import _lib, build, ops  # noqa: E402
+
+build.build(experiment=True)      # the knobs below exist only in the -DTSIM_EXPERIMENT flavour (libtsim_exp.so)
+_lib.use_experiment_build()
 
 dev = torch.device("cuda")
 shapes = [(1_000_000, 1024, 768, 10), (1_000_000, 1024, 768, 100), (250_000, 4096, 384, 50), (1_000_000, 64, 768, 10)]

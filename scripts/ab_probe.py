@@ -10,7 +10,10 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bench import make_shard  # noqa: E402
-from text_similarity_b200 import ops  # noqa: E402
+from text_similarity_b200 import _lib, build, ops  # noqa: E402
+
+build.build(experiment=True)      # the knobs below exist only in the -DTSIM_EXPERIMENT flavour (libtsim_exp.so)
+_lib.use_experiment_build()
 
 rows = int(os.environ.get("ROWS", "10000000"))
 Q, D, k = int(os.environ.get("Q", "4096")), 768, int(os.environ.get("K", "10"))

@@ -6,7 +6,10 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from text_similarity_b200 import ops  # noqa: E402
+from text_similarity_b200 import _lib, build, ops  # noqa: E402
+
+build.build(experiment=True)      # the knobs below exist only in the -DTSIM_EXPERIMENT flavour (libtsim_exp.so)
+_lib.use_experiment_build()
 
 dev = torch.device("cuda")
 

@@ -26,7 +26,7 @@ def test_header_symbols_are_exported(lib):
 
 def test_version_and_workspace_planning(lib):
     from text_similarity_b200 import _lib
-    assert lib.tsim_version() == 1
+    assert lib.tsim_version() == _lib.ABI_VERSION == 2
     # BASELINE configs: workspace stays a small fraction of the 180 GB of HBM
     for (Q, N, D, k) in [(100, 10_000, 384, 10), (1024, 1_000_000, 768, 10), (4096, 1_250_000, 768, 100),
                          (32, 12_500_000, 384, 10), (1, 10_000_000, 768, 10)]:
@@ -55,3 +55,48 @@ def test_ops_refuse_cpu_tensors():
         ops.search_topk(torch.randn(2, 8), torch.randn(5, 8), 2)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.pool_norm(torch.randn(2, 3, 8), torch.ones(2, 3, dtype=torch.int64))
+
+
+def test_plan_handle_host_side(lib):
+    """tsim_plan_create / _workspace_bytes / _destroy are host-only: same workspace size as the plain query
+    function, NULL + message on an unsupported shape, and no environment reads / descriptor encodes."""
+    from text_similarity_b200 import _lib
+    before = _lib.counters()
+    h = lib.tsim_plan_create(4096, 1_250_000, 768, 100, _lib.BF16, _lib.BF16, _lib.MODE_AUTO, -1)
+    assert h
+    assert lib.tsim_plan_workspace_bytes(h) == lib.tsim_search_workspace_bytes(
+        4096, 1_250_000, 768, 100, _lib.BF16, _lib.BF16, _lib.MODE_AUTO)
+    lib.tsim_plan_destroy(h)
+    hs = lib.tsim_plan_create(100, 10_000, 384, 10, _lib.F32, _lib.F32, _lib.MODE_AUTO, _lib.BF16)
+    assert hs
+    assert lib.tsim_plan_workspace_bytes(hs) == lib.tsim_search_shadow_workspace_bytes(100, 10_000, 384, 10, _lib.BF16)
+    lib.tsim_plan_destroy(hs)
+    assert not lib.tsim_plan_create(8, 100, 30, 5, _lib.F32, _lib.F32, _lib.MODE_TENSOR, -1)
+    assert b"TSIM_MODE_TENSOR" in lib.tsim_last_error()
+    assert not lib.tsim_plan_create(8, 100, 32, 5, _lib.F32, _lib.F32, _lib.MODE_AUTO, _lib.F16)   # shadow must be bf16
+    assert lib.tsim_plan_workspace_bytes(None) == 0
+    lib.tsim_plan_destroy(None)
+    after = _lib.counters()
+    assert after["env_reads"] == before["env_reads"] == 0
+    assert after["map_encodes"] == before["map_encodes"]
+    assert after["plans"] > before["plans"]
+    rc = lib.tsim_plan_search(None, None, 0, None, 0, None, None, 0, None, 0, 0, -1, None, None, None, None, None, 0, None)
+    assert rc == _lib.ERR_INVALID_ARG
+
+
+def test_release_library_has_no_experiment_knobs(lib, monkeypatch):
+    """The library the package loads reads no environment variable: the knob names are not even in the binary
+    (they exist only in libtsim_exp.so, built with -DTSIM_EXPERIMENT for scripts/ab_*.py), and planning is the
+    same whatever TSIM_* variables say."""
+    from text_similarity_b200 import _lib
+    assert lib.tsim_build_flags() == 0
+    blob = open(_lib.LIB_PATH, "rb").read()
+    for knob in (b"TSIM_DEBUG", b"TSIM_NO_PAIR", b"TSIM_NO_BOOT", b"TSIM_HOT_SCALED", b"TSIM_ROLES_LOW",
+                 b"TSIM_STATIC_UNITS", b"TSIM_POOL_DEBUG", b"TSIM_CHUNK_ROWS", b"TSIM_NO_RETRY", b"TSIM_NO_LADDER"):
+        assert knob not in blob, knob
+    args = (4096, 10_000_000, 768, 10, _lib.BF16, _lib.BF16, _lib.MODE_AUTO)
+    base = lib.tsim_search_workspace_bytes(*args)
+    for name, val in (("TSIM_DEBUG", "2"), ("TSIM_NO_PAIR", "1"), ("TSIM_NO_BOOT", "1"), ("TSIM_CHUNK_ROWS", "65536")):
+        monkeypatch.setenv(name, val)
+    assert lib.tsim_search_workspace_bytes(*args) == base
+    assert _lib.counters()["env_reads"] == 0

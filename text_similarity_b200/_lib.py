@@ -11,6 +11,8 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtsim.so")
+EXPERIMENT_LIB_PATH = os.path.join(HERE, "libtsim_exp.so")   # -DTSIM_EXPERIMENT build, scripts/ab_*.py only
+ABI_VERSION = 2
 
 # element-type codes (include/tsim.h)
 F32, F16, BF16, E4M3 = 0, 1, 2, 3
@@ -36,6 +38,14 @@ SIGNATURES = {
                                         c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p,
                                         c_int64, c_int64, c_int64, c_int, c_int64, c_int64,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tsim_plan_create": (c_void_p, [c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int]),
+    "tsim_plan_destroy": (None, [c_void_p]),
+    "tsim_plan_workspace_bytes": (c_size_t, [c_void_p]),
+    "tsim_plan_search": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+                                 c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tsim_debug_counters": (None, [POINTER(ctypes.c_uint64)]),
+    "tsim_build_flags": (c_int, []),
     "tsim_set_timing_events": (c_int, [c_void_p, c_void_p]),
     "tsim_launch_count": (ctypes.c_uint64, []),
     "tsim_merge_topk": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
@@ -47,6 +57,21 @@ _lib = None
 
 class TsimError(RuntimeError):
     """A libtsim call failed (CUDA error or workspace problem)."""
+
+
+def use_experiment_build() -> None:
+    """Measurement scripts only: bind the -DTSIM_EXPERIMENT flavour (environment knobs compiled in) instead
+    of the release library.  Must be called before the first load()."""
+    global LIB_PATH
+    if _lib is not None:
+        raise TsimError("use_experiment_build() must precede the first load()")
+    LIB_PATH = EXPERIMENT_LIB_PATH
+
+
+def counters() -> dict:
+    out = (ctypes.c_uint64 * 4)()
+    load().tsim_debug_counters(out)
+    return {"launches": out[0], "map_encodes": out[1], "env_reads": out[2], "plans": out[3]}
 
 
 def load() -> ctypes.CDLL:
@@ -63,8 +88,8 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.tsim_version() != 1:
-        raise TsimError(f"libtsim ABI version {lib.tsim_version()} != 1")
+    if lib.tsim_version() != ABI_VERSION:
+        raise TsimError(f"libtsim ABI version {lib.tsim_version()} != {ABI_VERSION}")
     _lib = lib
     return lib
 

@@ -1,8 +1,11 @@
 """Build libtsim.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
 
-    python -m text_similarity_b200.build [--force] [--verbose]
+    python -m text_similarity_b200.build [--force] [--verbose] [--experiment]
 
-The .so is git-ignored but travels to the GPU box with the repo snapshot.
+Every .cu is compiled to an object in parallel (one nvcc per file), then linked.  The .so is git-ignored
+but travels to the GPU box with the repo snapshot.  ``--experiment`` builds libtsim_exp.so with
+-DTSIM_EXPERIMENT (environment knobs and in-kernel diagnosis switches compiled in) for scripts/ab_*.py;
+the package itself only ever loads the release library.
 """
 from __future__ import annotations
 
@@ -11,10 +14,13 @@ import os
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtsim.so")
+LIB_EXPERIMENT = os.path.join(HERE, "libtsim_exp.so")
+OBJ_DIR = os.path.join(HERE, "build")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC_FLAGS = [
@@ -22,7 +28,6 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo",
     "-Xcompiler", "-fPIC",
-    "-shared",
     "--expt-relaxed-constexpr",
 ]
 
@@ -31,12 +36,19 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
-def _stale() -> bool:
-    if not os.path.exists(LIB):
+def _deps():
+    return glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
+
+
+def _newer(path: str, than: float) -> bool:
+    return os.path.getmtime(path) > than
+
+
+def _stale(lib: str) -> bool:
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
-    return any(os.path.getmtime(d) > t for d in deps)
+    t = os.path.getmtime(lib)
+    return any(_newer(d, t) for d in sources() + _deps())
 
 
 def find_nvcc() -> str:
@@ -46,17 +58,42 @@ def find_nvcc() -> str:
     return nvcc
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
-        return LIB
-    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-    if res.returncode != 0:
+def build(force: bool = False, verbose: bool = False, experiment: bool = False) -> str:
+    lib = LIB_EXPERIMENT if experiment else LIB
+    if not force and not _stale(lib):
+        return lib
+    nvcc = find_nvcc()
+    flags = NVCC_FLAGS + (["-DTSIM_EXPERIMENT"] if experiment else []) + (["-Xptxas", "-v"] if verbose else [])
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    hdr_time = max(os.path.getmtime(d) for d in _deps())
+    tag = "exp" if experiment else "rel"
+
+    def compile_one(src: str):
+        obj = os.path.join(OBJ_DIR, f"{os.path.splitext(os.path.basename(src))[0]}.{tag}.o")
+        if (not force and os.path.exists(obj) and not _newer(src, os.path.getmtime(obj))
+                and os.path.getmtime(obj) > hdr_time):
+            return obj, None
+        res = subprocess.run([nvcc] + flags + ["-c", "-o", obj, src], capture_output=True, text=True)
+        return obj, res
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, sources()))
+    failed = False
+    for obj, res in results:
+        if res is None:
+            continue
+        if verbose or res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+        failed = failed or res.returncode != 0
+    if failed:
         raise RuntimeError("nvcc failed building libtsim.so")
-    return LIB
+    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib]
+                         + [obj for obj, _ in results], capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed linking libtsim.so")
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, experiment="--experiment" in sys.argv))

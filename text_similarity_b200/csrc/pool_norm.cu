@@ -418,7 +418,7 @@ pool_norm_warp_kernel(PoolArgs a, int64_t nitems, int CT, int stage_bytes, int* 
     const PwHdr* h = hdr + st;
     const int ntok = h->ntok;
     const uint4* src = (const uint4*)(data + (size_t)st * stage_bytes);
-    if (!(a.dbg & 1)) {
+    if (!(TSIM_KNOB_DEV(a.dbg) & 1)) {
       for (int t = 0; t < ntok; t += 2) {
         // two tokens per step, loads first; a masked token's values must not reach the sum (they may be Inf/NaN)
         const bool ok1 = t + 1 < ntok;
@@ -677,10 +677,7 @@ int pool_splits(int64_t B, int64_t L) {
 // The streaming kernel needs token rows that are contiguous within a sentence (one bulk copy per
 // chunk) and 16-byte granularity.  TSIM_POOL_MODE=1 (experiment knob) forces the register-staged kernel.
 int pool_mode() {
-  const char* m = getenv("TSIM_POOL_MODE");
-  const char* v1 = getenv("TSIM_POOL_V1");
-  if (v1 && v1[0] == '1') return 1;
-  return m ? atoi(m) : 0;
+  return knob_int("TSIM_POOL_MODE", 0);
 }
 // warp-autonomous variant: at most 8 sixteen-byte columns per lane (row <= 4 KB), items of <= 256 tokens
 bool pool_warp_ok(const PoolArgs& a, int esz, bool vec_ok) {
@@ -784,7 +781,7 @@ extern "C" int tsim_pool_norm(const void* tok, int tok_dt, const void* mask, int
   a.out = out; a.out_dt = out_dt; a.out_stride = out_stride; a.out_rows = out_rows;
   a.out_inv = out_inv_norm; a.normalize = normalize;
   a.partial = nullptr; a.ticket = nullptr;
-  { const char* d = getenv("TSIM_POOL_DEBUG"); a.dbg = d ? atoi(d) : 0; }
+  a.dbg = knob_int("TSIM_POOL_DEBUG", 0);   // experiment knob, compiled out of the release library
   const size_t ticket_al = (((size_t)B * sizeof(int) + 255) / 256) * 256;
   const size_t need = 256 + (a.S > 1 ? ticket_al + (size_t)B * a.S * D * sizeof(float) : 0);
   if (!ws || ws_bytes < need) { set_error("pool_norm: workspace too small (%zu < %zu)", ws_bytes, need); return TSIM_ERR_WORKSPACE; }

@@ -419,14 +419,13 @@ int launch_search_exact(const void* q, int q_dt, int64_t q_stride, const void* c
   // two CTAs per SM (one stages while the other multiplies).  Measured on 1M x 768 fp32 (scripts/ab_exact.py),
   // Q = 1024: k = 10 92.9 ms / k = 100 103.4 ms, against 90.7 / 111.3 ms with 128 queries per CTA and one CTA per
   // SM, 116.4 / 128.5 ms with 64 queries and one CTA; Q = 64: 6.4 ms against 7.9-12.4 ms.
-  const char* nomma = getenv("TSIM_NO_MMA_SCAN");       // experiment knob
   // (a fallback launch does not know how many queries are flagged: up to 8 group CTAs per slice stride over them)
-  if (ex_rinv && Q > 32 && N > 0 && !(nomma && nomma[0] == '1')) {
+  if (ex_rinv && Q > 32 && N > 0 && !knob_on("TSIM_NO_MMA_SCAN")) {   // experiment knob
     int MF = 1, minb = 2;
-    if (const char* v = getenv("TSIM_MMA_VARIANT")) {   // experiment knob: "<8-query fragments per warp>x<CTAs per SM>"
-      if (v[0] == '1' && v[1] && v[2] == '1') minb = 1;
-      if (v[0] == '2' && mma_smem_bytes(k, 2) <= 227 * 1024) { MF = 2; minb = 1; }
-    }
+    // experiment knob: 11 = one 8-query fragment per warp x one CTA per SM, 21 = two fragments x one CTA
+    const int variant = knob_int("TSIM_MMA_VARIANT", 12);
+    if (variant == 11) minb = 1;
+    if (variant == 21 && mma_smem_bytes(k, 2) <= 227 * 1024) { MF = 2; minb = 1; }
     const size_t msmem = mma_smem_bytes(k, MF);
     int64_t mgroups = (Q + 64 * MF - 1) / (64 * MF);
     if (flag_cnt && mgroups > 8) mgroups = 8;

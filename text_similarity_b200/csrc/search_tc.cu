@@ -524,8 +524,9 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     if (q_live <= 0) return;
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kWarpTma = a.roles_low ? 0 : 4, kWarpMma = a.roles_low ? 1 : 5, kWarpAlloc = a.roles_low ? 2 : 6;
-  const bool is_epi = a.roles_low ? warp >= 4 : warp < 4;
+  const int roles_low = TSIM_KNOB_DEV(a.roles_low), dbg = TSIM_KNOB_DEV(a.dbg);   // constants 0 in the release build
+  const int kWarpTma = roles_low ? 0 : 4, kWarpMma = roles_low ? 1 : 5, kWarpAlloc = roles_low ? 2 : 6;
+  const bool is_epi = roles_low ? warp >= 4 : warp < 4;
   // a pair = cluster of 2 CTAs: rank 0 (leader) issues the MMAs for both, each CTA loads its own 128
   // queries and its own half of the corpus tile, and scans its own 128 TMEM lanes
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
@@ -575,8 +576,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
               tma_load_2d_pair(sa + A_BYTES, &tmap_c, fb, kb * BK, row0 + (int)rank * (BN / 2));
             } else {
               const uint32_t fb = smem_u32(&full_bar[stage]);
-              mbar_arrive_expect_tx(fb, (a.dbg & 1) ? B_BYTES : STAGE_BYTES);
-              if (!(a.dbg & 1)) tma_load_2d(sa, &tmap_q, fb, kb * BK, un.qb * BM);
+              mbar_arrive_expect_tx(fb, (dbg & 1) ? B_BYTES : STAGE_BYTES);
+              if (!(dbg & 1)) tma_load_2d(sa, &tmap_q, fb, kb * BK, un.qb * BM);
               tma_load_2d(sa + A_BYTES, &tmap_c, fb, kb * BK, row0);
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -603,7 +604,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             const uint64_t bdesc = make_umma_desc(sa + A_BYTES);
 #pragma unroll
             for (int k = 0; k < BK_BYTES / UMMA_K_BYTES; ++k) {
-              if (a.dbg & 2) break;
+              if (dbg & 2) break;
               // advance 32 bytes (16 bf16 / 32 e4m3) inside the 128-byte swizzle row: +2 in >>4 units
               if (PAIR) tc_mma_pair<FP8>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (kb | k) ? 1u : 0u);
               else tc_mma<FP8>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (kb | k) ? 1u : 0u);
@@ -667,7 +668,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         mbar_wait(smem_u32(&tfull_bar[acc]), aphase);
         tc_fence_after();
         const uint32_t tbase = tmem_base + lane_addr + (uint32_t)acc * BN;
-        const int nchunks = (a.dbg & 4) ? 0 : (ncols + 31) / 32;
+        const int nchunks = (dbg & 4) ? 0 : (ncols + 31) / 32;
 #pragma unroll 1
         for (int c = 0; c < nchunks; ++c) {
           uint32_t v[32];
@@ -687,7 +688,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           }
           const float mxr = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
           const float2 mm = *reinterpret_cast<const float2*>(cn + BN + 2 * c);
-          const bool fire = mxr * (mxr >= 0.f ? mm.x : mm.y) > thr || !(mm.x < INFINITY) || a.hot_scaled;
+          const bool fire = mxr * (mxr >= 0.f ? mm.x : mm.y) > thr || !(mm.x < INFINITY) || TSIM_KNOB_DEV(a.hot_scaled);
           // Exact path, entered by the whole warp when any lane may have a candidate; rare once the lists are warm.
           if (__any_sync(0xffffffffu, fire)) {
             const float4* cn4 = (const float4*)(cn + c * 32);
@@ -767,6 +768,7 @@ int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t D, int64_t 
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return TSIM_ERR_CUDA; }
+  count_map_encode();
   return TSIM_OK;
 }
 
@@ -798,17 +800,54 @@ int launch_cfg(const CUtensorMap& mq, const CUtensorMap& mc, const TcArgs& a, cu
 
 }  // namespace
 
+// Descriptor cache of a plan handle: a handful of (array, box) combinations per plan (queries or their padded
+// copy, the corpus with the lone-CTA and the pair box, the retry stage's compact query block), least recently
+// used entry replaced.
+struct MapCache {
+  struct Entry { const void* base; int64_t rows, D, stride; int box_rows, esz; uint64_t tick; CUtensorMap map; };
+  static constexpr int kCap = 16;
+  Entry e[kCap];
+  int n = 0;
+  uint64_t tick = 0;
+};
+MapCache* map_cache_create() { return new MapCache(); }
+void map_cache_destroy(MapCache* c) { delete c; }
+
+static int get_map(MapCache* c, CUtensorMap* m, const void* base, int64_t rows, int64_t D, int64_t stride, int box_rows,
+                   int esz) {
+  if (!c) return make_map(m, base, rows, D, stride, box_rows, esz);
+  ++c->tick;
+  for (int i = 0; i < c->n; ++i) {
+    MapCache::Entry& en = c->e[i];
+    if (en.base == base && en.rows == rows && en.D == D && en.stride == stride && en.box_rows == box_rows && en.esz == esz) {
+      en.tick = c->tick;
+      *m = en.map;
+      return TSIM_OK;
+    }
+  }
+  const int rc = make_map(m, base, rows, D, stride, box_rows, esz);
+  if (rc) return rc;
+  int slot = c->n;
+  if (c->n < MapCache::kCap) ++c->n;
+  else {
+    slot = 0;
+    for (int i = 1; i < MapCache::kCap; ++i) if (c->e[i].tick < c->e[slot].tick) slot = i;
+  }
+  c->e[slot] = {base, rows, D, stride, box_rows, esz, c->tick, *m};
+  return TSIM_OK;
+}
+
 int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_t c_stride, int dt,
                      const float* c_inv, int64_t Q, int64_t N, int64_t D, int self_on, int64_t self_off,
                      const SearchPlan& p, int pass, uint64_t* cand, uint32_t* thr, uint32_t* ladder, uint64_t* sched,
-                     cudaStream_t st, const int32_t* q_count, const int32_t* q_map, int q_skip) {
+                     cudaStream_t st, MapCache* maps, const int32_t* q_count, const int32_t* q_map, int q_skip) {
   CUtensorMap mq, mc;
   const int qrows = p.pair ? 2 * BM : BM;
   // q holds QB * qrows rows (the API pads the last query block with zero rows)
   const int esz = dt == TSIM_E4M3 ? 1 : 2;
-  int rc = make_map(&mq, q, (int64_t)p.QB * qrows, D, q_stride, BM, esz);
+  int rc = get_map(maps, &mq, q, (int64_t)p.QB * qrows, D, q_stride, BM, esz);
   if (rc) return rc;
-  rc = make_map(&mc, corpus, N, D, c_stride, p.pair ? BN / 2 : BN, esz);
+  rc = get_map(maps, &mc, corpus, N, D, c_stride, p.pair ? BN / 2 : BN, esz);
   if (rc) return rc;
   TcArgs a;
   a.c_inv = c_inv; a.Q = Q; a.N = N;
@@ -841,14 +880,11 @@ int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_
   a.q_count = q_count; a.q_map = q_map; a.q_skip = q_skip;
   // every tcgen05 launch of a call claims from its own zeroed area (mini sample | sample | main)
   const int area = pass == TC_PASS_MINI ? 0 : (pass == TC_PASS_SAMPLE || pass == TC_PASS_SAMPLE_REST) ? 1 : 2;
-  const char* su = getenv("TSIM_STATIC_UNITS");   // experiment knob: static round-robin dealing
-  a.sched = (sched && !p.sticky && !(su && su[0] == '1')) ? sched + (size_t)area * (p.sched_area / 8) : nullptr;
-  const char* dbg = getenv("TSIM_DEBUG");
-  a.dbg = dbg ? atoi(dbg) : 0;
-  const char* rl = getenv("TSIM_ROLES_LOW");
-  a.roles_low = (rl && rl[0] == '1') ? 1 : 0;
-  const char* hs = getenv("TSIM_HOT_SCALED");
-  a.hot_scaled = (hs && hs[0] == '1') ? 1 : 0;
+  // experiment knobs (compiled out of the release library): static round-robin dealing, diagnosis bits, warp roles
+  a.sched = (sched && !p.sticky && !knob_on("TSIM_STATIC_UNITS")) ? sched + (size_t)area * (p.sched_area / 8) : nullptr;
+  a.dbg = knob_int("TSIM_DEBUG", 0);
+  a.roles_low = knob_on("TSIM_ROLES_LOW") ? 1 : 0;
+  a.hot_scaled = knob_on("TSIM_HOT_SCALED") ? 1 : 0;
 #define TSIM_DISPATCH(FP8)                                                       \
   if (p.pair) {                                                                  \
     switch (p.KP) {                                                              \

@@ -4,14 +4,25 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <new>
+
 #include "tsim_common.cuh"
 
 namespace tsim {
 
 static thread_local char g_err[512] = "";
 static thread_local cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
-static unsigned long long g_launches = 0;
+static unsigned long long g_launches = 0, g_encodes = 0, g_env_reads = 0, g_plans = 0;
 void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
+void count_map_encode() { __atomic_add_fetch(&g_encodes, 1ull, __ATOMIC_RELAXED); }
+
+#ifdef TSIM_EXPERIMENT
+int knob_int(const char* name, int dflt) {
+  __atomic_add_fetch(&g_env_reads, 1ull, __ATOMIC_RELAXED);
+  const char* v = getenv(name);
+  return (v && v[0]) ? atoi(v) : dflt;
+}
+#endif
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -49,6 +60,7 @@ static bool tensor_shape_ok(int64_t Q, int64_t N, int64_t D, int k, int q_dt, in
 int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt, int mode,
                      bool need_invnorm, bool shadow, SearchPlan* p) {
   memset(p, 0, sizeof(*p));
+  __atomic_add_fetch(&g_plans, 1ull, __ATOMIC_RELAXED);
   const int sms = device_sm_count();
   // a shadow pass needs the widest lists: the candidates must reach 2 * kShadowEps below the k-th best
   const bool ok = tensor_shape_ok(Q, N, D, k, q_dt, c_dt) && (!shadow || k <= 24);
@@ -63,8 +75,7 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
   if (p->use_tensor) {
     p->KP = shadow ? 112 : k <= 10 ? 16 : k <= 24 ? 32 : k <= 52 ? 64 : 112;
     // more than one 128-query block: CTA pairs (cta_group::2) share each corpus tile between two SMs
-    const char* nopair = getenv("TSIM_NO_PAIR");
-    p->pair = (Q > 128 && !(nopair && nopair[0] == '1')) ? 1 : 0;
+    p->pair = (Q > 128 && !knob_on("TSIM_NO_PAIR")) ? 1 : 0;
     const int qrows = p->pair ? 256 : 128;
     const int workers = p->pair ? sms / 2 : sms;
     p->QB = (int)((Q + qrows - 1) / qrows);
@@ -78,12 +89,11 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
       // Bootstrap: with >= 2 queries the per-CTA lists' warm-up (every early score is a candidate)
       // costs more than two extra launches (measured on the fp8 12.5M x 384 shard: Q = 8 1.23 -> 1.02 ms); scan 1 strided sample tile per worker first and turn
       // their union's KP-th best into every query's starting threshold.
-      const char* noboot = getenv("TSIM_NO_BOOT");
-      int64_t minq = 2;
-      if (const char* e = getenv("TSIM_BOOT_MINQ")) { int64_t v = atoll(e); if (v >= 1) minq = v; }   // experiment knob
-      if (Q >= minq && T >= 32 * (int64_t)p->Gq && !(noboot && noboot[0] == '1')) {
-        int64_t tpw = 1;                                                // sample tiles per worker
-        if (const char* e = getenv("TSIM_BOOT_TPW")) { int64_t v = atoll(e); if (v >= 1 && v <= 16) tpw = v; }
+      int64_t minq = knob_int("TSIM_BOOT_MINQ", 2);
+      if (minq < 1) minq = 2;
+      if (Q >= minq && T >= 32 * (int64_t)p->Gq && !knob_on("TSIM_NO_BOOT")) {
+        int64_t tpw = knob_int("TSIM_BOOT_TPW", 1);                     // sample tiles per worker
+        if (tpw < 1 || tpw > 16) tpw = 1;
         p->boot_stride = T / (tpw * (int64_t)p->Gq);                    // >= 2
         p->boot_tiles = (T + p->boot_stride - 1) / p->boot_stride;      // every multiple of the stride below T
         p->boot_slots = p->Gq;
@@ -96,8 +106,7 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
       // raising.  With thresholds global, short units (16K rows) win: the units that share a corpus
       // chunk drift less, so the chunk is re-read from DRAM less often.  Small corpora keep one launch
       // and long units.
-      const char* noboot = getenv("TSIM_NO_BOOT");
-      const bool boot = T >= 24 * 64 && !(noboot && noboot[0] == '1');
+      const bool boot = T >= 24 * 64 && !knob_on("TSIM_NO_BOOT");
       int64_t nct = (8 * (int64_t)workers + p->QB - 1) / p->QB;  // aim at >= ~8 units per worker
       if (nct < 1) nct = 1;
       int64_t R = (N + nct - 1) / nct;
@@ -105,10 +114,7 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
       if (R < 256) R = 256;
       const int64_t rcap = boot ? 16384 : 65536;
       if (R > rcap) R = rcap;
-      if (const char* cr = getenv("TSIM_CHUNK_ROWS")) {     // experiment knob: rows per unit
-        int64_t v = atoll(cr);
-        if (v >= 256) R = v / 256 * 256;
-      }
+      if (const int64_t v = knob_int("TSIM_CHUNK_ROWS", 0); v >= 256) R = v / 256 * 256;   // experiment knob: rows per unit
       // bound the candidate buffer (Q * NC * KP * 8 bytes) to ~2 GB
       while ((double)Q * (double)((N + R - 1) / R) * p->KP * 8.0 > 2.0e9 && R < ((int64_t)1 << 30)) R *= 2;
       p->R = R;
@@ -117,14 +123,13 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
         // Sample = every boot_stride-th tile, ~1/64 of the corpus.  Its first launch (every
         // mini_mult-th sample tile, about 4 tiles, one-tile units) is the only one that runs with
         // cold lists; the rest of the sample and the main launch start from thresholds + a ladder.
-        int64_t div = 64;                                               // sample = 1 / div of the tiles
-        if (const char* e = getenv("TSIM_BOOT_DIV")) { int64_t v = atoll(e); if (v >= 4 && v <= 1024) div = v; }
+        int64_t div = knob_int("TSIM_BOOT_DIV", 64);                    // sample = 1 / div of the tiles
+        if (div < 4 || div > 1024) div = 64;
         int64_t want = T / div;
         if (want < 8) want = 8;
         p->boot_stride = T / want;                                       // >= 2
         p->boot_tiles = (T + p->boot_stride - 1) / p->boot_stride;
-        const char* nomini = getenv("TSIM_NO_MINI");                     // experiment knob: one cold sample launch
-        if (!(nomini && nomini[0] == '1')) {
+        if (!knob_on("TSIM_NO_MINI")) {                                  // experiment knob: one cold sample launch
           p->mini_mult = (p->boot_tiles + 3) / 4;
           if (p->mini_mult < 2) p->mini_mult = 2;
           p->mini_tiles = (p->boot_tiles + p->mini_mult - 1) / p->mini_mult;
@@ -159,7 +164,7 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
     // slices than it takes to fill the GPU a few times over (Q = 1024, k = 100: 296 slices cost 133K list
     // insertions per query, 37 slices 24K)
     int64_t cap = (4 * (int64_t)sms + (Q + 63) / 64 - 1) / ((Q + 63) / 64);
-    if (const char* e = getenv("TSIM_SCAN_SLICES")) { int64_t v = atoll(e); if (v >= 1) cap = v; }   // experiment knob
+    if (const int64_t v = knob_int("TSIM_SCAN_SLICES", 0); v >= 1) cap = v;   // experiment knob
     if (cap < 1) cap = 1;
     if (S > cap) S = cap;
   }
@@ -176,9 +181,8 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
   p->sched_area = (p->use_tensor && !p->sticky) ? 256 + (size_t)sms * 32 * sizeof(uint64_t) : 0;
   off += 3 * p->sched_area;
   // retry stage: its thresholds and level-2 flag count sit in the same zeroed span
-  const char* noretry = getenv("TSIM_NO_RETRY");   // experiment knob: flagged queries go straight to the float64 scan
-  p->retry = 0;
-  if (p->use_tensor && !shadow && p->KP < kRetryKP && !(noretry && noretry[0] == '1')) {
+  p->retry = 0;   // TSIM_NO_RETRY (experiment knob): flagged queries go straight to the float64 scan
+  if (p->use_tensor && !shadow && p->KP < kRetryKP && !knob_on("TSIM_NO_RETRY")) {
     const int64_t rounds = (Q + kRetryQ - 1) / kRetryQ;
     p->retry = (int)(rounds < kRetryMaxRounds ? rounds : kRetryMaxRounds);
   }
@@ -218,6 +222,19 @@ using namespace tsim;
 extern "C" int tsim_version(void) { return TSIM_ABI_VERSION; }
 extern "C" const char* tsim_last_error(void) { return g_err; }
 extern "C" uint64_t tsim_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+extern "C" void tsim_debug_counters(uint64_t out[4]) {
+  out[0] = __atomic_load_n(&g_launches, __ATOMIC_RELAXED);
+  out[1] = __atomic_load_n(&g_encodes, __ATOMIC_RELAXED);
+  out[2] = __atomic_load_n(&g_env_reads, __ATOMIC_RELAXED);
+  out[3] = __atomic_load_n(&g_plans, __ATOMIC_RELAXED);
+}
+extern "C" int tsim_build_flags(void) {
+#ifdef TSIM_EXPERIMENT
+  return 1;
+#else
+  return 0;
+#endif
+}
 extern "C" int tsim_set_timing_events(void* start, void* stop) {
   g_ev_start = (cudaEvent_t)start;
   g_ev_stop = (cudaEvent_t)stop;
@@ -256,8 +273,9 @@ static int search_impl(const void* q, int q_dt, int64_t q_stride, const void* co
                        const float* corpus_inv_norm, int64_t Q, int64_t N,
                        int64_t D, int k, int64_t idx_base, int64_t exclude_self_base, int mode,
                        float* out_score, double* out_score64, int64_t* out_idx,
-                       int32_t* out_flags, void* ws, size_t ws_bytes, void* stream) {
-  int rc = check_search_args(Q, N, D, k, q_dt, c_dt, mode);
+                       int32_t* out_flags, void* ws, size_t ws_bytes, void* stream,
+                       const SearchPlan* prepared = nullptr, MapCache* maps = nullptr) {
+  int rc = prepared ? TSIM_OK : check_search_args(Q, N, D, k, q_dt, c_dt, mode);
   if (rc) return rc;
   if (Q == 0) return TSIM_OK;
   TSIM_CHECK_ARG(q && out_score && out_idx, "search: null pointer");
@@ -265,7 +283,8 @@ static int search_impl(const void* q, int q_dt, int64_t q_stride, const void* co
   TSIM_CHECK_ARG(q_stride >= D && c_stride >= D, "search: row stride smaller than D");
   cudaStream_t st = (cudaStream_t)stream;
   SearchPlan p;
-  rc = make_search_plan(Q, N, D, k, shadow ? t_dt : q_dt, shadow ? t_dt : c_dt, mode, true, shadow, &p);
+  if (prepared) p = *prepared;     // a plan handle (tsim_plan_create): no planning, cached TMA descriptors
+  else rc = make_search_plan(Q, N, D, k, shadow ? t_dt : q_dt, shadow ? t_dt : c_dt, mode, true, shadow, &p);
   if (rc) return rc;
   if (!ws || ws_bytes < p.total) {
     set_error("search: workspace too small (%zu < %zu bytes)", ws_bytes, p.total);
@@ -320,25 +339,24 @@ static int search_impl(const void* q, int q_dt, int64_t q_stride, const void* co
     uint64_t* cand = (uint64_t*)(w + p.off_cand);
     uint32_t* ladder = nullptr;
     if (p.boot_tiles) {
-      const char* nolad = getenv("TSIM_NO_LADDER");   // experiment knob
-      uint32_t* lad = (nolad && nolad[0] == '1') ? nullptr : (uint32_t*)(w + p.off_ladder);
+      uint32_t* lad = knob_on("TSIM_NO_LADDER") ? nullptr : (uint32_t*)(w + p.off_ladder);   // experiment knob
       if (p.mini_mult) {
         rc = launch_search_tc(qt, qt_stride, tcorpus, tc_stride, t_dt, c_inv, Q, N, D, self_on, self_off, p,
-                              TC_PASS_MINI, cand, thr, nullptr, sched, st);
+                              TC_PASS_MINI, cand, thr, nullptr, sched, st, maps);
         if (rc) return rc;
         rc = launch_tighten(Q, p, (int)p.mini_slots, cand, thr, lad, st);
         if (rc) return rc;
         ladder = lad;
       }
       rc = launch_search_tc(qt, qt_stride, tcorpus, tc_stride, t_dt, c_inv, Q, N, D, self_on, self_off, p,
-                            p.mini_mult ? TC_PASS_SAMPLE_REST : TC_PASS_SAMPLE, cand, thr, ladder, sched, st);
+                            p.mini_mult ? TC_PASS_SAMPLE_REST : TC_PASS_SAMPLE, cand, thr, ladder, sched, st, maps);
       if (rc) return rc;
       rc = launch_tighten(Q, p, (int)(p.mini_slots + p.boot_slots), cand, thr, lad, st);   // re-levels the ladder
       if (rc) return rc;
       ladder = lad;
     }
     rc = launch_search_tc(qt, qt_stride, tcorpus, tc_stride, t_dt, c_inv, Q, N, D, self_on, self_off, p,
-                          p.boot_tiles ? TC_PASS_MAIN : TC_PASS_ALL, cand, thr, ladder, sched, st);
+                          p.boot_tiles ? TC_PASS_MAIN : TC_PASS_ALL, cand, thr, ladder, sched, st, maps);
     if (rc) return rc;
     if (timed) TSIM_CUDA(cudaEventRecord(g_ev_stop, st));
     SelRetry first = {nullptr, nullptr, p.retry * kRetryQ, 0, 0, w + p.off_r_q, D};
@@ -362,7 +380,7 @@ static int search_impl(const void* q, int q_dt, int64_t q_stride, const void* co
       for (int r = 0; r < p.retry; ++r) {
         uint32_t* r_thr = (uint32_t*)(w + p.off_r_thr) + (size_t)r * kRetryQ;
         rc = launch_search_tc(w + p.off_r_q + (size_t)r * kRetryQ * rowb, D, tcorpus, tc_stride, t_dt, c_inv, kRetryQ, N, D,
-                              self_on, self_off, pr, TC_PASS_ALL, r_cand, r_thr, nullptr, nullptr, st,
+                              self_on, self_off, pr, TC_PASS_ALL, r_cand, r_thr, nullptr, nullptr, st, maps,
                               flag_cnt, flag_list + (size_t)r * kRetryQ, r * kRetryQ);
         if (rc) return rc;
         SelRetry again = {flag_cnt, flag_list, p.retry * kRetryQ, r * kRetryQ, r == p.retry - 1, nullptr, 0};
@@ -416,6 +434,58 @@ extern "C" int tsim_search_topk_shadow(const void* q, int q_dt, int64_t q_stride
   return search_impl(q, q_dt, q_stride, corpus, c_dt, c_stride, q_shadow, qs_stride, corpus_shadow, cs_stride,
                      shadow_dt, true, shadow_inv_norm, Q, N, D, k, idx_base, exclude_self_base, TSIM_MODE_AUTO,
                      out_score, out_score64, out_idx, out_flags, ws, ws_bytes, stream);
+}
+
+// ---- plan handles ----------------------------------------------------------------------------
+struct tsim_plan {
+  SearchPlan p;
+  int64_t Q, N, D;
+  int k, q_dt, c_dt, mode, shadow_dt;   // shadow_dt < 0: no shadow
+  MapCache* maps;
+};
+
+extern "C" tsim_plan_t* tsim_plan_create(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt, int mode,
+                                         int shadow_dt) {
+  const bool shadow = shadow_dt >= 0;
+  if (shadow && shadow_dt != TSIM_BF16) { set_error("plan: the shadow must be bf16 (got dtype %d)", shadow_dt); return nullptr; }
+  if (check_search_args(Q, N, D, k, q_dt, c_dt, shadow ? TSIM_MODE_AUTO : mode) != TSIM_OK) return nullptr;
+  tsim_plan* h = new (std::nothrow) tsim_plan();
+  if (!h) { set_error("plan: out of host memory"); return nullptr; }
+  h->Q = Q; h->N = N; h->D = D; h->k = k; h->q_dt = q_dt; h->c_dt = c_dt;
+  h->mode = shadow ? TSIM_MODE_AUTO : mode; h->shadow_dt = shadow ? shadow_dt : -1;
+  if (make_search_plan(Q, N, D, k, shadow ? shadow_dt : q_dt, shadow ? shadow_dt : c_dt, h->mode, true, shadow, &h->p) != TSIM_OK) {
+    delete h;
+    return nullptr;
+  }
+  h->maps = map_cache_create();
+  return h;
+}
+
+extern "C" void tsim_plan_destroy(tsim_plan_t* h) {
+  if (!h) return;
+  map_cache_destroy(h->maps);
+  delete h;
+}
+
+extern "C" size_t tsim_plan_workspace_bytes(const tsim_plan_t* h) { return h ? h->p.total : 0; }
+
+extern "C" int tsim_plan_search(tsim_plan_t* h, const void* q, int64_t q_stride, const void* corpus, int64_t c_stride,
+                                const float* corpus_inv_norm, const void* q_shadow, int64_t qs_stride,
+                                const void* corpus_shadow, int64_t cs_stride, int64_t idx_base,
+                                int64_t exclude_self_base, float* out_score, double* out_score64, int64_t* out_idx,
+                                int32_t* out_flags, void* ws, size_t ws_bytes, void* stream) {
+  TSIM_CHECK_ARG(h, "plan_search: null plan");
+  const bool shadow = h->shadow_dt >= 0;
+  if (shadow) {
+    TSIM_CHECK_ARG(q_shadow && (h->N == 0 || corpus_shadow), "plan_search: this plan needs the bf16 shadows");
+    TSIM_CHECK_ARG(qs_stride >= h->D && cs_stride >= h->D, "plan_search: shadow row stride smaller than D");
+    return search_impl(q, h->q_dt, q_stride, corpus, h->c_dt, c_stride, q_shadow, qs_stride, corpus_shadow, cs_stride,
+                       h->shadow_dt, true, corpus_inv_norm, h->Q, h->N, h->D, h->k, idx_base, exclude_self_base,
+                       TSIM_MODE_AUTO, out_score, out_score64, out_idx, out_flags, ws, ws_bytes, stream, &h->p, h->maps);
+  }
+  return search_impl(q, h->q_dt, q_stride, corpus, h->c_dt, c_stride, q, q_stride, corpus, c_stride, h->c_dt, false,
+                     corpus_inv_norm, h->Q, h->N, h->D, h->k, idx_base, exclude_self_base, h->mode, out_score,
+                     out_score64, out_idx, out_flags, ws, ws_bytes, stream, &h->p, h->maps);
 }
 
 extern "C" int tsim_merge_topk(const double* sc, const int64_t* ix, int64_t Q, int64_t n_lists, int k_in,

@@ -33,6 +33,20 @@ constexpr int kLadder = 16;
 
 void set_error(const char* fmt, ...);
 
+// ---- experiment knobs ---------------------------------------------------------------------
+// The release library reads NO environment variable: every knob below is its default, folded at compile
+// time, and the diagnosis switches inside the kernels (skip the MMAs, skip the epilogue ...) do not exist.
+// `python -m text_similarity_b200.build --experiment` builds libtsim_exp.so with -DTSIM_EXPERIMENT, in which
+// the knobs are environment variables read per call (scripts/ab_*.py interleave settings in one process).
+#ifdef TSIM_EXPERIMENT
+int knob_int(const char* name, int dflt);     // atoi(getenv(name)) or dflt; counted (tsim_debug_counters)
+#define TSIM_KNOB_DEV(x) (x)
+#else
+inline int knob_int(const char*, int dflt) { return dflt; }
+#define TSIM_KNOB_DEV(x) 0
+#endif
+inline bool knob_on(const char* name) { return knob_int(name, 0) == 1; }
+
 #define TSIM_CHECK_ARG(cond, ...)          \
   do {                                     \
     if (!(cond)) {                         \
@@ -260,10 +274,15 @@ struct SelRetry {
 // pass: 0 = the whole corpus in one launch; 1 = bootstrap sample (all of it); 2 = main (everything
 // that is not a sample tile); 3 = mini sample (first of two sample launches); 4 = rest of the sample
 enum { TC_PASS_ALL = 0, TC_PASS_SAMPLE = 1, TC_PASS_MAIN = 2, TC_PASS_MINI = 3, TC_PASS_SAMPLE_REST = 4 };
+// TMA descriptors kept by a plan handle (tsim_plan_create), keyed by (base, rows, D, stride, box, element size):
+// a repeated search of the same arrays encodes nothing.  Null: encode per launch.
+struct MapCache;
+MapCache* map_cache_create();
+void map_cache_destroy(MapCache* c);
 int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_t c_stride, int dt,
                      const float* c_inv, int64_t Q, int64_t N, int64_t D,
                      int self_on, int64_t self_off, const SearchPlan& p, int pass, uint64_t* cand,
-                     uint32_t* thr, uint32_t* ladder, uint64_t* sched, cudaStream_t st,
+                     uint32_t* thr, uint32_t* ladder, uint64_t* sched, cudaStream_t st, MapCache* maps = nullptr,
                      const int32_t* q_count = nullptr, const int32_t* q_map = nullptr, int q_skip = 0);
 int launch_tighten(int64_t Q, const SearchPlan& p, int nslots, const uint64_t* cand, uint32_t* thr,
                    uint32_t* ladder, cudaStream_t st);
@@ -291,6 +310,7 @@ int launch_row_inv_norm(const void* x, int dt, int64_t N, int64_t D, int64_t str
                         cudaStream_t st);
 
 int device_sm_count();
-void count_launch();   // bumps the counter behind tsim_launch_count()
+void count_launch();       // bumps the counter behind tsim_launch_count()
+void count_map_encode();   // ... and the cuTensorMapEncodeTiled count of tsim_debug_counters()
 
 }  // namespace tsim

@@ -5,6 +5,8 @@ sm_100a reached through ctypes.  All functions require CUDA tensors and raise ot
 """
 from __future__ import annotations
 
+import atexit
+from collections import OrderedDict
 from typing import Optional, Tuple
 
 import torch
@@ -18,6 +20,48 @@ _MASK_DT = {torch.int64: _lib.I64, torch.int32: _lib.I32, torch.uint8: _lib.U8, 
 _MODES = {"auto": _lib.MODE_AUTO, "exact": _lib.MODE_EXACT, "tensor": _lib.MODE_TENSOR}
 
 _workspaces = {}
+
+# Plan handles (tsim_plan_create): launch plan + cached TMA descriptors per (device, shape, k, dtypes, mode).
+# Python owns them: least recently used ones are destroyed past _PLAN_CAP, the rest at interpreter exit.
+_plans: "OrderedDict[tuple, int]" = OrderedDict()
+_PLAN_CAP = 256
+
+
+def _plan(dev: torch.device, Q: int, N: int, D: int, k: int, q_dt: int, c_dt: int, mode: int, shadow_dt: int) -> int:
+    key = (dev.index, Q, N, D, k, q_dt, c_dt, mode, shadow_dt)
+    h = _plans.get(key)
+    if h is not None:
+        _plans.move_to_end(key)
+        return h
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        h = lib.tsim_plan_create(Q, N, D, k, q_dt, c_dt, mode, shadow_dt)
+    if not h:
+        _lib.check(_lib.ERR_UNSUPPORTED if mode == _lib.MODE_TENSOR else _lib.ERR_INVALID_ARG, "tsim_plan_create")
+    _plans[key] = h
+    while len(_plans) > _PLAN_CAP:
+        _, old = _plans.popitem(last=False)
+        lib.tsim_plan_destroy(old)
+    return h
+
+
+def search_workspace_bytes(Q: int, N: int, D: int, k: int, q_dtype: torch.dtype, c_dtype: torch.dtype,
+                           mode: str = "auto", shadow: bool = False, device: Optional[torch.device] = None) -> int:
+    """Bytes of workspace ``search_topk`` needs for this call shape (for callers that own their workspace,
+    e.g. one per captured CUDA graph)."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    h = _plan(dev, Q, N, D, int(k), _DT[q_dtype], _DT[c_dtype], _lib.MODE_AUTO if shadow else _MODES[mode],
+              _lib.BF16 if shadow else -1)
+    return int(_lib.load().tsim_plan_workspace_bytes(h))
+
+
+@atexit.register
+def _destroy_plans() -> None:
+    if _lib._lib is None:
+        return
+    while _plans:
+        _, h = _plans.popitem()
+        _lib._lib.tsim_plan_destroy(h)
 
 
 def _require_cuda(*tensors: torch.Tensor) -> torch.device:
@@ -75,6 +119,10 @@ def pool_norm(token_embeddings: torch.Tensor, attention_mask: torch.Tensor, *,
     dev = _require_cuda(token_embeddings, attention_mask, out, out_rows, out_inv_norm)
     if token_embeddings.dim() != 3:
         raise ValueError("token_embeddings must be [batch, seq_len, embed_size]")  # modules.py:159
+    if torch.is_grad_enabled() and token_embeddings.requires_grad:
+        # the kernel has no backward: refusing beats returning a detached tensor that silently drops gradients
+        raise RuntimeError("pool_norm (CUDA kernel K1) is inference-only: call it under torch.no_grad() or detach "
+                           "the token embeddings; training through the pooler is outside this build")
     B, L, D = token_embeddings.shape
     if attention_mask.shape != (B, L):
         raise ValueError(f"attention_mask shape {tuple(attention_mask.shape)} != {(B, L)}")
@@ -141,12 +189,15 @@ def search_topk(queries: torch.Tensor, corpus: torch.Tensor, k: int, *,
                 return_score64: bool = False, return_flags: bool = False,
                 out_scores: Optional[torch.Tensor] = None, out_idx: Optional[torch.Tensor] = None,
                 out_score64: Optional[torch.Tensor] = None,
-                corpus_shadow: Optional[torch.Tensor] = None, shadow_inv_norm: Optional[torch.Tensor] = None):
+                corpus_shadow: Optional[torch.Tensor] = None, shadow_inv_norm: Optional[torch.Tensor] = None,
+                workspace: Optional[torch.Tensor] = None):
     """K2 + K3 -- exact cosine top-k of every query row against every corpus row.
 
     Returns (scores float32 [Q, k], idx int64 [Q, k]) best first, ties by lower index, idx -1 /
     score -inf past the last available row; optionally the float64 scores and the per-query
     stage flags (0: first tensor pass, 2: wide retry pass, 1: float64 scan).  Replaces the loop at reference src/pipeline/search_pipeline.py:73-79.
+    ``workspace``: a caller-owned uint8 scratch tensor of at least ``search_workspace_bytes(...)`` bytes (a captured
+    CUDA graph must own the buffer it replays into); default: a growable per-(device, stream) buffer.
     """
     lib = _lib.load()
     dev = _require_cuda(queries, corpus, corpus_inv_norm)
@@ -176,44 +227,34 @@ def search_topk(queries: torch.Tensor, corpus: torch.Tensor, k: int, *,
     idx = _out(out_idx, torch.int64)
     s64 = _out(out_score64, torch.float64) if (return_score64 or out_score64 is not None) else None
     flags = torch.empty(Q, dtype=torch.int32, device=dev) if return_flags else None
-    if corpus_shadow is not None and mode == "auto" and N > 0:
+    shadow = corpus_shadow is not None and mode == "auto" and N > 0
+    q_shadow = None
+    if shadow:
         # fp32 / fp16 rows: candidates from the bf16 shadows on the tensor cores, float64 re-score on the originals
         _require_cuda(corpus_shadow, shadow_inv_norm)
         if corpus_shadow.shape != corpus.shape or corpus_shadow.dtype != torch.bfloat16 or corpus_shadow.stride(1) != 1:
             raise ValueError("corpus_shadow must be a bfloat16 [N, D] tensor with contiguous rows")
         q_shadow = queries.to(torch.bfloat16).contiguous()
-        nbytes = lib.tsim_search_shadow_workspace_bytes(Q, N, D, k, _lib.BF16)
-        if nbytes == 0:
-            _lib.check(_lib.ERR_INVALID_ARG, "tsim_search_shadow_workspace_bytes")
+    plan = _plan(dev, Q, N, D, k, _dt(queries), _dt(corpus), _lib.MODE_AUTO if shadow else _MODES[mode],
+                 _lib.BF16 if shadow else -1)
+    nbytes = lib.tsim_plan_workspace_bytes(plan)
+    if workspace is None:
         ws = _workspace(dev, nbytes, "search")
-        with torch.cuda.device(dev):
-            rc = lib.tsim_search_topk_shadow(queries.data_ptr(), _dt(queries), queries.stride(0),
-                                             corpus.data_ptr(), _dt(corpus), corpus.stride(0),
-                                             q_shadow.data_ptr(), q_shadow.stride(0),
-                                             corpus_shadow.data_ptr(), corpus_shadow.stride(0), _lib.BF16,
-                                             _ptr(shadow_inv_norm), Q, N, D, k, int(idx_base), int(exclude_self_base),
-                                             scores.data_ptr(), _ptr(s64), idx.data_ptr(), _ptr(flags),
-                                             ws.data_ptr(), ws.numel(), _stream(dev))
-        _lib.check(rc, "tsim_search_topk_shadow")
-        res = [scores, idx]
-        if return_score64 or out_score64 is not None:
-            res.append(s64)
-        if return_flags:
-            res.append(flags)
-        return tuple(res)
-    nbytes = lib.tsim_search_workspace_bytes(Q, N, D, k, _dt(queries), _dt(corpus), _MODES[mode])
-    if nbytes == 0:
-        _lib.check(_lib.ERR_INVALID_ARG if mode != "tensor" else _lib.ERR_UNSUPPORTED,
-                   "tsim_search_workspace_bytes")
-    ws = _workspace(dev, nbytes, "search")
+    else:
+        _require_cuda(workspace)
+        if workspace.dtype != torch.uint8 or not workspace.is_contiguous() or workspace.numel() < nbytes:
+            raise ValueError(f"workspace must be a contiguous uint8 tensor of >= {nbytes} bytes")
+        ws = workspace
+    inv = shadow_inv_norm if shadow else corpus_inv_norm
     with torch.cuda.device(dev):
-        rc = lib.tsim_search_topk(queries.data_ptr(), _dt(queries), queries.stride(0),
-                                  corpus.data_ptr() if N else None, _dt(corpus), corpus.stride(0) if N else D,
-                                  _ptr(corpus_inv_norm), Q, N, D, k, int(idx_base),
-                                  int(exclude_self_base), _MODES[mode],
+        rc = lib.tsim_plan_search(plan, queries.data_ptr(), queries.stride(0),
+                                  corpus.data_ptr() if N else None, corpus.stride(0) if N else D, _ptr(inv),
+                                  _ptr(q_shadow), q_shadow.stride(0) if shadow else 0,
+                                  _ptr(corpus_shadow) if shadow else None, corpus_shadow.stride(0) if shadow else 0,
+                                  int(idx_base), int(exclude_self_base),
                                   scores.data_ptr(), _ptr(s64), idx.data_ptr(), _ptr(flags),
                                   ws.data_ptr(), ws.numel(), _stream(dev))
-    _lib.check(rc, "tsim_search_topk")
+    _lib.check(rc, "tsim_plan_search")
     res = [scores, idx]
     if return_score64 or out_score64 is not None:
         res.append(s64)

@@ -72,8 +72,17 @@ class SentenceMiningPipeline(SearchPipeline):
         super().__init__(*args, **kwargs)
         self.corpus_chunk_size = int(corpus_chunk_size)
         self._cache_key = None
+        self._cache_obj = None        # the cached corpus object itself: `is`, not id() (ids are recycled)
         self._cache: List[Tuple[int, _EncodedCorpus]] = []
         self.last_corpus_encode_seconds = 0.0
+
+    def invalidate(self) -> None:
+        """Forget the encoded corpus (rows, inverse norms, bf16 shadows).  Call after editing a corpus LIST in
+        place (same object, same length: nothing the pipeline could notice); in-place edits of a corpus TENSOR
+        are noticed through its version counter."""
+        self._cache_key, self._cache_obj, self._cache = None, None, []
+
+    reindex = invalidate
 
     # -- encoding ---------------------------------------------------------------------------------
     def _dtype(self) -> torch.dtype:
@@ -89,8 +98,11 @@ class SentenceMiningPipeline(SearchPipeline):
 
     def _corpus_chunks(self, corpus: TextOrTensor) -> List[Tuple[int, _EncodedCorpus]]:
         """[(first global row, encoded chunk)], cached while the same corpus object is searched."""
-        key = (id(corpus), len(corpus), self.corpus_chunk_size)
-        if key == self._cache_key:
+        if isinstance(corpus, torch.Tensor):
+            key = (corpus.data_ptr(), corpus._version, tuple(corpus.shape), corpus.dtype, self.corpus_chunk_size)
+        else:
+            key = (len(corpus), self.corpus_chunk_size)
+        if corpus is self._cache_obj and key == self._cache_key:
             return self._cache
         chunks = []
         start_time = time.time()
@@ -108,7 +120,7 @@ class SentenceMiningPipeline(SearchPipeline):
                 inv = ops.row_inv_norm(rows)
             chunks.append((begin, _EncodedCorpus(rows, inv)))
         self.last_corpus_encode_seconds = time.time() - start_time  # reference prints this (:65-71)
-        self._cache_key, self._cache = key, chunks
+        self._cache_key, self._cache_obj, self._cache = key, corpus, chunks
         return chunks
 
     # -- search -----------------------------------------------------------------------------------

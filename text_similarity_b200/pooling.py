@@ -40,7 +40,9 @@ class AvgPoolingStrategy(PoolingStrategy):
     Drop-in for reference modules.py:154-171 (parameter-free, empty state_dict).  ``forward``
     returns the un-normalised fp32 mean exactly like the reference; ``pool_normalized`` is the
     fused form the search pipeline uses (mean -> L2 normalise -> bf16/fp8 cast + inverse norms in
-    one pass over the token tensor).
+    one pass over the token tensor).  Inference-only: the kernel has no backward, and pooling a tensor
+    that requires grad outside ``torch.no_grad()`` raises instead of silently dropping the gradient (the
+    reference's pooler is also used in training, modules.py:154-171; training is outside this build).
     """
 
     def forward(self, embeddings: torch.Tensor, features):

@@ -90,22 +90,29 @@ class ShardedCorpus:
         s64 = torch.empty(Q, k, dtype=torch.float64, device=dev)
         idx = torch.empty(Q, k, dtype=torch.int64, device=dev)
         scores = torch.empty(Q, k, dtype=torch.float32, device=dev)
+        # The graph replays raw pointers: it owns its workspace (kept alive in self._graphs next to the graph),
+        # never the growable per-stream cache of ops, whose buffers are replaced -- and freed -- when a later
+        # call on a recycled stream handle needs more room.
+        shadowed = self.shadow is not None and mode == "auto"
+        ws = torch.empty(ops.search_workspace_bytes(Q, self.shard.shape[0], self.shard.shape[1], k, dtype,
+                                                    self.shard.dtype, mode, shadow=shadowed, device=dev),
+                         dtype=torch.uint8, device=dev)
 
         def run():
             ops.search_topk(q_static, self.shard, k, corpus_inv_norm=self.inv_norm, idx_base=self.idx_base,
                             exclude_self_base=exclude_self_base, mode=mode, out_scores=scores,
-                            out_score64=s64, out_idx=idx, **self._shadow_kw())
+                            out_score64=s64, out_idx=idx, workspace=ws, **self._shadow_kw())
 
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            run()                      # warm-up on the capture stream: sizes that stream's workspace
+            run()                      # warm-up on the capture stream (module load, function attributes)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=side):
             run()
-        g = self._graphs[key] = (graph, q_static, scores, s64, idx)
+        g = self._graphs[key] = (graph, q_static, scores, s64, idx, ws)
         return g
 
     def search_graphed(self, queries: torch.Tensor, k: int, exclude_self_base: int = -1, mode: str = "auto"
@@ -113,7 +120,7 @@ class ShardedCorpus:
         """`search` with the local search replayed from a CUDA graph captured on first use of this
         (batch size, k, dtype).  The returned tensors are the graph's static outputs: consume them
         before the next call with the same shape (or clone)."""
-        graph, q_static, scores, s64, idx = self._graph(queries.shape[0], k, queries.dtype, exclude_self_base, mode)
+        graph, q_static, scores, s64, idx, _ws = self._graph(queries.shape[0], k, queries.dtype, exclude_self_base, mode)
         q_static.copy_(queries, non_blocking=True)
         graph.replay()
         if self.world == 1:

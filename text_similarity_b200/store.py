@@ -178,7 +178,10 @@ class EmbeddingStore:
         scores, pos = ops.search_topk(q, self.rows[:self.n], k, corpus_inv_norm=self.inv_norm[:self.n], mode=mode)
         if return_positions:
             return scores, pos
-        return scores, self.ids[:self.n][pos]
+        # positions past the last row the kernels could return (-1: fewer than k finite-scoring rows) stay -1
+        # instead of wrapping around to the last live row's label
+        labels = torch.where(pos >= 0, self.ids[:self.n][pos.clamp_min(0)], torch.full_like(pos, -1))
+        return scores, labels
 
     # -- persistence ------------------------------------------------------------------------------
     def save(self, path: str, world: int = 1, rank: int = 0) -> None:
