@@ -203,6 +203,18 @@ uint64_t tsim_launch_count(void);
 /* Process-wide counters for tests: out[0] kernels launched, out[1] cuTensorMapEncodeTiled calls, out[2]
  * environment variables read (always 0 in the release library: it reads none), out[3] launch plans made. */
 void tsim_debug_counters(uint64_t out[4]);
+/* Test hooks for the error bound the completeness proof rests on (tests/test_gpu_eps.py).
+ * tsim_debug_eps: the bound of |tensor-core cosine - exact cosine| (units of ||q|| ||c||) the library assumes for
+ * rows of width D and element type dt (shadow != 0: for a bf16 shadow of fp32 / fp16 rows).
+ * tsim_debug_tensor_pass: ONE tcgen05 candidate pass with cold 112-entry lists and nothing else -- no sample, no
+ * threshold, no re-score.  q must hold 128 rows (rows Q..127 are read, their results unused), Q <= 128, both
+ * arrays of type dt (TSIM_BF16 / TSIM_E4M3).  Writes *out_lists = L = min(ceil(N / 256), SM count) (host) and
+ * out_keys [Q][L][112] packed keys, 0 = empty slot, else (ordered fp32 of dot(q, c) * corpus_inv_norm[c]) << 32 |
+ * (0xffffffff - row); list j holds the 112 best rows of tiles j, j + L, ...  thr_scratch: [Q] uint32 scratch. */
+float tsim_debug_eps(int64_t D, int dt, int shadow);
+int tsim_debug_tensor_pass(const void* q, int64_t q_stride, const void* corpus, int64_t c_stride, int dt,
+                           const float* corpus_inv_norm, int64_t Q, int64_t N, int64_t D,
+                           uint64_t* out_keys, int64_t* out_lists, uint32_t* thr_scratch, void* stream);
 /* Bit 0: built with -DTSIM_EXPERIMENT (environment knobs and in-kernel diagnosis switches compiled in;
  * never the library the package loads by default). */
 int tsim_build_flags(void);

@@ -46,6 +46,9 @@ SIGNATURES = {
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tsim_debug_counters": (None, [POINTER(ctypes.c_uint64)]),
     "tsim_build_flags": (c_int, []),
+    "tsim_debug_eps": (c_float, [c_int64, c_int, c_int]),
+    "tsim_debug_tensor_pass": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int64,
+                                       c_int64, c_void_p, POINTER(c_int64), c_void_p, c_void_p]),
     "tsim_set_timing_events": (c_int, [c_void_p, c_void_p]),
     "tsim_launch_count": (ctypes.c_uint64, []),
     "tsim_merge_topk": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,

@@ -64,7 +64,7 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
   const int sms = device_sm_count();
   // a shadow pass needs the widest lists: the candidates must reach 2 * kShadowEps below the k-th best
   const bool ok = tensor_shape_ok(Q, N, D, k, q_dt, c_dt) && (!shadow || k <= 24);
-  p->eps = shadow ? kShadowEps : kApproxEps;
+  p->eps = shadow ? shadow_eps(D) : approx_eps(D, dtype_size(c_dt));
   if (mode == TSIM_MODE_TENSOR && !ok) {
     set_error("search: TSIM_MODE_TENSOR needs bf16 (D %% 8 == 0) or e4m3 (D %% 16 == 0) queries AND corpus, k <= 100 "
               "(got q_dt=%d c_dt=%d D=%lld k=%d)", q_dt, c_dt, (long long)D, k);
@@ -434,6 +434,33 @@ extern "C" int tsim_search_topk_shadow(const void* q, int q_dt, int64_t q_stride
   return search_impl(q, q_dt, q_stride, corpus, c_dt, c_stride, q_shadow, qs_stride, corpus_shadow, cs_stride,
                      shadow_dt, true, shadow_inv_norm, Q, N, D, k, idx_base, exclude_self_base, TSIM_MODE_AUTO,
                      out_score, out_score64, out_idx, out_flags, ws, ws_bytes, stream);
+}
+
+// ---- test hooks ---------------------------------------------------------------------------------
+extern "C" float tsim_debug_eps(int64_t D, int dt, int shadow) {
+  return shadow ? shadow_eps(D) : approx_eps(D, dtype_size(dt) ? dtype_size(dt) : 2);
+}
+
+extern "C" int tsim_debug_tensor_pass(const void* q, int64_t q_stride, const void* corpus, int64_t c_stride, int dt,
+                                      const float* corpus_inv_norm, int64_t Q, int64_t N, int64_t D,
+                                      uint64_t* out_keys, int64_t* out_lists, uint32_t* thr_scratch, void* stream) {
+  TSIM_CHECK_ARG(Q >= 1 && Q <= 128 && N >= 1 && N < (int64_t)0x7fffff00, "debug_tensor_pass: needs 1 <= Q <= 128, N >= 1");
+  TSIM_CHECK_ARG(tensor_shape_ok(Q, N, D, 100, dt, dt), "debug_tensor_pass: bf16 (D %% 8 == 0) or e4m3 (D %% 16 == 0) only");
+  TSIM_CHECK_ARG(q && corpus && corpus_inv_norm && out_keys && out_lists && thr_scratch, "debug_tensor_pass: null pointer");
+  const int per16 = 16 / dtype_size(dt);
+  TSIM_CHECK_ARG((((uintptr_t)q | (uintptr_t)corpus) & 15) == 0 && q_stride % per16 == 0 && c_stride % per16 == 0,
+                 "debug_tensor_pass: TMA needs 16-byte aligned bases and row strides");
+  const int64_t T = (N + 255) / 256;
+  const int sms = device_sm_count();
+  SearchPlan pr;
+  memset(&pr, 0, sizeof(pr));
+  pr.use_tensor = 1; pr.eps = approx_eps(D, dtype_size(dt)); pr.KP = kRetryKP; pr.pair = 0; pr.QB = 1; pr.sticky = 1;
+  pr.Gq = (int)(T < sms ? T : sms); pr.R = 256; pr.NC = pr.Gq;
+  *out_lists = pr.NC;
+  cudaStream_t st = (cudaStream_t)stream;
+  TSIM_CUDA(cudaMemsetAsync(thr_scratch, 0, (size_t)Q * sizeof(uint32_t), st));
+  return launch_search_tc(q, q_stride, corpus, c_stride, dt, corpus_inv_norm, Q, N, D, 0, 0, pr, TC_PASS_ALL, out_keys,
+                          thr_scratch, nullptr, nullptr, st);
 }
 
 // ---- plan handles ----------------------------------------------------------------------------

@@ -14,15 +14,29 @@ namespace tsim {
 constexpr double kCosEps = 1e-8;   // F.cosine_similarity eps, reference search_pipeline.py:77
 constexpr float kPoolEps = 1e-9f;  // clamp in AvgPoolingStrategy, reference modules.py:168
 
-// Relative error bound assumed for a tensor-core (bf16 x bf16 -> fp32) cosine, in units of
-// ||q|| * ||c||.  Candidates are proven complete when the approximate k-th and KP-th best
-// differ by more than 2 * kApproxEps (see select_merge.cu); tests measure the real error.
-constexpr float kApproxEps = 5e-5f;
+// Error bound of a tensor-core (bf16 x bf16 or e4m3 x e4m3 -> fp32) cosine, in units of ||q|| * ||c||:
+// |approx - exact| <= approx_eps(D, element size).  Candidates are proven complete when the approximate k-th
+// and KP-th best differ by more than 2 * eps * ||q|| (select_merge.cu).
+// Model: the products are exact in fp32; tcgen05 adds the K = 16 (bf16) / 32 (e4m3) products of one MMA step to
+// the fp32 accumulator with truncation, i.e. at most one ulp (2^-23 relative) of the running sum per step, and
+// every running sum is bounded by sum |q_i c_i| <= ||q|| ||c||.  So the error is at most steps * 2^-23 (one-sided
+// truncation does not average out: near-duplicate rows, whose products are all positive, do approach half of it).
+// approx_eps = 4 x that bound, floored at 5e-5 (which also covers the fp32 inverse-norm scaling, ~2^-22).
+// MEASURED (tests/test_gpu_eps.py, B200): max |approx - exact| / (||q|| ||c||) over unit-norm, 10^3-dynamic-range,
+// cancellation-heavy (+x, -x) and near-duplicate rows stays below 1/4 of approx_eps for D = 64 ... 16384, both dtypes.
+constexpr float kApproxEpsFloor = 5e-5f;
+__host__ __device__ inline float approx_eps(int64_t D, int esz) {
+  const int64_t per_step = esz == 1 ? 32 : 16;
+  const float steps = (float)((D + per_step - 1) / per_step);
+  const float e = steps * 4.76837158e-7f;   // steps * 2^-21 = 4 * steps * 2^-23
+  return e > kApproxEpsFloor ? e : kApproxEpsFloor;
+}
 // The same bound when the tensor pass runs on a bf16 SHADOW of fp32 / fp16 rows (both operands rounded
 // to 8 mantissa bits): |cos_shadow - cos| <= 2 * 2^-9 * 1.002 = 3.92e-3 (each unit vector moves by at most
 // its relative rounding error), the shadow query's norm is off by <= 2^-9 (1.95e-3 of a score <= 1), plus
-// the tensor-core term: 5.93e-3, rounded up.
+// the tensor-core term (5e-5 up to D = 1664; shadow_eps adds what approx_eps exceeds that by): 5.93e-3, rounded up.
 constexpr float kShadowEps = 6e-3f;
+__host__ __device__ inline float shadow_eps(int64_t D) { return kShadowEps + (approx_eps(D, 2) - kApproxEpsFloor); }
 
 // Threshold ladder (search_tc.cu / select_merge.cu): per query, kLadder ascending score levels
 // level(i) = base + i * step and the number of candidate rows seen so far in [level(i), level(i+1));
