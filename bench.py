@@ -14,10 +14,23 @@ Prints ONE JSON line (rank 0).  `value` = device-resident throughput (queries al
 `e2e` = the same through the public Python API with the query batch copied from pinned host
 memory and the results copied back every step.  `roofline` describes the dominant kernel
 (the tcgen05 search kernel) timed with CUDA events on its own stream via the C-ABI hook.
+
+The run checks itself: after the timed loops the outputs of the LAST TIMED STEP are compared with the
+float64 exact scan (mode="exact") on a block of queries (indices and float64 score bits), every returned
+score is recomputed in float64 from the gathered rows, and at N > 1 the merged result is compared with an
+independent torch merge of the gathered per-shard exact results.  `verified` carries the counts; a mismatch
+makes the process exit non-zero.
+
+`regimes` (also nested under `roofline.regimes`, which the driver's record keeps) reports the other BASELINE
+configs on the same box, each with its own roofline and its own spot check: the HBM-bound small batches,
+config 2 (1M x 768, Q = 1024), config 3 as specified (k = 100, all-gather + merge at N > 1), config 4
+(100M x 384 e4m3 sharded over the N GPUs, Q = 1 / 8 / 32), config 5 (all-pairs top-5 over 1M x 768, corpus-side
+and query-side split), K1 (pooling kernel) and the reference's per-query CPU loop.
 """
 from __future__ import annotations
 
 import argparse
+import glob
 import json
 import os
 import statistics
@@ -38,6 +51,7 @@ WORKLOADS = {
 }
 DEFAULT_WORKLOAD = "10Mx768_q4096_top10"
 METRIC = "queries/sec exact top-10 over 10Mx768 bf16 corpus"
+ALL_REGIMES = ("hbm", "cfg2", "cfg3", "cfg4", "cfg5", "k1", "cpu_loop")
 
 
 def load_peaks():
@@ -48,6 +62,34 @@ def load_peaks():
         return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
                 "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def tracked_traffic(kernel: str, workload: str):
+    """DRAM bytes per launch of the dominant kernel from the newest tracked ncu summary that names this workload
+    (profiles/*traffic*.json: {"kernel", "workload", "git", "dram_bytes_read", "dram_bytes_write", "source"}).
+    Returns (bytes or None, description)."""
+    best = None
+    for fn in sorted(glob.glob(os.path.join(ROOT, "profiles", "*traffic*.json"))):
+        try:
+            with open(fn) as f:
+                rec = json.load(f)
+        except (OSError, ValueError):
+            continue
+        for r in rec if isinstance(rec, list) else [rec]:
+            if r.get("kernel") == kernel and r.get("workload") == workload:
+                best = r
+    if best is None:
+        return None, None
+    return (float(best["dram_bytes_read"]) + float(best["dram_bytes_write"]),
+            f"{best.get('source', '?')} (ncu --set full at git {best.get('git', '?')})")
+
+
+def shared_config(workload: str, world: int) -> dict:
+    """The `config` object: identical in both arms so the driver's same_config check compares like with like."""
+    N, D, Q, k = WORKLOADS[workload]
+    return {"workload": workload, "corpus_rows": N, "dim": D, "queries_per_step": Q, "k": k,
+            "n_gpus": world, "rows_per_gpu": (N + world - 1) // world,
+            "cache": "inputs larger than L2 (the corpus is streamed from HBM every step)"}
 
 
 class ClockSampler:
@@ -104,45 +146,81 @@ class ClockSampler:
                 "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_shard(rows: int, D: int, seed: int, dev) -> torch.Tensor:
-    """Synthetic unit-norm bf16 corpus rows, generated on the device in chunks."""
+def make_shard(rows: int, D: int, seed: int, dev, dtype=torch.bfloat16) -> torch.Tensor:
+    """Synthetic unit-norm corpus rows, generated on the device in chunks.  e4m3 rows are stored
+    times 64 (cosine is scale free; the inverse norms carry the factor)."""
     g = torch.Generator(device=dev).manual_seed(seed)
-    out = torch.empty(rows, D, dtype=torch.bfloat16, device=dev)
+    out = torch.empty(rows, D, dtype=dtype, device=dev)
     step = 1 << 18
     for s in range(0, rows, step):
         n = min(step, rows - s)
         x = torch.randn(n, D, generator=g, device=dev, dtype=torch.float32)
         x = x / x.norm(dim=-1, keepdim=True)
-        out[s:s + n] = x.to(torch.bfloat16)
+        out[s:s + n] = (x * 64 if dtype == torch.float8_e4m3fn else x).to(dtype)
     return out
 
 
-def cpu_reference_qps(N_full: int, D: int, k: int, budget_s: float = 12.0):
-    """The reference's CPU search (cos_sim + topk, metrics.py:99-101 + search_pipeline.py:78, as
-    restated in oracle/oracle.py) on a bounded sample of the workload, all host threads, repeated
-    for about `budget_s` seconds; scaled linearly in N to the full corpus (stated in `sample`)."""
+# ---------------------------------------------------------------------------------------------------
+# CPU arms (the only places that execute oracle/)
+# ---------------------------------------------------------------------------------------------------
+def _cpu_sample(N_full: int, D: int, n_rows: int, n_q: int):
+    g = torch.Generator().manual_seed(1234)
+    return torch.randn(n_q, D, generator=g), torch.randn(min(N_full, n_rows), D, generator=g)
+
+
+def cpu_reference_steps(N_full: int, D: int, Q_full: int, k: int, steps: int, warmup: int, budget_s: float):
+    """The reference's CPU search (cos_sim + topk, metrics.py:99-101 + search_pipeline.py:78, as restated in
+    oracle/oracle.py), all host threads.  One step = one pass over a BOUNDED SAMPLE of the workload (128 fp32
+    queries x 500k rows); `steps` such passes are timed (fewer if the budget runs out) and the rate is scaled
+    linearly in N to the full corpus (stated in `sample`)."""
     from oracle import oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    n_s = min(N_full, 500_000)
-    q_s = 128
-    g = torch.Generator().manual_seed(1234)
-    corpus = torch.randn(n_s, D, generator=g)
-    queries = torch.randn(q_s, D, generator=g)
-    O.search_cos_sim_literal(queries[:4], corpus[:1000], k)  # warm-up
+    queries, corpus = _cpu_sample(N_full, D, 500_000, 128)
+    n_s, q_s = corpus.shape[0], queries.shape[0]
+    O.search_cos_sim_literal(queries[:4], corpus[:1000], k)
+    t_w = time.perf_counter()
+    for _ in range(max(1, min(warmup, 2))):
+        O.search_cos_sim_literal(queries, corpus, k)
+        if time.perf_counter() - t_w > 0.25 * budget_s:
+            break
+    t0 = time.perf_counter()
+    done = 0
+    while done < max(1, steps):
+        O.search_cos_sim_literal(queries, corpus, k)
+        done += 1
+        if time.perf_counter() - t0 >= budget_s:
+            break
+    el = time.perf_counter() - t0
+    per_step = el / done
+    qps_full = (q_s / per_step) * n_s / N_full
+    sample = (f"one step = {q_s} fp32 queries x {n_s} rows x {D} (cos_sim + torch.topk); {done} steps timed in {el:.1f} s "
+              f"({per_step:.3f} s each) on {cores} threads; queries/s scaled linearly in N to {N_full} rows")
+    return qps_full, cores, sample, per_step, done
+
+
+def cpu_loop_variant_i(N_full: int, D: int, k: int, budget_s: float = 6.0):
+    """BASELINE.md section 3 variant (i): the reference's per-query loop as written
+    (F.cosine_similarity(q.expand_as(C), C, -1) + torch.topk per query, search_pipeline.py:73-79; oracle
+    search_literal), fp32, all host threads, on a bounded sample, scaled linearly in N."""
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    queries, corpus = _cpu_sample(N_full, D, 200_000, 8)
+    O.search_literal(queries[:1], corpus[:1000], k)
     t0 = time.perf_counter()
     done = 0
     while True:
-        O.search_cos_sim_literal(queries, corpus, k)
-        done += 1
+        O.search_literal(queries, corpus, k)
+        done += queries.shape[0]
         el = time.perf_counter() - t0
-        if el >= budget_s or done >= 200:
+        if el >= budget_s or done >= 512:
             break
-    per_call = el / done
-    qps_full = (q_s / per_call) * n_s / N_full
-    sample = (f"{q_s} fp32 queries x {n_s} rows x {D} (cos_sim + torch.topk), {done} reps in {el:.1f} s "
-              f"({per_call:.3f} s each) on {cores} threads; scaled linearly in N to {N_full} rows")
-    return qps_full, cores, sample, el
+    qps_full = (done / el) * corpus.shape[0] / N_full
+    return {"name": "cpu_loop_variant_i", "value": qps_full, "unit": "queries/s", "cores": cores, "kind": "port",
+            "sample": f"{done} fp32 queries, one at a time, x {corpus.shape[0]} rows x {D} in {el:.1f} s on {cores} threads; "
+                      f"scaled linearly in N to {N_full} rows",
+            "what": "reference per-query loop: F.cosine_similarity(q.expand_as(C), C, -1) + torch.topk (search_pipeline.py:73-79)"}
 
 
 def run_reference(args, out_fd):
@@ -151,17 +229,15 @@ def run_reference(args, out_fd):
     if rank != 0:
         return
     steps = max(1, args.steps)
-    t0 = time.perf_counter()
-    qps, cores, sample, spent = cpu_reference_qps(N, D, k, budget_s=min(90.0, max(10.0, 3.0 * steps)))
-    ms_per_step = Q / qps * 1e3
+    qps, cores, sample, per_step, done = cpu_reference_steps(N, D, Q, k, steps, args.warmup,
+                                                             budget_s=min(120.0, max(10.0, 4.0 * steps)))
     line = {
         "impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "steps": done, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "corpus_rows": N, "dim": D, "queries_per_step": Q, "k": k,
-                   "rows_per_gpu": N, "sharding": "none (host CPU)", "cache": "n/a (CPU)",
-                   "scores": "fp32 cos_sim + torch.topk, as the reference computes them",
-                   "note": "CPU arm: oracle port of the reference's cos_sim+topk search on host cores"},
+        "config": shared_config(args.workload, args.gpus),
+        "note": "CPU arm: oracle port of the reference's cos_sim + torch.topk search on the host cores; one step is a "
+                "bounded sample of the workload (ms_per_step is the sample's), value is scaled to the full corpus",
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -182,6 +258,201 @@ def _emit(fd: int, line: dict) -> None:
     os.write(fd, (json.dumps(line) + "\n").encode())
 
 
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+class Ctx:
+    """What every measurement needs: device, process group, library handle, peaks."""
+
+    def __init__(self, args):
+        from text_similarity_b200 import _lib
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus:
+            raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={self.world}: launch with torch.distributed.run")
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+        self.group = self.dist.group.WORLD if self.dist else None
+        self.lib = _lib.load()
+        self.peaks = load_peaks()
+        self.ridge = self.peaks["bf16_tflops"] * 1e12 / (self.peaks["hbm_gbs"] * 1e9)
+
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        if not self.dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, t: torch.Tensor) -> torch.Tensor:
+        if self.dist:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t
+
+    def timed(self, fn, reps: int, warm: int = 3, hook: bool = False):
+        """(whole-call ms per rep, candidate-pass kernel ms per rep or None): barrier + synchronize on both sides,
+        CUDA events, max over ranks.  hook: the C-ABI timing hook records events around the candidate-pass
+        kernels of every call (the last search call of a rep if fn makes several)."""
+        for _ in range(warm):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0 = [torch.cuda.Event(enable_timing=True) for _ in range(reps)] if hook else []
+        k1 = [torch.cuda.Event(enable_timing=True) for _ in range(reps)] if hook else []
+        for ev in k0 + k1:
+            ev.record()           # torch creates the CUDA event lazily: materialise the handles up front
+        self.barrier()
+        e0.record()
+        for i in range(reps):
+            if hook:
+                self.lib.tsim_set_timing_events(k0[i].cuda_event, k1[i].cuda_event)
+            fn()
+        if hook:
+            self.lib.tsim_set_timing_events(None, None)
+        e1.record()
+        self.barrier()
+        whole = self.max_over_ranks(e0.elapsed_time(e1) / reps)
+        kern = self.max_over_ranks(statistics.mean(a.elapsed_time(b) for a, b in zip(k0, k1))) if hook else None
+        return whole, kern
+
+    def search_roofline(self, rows: int, D: int, esize: int, Q: int, k: int, ms: float, kernel_ms):
+        """Roofline entry of one search on THIS rank's shard: bound picked by arithmetic intensity against the
+        measured ridge; achieved = algorithmic flops or bytes / kernel time (whole-call time when no hook)."""
+        t = (kernel_ms if kernel_ms else ms) * 1e-3
+        flops = 2.0 * Q * rows * D
+        bytes_alg = rows * D * esize + rows * 4 + Q * D * esize + Q * k * 12
+        peak_tf = self.peaks["bf16_tflops"] * (2.0 if esize == 1 else 1.0)    # fp8 tensor peak = 2 x bf16
+        ridge = peak_tf * 1e12 / (self.peaks["hbm_gbs"] * 1e9)
+        if flops / bytes_alg > ridge:
+            ach = flops / t / 1e12
+            r = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf}
+        else:
+            ach = bytes_alg / t / 1e9
+            r = {"bound": "hbm", "achieved": ach, "peak": self.peaks["hbm_gbs"], "unit": "GB/s",
+                 "frac": ach / self.peaks["hbm_gbs"], "achieved_whole_call": bytes_alg / (ms * 1e-3) / 1e9}
+        r.update({"timed": "candidate-pass kernels (C-ABI event hook)" if kernel_ms else "whole call",
+                  "kernel_ms": kernel_ms, "algorithmic_flops": flops, "algorithmic_bytes": bytes_alg, "traffic": None})
+        return r
+
+
+def torch_merge_reference(s64_all: torch.Tensor, idx_all: torch.Tensor, k: int):
+    """Independent merge of gathered per-shard lists [world, n, k] -> top-k by (score desc, index asc), in plain
+    torch (stable sorts), for checking the merge kernel + all-gather layout."""
+    world, n, kk = idx_all.shape
+    s = s64_all.permute(1, 0, 2).reshape(n, world * kk)
+    i = idx_all.permute(1, 0, 2).reshape(n, world * kk)
+    pad = i < 0
+    s = torch.where(pad, torch.full_like(s, float("-inf")), s)
+    i = torch.where(pad, torch.full_like(i, torch.iinfo(torch.int64).max), i)
+    o1 = torch.argsort(i, dim=1, stable=True)
+    s, i = torch.gather(s, 1, o1), torch.gather(i, 1, o1)
+    o2 = torch.argsort(s, dim=1, descending=True, stable=True)
+    s, i = torch.gather(s, 1, o2)[:, :k], torch.gather(i, 1, o2)[:, :k]
+    i = torch.where(i == torch.iinfo(torch.int64).max, torch.full_like(i, -1), i)
+    return s, i
+
+
+def _gather_rows(shard: torch.Tensor, loc: torch.Tensor) -> torch.Tensor:
+    if shard.element_size() == 1:      # advanced indexing is not implemented for float8: gather the bytes
+        return shard.view(torch.uint8)[loc].view(shard.dtype)
+    return shard[loc]
+
+
+def verify_search(ctx: Ctx, corp, q: torch.Tensor, k: int, got_idx: torch.Tensor, got_s64: torch.Tensor,
+                  n_block: int, exclude_self_base: int = -1) -> dict:
+    """Check a search result (this rank's copy of the GLOBAL result) against independent computations:
+      1. a contiguous block of queries is re-run with the float64 exact scan on every shard, the per-shard lists
+         are gathered and merged in plain torch: indices AND float64 score bits must equal `got`;
+      2. every returned score is recomputed in float64 from the gathered rows (|diff| <= 1e-12);
+      3. every list is ordered by (score desc, index asc).
+    All ranks take part in the collectives; the counts are rank 0's."""
+    Q = q.shape[0]
+    n = min(n_block, Q)
+    off = ((Q - n) // 3) if Q > n else 0
+    qs = q[off:off + n].contiguous()
+    base = exclude_self_base + off if exclude_self_base >= 0 else -1
+    _, li, l64 = corp.search_local(qs, k, mode="exact", return_score64=True, exclude_self_base=base)
+    if ctx.dist:
+        gi = torch.empty(ctx.world, n, k, dtype=torch.int64, device=ctx.dev)
+        gs = torch.empty(ctx.world, n, k, dtype=torch.float64, device=ctx.dev)
+        ctx.dist.all_gather_into_tensor(gi, li.contiguous())
+        ctx.dist.all_gather_into_tensor(gs, l64.contiguous())
+    else:
+        gi, gs = li[None], l64[None]
+    ref_s, ref_i = torch_merge_reference(gs, gi, k)
+    blk_i, blk_s = got_idx[off:off + n], got_s64[off:off + n]
+    idx_bad = int((ref_i != blk_i).any(dim=1).sum())
+    score_bad = int((ref_s.view(torch.int64) != blk_s.view(torch.int64)).any(dim=1).sum())
+    # 2. float64 re-score of every returned (query, row) from the rows themselves
+    rows_local = corp.shard.shape[0]
+    max_err = 0.0
+    step = max(1, (1 << 22) // max(1, k * q.shape[1]))
+    qd_norm = q.double().norm(dim=-1).clamp_min(1e-8)
+    recomputed = torch.zeros(Q, k, dtype=torch.float64, device=ctx.dev)
+    for b in range(0, Q, step):
+        e = min(Q, b + step)
+        loc = got_idx[b:e] - corp.idx_base
+        mine = (got_idx[b:e] >= 0) & (loc >= 0) & (loc < rows_local)
+        r = _gather_rows(corp.shard, loc.clamp(0, max(rows_local - 1, 0))).double()   # [q, k, D]
+        dot = (r * q[b:e].double()[:, None, :]).sum(-1)
+        cos = dot / (qd_norm[b:e, None] * r.norm(dim=-1).clamp_min(1e-8))
+        recomputed[b:e] = torch.where(mine, cos, torch.zeros_like(cos))
+    recomputed = ctx.sum_over_ranks(recomputed)
+    valid = got_idx >= 0
+    if valid.any():
+        max_err = float((recomputed - got_s64)[valid].abs().max())
+    # 3. order
+    s_a, s_b = got_s64[:, :-1], got_s64[:, 1:]
+    i_a, i_b = got_idx[:, :-1], got_idx[:, 1:]
+    both = (i_a >= 0) & (i_b >= 0)
+    disorder = int((both & ((s_a < s_b) | ((s_a == s_b) & (i_a > i_b)))).any(dim=1).sum()) if k > 1 else 0
+    mism = idx_bad + score_bad + disorder + (1 if max_err > 1e-12 else 0)
+    return {"queries": n, "mismatches": mism, "index_mismatches": idx_bad, "score64_mismatches": score_bad,
+            "rescored": int(valid.sum()), "max_rescore_err": max_err, "disordered_lists": disorder,
+            "checked_against": "float64 exact scan per shard + independent torch merge"
+                               + (f" of {ctx.world} gathered shard results" if ctx.world > 1 else "")}
+
+
+def regime_search(ctx: Ctx, name: str, corp, q: torch.Tensor, k: int, rows_global: int, esize: int, reps: int,
+                  graphed: bool = False, verify: int = 32, extra: dict = None) -> dict:
+    """One search regime: whole call (max over ranks, incl. all-gather + merge at N > 1), candidate-pass kernels
+    via the event hook (eager calls), its roofline on this rank's shard, and a spot check against the exact scan."""
+    Q, D = q.shape
+    eager = lambda: corp.search(q, k)                                   # noqa: E731
+    ms_eager, kern = ctx.timed(eager, reps, warm=3, hook=True)
+    ms, used_graph = ms_eager, False
+    if graphed:
+        try:
+            corp.search_graphed(q, k)
+            ms_g, _ = ctx.timed(lambda: corp.search_graphed(q, k), reps, warm=3)
+            ms, used_graph = ms_g, True
+        except Exception as exc:  # noqa: BLE001
+            print(f"[bench] CUDA-graph capture failed for {name} ({exc}); eager only", file=sys.stderr)
+    out = {"name": name, "n_gpus": ctx.world, "corpus_rows": rows_global, "rows_per_gpu": corp.shard.shape[0], "dim": D,
+           "queries_per_step": Q, "k": k, "dtype": str(q.dtype).replace("torch.", ""),
+           "value": Q / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms, "ms_per_step_eager": ms_eager,
+           "cuda_graph": used_graph, "includes": "local search" + (" + all-gather + merge" if ctx.world > 1 else ""),
+           "roofline": ctx.search_roofline(corp.shard.shape[0], D, esize, Q, k, ms, kern)}
+    if verify:
+        res = corp.search(q, k, return_score64=True)
+        out["verified"] = verify_search(ctx, corp, q, k, res[1], res[2], verify)
+    if extra:
+        out.update(extra)
+    return out
+
+
 def main():
     out_fd = _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -193,41 +464,31 @@ def main():
     ap.add_argument("--queries", type=int, default=0, help="override queries per step")
     ap.add_argument("--k", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--small-q", default="1,32", help="extra HBM-regime batch sizes reported under 'regimes' (N=1)")
+    ap.add_argument("--regimes", default="all", help="comma list of %s, 'all' or 'none'" % (ALL_REGIMES,))
+    ap.add_argument("--verify-queries", type=int, default=128)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args, out_fd)
 
-    from text_similarity_b200 import _lib, ops
-    from text_similarity_b200.sharded import ShardedCorpus
+    from text_similarity_b200 import ops
+    from text_similarity_b200.sharded import (ShardedCorpus, all_pairs_corpus_sharded, all_pairs_query_sharded,
+                                              shard_bounds)
 
+    ctx = Ctx(args)
+    dev, world, rank, lib, peaks = ctx.dev, ctx.world, ctx.rank, ctx.lib, ctx.peaks
     N, D, Q, k = WORKLOADS[args.workload]
     Q = args.queries or Q
     k = args.k or k
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-
-    lib = _lib.load()
-    peaks = load_peaks()
     steps, warmup = args.steps, max(args.warmup, 0)
+    want = set(ALL_REGIMES) if args.regimes == "all" else set(x for x in args.regimes.split(",") if x and x != "none")
+    if args.workload != DEFAULT_WORKLOAD:
+        want &= {"hbm", "cpu_loop"}
 
     # ---- data: contiguous row shard of the synthetic corpus, query batches -------------------
-    rows_per = (N + world - 1) // world
-    r0 = rank * rows_per
-    rows = max(0, min(N, r0 + rows_per) - r0)
+    r0, r1 = shard_bounds(N, world, rank)
+    rows = r1 - r0
     shard = make_shard(rows, D, seed=1234 + rank, dev=dev)
-    corpus = ShardedCorpus(shard, idx_base=r0, group=dist.group.WORLD if dist else None)
+    corpus = ShardedCorpus(shard, idx_base=r0, group=ctx.group)
     nbatch = 4
     gq = torch.Generator(device="cpu").manual_seed(4321)
     host_batches = []
@@ -239,85 +500,60 @@ def main():
     host_scores = torch.empty(Q, k, dtype=torch.float32).pin_memory()
     host_idx = torch.empty(Q, k, dtype=torch.int64).pin_memory()
     torch.cuda.synchronize()
-
-    def barrier():
-        if dist:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms: float) -> float:
-        if not dist:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- small-batch (HBM-bound) regime, 1 GPU only: same kernels, small Q.  Measured BEFORE the heavy
-    # tensor-bound loop: a small-batch search alone does not hit the 1 kW power cap, the loop below does.
     regimes = []
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    def small_batch_regime(corp, qbatch, n_rows, dim, esize, label):
-        """One HBM-regime entry: whole call via CUDA-graph replay, candidate-pass kernels via the timing hook."""
-        sq = qbatch.shape[0]
-        run, graphed = (lambda: corp.search_graphed(qbatch, k)), True
-        try:
-            run()
-        except Exception as exc:  # noqa: BLE001
-            print(f"[bench] CUDA-graph capture failed ({exc}); eager launches", file=sys.stderr)
-            run, graphed = (lambda: corp.search(qbatch, k)), False
-        for _ in range(3):
-            run()
-        reps = 10
-        a0 = [torch.cuda.Event(enable_timing=True) for _ in range(reps)]
-        a1 = [torch.cuda.Event(enable_timing=True) for _ in range(reps)]
-        for ev in a0 + a1:
-            ev.record()
-        torch.cuda.synchronize()
-        e0.record()
-        for i in range(reps):
-            run()
-        e1.record()
-        torch.cuda.synchronize()
-        # candidate-pass kernels alone (eager calls: the timing hook records events around them)
-        for i in range(reps):
-            lib.tsim_set_timing_events(a0[i].cuda_event, a1[i].cuda_event)
-            corp.search(qbatch, k)
-        lib.tsim_set_timing_events(None, None)
-        torch.cuda.synchronize()
-        km = statistics.mean(x.elapsed_time(y) for x, y in zip(a0, a1))
-        b_alg = n_rows * dim * esize + n_rows * 4 + sq * dim * esize + sq * k * 12
-        f_alg = 2.0 * sq * n_rows * dim
-        return {"workload": label, "queries_per_step": sq, "queries_per_s": reps * sq / (e0.elapsed_time(e1) * 1e-3),
-                "ms_per_step": e0.elapsed_time(e1) / reps, "kernel_ms": km, "cuda_graph": graphed,
-                "roofline": {"bound": "hbm", "achieved": b_alg / (km * 1e-3) / 1e9,
-                             "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                             "frac": b_alg / (km * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                             "achieved_whole_call": b_alg / (e0.elapsed_time(e1) / reps * 1e-3) / 1e9,
-                             "tflops": f_alg / (km * 1e-3) / 1e12}}
-
-    if world == 1 and args.small_q:
-        small = [int(x) for x in args.small_q.split(",") if x]
-        for sq in small:
-            regimes.append(small_batch_regime(corpus, dev_batches[0][:sq].contiguous(), rows, D, 2, args.workload))
-        if args.workload == DEFAULT_WORKLOAD:
-            # BASELINE config 4's per-GPU shape: one 12.5M x 384 e4m3 shard of the 100M-row corpus (4.8 GB)
-            n8, d8 = 12_500_000, 384
-            g8 = torch.Generator(device=dev).manual_seed(99)
-            c8 = torch.empty(n8, d8, dtype=torch.float8_e4m3fn, device=dev)
-            for s0 in range(0, n8, 1 << 20):
-                n = min(1 << 20, n8 - s0)
-                x = torch.randn(n, d8, generator=g8, device=dev)
-                c8[s0:s0 + n] = (x / x.norm(dim=-1, keepdim=True) * 64).to(torch.float8_e4m3fn)
-            corpus8 = ShardedCorpus(c8)
-            for sq in small:
-                x = torch.randn(sq, d8, generator=g8, device=dev)
-                q8 = (x / x.norm(dim=-1, keepdim=True) * 64).to(torch.float8_e4m3fn)
-                regimes.append(small_batch_regime(corpus8, q8, n8, d8, 1, "12.5Mx384_e4m3_shard_top10"))
-            del corpus8, c8
-            torch.cuda.empty_cache()
-        torch.cuda.synchronize()
-        time.sleep(0.5)
+    # ---- small-batch (HBM-bound) regimes first: a small-batch search alone does not hit the 1 kW power cap, the
+    # tensor-bound loops below do -------------------------------------------------------------------------
+    if "hbm" in want:
+        for sq in (1, 32):
+            regimes.append(regime_search(ctx, f"hbm_{args.workload.split('_')[0]}_bf16_q{sq}_top{k}", corpus,
+                                         dev_batches[0][:sq].contiguous(), k, N, 2, reps=10, graphed=True, verify=sq))
+    if "cfg4" in want:
+        # BASELINE config 4: 100M x 384 e4m3 rows sharded over the N GPUs of the box (N = 8: 12.5M rows = 4.8 GB per
+        # GPU; N = 1: the whole 38.4 GB on one GPU), batch 1 / 8 / 32, incl. the all-gather + merge at N > 1
+        n4, d4 = 100_000_000, 384
+        a0, a1 = shard_bounds(n4, world, rank)
+        c4 = make_shard(a1 - a0, d4, seed=99 + rank, dev=dev, dtype=torch.float8_e4m3fn)
+        corp4 = ShardedCorpus(c4, idx_base=a0, group=ctx.group)
+        q4 = make_shard(32, d4, seed=77, dev=dev, dtype=torch.float8_e4m3fn)
+        for sq in (1, 8, 32):
+            regimes.append(regime_search(ctx, f"cfg4_100Mx384_e4m3_q{sq}_top10", corp4, q4[:sq].contiguous(), 10, n4, 1,
+                                         reps=10, graphed=True, verify=sq))
+        if world == 1:
+            # the per-GPU shape of the 8-GPU split on its own (first 12.5M rows of the same matrix)
+            corp4s = ShardedCorpus(c4[:12_500_000], inv_norm=corp4.inv_norm[:12_500_000])
+            for sq in (1, 32):
+                regimes.append(regime_search(ctx, f"cfg4_shard_12.5Mx384_e4m3_q{sq}_top10", corp4s, q4[:sq].contiguous(),
+                                             10, 12_500_000, 1, reps=10, graphed=True, verify=sq))
+            del corp4s
+        del corp4, c4
+        torch.cuda.empty_cache()
+    if "k1" in want:
+        # K1: fused masked mean-pool + L2 normalise + bf16 cast (data-parallel: every rank pools its own batch)
+        B1, L1, D1 = 16_384, 64, 768
+        g1 = torch.Generator(device=dev).manual_seed(5 + rank)
+        tok = torch.randn(B1, L1, D1, generator=g1, device=dev, dtype=torch.bfloat16)
+        mask = torch.ones(B1, L1, dtype=torch.int64, device=dev)
+        out1 = torch.empty(B1, D1, dtype=torch.bfloat16, device=dev)
+        inv1 = torch.empty(B1, dtype=torch.float32, device=dev)
+        run1 = lambda: ops.pool_norm(tok, mask, out=out1, out_inv_norm=inv1, normalize=True)   # noqa: E731
+        ms1, _ = ctx.timed(run1, 20, warm=3)
+        live = int(mask.sum())                               # trailing padding is never read
+        b_alg = live * D1 * 2 + B1 * L1 * 8 + B1 * D1 * 2 + B1 * 4
+        from oracle import oracle as O                       # checker only: 64 rows against the CPU oracle
+        exp_rows, _ = O.pool_normalize_cast(tok[:64].float().cpu(), mask[:64].cpu(), torch.bfloat16)
+        k1_err = float((out1[:64].float().cpu() - exp_rows.float()).abs().max())
+        regimes.append({"name": "k1_pool_norm_b16384_l64_d768_bf16", "n_gpus": world, "value": world * B1 / (ms1 * 1e-3),
+                        "unit": "sentences/s", "ms_per_step": ms1, "tokens_live": live,
+                        "roofline": {"bound": "hbm", "achieved": b_alg / (ms1 * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                                     "unit": "GB/s", "frac": b_alg / (ms1 * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                     "algorithmic_bytes": b_alg, "timed": "whole call (one kernel), L2 flushed by size: "
+                                     "1.6 GB of tokens per call", "traffic": None},
+                        "verified": {"rows": 64, "max_abs_err_vs_oracle": k1_err, "mismatches": int(k1_err > 2 ** -8)}})
+        del tok, mask, out1
+        torch.cuda.empty_cache()
+    torch.cuda.synchronize()
+    time.sleep(0.5)
 
     # ---- device-resident timed region ---------------------------------------------------------
     ev_k0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
@@ -326,45 +562,53 @@ def main():
         ev.record()  # torch creates the CUDA event lazily: materialise the handles up front
     for i in range(warmup):
         corpus.search(dev_batches[i % nbatch], k)
-    barrier()
-    sampler = ClockSampler(local)
+    ctx.barrier()
+    sampler = ClockSampler(ctx.local)
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = lib.tsim_launch_count()
+    last = None
     e0.record()
     for i in range(steps):
         lib.tsim_set_timing_events(ev_k0[i].cuda_event, ev_k1[i].cuda_event)
-        corpus.search(dev_batches[i % nbatch], k)
+        last = corpus.search(dev_batches[i % nbatch], k, return_score64=True)
     lib.tsim_set_timing_events(None, None)
     e1.record()
     gpu_launches = int(lib.tsim_launch_count() - launches0)   # libtsim kernels launched in the timed region
-    barrier()
-    total_ms = max_over_ranks(e0.elapsed_time(e1))
+    ctx.barrier()
+    total_ms = ctx.max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
-    kern_ms = statistics.mean(a.elapsed_time(b) for a, b in zip(ev_k0, ev_k1))
-    kern_ms = max_over_ranks(kern_ms)
+    kern_ms = ctx.max_over_ranks(statistics.mean(a.elapsed_time(b) for a, b in zip(ev_k0, ev_k1)))
     value = steps * Q / (total_ms * 1e-3)
+
+    # ---- the timed outputs, checked (the result tensors of the LAST timed step) -----------------
+    verified = verify_search(ctx, corpus, dev_batches[(steps - 1) % nbatch], k, last[1], last[2], args.verify_queries)
+    verified["what"] = "outputs of the last timed step of the device-resident loop"
 
     # ---- end-to-end timed region: pinned host queries in, host results out, every step --------
     for i in range(min(warmup, 2)):
         corpus.search_host(host_batches[i % nbatch], k, host_scores, host_idx)
-    barrier()
+    ctx.barrier()
     e0.record()
     for i in range(steps):
         corpus.search_host(host_batches[i % nbatch], k, host_scores, host_idx)
     e1.record()
-    barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    ctx.barrier()
+    e2e_ms = ctx.max_over_ranks(e0.elapsed_time(e1))
     e2e = steps * Q / (e2e_ms * 1e-3)
+    # the host copy of the last e2e step must be the device result of the same batch
+    e2e_same = bool(torch.equal(host_idx.to(dev), corpus.search(dev_batches[(steps - 1) % nbatch], k)[1]))
+    verified["e2e_host_copy_matches"] = e2e_same
+    if not e2e_same:
+        verified["mismatches"] += 1
 
     # ---- roofline of the dominant kernel (per launch, this rank's shard) ----------------------
     flops = 2.0 * Q * rows * D
     bytes_alg = rows * D * 2 + rows * 4 + Q * D * 2 + Q * k * 12
     tflops = flops / (kern_ms * 1e-3) / 1e12
     gbs = bytes_alg / (kern_ms * 1e-3) / 1e9
-    ridge = peaks["bf16_tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
-    tensor_bound = (flops / bytes_alg) > ridge
+    tensor_bound = (flops / bytes_alg) > ctx.ridge
     if tensor_bound:
         roofline = {"bound": "tensor", "achieved": tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": tflops / peaks["bf16_tflops"],
@@ -372,19 +616,71 @@ def main():
     else:
         roofline = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": gbs / peaks["hbm_gbs"], "traffic": None}
-    if world == 1 and args.workload == DEFAULT_WORKLOAD and Q == WORKLOADS[DEFAULT_WORKLOAD][2]:
-        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload, one ncu --set full
-        # capture (profiles/r01i_search_tc_bench_q4096.ncu_raw.txt)
-        roofline["traffic"] = 16.87e9 + 0.33e9   # main-pass launch (98.4 % of the rows; the sample passes are not in this figure)
-        roofline["traffic_source"] = "profiles/r01i_search_tc_bench_q4096.ncu_raw.txt"
+    if world == 1 and Q == WORKLOADS[args.workload][2] and k == WORKLOADS[args.workload][3]:
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload: read from the newest tracked
+        # ncu summary (profiles/*traffic*.json), never typed in here; absent -> null
+        roofline["traffic"], roofline["traffic_source"] = tracked_traffic("search_tc_kernel", args.workload)
     roofline.update({"kernel": "search_tc_kernel", "kernel_ms": kern_ms, "peak_source": peaks["source"],
                      "algorithmic_flops": flops, "algorithmic_bytes": bytes_alg})
 
-    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload ----------------
+    # ---- tensor-bound regimes (after the headline loops) ----------------------------------------
+    if "cfg2" in want and world == 1:
+        # BASELINE config 2: 1M x 768 bf16, 1024 queries, top-10 on one GPU (the first 1M rows of the same corpus)
+        corp2 = ShardedCorpus(shard[:1_000_000], inv_norm=corpus.inv_norm[:1_000_000])
+        regimes.append(regime_search(ctx, "cfg2_1Mx768_q1024_top10", corp2, dev_batches[1][:1024].contiguous(), 10,
+                                     1_000_000, 2, reps=20, verify=64))
+        del corp2
+    if "cfg3" in want:
+        # BASELINE config 3 as specified: the 10M x 768 corpus sharded over the N GPUs, 4096 queries, top-100
+        regimes.append(regime_search(ctx, "cfg3_10Mx768_q4096_top100", corpus, dev_batches[2], 100, N, 2,
+                                     reps=max(3, min(10, steps)), verify=64))
+    if "cfg5" in want:
+        # BASELINE config 5: all-pairs cosine + top-5 neighbours over 1M x 768 (self excluded).  Two splits (SURVEY.md
+        # 8e): corpus rows sharded (one all-gather + merge per 16K-query tile), or queries sharded with the 1.5 GB
+        # matrix replicated (no collective at all).  One "step" = the whole job.
+        n5, k5 = 1_000_000, 5
+        full5 = shard[:n5] if world == 1 else make_shard(n5, D, seed=555, dev=dev)
+        inv5 = corpus.inv_norm[:n5] if world == 1 else ops.row_inv_norm(full5)
+        b0, b1 = shard_bounds(n5, world, rank)
+        corp5 = ShardedCorpus(full5[b0:b1], idx_base=b0, group=ctx.group, inv_norm=inv5[b0:b1])
+        s5 = torch.empty(n5, k5, dtype=torch.float32, device=dev)
+        i5 = torch.empty(n5, k5, dtype=torch.int64, device=dev)
+        job_flops = 2.0 * n5 * n5 * D
+
+        def entry(split, ms, ver):
+            tf = job_flops / world / (ms * 1e-3) / 1e12
+            return {"name": f"cfg5_allpairs_1Mx768_top5_{split}_split", "n_gpus": world, "value": n5 / (ms * 1e-3),
+                    "unit": "rows/s", "ms_per_step": ms, "k": k5,
+                    "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                                 "frac": tf / peaks["bf16_tflops"], "timed": "whole job (max over ranks)",
+                                 "algorithmic_flops": job_flops / world, "traffic": None},
+                    "verified": ver}
+        run5 = lambda: all_pairs_corpus_sharded(corp5, full5, k5, out_scores=s5, out_idx=i5)   # noqa: E731
+        ms5, _ = ctx.timed(run5, 2, warm=1)
+        # spot check one 16K-query tile: exact scan per shard + torch merge, self excluded
+        tb = 16_384 * 7
+        res5 = corp5.search(full5[tb:tb + 16_384], k5, exclude_self_base=tb, return_score64=True)
+        ver5 = verify_search(ctx, corp5, full5[tb:tb + 16_384], k5, res5[1], res5[2], 40, exclude_self_base=tb)
+        ver5["mismatches"] += int(not torch.equal(res5[1], i5[tb:tb + 16_384]))   # the job's rows == the checked rows
+        regimes.append(entry("corpus", ms5, ver5))
+        if world > 1:
+            runq = lambda: all_pairs_query_sharded(full5, inv5, k5, world, rank)   # noqa: E731
+            msq, _ = ctx.timed(runq, 2, warm=1)
+            sq_, iq_, q0 = all_pairs_query_sharded(full5, inv5, k5, world, rank)
+            same = torch.tensor([int(torch.equal(iq_, i5[q0:q0 + iq_.shape[0]]))], device=dev)
+            if ctx.dist:
+                ctx.dist.all_reduce(same, op=ctx.dist.ReduceOp.MIN)
+            regimes.append(entry("query", msq, {"rows": n5, "mismatches": int(1 - int(same.item())),
+                                                "checked_against": "indices of the corpus-split job on every rank"}))
+        del corp5, s5, i5
+
+    # ---- CPU baselines (rank 0, N = 1 only): bounded samples of the same workload ----------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        qps, cores, sample, _ = cpu_reference_qps(N, D, k, budget_s=12.0)
+        qps, cores, sample, _, _ = cpu_reference_steps(N, D, Q, k, 100, 1, budget_s=12.0)
         cpu_baseline = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample}
+        if "cpu_loop" in want:
+            regimes.append(cpu_loop_variant_i(N, D, k))
 
     # ---- stock PyTorch on the same GPU (rank 0, N = 1 only; SURVEY.md 8d's second baseline): cuBLAS
     # `Q @ chunk.T` -> torch.topk per chunk -> topk of the concatenated lists.  bf16 scores, so its indices are
@@ -415,24 +711,29 @@ def main():
         except Exception as exc:  # noqa: BLE001  (informational leg: never fail the bench on it)
             torch_gpu = {"value": None, "error": str(exc)[:200]}
 
+    bad = verified["mismatches"] + sum(r.get("verified", {}).get("mismatches", 0) for r in regimes)
     if rank == 0:
+        roofline["regimes"] = regimes           # nested copies: the driver's record keeps the known objects whole
+        roofline["verified"] = verified
         line = {
             "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": total_ms / steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": args.workload, "corpus_rows": N, "dim": D, "queries_per_step": Q, "k": k,
-                       "rows_per_gpu": rows_per, "sharding": f"contiguous rows x{world}, 1 all-gather + merge",
-                       "cache": "inputs larger than L2 (corpus shard %.1f GB per step)" % (rows * D * 2 / 1e9),
-                       "scores": "float64 re-scored, exact index match vs oracle"},
+            "config": shared_config(args.workload, world) if not (args.queries or args.k) else
+            dict(shared_config(args.workload, world), queries_per_step=Q, k=k),
+            "note": f"contiguous rows x{world}, one all-gather + merge; results ranked on float64 re-scores of the stored rows",
             "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": Q * D * 2,
                     "d2h_bytes_per_step": Q * k * 12, "ms_per_step": e2e_ms / steps},
             "gpu_launches": gpu_launches,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "torch_gpu_baseline": torch_gpu, "clocks": clocks,
-            "regimes": regimes,
+            "verified": verified, "regimes": regimes,
         }
         _emit(out_fd, line)
-    if dist:
-        dist.destroy_process_group()
+    if ctx.dist:
+        ctx.dist.destroy_process_group()
+    if bad:
+        print(f"[bench] VERIFICATION FAILED: {bad} mismatching checks (see `verified` in the JSON line)", file=sys.stderr)
+        sys.exit(3)
 
 
 if __name__ == "__main__":

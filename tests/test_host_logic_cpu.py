@@ -160,10 +160,14 @@ def test_bench_reference_arm_contract(monkeypatch):
 
     _sys.path.insert(0, root)
     import bench
-    qps, cores, sample, spent = bench.cpu_reference_qps(20_000, 64, 10, budget_s=0.2)
-    assert qps > 0 and cores >= 1 and "scaled linearly" in sample
+    monkeypatch.setattr(bench, "_cpu_sample", lambda N, D, n_rows, n_q: (torch.randn(8, D), torch.randn(2000, D)))
+    qps, cores, sample, per_step, done = bench.cpu_reference_steps(20_000, 64, 4096, 10, steps=3, warmup=1, budget_s=5.0)
+    assert qps > 0 and cores >= 1 and "scaled linearly" in sample and done == 3 and per_step > 0
+    loop = bench.cpu_loop_variant_i(20_000, 64, 10, budget_s=0.2)
+    assert loop["value"] > 0 and loop["kind"] == "port" and "per-query loop" in loop["what"]
 
-    monkeypatch.setattr(bench, "cpu_reference_qps", lambda N, D, k, budget_s=12.0: (12.5, 4, "stub sample", 0.1))
+    monkeypatch.setattr(bench, "cpu_reference_steps",
+                        lambda N, D, Q, k, steps, warmup, budget_s: (12.5, 4, "stub sample", 0.1, steps))
     lines = []
     monkeypatch.setattr(bench, "_emit", lambda fd, line: lines.append(line))
     args = type("A", (), {"workload": bench.DEFAULT_WORKLOAD, "steps": 2, "warmup": 1, "gpus": 1})()
@@ -176,6 +180,32 @@ def test_bench_reference_arm_contract(monkeypatch):
         assert key in line, key
     assert line["impl"] == "reference" and line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["config"]["workload"] == bench.DEFAULT_WORKLOAD and line["vs_baseline"] is None
+    # both arms describe the workload with the SAME config object, and a step of the CPU arm is the bounded sample
+    assert line["config"] == bench.shared_config(bench.DEFAULT_WORKLOAD, 1)
+    assert line["steps"] == 2 and line["ms_per_step"] == pytest.approx(100.0)
+
+
+def test_bench_torch_merge_reference_matches_oracle():
+    """bench.py checks the merge kernel + all-gather layout against an independent torch merge: that merge itself
+    must agree with the oracle's (score desc, index asc, padding last)."""
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    _sys.path.insert(0, root)
+    import bench
+    from oracle import oracle as O
+    g = torch.Generator().manual_seed(3)
+    world, n, k = 4, 50, 7
+    s = torch.randint(0, 6, (world, n, k), generator=g).double() / 4        # many ties
+    i = torch.stack([torch.stack([torch.randperm(100, generator=g)[:k] + 100 * w for _ in range(n)]) for w in range(world)])
+    i[1, :, 5:] = -1                                                          # padding
+    # per-shard lists arrive best first
+    for w in range(world):
+        key = torch.where(i[w] < 0, torch.full_like(s[w], -1e9), s[w])
+        o = torch.argsort(key, dim=1, descending=True, stable=True)
+        s[w], i[w] = torch.gather(s[w], 1, o), torch.gather(i[w], 1, o)
+    ms, mi = bench.torch_merge_reference(s, i, k)
+    es, ei = O.merge_topk_exact(s.permute(1, 0, 2).reshape(n, -1), i.permute(1, 0, 2).reshape(n, -1), k)
+    assert torch.equal(mi, ei) and torch.equal(ms[mi >= 0], es[ei >= 0])
 
 
 def test_raw_maximum_bound_of_the_epilogue_filter_is_conservative():

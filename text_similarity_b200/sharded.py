@@ -133,11 +133,13 @@ class ShardedCorpus:
         return ops.search_topk(queries, self.shard, k, corpus_inv_norm=self.inv_norm,
                                idx_base=self.idx_base, **self._shadow_kw(), **kw)
 
-    def search(self, queries: torch.Tensor, k: int, exclude_self_base: int = -1, mode: str = "auto"
-               ) -> Tuple[torch.Tensor, torch.Tensor]:
-        """Global top-k on every rank: (scores float32 [Q, k], global rows int64 [Q, k])."""
+    def search(self, queries: torch.Tensor, k: int, exclude_self_base: int = -1, mode: str = "auto",
+               return_score64: bool = False):
+        """Global top-k on every rank: (scores float32 [Q, k], global rows int64 [Q, k]) and, with
+        ``return_score64``, the float64 scores the ranking was made on."""
         if self.world == 1:
-            return self.search_local(queries, k, exclude_self_base=exclude_self_base, mode=mode)
+            return self.search_local(queries, k, exclude_self_base=exclude_self_base, mode=mode,
+                                     return_score64=return_score64)
         Q = queries.shape[0]
         key = (Q, k)
         bufs = self._gather_buf.get(key)
@@ -151,8 +153,8 @@ class ShardedCorpus:
                         exclude_self_base=exclude_self_base, mode=mode,
                         out_score64=send[0].view(torch.float64), out_idx=send[1], **self._shadow_kw())
         s64, idx = gather_shard_results(send[0].view(torch.float64), send[1], self.group, bufs)
-        scores, _, rows = ops.merge_topk(s64, idx, k, self.world)
-        return scores, rows
+        scores, m64, rows = ops.merge_topk(s64, idx, k, self.world)
+        return (scores, rows, m64) if return_score64 else (scores, rows)
 
     def search_host(self, host_queries: torch.Tensor, k: int, host_scores: torch.Tensor,
                     host_idx: torch.Tensor, graphed: bool = False) -> None:
@@ -164,3 +166,41 @@ class ShardedCorpus:
             scores, rows = self.search(q, k)
         host_scores.copy_(scores, non_blocking=True)
         host_idx.copy_(rows, non_blocking=True)
+
+
+# ---- all-pairs mining over one embedding matrix (BASELINE config 5; reference: cos_sim over the whole matrix,
+# src/utils/metrics.py:469-507, and the paraphrase-mining consumers) ------------------------------------------
+def all_pairs_corpus_sharded(corpus: ShardedCorpus, all_rows: torch.Tensor, k: int, tile: int = 16_384,
+                             out_scores: Optional[torch.Tensor] = None, out_idx: Optional[torch.Tensor] = None
+                             ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Top-k neighbours of EVERY row (itself excluded) with the corpus side sharded: this rank scans its shard for
+    every query tile of ``all_rows`` (the whole matrix, replicated), one all-gather + merge per tile.  Every rank
+    ends with the full ([N, k] float32 scores, [N, k] int64 rows)."""
+    n = all_rows.shape[0]
+    dev = all_rows.device
+    scores = out_scores if out_scores is not None else torch.empty(n, k, dtype=torch.float32, device=dev)
+    idx = out_idx if out_idx is not None else torch.empty(n, k, dtype=torch.int64, device=dev)
+    for b in range(0, n, tile):
+        e = min(n, b + tile)
+        s, i = corpus.search(all_rows[b:e], k, exclude_self_base=b)
+        scores[b:e].copy_(s)
+        idx[b:e].copy_(i)
+    return scores, idx
+
+
+def all_pairs_query_sharded(full: torch.Tensor, inv_norm: torch.Tensor, k: int, world: int, rank: int,
+                            tile: int = 16_384) -> Tuple[torch.Tensor, torch.Tensor, int]:
+    """The same job with the QUERY side sharded and the corpus replicated ("replicas only", SURVEY.md 8e: a
+    1M x 768 bf16 matrix is 1.5 GB): rank r answers rows [r0, r1) against the whole matrix, no collective at
+    all; the result stays sharded by query.  Returns (scores [r1 - r0, k], rows [r1 - r0, k], r0)."""
+    n = full.shape[0]
+    r0, r1 = shard_bounds(n, world, rank)
+    dev = full.device
+    scores = torch.empty(r1 - r0, k, dtype=torch.float32, device=dev)
+    idx = torch.empty(r1 - r0, k, dtype=torch.int64, device=dev)
+    for b in range(r0, r1, tile):
+        e = min(r1, b + tile)
+        s, i = ops.search_topk(full[b:e], full, k, corpus_inv_norm=inv_norm, exclude_self_base=b)
+        scores[b - r0:e - r0].copy_(s)
+        idx[b - r0:e - r0].copy_(i)
+    return scores, idx, r0
