@@ -189,6 +189,15 @@ int tsim_merge_topk(const double* sc, const int64_t* ix, int64_t Q, int64_t n_li
                     int k_in, int k_out,
                     float* out_score, double* out_score64, int64_t* out_idx, void* stream);
 
+/* The same merge reading its lists in place from any regular layout: entry j of list l of query q sits at
+ * [l * list_stride + q * query_stride + j] (elements) of sc and of ix.  tsim_merge_topk is list_stride = k_in,
+ * query_stride = n_lists * k_in; the receive buffer of the NCCL all-gather of per-shard results -- n_lists
+ * messages of [Q, k] scores followed by [Q, k] rows -- is list_stride = 2 * Q * k, query_stride = k with
+ * ix = sc + Q * k: no re-layout copy between the collective and the merge. */
+int tsim_merge_topk_strided(const double* sc, const int64_t* ix, int64_t Q, int64_t n_lists, int k_in,
+                            int64_t list_stride, int64_t query_stride, int k_out,
+                            float* out_score, double* out_score64, int64_t* out_idx, void* stream);
+
 /* Measurement hook (bench.py / profiling only): when both events are non-NULL, the calling
  * thread's following tsim_search_topk calls record `start` immediately before and `stop`
  * immediately after the candidate-pass kernel (tcgen05 search, or the exact scan when that is

@@ -109,13 +109,38 @@ def test_retry_fp8(ops):
     assert a[3][3].item() == 2
 
 
-def test_no_retry_knob_matches(ops, monkeypatch):
+def test_release_library_ignores_the_no_retry_knob(ops, monkeypatch):
+    """TSIM_NO_RETRY exists only in the -DTSIM_EXPERIMENT flavour: the release library answers the duplicated
+    query with the retry pass whatever the environment says (no silent change of path), and the float64 scan
+    (mode="exact", inside _check) gives the same bits."""
     N, D, k = 200_000, 128, 10
     c = _dup_corpus(N, D, [(0, 30)], 99)
     q = _rows(32, D, 100)
     q[7] = c[0]
     a = _check(ops, q, c, k)
     monkeypatch.setenv("TSIM_NO_RETRY", "1")
+    monkeypatch.setenv("TSIM_DEBUG", "6")      # would skip the MMAs and the epilogue in the experiment build
     b = _check(ops, q, c, k)
-    assert a[3][7].item() == 2 and b[3][7].item() == 1
+    assert a[3][7].item() == 2 and b[3][7].item() == 2
     assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    from text_similarity_b200 import _lib
+    assert _lib.counters()["env_reads"] == 0
+
+
+def test_repeated_planned_search_encodes_no_descriptor(ops):
+    """Plan handles (tsim_plan_create): a repeated search over the same arrays makes no launch plan and encodes no
+    TMA descriptor (SURVEY.md 8b ownership row)."""
+    from text_similarity_b200 import _lib
+    c = _rows(300_000, 128, 5)
+    inv = ops.row_inv_norm(c)
+    q = _rows(256, 128, 6)                      # a multiple of the 256-query pair block: no padded copy
+    out = ops.search_topk(q, c, 10, corpus_inv_norm=inv, mode="tensor")
+    torch.cuda.synchronize()
+    before = _lib.counters()
+    for _ in range(3):
+        again = ops.search_topk(q, c, 10, corpus_inv_norm=inv, mode="tensor")
+    torch.cuda.synchronize()
+    after = _lib.counters()
+    assert torch.equal(out[1], again[1])
+    assert after["plans"] == before["plans"] and after["map_encodes"] == before["map_encodes"]
+    assert after["launches"] > before["launches"]

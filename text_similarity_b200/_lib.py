@@ -51,6 +51,8 @@ SIGNATURES = {
                                        c_int64, c_void_p, POINTER(c_int64), c_void_p, c_void_p]),
     "tsim_set_timing_events": (c_int, [c_void_p, c_void_p]),
     "tsim_launch_count": (ctypes.c_uint64, []),
+    "tsim_merge_topk_strided": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_int,
+                                        c_void_p, c_void_p, c_void_p, c_void_p]),
     "tsim_merge_topk": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p]),
 }

@@ -201,6 +201,11 @@ struct TcArgs {
   uint32_t* ladder;     // [Q][2 * kLadder] threshold ladder (main launch after a bootstrap), or null
   uint64_t* sched;      // round-robin: this launch's claim area (zeroed per call), or null = static dealing:
                         // [0] next-unit counter, then per worker a ring of kSchedRing claim records
+  // append mode (main pass of a bootstrapped plan with KP >= 32): candidates go to a per-query global list
+  uint64_t* app_keys;   // [Q][app_cap] packed keys
+  uint32_t* app_cnt;    // [Q] entries appended so far (may exceed app_cap: the overflow is dropped and the query flagged)
+  int app_cap;
+  int KP;               // list capacity the ladder counts against (the template's KP is 0 in append mode)
   const int32_t* q_count;  // retry pass: device-side number of live queries (<= Q), or null = Q
   const int32_t* q_map;    // retry pass: compact query -> query of the call (self-exclusion), or null
   int q_skip;              // retry pass: live queries = clamp(*q_count - q_skip, 0, Q)
@@ -412,6 +417,7 @@ struct RegList16 {
     if (thr > thr_in) atomicMax(thr_g, f32_to_ord(thr));
     return thr;
   }
+  __device__ __forceinline__ void tile_end() {}
   __device__ __forceinline__ void flush(uint64_t* dst) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) dst[j] = a[j] > -INFINITY ? pack_key(a[j], r[j]) : 0ull;
@@ -480,6 +486,7 @@ struct SmemList {
     if (thr > thr_in) atomicMax(thr_g, f32_to_ord(thr));
     return thr;
   }
+  __device__ __forceinline__ void tile_end() {}
   __device__ __forceinline__ void flush(uint64_t* dst) {
 #pragma unroll 4
     for (int j = 0; j < KP; ++j) {
@@ -489,8 +496,52 @@ struct SmemList {
   }
 };
 
+// Append mode (KP template argument 0): no list at all.  Once every query has a threshold near its final KP-th
+// best (sample passes + ladder), a row that beats it is simply APPENDED to the query's global list: select_rescore
+// sorts the few hundred survivors.  A row is dropped only by `score <= thr`, and thr is always a valid lower bound
+// of the KP-th best candidate that reaches select_rescore (the sample's KP-th best, or a ladder level with >= KP
+// appended rows at or above it), so the completeness proof is unchanged.  Shared memory holds only a staging column
+// of kAppStage keys per thread; it is written out with ONE atomicAdd per thread per tile, after the accumulator has
+// been handed back (or at once when it fills).  No list in shared memory = all pipeline stages back (6 for a pair).
+constexpr int kAppStage = 8;
+__device__ __noinline__ void append_write_out(uint64_t* gkeys, uint32_t* gcnt, int cap, const uint64_t* st, int n) {
+  const uint32_t pos = atomicAdd(gcnt, (uint32_t)n);
+#pragma unroll 1
+  for (int i = 0; i < n; ++i)
+    if (pos + i < (uint32_t)cap) gkeys[pos + i] = st[i * kEpiThreads];
+}
+struct AppendList {
+  uint64_t* st;         // this thread's staging column: st[i * kEpiThreads]
+  int n;
+  uint64_t* gkeys; uint32_t* gcnt; int cap;
+  __device__ __forceinline__ AppendList(float* s, uint32_t*, int*) : st((uint64_t*)s), n(0), gkeys(nullptr), gcnt(nullptr), cap(0) {}
+  __device__ __forceinline__ void bind(uint64_t* keys, uint32_t* cnt, int c) { gkeys = keys; gcnt = cnt; cap = c; }
+  __device__ __forceinline__ void reset() { n = 0; }
+  __device__ __forceinline__ void write_out() {
+    append_write_out(gkeys, gcnt, cap, st, n);
+    n = 0;
+  }
+  __device__ __forceinline__ float slow(const float* sc, float thr, int64_t row_base, int64_t self_row, int lim,
+                                        uint32_t*, Ladder& lad) {
+    uint32_t m = candidate_mask(sc, thr, row_base, self_row, lim);
+#pragma unroll 1
+    while (m) {
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      const float v = select32(sc, j);
+      lad.count(v);
+      st[n * kEpiThreads] = pack_key(v, (uint32_t)(row_base + j));
+      if (++n == kAppStage) write_out();
+    }
+    return thr;
+  }
+  __device__ __forceinline__ void tile_end() { if (n) write_out(); }
+  __device__ __forceinline__ void flush(uint64_t*) {}
+};
+
 template <int KP> struct ListFor { using type = SmemList<KP>; };
 template <> struct ListFor<16> { using type = RegList16; };
+template <> struct ListFor<0> { using type = AppendList; };
 
 template <int KP, int STAGES, bool PAIR, bool FP8>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -505,9 +556,10 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   constexpr int BK = FP8 ? BK_BYTES : BK_BYTES / 2;       // elements per k-block (TMA coordinates are in elements)
   constexpr uint32_t IDESC = FP8 ? Cfg<PAIR>::IDESC_E4M3 : Cfg<PAIR>::IDESC_BF16;
   unsigned char* tiles = smem;
+  constexpr int kListWords = KP ? 2 * KP : 2 * kAppStage;       // 32-bit words per thread: (score, row) lists, or staged keys
   float* list_s = (float*)(smem + (size_t)STAGES * STAGE_BYTES);
   uint32_t* list_i = (uint32_t*)(list_s + KP * kEpiThreads);
-  float* cnorm = (float*)(list_i + KP * kEpiThreads);
+  float* cnorm = list_s + kListWords * kEpiThreads;
   int* list_n = (int*)(cnorm + 2 * 4 * kCnStride);
   uint64_t* bars = (uint64_t*)(list_n + kEpiThreads);
   uint64_t* full_bar = bars;                 // [STAGES]  TMA -> MMA
@@ -623,7 +675,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     // ===================== epilogue: threshold filter + per-query lists =====================
     const int et = threadIdx.x & 127;            // 0..127 = TMEM lane = query within the block
     const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
-    typename ListFor<KP>::type list(list_s + et, list_i + et, list_n + et);
+    // (append mode: the staging column holds 8-byte keys, [entry][thread])
+    typename ListFor<KP>::type list(KP ? list_s + et : (float*)((uint64_t*)list_s + et), list_i + et, list_n + et);
     int acc = 0; uint32_t aphase = 0;
     Unit un;
     for (int it = 0; get_unit(a, it, wid, nw, false, un); ++it) {
@@ -634,6 +687,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       Ladder lad;
       lad.init((a.ladder && qvalid) ? a.ladder + (size_t)qg * (2 * kLadder) : nullptr);
       list.reset();
+      if constexpr (KP == 0) list.bind(a.app_keys + (size_t)(qvalid ? qg : 0) * a.app_cap, a.app_cnt + (qvalid ? qg : 0), a.app_cap);
       float thr = qvalid ? -INFINITY : INFINITY;   // padded query lanes never insert
       // Tile metadata (the 256 inverse norms, 8 per lane, and the query's shared threshold) is
       // fetched one tile ahead so its global-load latency hides behind the previous tile's work.
@@ -717,14 +771,15 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         if (++acc == 2) { acc = 0; aphase ^= 1; }
         // ladder: publish this tile's insertions, pick up everybody else's (after the accumulator
         // stage has been handed back: the MMA of the tile after next does not wait for this)
+        list.tile_end();     // append mode: this tile's staged keys -> the query's global list
         {
           const float t0 = thr;
-          thr = lad.flush(thr, (uint32_t)KP);
+          thr = lad.flush(thr, (uint32_t)(KP ? KP : a.KP));
           if (thr > t0) atomicMax(thr_g, f32_to_ord(thr));
         }
       }
       // flush this unit's list
-      if (qvalid) list.flush(a.cand + ((size_t)qg * a.NC + a.slot_base + un.slot) * KP);
+      if (qvalid && KP) list.flush(a.cand + ((size_t)qg * a.NC + a.slot_base + un.slot) * KP);
     }
   }
 
@@ -774,7 +829,7 @@ int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t D, int64_t 
 
 template <int KP, int STAGES, bool PAIR, bool FP8>
 int launch_cfg(const CUtensorMap& mq, const CUtensorMap& mc, const TcArgs& a, cudaStream_t st) {
-  size_t smem = 1024 + (size_t)STAGES * Cfg<PAIR>::STAGE_BYTES + (size_t)KP * kEpiThreads * 8 + 2 * 4 * kCnStride * 4 +
+  size_t smem = 1024 + (size_t)STAGES * Cfg<PAIR>::STAGE_BYTES + (size_t)(KP ? KP : kAppStage) * kEpiThreads * 8 + 2 * 4 * kCnStride * 4 +
                 kEpiThreads * 4 + (2 * STAGES + 4) * 8 + 16;
   auto kern = search_tc_kernel<KP, STAGES, PAIR, FP8>;
   TSIM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -840,7 +895,8 @@ static int get_map(MapCache* c, CUtensorMap* m, const void* base, int64_t rows, 
 int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_t c_stride, int dt,
                      const float* c_inv, int64_t Q, int64_t N, int64_t D, int self_on, int64_t self_off,
                      const SearchPlan& p, int pass, uint64_t* cand, uint32_t* thr, uint32_t* ladder, uint64_t* sched,
-                     cudaStream_t st, MapCache* maps, const int32_t* q_count, const int32_t* q_map, int q_skip) {
+                     cudaStream_t st, MapCache* maps, const int32_t* q_count, const int32_t* q_map, int q_skip,
+                     uint64_t* app_keys, uint32_t* app_cnt) {
   CUtensorMap mq, mc;
   const int qrows = p.pair ? 2 * BM : BM;
   // q holds QB * qrows rows (the API pads the last query block with zero rows)
@@ -878,6 +934,8 @@ int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_
   a.self_on = self_on; a.self_off = self_off;
   a.cand = cand; a.thr = thr; a.ladder = ladder;
   a.q_count = q_count; a.q_map = q_map; a.q_skip = q_skip;
+  const bool append = pass == TC_PASS_MAIN && p.append;
+  a.app_keys = append ? app_keys : nullptr; a.app_cnt = append ? app_cnt : nullptr; a.app_cap = p.app_cap; a.KP = p.KP;
   // every tcgen05 launch of a call claims from its own zeroed area (mini sample | sample | main)
   const int area = pass == TC_PASS_MINI ? 0 : (pass == TC_PASS_SAMPLE || pass == TC_PASS_SAMPLE_REST) ? 1 : 2;
   // experiment knobs (compiled out of the release library): static round-robin dealing, diagnosis bits, warp roles
@@ -886,6 +944,10 @@ int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_
   a.roles_low = knob_on("TSIM_ROLES_LOW") ? 1 : 0;
   a.hot_scaled = knob_on("TSIM_HOT_SCALED") ? 1 : 0;
 #define TSIM_DISPATCH(FP8)                                                       \
+  if (append) {                                                                  \
+    if (p.pair) return launch_cfg<0, 6, true, FP8>(mq, mc, a, st);               \
+    return launch_cfg<0, 4, false, FP8>(mq, mc, a, st);                          \
+  }                                                                              \
   if (p.pair) {                                                                  \
     switch (p.KP) {                                                              \
       case 16: return launch_cfg<16, 6, true, FP8>(mq, mc, a, st);               \

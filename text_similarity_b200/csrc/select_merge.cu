@@ -209,6 +209,8 @@ struct SelArgs {
   // retry stage (SelRetry, tsim_common.cuh): r_in_list != null -> this launch IS the retry pass
   const int32_t* r_in_cnt; const int32_t* r_in_list; int r_cap; int r_skip; int r_forward;
   void* r_q; int64_t r_q_stride;
+  // append mode: the main pass's survivors, app_keys[q][0 .. min(app_cnt[q], app_cap)) (null: lists only)
+  const uint64_t* app_keys; const uint32_t* app_cnt; int app_cap;
 };
 
 __global__ void __launch_bounds__(kSelThreads) select_rescore_kernel(SelArgs a) {
@@ -232,43 +234,53 @@ __global__ void __launch_bounds__(kSelThreads) select_rescore_kernel(SelArgs a) 
     q = a.r_in_list[a.r_skip + slot];
   }
   const uint32_t thr_ord = a.thr[slot];  // 0: no unit list ever filled -> nothing was dropped
-  const uint64_t* src = a.cand + (size_t)slot * a.NC * a.KP;
-  const int64_t total = a.NC * a.KP;
   if (tid == 0) n_sh = 0;
   __syncthreads();
 
   // ---- gather surviving keys; sort; keep the best KP --------------------------------------
-  int64_t cursor = 0;
+  // two sources: the per-unit lists of the candidate passes, and (append mode) the main pass's global list
+  uint32_t app_n = 0;
+  bool app_overflow = false;
+  if (a.app_keys) {
+    app_n = a.app_cnt[slot];
+    app_overflow = app_n > (uint32_t)a.app_cap;      // rows were dropped unseen: the proof cannot hold
+    if (app_overflow) app_n = (uint32_t)a.app_cap;
+  }
   int n = 0;
-  while (cursor < total) {
-    int64_t take = min((int64_t)(kKeyCap - n), total - cursor);
-    for (int64_t i0 = tid; i0 < take; i0 += (int64_t)blockDim.x * 8) {   // eight independent loads in flight
-      uint64_t key[8];
+  for (int part = 0; part < 2; ++part) {
+    const uint64_t* src = part == 0 ? a.cand + (size_t)slot * a.NC * a.KP : a.app_keys + (size_t)slot * a.app_cap;
+    const int64_t total = part == 0 ? a.NC * a.KP : (int64_t)app_n;
+    int64_t cursor = 0;
+    while (cursor < total) {
+      int64_t take = min((int64_t)(kKeyCap - n), total - cursor);
+      for (int64_t i0 = tid; i0 < take; i0 += (int64_t)blockDim.x * 8) {   // eight independent loads in flight
+        uint64_t key[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int64_t i = i0 + (int64_t)u * blockDim.x;
-        key[u] = i < take ? __ldcg(src + cursor + i) : 0ull;
-      }
+        for (int u = 0; u < 8; ++u) {
+          const int64_t i = i0 + (int64_t)u * blockDim.x;
+          key[u] = i < take ? __ldcg(src + cursor + i) : 0ull;
+        }
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (key[u] != 0 && (uint32_t)(key[u] >> 32) >= thr_ord) keys[atomicAdd(&n_sh, 1)] = key[u];
-    }
-    cursor += take;
-    __syncthreads();
-    n = n_sh;
-    if (cursor < total && n > kKeyCap / 2) {
-      const int kept = keep_top_scores(keys, n, a.KP, sel_out, sel_hist, sel_sh);
-      if (kept == n) {              // massive ties: sort and truncate
-        int np = next_pow2(n);
-        for (int i = n + tid; i < np; i += blockDim.x) keys[i] = 0;
-        __syncthreads();
-        sort_keys_desc(keys, np);
-        n = min(n, a.KP);
-      } else {
-        n = kept;
+        for (int u = 0; u < 8; ++u)
+          if (key[u] != 0 && (uint32_t)(key[u] >> 32) >= thr_ord) keys[atomicAdd(&n_sh, 1)] = key[u];
       }
-      if (tid == 0) n_sh = n;
+      cursor += take;
       __syncthreads();
+      n = n_sh;
+      if ((cursor < total || part == 0) && n > kKeyCap / 2) {
+        const int kept = keep_top_scores(keys, n, a.KP, sel_out, sel_hist, sel_sh);
+        if (kept == n) {              // massive ties: sort and truncate
+          int np = next_pow2(n);
+          for (int i = n + tid; i < np; i += blockDim.x) keys[i] = 0;
+          __syncthreads();
+          sort_keys_desc(keys, np);
+          n = min(n, a.KP);
+        } else {
+          n = kept;
+        }
+        if (tid == 0) n_sh = n;
+        __syncthreads();
+      }
     }
   }
   {
@@ -308,6 +320,7 @@ __global__ void __launch_bounds__(kSelThreads) select_rescore_kernel(SelArgs a) 
     float a_kp = key_score(keys[m - 1]);
     flagged = !((double)a_k - (double)a_kp > 2.0 * (double)a.eps * qn) || (m < a.KP);
   }
+  flagged = flagged || app_overflow;
 
   for (int j = tid; j < m; j += blockDim.x) { ei[j] = (int64_t)key_idx(keys[j]); es[j] = 0.0; }
   __syncthreads();
@@ -493,8 +506,12 @@ __global__ void __launch_bounds__(kSelThreads) merge_exact_lists_kernel(ExMergeA
 // (8 lists of 100: 332 -> ~60 us at Q = 4096 against the 55-stage bitonic sort).  Equal (score, index)
 // pairs in two lists (overlapping shards; not expected) are ordered by list number so ranks stay unique.
 // Anything else (unsorted input) takes the bitonic sort.
+// Input addressing: entry j of list l of query q sits at [l * list_stride + q * query_stride + j] of `sc` / `ix_in`
+// (query-major rows: list_stride = k_in, query_stride = n_lists * k_in; the rank-major receive buffer of an
+// all-gather is read in place with list_stride = one rank's message).
 __global__ void __launch_bounds__(kSelThreads) merge_topk_kernel(const double* sc, const int64_t* ix_in,
                                                                 int64_t total, int k_in, int k_out,
+                                                                int64_t list_stride, int64_t query_stride,
                                                                 float* out_score, double* out_score64,
                                                                 int64_t* out_idx) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -504,8 +521,9 @@ __global__ void __launch_bounds__(kSelThreads) merge_topk_kernel(const double* s
   const int64_t q = blockIdx.x;
   for (int i = threadIdx.x; i < np; i += blockDim.x) {
     bool ok = i < total;
-    s[i] = ok ? sc[q * total + i] : 0.0;
-    ix[i] = ok ? ix_in[q * total + i] : -1;
+    const int64_t at = ok ? (int64_t)(i / k_in) * list_stride + q * query_stride + (i % k_in) : 0;
+    s[i] = ok ? sc[at] : 0.0;
+    ix[i] = ok ? ix_in[at] : -1;
   }
   __syncthreads();
   int unsorted = 0, valid = 0;
@@ -572,7 +590,8 @@ int launch_select_rescore(const void* q, int q_dt, int64_t q_stride, const void*
                           int64_t idx_base, const SearchPlan& p, const uint64_t* cand,
                           const uint32_t* thr, int32_t* flag_cnt, int32_t* flag_list,
                           float* out_score, double* out_score64, int64_t* out_idx,
-                          int32_t* out_flags, cudaStream_t st, const SelRetry* retry) {
+                          int32_t* out_flags, cudaStream_t st, const SelRetry* retry,
+                          const uint64_t* app_keys, const uint32_t* app_cnt) {
   SelArgs a;
   a.q = q; a.q_dt = q_dt; a.q_stride = q_stride;
   a.corpus = corpus; a.c_dt = c_dt; a.c_stride = c_stride;
@@ -583,6 +602,7 @@ int launch_select_rescore(const void* q, int q_dt, int64_t q_stride, const void*
   a.r_in_cnt = retry ? retry->in_cnt : nullptr; a.r_in_list = retry ? retry->in_list : nullptr;
   a.r_cap = retry ? retry->cap : 0; a.r_q = retry ? retry->r_q : nullptr; a.r_q_stride = retry ? retry->r_q_stride : 0;
   a.r_skip = retry ? retry->skip : 0; a.r_forward = retry ? retry->forward : 0;
+  a.app_keys = app_keys; a.app_cnt = app_cnt; a.app_cap = p.app_cap;
   // a retry pass launches one block per compact slot: Q = the slot capacity there
   select_rescore_kernel<<<(unsigned)Q, kSelThreads, 0, st>>>(a);
   TSIM_CUDA(cudaGetLastError());
@@ -618,15 +638,16 @@ int launch_merge_exact_lists(const void* q, int q_dt, int64_t q_stride, const vo
 }
 
 int launch_merge_topk(const double* sc, const int64_t* ix, int64_t Q, int64_t n_lists, int k_in,
-                      int k_out, float* out_score, double* out_score64, int64_t* out_idx,
-                      cudaStream_t st) {
+                      int k_out, int64_t list_stride, int64_t query_stride, float* out_score, double* out_score64,
+                      int64_t* out_idx, cudaStream_t st) {
   int64_t total = n_lists * (int64_t)k_in;
   int np = 1;
   while (np < total) np <<= 1;
   size_t smem = (size_t)np * (sizeof(double) + sizeof(int64_t));
   if (smem > 48 * 1024)
     TSIM_CUDA(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  merge_topk_kernel<<<(unsigned)Q, kSelThreads, smem, st>>>(sc, ix, total, k_in, k_out, out_score, out_score64, out_idx);
+  merge_topk_kernel<<<(unsigned)Q, kSelThreads, smem, st>>>(sc, ix, total, k_in, k_out, list_stride, query_stride,
+                                                            out_score, out_score64, out_idx);
   TSIM_CUDA(cudaGetLastError());
   count_launch();
   return TSIM_OK;

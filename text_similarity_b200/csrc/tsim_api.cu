@@ -147,12 +147,18 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
         p->boot_tpc = best_tpc;
         p->boot_slots = (rest + p->boot_tpc - 1) / p->boot_tpc;
       }
-      p->NC = p->boot_tiles ? p->mini_slots + p->boot_slots + (T - p->boot_tiles + tpc - 1) / tpc : (T + tpc - 1) / tpc;
+      // KP >= 32 with a bootstrap sample: the main pass appends to per-query global lists instead of keeping
+      // KP-entry lists in shared memory (search_tc.cu, AppendList); only the sample passes write list slots
+      p->append = (p->boot_tiles && p->KP >= 32 && !knob_on("TSIM_NO_APPEND")) ? 1 : 0;
+      p->app_cap = 4096;
+      if (p->append) p->NC = p->mini_slots + p->boot_slots;
+      else p->NC = p->boot_tiles ? p->mini_slots + p->boot_slots + (T - p->boot_tiles + tpc - 1) / tpc : (T + tpc - 1) / tpc;
     } else {
       p->R = 256;
       p->NC = p->boot_tiles ? 2 * p->Gq : p->Gq;
     }
     p->off_cand = off; off = align_up(off + (size_t)Q * p->NC * p->KP * sizeof(uint64_t), 256);
+    if (p->append) { p->off_app_keys = off; off = align_up(off + (size_t)Q * p->app_cap * sizeof(uint64_t), 256); }
   }
   // exact scan (whole-call path, or fallback for flagged queries)
   int64_t S = (N + 1023) / 1024;
@@ -180,6 +186,7 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
   p->off_sched = off;
   p->sched_area = (p->use_tensor && !p->sticky) ? 256 + (size_t)sms * 32 * sizeof(uint64_t) : 0;
   off += 3 * p->sched_area;
+  if (p->append) { p->off_app_cnt = off; off = align_up(off + (size_t)Q * sizeof(uint32_t), 256); }   // zeroed with thr
   // retry stage: its thresholds and level-2 flag count sit in the same zeroed span
   p->retry = 0;   // TSIM_NO_RETRY (experiment knob): flagged queries go straight to the float64 scan
   if (p->use_tensor && !shadow && p->KP < kRetryKP && !knob_on("TSIM_NO_RETRY")) {
@@ -313,7 +320,9 @@ static int search_impl(const void* q, int q_dt, int64_t q_stride, const void* co
 
   if (p.use_tensor) {
     // thr, flag_cnt, the unit-claim areas and the retry stage's thr / flag_cnt are adjacent: one memset
-    const size_t zero_end = p.retry ? p.off_r_flagcnt + 256 : p.off_sched + 3 * p.sched_area;
+    const size_t zero_end = p.retry ? p.off_r_flagcnt + 256
+                                    : p.append ? p.off_app_cnt + align_up((size_t)Q * sizeof(uint32_t), 256)
+                                               : p.off_sched + 3 * p.sched_area;
     TSIM_CUDA(cudaMemsetAsync(thr, 0, zero_end - p.off_thr, st));
     uint64_t* sched = p.sched_area ? (uint64_t*)(w + p.off_sched) : nullptr;
     const float* c_inv = corpus_inv_norm;
@@ -355,14 +364,18 @@ static int search_impl(const void* q, int q_dt, int64_t q_stride, const void* co
       if (rc) return rc;
       ladder = lad;
     }
+    uint64_t* app_keys = p.append ? (uint64_t*)(w + p.off_app_keys) : nullptr;
+    uint32_t* app_cnt = p.append ? (uint32_t*)(w + p.off_app_cnt) : nullptr;
     rc = launch_search_tc(qt, qt_stride, tcorpus, tc_stride, t_dt, c_inv, Q, N, D, self_on, self_off, p,
-                          p.boot_tiles ? TC_PASS_MAIN : TC_PASS_ALL, cand, thr, ladder, sched, st, maps);
+                          p.boot_tiles ? TC_PASS_MAIN : TC_PASS_ALL, cand, thr, ladder, sched, st, maps,
+                          nullptr, nullptr, 0, app_keys, app_cnt);
     if (rc) return rc;
     if (timed) TSIM_CUDA(cudaEventRecord(g_ev_stop, st));
     SelRetry first = {nullptr, nullptr, p.retry * kRetryQ, 0, 0, w + p.off_r_q, D};
     rc = launch_select_rescore(q, q_dt, q_stride, corpus, c_dt, c_stride, Q, N, D, k, idx_base, p,
                                (const uint64_t*)(w + p.off_cand), thr, flag_cnt, flag_list,
-                               out_score, out_score64, out_idx, out_flags, st, p.retry ? &first : nullptr);
+                               out_score, out_score64, out_idx, out_flags, st, p.retry ? &first : nullptr,
+                               app_keys, app_cnt);
     if (rc) return rc;
     if (p.retry) {
       // Queries whose KP candidates could not be proven complete (ties straddling ranks k..KP) are re-run
@@ -523,6 +536,19 @@ extern "C" int tsim_merge_topk(const double* sc, const int64_t* ix, int64_t Q, i
                  (long long)(n_lists * (int64_t)k_in));
   if (Q == 0) return TSIM_OK;
   TSIM_CHECK_ARG(sc && ix && out_score && out_idx, "merge_topk: null pointer");
-  return launch_merge_topk(sc, ix, Q, n_lists, k_in, k_out, out_score, out_score64, out_idx,
+  return launch_merge_topk(sc, ix, Q, n_lists, k_in, k_out, k_in, n_lists * (int64_t)k_in, out_score, out_score64,
+                           out_idx, (cudaStream_t)stream);
+}
+
+extern "C" int tsim_merge_topk_strided(const double* sc, const int64_t* ix, int64_t Q, int64_t n_lists, int k_in,
+                                       int64_t list_stride, int64_t query_stride, int k_out, float* out_score,
+                                       double* out_score64, int64_t* out_idx, void* stream) {
+  TSIM_CHECK_ARG(Q >= 0 && n_lists >= 1 && k_in >= 1 && k_out >= 1, "merge_topk_strided: bad shape");
+  TSIM_CHECK_ARG(n_lists * (int64_t)k_in <= 4096, "merge_topk_strided: n_lists * k_in = %lld exceeds 4096",
+                 (long long)(n_lists * (int64_t)k_in));
+  TSIM_CHECK_ARG(list_stride >= 0 && query_stride >= k_in, "merge_topk_strided: bad strides");
+  if (Q == 0) return TSIM_OK;
+  TSIM_CHECK_ARG(sc && ix && out_score && out_idx, "merge_topk_strided: null pointer");
+  return launch_merge_topk(sc, ix, Q, n_lists, k_in, k_out, list_stride, query_stride, out_score, out_score64, out_idx,
                            (cudaStream_t)stream);
 }

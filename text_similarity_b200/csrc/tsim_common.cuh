@@ -241,6 +241,12 @@ struct SearchPlan {
   // thresholds and a ladder from the first.  Cold lists are expensive (every early row is inserted),
   // so only a handful of tiles ever see them.
   int64_t mini_mult, mini_tiles, mini_slots;
+  // Append mode (round-robin plans with a bootstrap sample and KP >= 32): the MAIN pass keeps no lists; rows that
+  // beat the query's threshold are appended to app_keys[q][0 .. app_cap) (count in app_cnt[q], zeroed with thr).
+  // NC then counts the sample passes' list slots only.
+  int append;
+  int app_cap;
+  size_t off_app_keys, off_app_cnt;
   int64_t R;           // round-robin: corpus rows per unit (multiple of 256)
   int64_t NC;          // candidate lists per query: chunks ceil(N / R), or Gq when sticky
   // exact path
@@ -297,7 +303,8 @@ int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_
                      const float* c_inv, int64_t Q, int64_t N, int64_t D,
                      int self_on, int64_t self_off, const SearchPlan& p, int pass, uint64_t* cand,
                      uint32_t* thr, uint32_t* ladder, uint64_t* sched, cudaStream_t st, MapCache* maps = nullptr,
-                     const int32_t* q_count = nullptr, const int32_t* q_map = nullptr, int q_skip = 0);
+                     const int32_t* q_count = nullptr, const int32_t* q_map = nullptr, int q_skip = 0,
+                     uint64_t* app_keys = nullptr, uint32_t* app_cnt = nullptr);
 int launch_tighten(int64_t Q, const SearchPlan& p, int nslots, const uint64_t* cand, uint32_t* thr,
                    uint32_t* ladder, cudaStream_t st);
 int launch_select_rescore(const void* q, int q_dt, int64_t q_stride, const void* corpus, int c_dt,
@@ -305,7 +312,8 @@ int launch_select_rescore(const void* q, int q_dt, int64_t q_stride, const void*
                           int64_t idx_base, const SearchPlan& p, const uint64_t* cand,
                           const uint32_t* thr, int32_t* flag_cnt, int32_t* flag_list,
                           float* out_score, double* out_score64, int64_t* out_idx,
-                          int32_t* out_flags, cudaStream_t st, const SelRetry* retry = nullptr);
+                          int32_t* out_flags, cudaStream_t st, const SelRetry* retry = nullptr,
+                          const uint64_t* app_keys = nullptr, const uint32_t* app_cnt = nullptr);
 int launch_search_exact(const void* q, int q_dt, int64_t q_stride, const void* corpus, int c_dt,
                         int64_t c_stride, int64_t Q, int64_t N, int64_t D, int k,
                         int self_on, int64_t self_off, const SearchPlan& p, const int32_t* flag_cnt,
@@ -318,8 +326,8 @@ int launch_merge_exact_lists(const void* q, int q_dt, int64_t q_stride, const vo
                              const uint32_t* ex_idx, float* out_score, double* out_score64,
                              int64_t* out_idx, int32_t* out_flags, cudaStream_t st);
 int launch_merge_topk(const double* sc, const int64_t* ix, int64_t Q, int64_t n_lists, int k_in,
-                      int k_out, float* out_score, double* out_score64, int64_t* out_idx,
-                      cudaStream_t st);
+                      int k_out, int64_t list_stride, int64_t query_stride, float* out_score, double* out_score64,
+                      int64_t* out_idx, cudaStream_t st);
 int launch_row_inv_norm(const void* x, int dt, int64_t N, int64_t D, int64_t stride, float* out,
                         cudaStream_t st);
 

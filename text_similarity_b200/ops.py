@@ -288,3 +288,23 @@ def merge_topk(scores64: torch.Tensor, idx: torch.Tensor, k_out: int, n_lists: i
                                  _stream(dev))
     _lib.check(rc, "tsim_merge_topk")
     return out_s, out_s64, out_i
+
+
+def merge_gathered(recv: torch.Tensor, Q: int, k: int, world: int
+                   ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """K3 second pass straight on the receive buffer of the all-gather of per-shard results: ``recv`` is int64
+    [world * 2, Q, k] -- per rank a [Q, k] block of float64 score bits followed by a [Q, k] block of global rows --
+    read in place (tsim_merge_topk_strided), no permute / reshape copy.  Returns (scores float32, scores float64,
+    rows int64), each [Q, k]."""
+    lib = _lib.load()
+    dev = _require_cuda(recv)
+    if recv.dtype != torch.int64 or not recv.is_contiguous() or recv.numel() != world * 2 * Q * k:
+        raise ValueError(f"recv must be a contiguous int64 tensor of {world * 2 * Q * k} elements")
+    out_s = torch.empty(Q, k, dtype=torch.float32, device=dev)
+    out_s64 = torch.empty(Q, k, dtype=torch.float64, device=dev)
+    out_i = torch.empty(Q, k, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.tsim_merge_topk_strided(recv.data_ptr(), recv.data_ptr() + Q * k * 8, Q, world, k, 2 * Q * k, k, k,
+                                         out_s.data_ptr(), out_s64.data_ptr(), out_i.data_ptr(), _stream(dev))
+    _lib.check(rc, "tsim_merge_topk_strided")
+    return out_s, out_s64, out_i

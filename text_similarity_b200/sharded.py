@@ -26,7 +26,9 @@ def gather_shard_results(score64: torch.Tensor, idx: torch.Tensor, group, bufs=N
                          ) -> Tuple[torch.Tensor, torch.Tensor]:
     """The ONE collective of the search: all-gather every rank's [Q, k] (float64 score, int64 global
     row) lists and lay them out as [Q, world * k] merge input (rank-major inside a query row).
-    Works on any backend (NCCL over NVLink in production, gloo in the CPU tests)."""
+    Works on any backend (NCCL over NVLink in production, gloo in the CPU tests).  The GPU path
+    (ShardedCorpus.search) does the same all-gather but merges the receive buffer in place
+    (ops.merge_gathered), without this function's permute + reshape copy."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
     Q, k = idx.shape
@@ -87,8 +89,10 @@ class ShardedCorpus:
             return g
         dev = self.shard.device
         q_static = torch.zeros(Q, self.shard.shape[1], dtype=dtype, device=dev)
-        s64 = torch.empty(Q, k, dtype=torch.float64, device=dev)
-        idx = torch.empty(Q, k, dtype=torch.int64, device=dev)
+        # float64 scores and global rows land in the all-gather send buffer (one message: scores, then rows)
+        send = torch.empty(2, Q, k, dtype=torch.int64, device=dev)
+        recv = torch.empty(self.world * 2, Q, k, dtype=torch.int64, device=dev) if self.world > 1 else None
+        s64, idx = send[0].view(torch.float64), send[1]
         scores = torch.empty(Q, k, dtype=torch.float32, device=dev)
         # The graph replays raw pointers: it owns its workspace (kept alive in self._graphs next to the graph),
         # never the growable per-stream cache of ops, whose buffers are replaced -- and freed -- when a later
@@ -112,7 +116,7 @@ class ShardedCorpus:
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=side):
             run()
-        g = self._graphs[key] = (graph, q_static, scores, s64, idx, ws)
+        g = self._graphs[key] = (graph, q_static, scores, send, recv, ws)
         return g
 
     def search_graphed(self, queries: torch.Tensor, k: int, exclude_self_base: int = -1, mode: str = "auto"
@@ -120,13 +124,15 @@ class ShardedCorpus:
         """`search` with the local search replayed from a CUDA graph captured on first use of this
         (batch size, k, dtype).  The returned tensors are the graph's static outputs: consume them
         before the next call with the same shape (or clone)."""
-        graph, q_static, scores, s64, idx, _ws = self._graph(queries.shape[0], k, queries.dtype, exclude_self_base, mode)
+        Q = queries.shape[0]
+        graph, q_static, scores, send, recv, _ws = self._graph(Q, k, queries.dtype, exclude_self_base, mode)
         q_static.copy_(queries, non_blocking=True)
         graph.replay()
         if self.world == 1:
-            return scores, idx
-        g64, gidx = gather_shard_results(s64, idx, self.group)
-        merged, _, rows = ops.merge_topk(g64, gidx, k, self.world)
+            return scores, send[1]
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(recv, send, group=self.group)
+        merged, _, rows = ops.merge_gathered(recv, Q, k, self.world)    # reads the rank-major buffer in place
         return merged, rows
 
     def search_local(self, queries: torch.Tensor, k: int, **kw):
@@ -152,8 +158,9 @@ class ShardedCorpus:
         ops.search_topk(queries, self.shard, k, corpus_inv_norm=self.inv_norm, idx_base=self.idx_base,
                         exclude_self_base=exclude_self_base, mode=mode,
                         out_score64=send[0].view(torch.float64), out_idx=send[1], **self._shadow_kw())
-        s64, idx = gather_shard_results(send[0].view(torch.float64), send[1], self.group, bufs)
-        scores, m64, rows = ops.merge_topk(s64, idx, k, self.world)
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(recv, send, group=self.group)        # THE collective of the search
+        scores, m64, rows = ops.merge_gathered(recv, Q, k, self.world)   # K3 reads the rank-major buffer in place
         return (scores, rows, m64) if return_score64 else (scores, rows)
 
     def search_host(self, host_queries: torch.Tensor, k: int, host_scores: torch.Tensor,
