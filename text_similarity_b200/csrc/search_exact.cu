@@ -69,6 +69,8 @@ __global__ void __launch_bounds__(kExThreads) search_exact_kernel(ExArgs a) {
   uint32_t* li_all = (uint32_t*)(ls_all + 8 * a.k);   // [8][k]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_trigger();
+  pdl_wait();
   const int64_t nq = a.flag_cnt ? (int64_t)*a.flag_cnt : a.Q;
   const int64_t ngroups = (nq + 7) / 8;
   const int slice = blockIdx.x;
@@ -233,6 +235,8 @@ __device__ __forceinline__ void fetch_rows_at_dt(float (&pre)[NR], int dt, const
 // (flag_cnt given) leaves at once when no query is flagged
 __global__ void __launch_bounds__(256) row_rinv_f64_kernel(const void* corpus, int c_dt, int64_t c_stride, int64_t N,
                                                            int64_t D, const int32_t* flag_cnt, double* rinv) {
+  pdl_trigger();
+  pdl_wait();
   if (flag_cnt && *flag_cnt == 0) return;
   const int lane = threadIdx.x & 31;
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -264,6 +268,8 @@ __global__ void __launch_bounds__(kExThreads, MINB) search_exact_mma_kernel(ExAr
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int fr = lane >> 2, fk = lane & 3;              // fragment row / k index of this lane
+  pdl_trigger();
+  pdl_wait();
   // whole-call scan: slot = query.  Fallback launch: slot b = the b-th flagged query, count read on the device
   const int64_t nq = a.flag_cnt ? (int64_t)*a.flag_cnt : a.Q;
   const int64_t ngroups = (nq + QG - 1) / QG;
@@ -431,14 +437,13 @@ int launch_search_exact(const void* q, int q_dt, int64_t q_stride, const void* c
     if (flag_cnt && mgroups > 8) mgroups = 8;
     if (msmem <= 227 * 1024 && (int64_t)p.S * mgroups >= 64) {
       const int64_t nb = (N + 7) / 8;
-      row_rinv_f64_kernel<<<(unsigned)(nb < 8 * 148 ? nb : 8 * 148), 256, 0, st>>>(corpus, c_dt, c_stride, N, D, flag_cnt, ex_rinv);
-      TSIM_CUDA(cudaGetLastError());
+      TSIM_CUDA(launch_pdl(row_rinv_f64_kernel, dim3((unsigned)(nb < 8 * 148 ? nb : 8 * 148)), dim3(256), 0, st, corpus, c_dt,
+                           c_stride, N, D, flag_cnt, ex_rinv));
       count_launch();
       dim3 mgrid((unsigned)p.S, (unsigned)(mgroups < 4096 ? mgroups : 4096));
       auto kern = MF == 2 ? search_exact_mma_kernel<2, 1> : minb == 2 ? search_exact_mma_kernel<1, 2> : search_exact_mma_kernel<1, 1>;
       TSIM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-      kern<<<mgrid, kExThreads, msmem, st>>>(a);
-      TSIM_CUDA(cudaGetLastError());
+      TSIM_CUDA(launch_pdl(kern, mgrid, dim3(kExThreads), msmem, st, a));
       count_launch();
       return TSIM_OK;
     }
@@ -451,8 +456,7 @@ int launch_search_exact(const void* q, int q_dt, int64_t q_stride, const void* c
   // CTAs stride over however many groups there turn out to be (usually none -> they exit)
   int gy = (int)(flag_cnt ? (groups < 8 ? groups : 8) : (groups < 4096 ? groups : 4096));
   dim3 grid((unsigned)p.S, (unsigned)gy);
-  search_exact_kernel<<<grid, kExThreads, smem, st>>>(a);
-  TSIM_CUDA(cudaGetLastError());
+  TSIM_CUDA(launch_pdl(search_exact_kernel, grid, dim3(kExThreads), smem, st, a));
   count_launch();
   return TSIM_OK;
 }

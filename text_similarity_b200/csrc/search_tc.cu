@@ -496,20 +496,24 @@ struct SmemList {
   }
 };
 
-// Append mode (KP template argument 0): no list at all.  Once every query has a threshold near its final KP-th
+// Append mode (negative KP template argument = staging entries per thread): no list at all.  Once every query has a threshold near its final KP-th
 // best (sample passes + ladder), a row that beats it is simply APPENDED to the query's global list: select_rescore
 // sorts the few hundred survivors.  A row is dropped only by `score <= thr`, and thr is always a valid lower bound
 // of the KP-th best candidate that reaches select_rescore (the sample's KP-th best, or a ladder level with >= KP
 // appended rows at or above it), so the completeness proof is unchanged.  Shared memory holds only a staging column
-// of kAppStage keys per thread; it is written out with ONE atomicAdd per thread per tile, after the accumulator has
+// of a few keys per thread; it is written out with ONE atomicAdd per thread per tile, after the accumulator has
 // been handed back (or at once when it fills).  No list in shared memory = all pipeline stages back (6 for a pair).
-constexpr int kAppStage = 8;
+// Staging entries per thread: 8 for the main pass (~0.2 candidates per query per tile), 40 for the sample passes,
+// whose thresholds are still loose (tens of candidates per query per tile: one flush per tile instead of one
+// atomic round trip per 8 rows).  Encoded as a NEGATIVE KP template argument of the kernel.
+constexpr int kAppStageMain = 8, kAppStageSample = 40;
 __device__ __noinline__ void append_write_out(uint64_t* gkeys, uint32_t* gcnt, int cap, const uint64_t* st, int n) {
   const uint32_t pos = atomicAdd(gcnt, (uint32_t)n);
 #pragma unroll 1
   for (int i = 0; i < n; ++i)
     if (pos + i < (uint32_t)cap) gkeys[pos + i] = st[i * kEpiThreads];
 }
+template <int STAGE>
 struct AppendList {
   uint64_t* st;         // this thread's staging column: st[i * kEpiThreads]
   int n;
@@ -531,7 +535,7 @@ struct AppendList {
       const float v = select32(sc, j);
       lad.count(v);
       st[n * kEpiThreads] = pack_key(v, (uint32_t)(row_base + j));
-      if (++n == kAppStage) write_out();
+      if (++n == STAGE) write_out();
     }
     return thr;
   }
@@ -541,7 +545,8 @@ struct AppendList {
 
 template <int KP> struct ListFor { using type = SmemList<KP>; };
 template <> struct ListFor<16> { using type = RegList16; };
-template <> struct ListFor<0> { using type = AppendList; };
+template <> struct ListFor<-kAppStageMain> { using type = AppendList<kAppStageMain>; };
+template <> struct ListFor<-kAppStageSample> { using type = AppendList<kAppStageSample>; };
 
 template <int KP, int STAGES, bool PAIR, bool FP8>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -556,9 +561,9 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   constexpr int BK = FP8 ? BK_BYTES : BK_BYTES / 2;       // elements per k-block (TMA coordinates are in elements)
   constexpr uint32_t IDESC = FP8 ? Cfg<PAIR>::IDESC_E4M3 : Cfg<PAIR>::IDESC_BF16;
   unsigned char* tiles = smem;
-  constexpr int kListWords = KP ? 2 * KP : 2 * kAppStage;       // 32-bit words per thread: (score, row) lists, or staged keys
+  constexpr int kListWords = KP > 0 ? 2 * KP : -2 * KP;       // 32-bit words per thread: (score, row) lists, or staged keys
   float* list_s = (float*)(smem + (size_t)STAGES * STAGE_BYTES);
-  uint32_t* list_i = (uint32_t*)(list_s + KP * kEpiThreads);
+  uint32_t* list_i = (uint32_t*)(list_s + (KP > 0 ? KP : 0) * kEpiThreads);
   float* cnorm = list_s + kListWords * kEpiThreads;
   int* list_n = (int*)(cnorm + 2 * 4 * kCnStride);
   uint64_t* bars = (uint64_t*)(list_n + kEpiThreads);
@@ -570,7 +575,9 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
   // retry pass: the number of live queries is only known on the device; usually none -> leave at once
   int64_t q_live = a.Q;
+  pdl_trigger();
   if (a.q_count) {
+    pdl_wait();          // the flagged count is the previous kernel's output
     const int64_t c = (int64_t)*a.q_count - a.q_skip;
     q_live = c < a.Q ? c : a.Q;
     if (q_live <= 0) return;
@@ -608,6 +615,9 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   if (PAIR) cluster_sync_all(); else __syncthreads();   // barrier inits visible to the peer before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail; from here on
+  // its outputs (thresholds, ladder, padded queries, claim areas) are read
+  pdl_wait();
 
   if (warp == kWarpTma) {
     // ===================== TMA producer =====================
@@ -676,7 +686,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const int et = threadIdx.x & 127;            // 0..127 = TMEM lane = query within the block
     const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
     // (append mode: the staging column holds 8-byte keys, [entry][thread])
-    typename ListFor<KP>::type list(KP ? list_s + et : (float*)((uint64_t*)list_s + et), list_i + et, list_n + et);
+    typename ListFor<KP>::type list(KP > 0 ? list_s + et : (float*)((uint64_t*)list_s + et), list_i + et, list_n + et);
     int acc = 0; uint32_t aphase = 0;
     Unit un;
     for (int it = 0; get_unit(a, it, wid, nw, false, un); ++it) {
@@ -687,7 +697,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       Ladder lad;
       lad.init((a.ladder && qvalid) ? a.ladder + (size_t)qg * (2 * kLadder) : nullptr);
       list.reset();
-      if constexpr (KP == 0) list.bind(a.app_keys + (size_t)(qvalid ? qg : 0) * a.app_cap, a.app_cnt + (qvalid ? qg : 0), a.app_cap);
+      if constexpr (KP < 0) list.bind(a.app_keys + (size_t)(qvalid ? qg : 0) * a.app_cap, a.app_cnt + (qvalid ? qg : 0), a.app_cap);
       float thr = qvalid ? -INFINITY : INFINITY;   // padded query lanes never insert
       // Tile metadata (the 256 inverse norms, 8 per lane, and the query's shared threshold) is
       // fetched one tile ahead so its global-load latency hides behind the previous tile's work.
@@ -774,12 +784,12 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         list.tile_end();     // append mode: this tile's staged keys -> the query's global list
         {
           const float t0 = thr;
-          thr = lad.flush(thr, (uint32_t)(KP ? KP : a.KP));
+          thr = lad.flush(thr, (uint32_t)(KP > 0 ? KP : a.KP));
           if (thr > t0) atomicMax(thr_g, f32_to_ord(thr));
         }
       }
       // flush this unit's list
-      if (qvalid && KP) list.flush(a.cand + ((size_t)qg * a.NC + a.slot_base + un.slot) * KP);
+      if (qvalid && KP > 0) list.flush(a.cand + ((size_t)qg * a.NC + a.slot_base + un.slot) * KP);
     }
   }
 
@@ -829,7 +839,7 @@ int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t D, int64_t 
 
 template <int KP, int STAGES, bool PAIR, bool FP8>
 int launch_cfg(const CUtensorMap& mq, const CUtensorMap& mc, const TcArgs& a, cudaStream_t st) {
-  size_t smem = 1024 + (size_t)STAGES * Cfg<PAIR>::STAGE_BYTES + (size_t)(KP ? KP : kAppStage) * kEpiThreads * 8 + 2 * 4 * kCnStride * 4 +
+  size_t smem = 1024 + (size_t)STAGES * Cfg<PAIR>::STAGE_BYTES + (size_t)(KP > 0 ? KP : -KP) * kEpiThreads * 8 + 2 * 4 * kCnStride * 4 +
                 kEpiThreads * 4 + (2 * STAGES + 4) * 8 + 16;
   auto kern = search_tc_kernel<KP, STAGES, PAIR, FP8>;
   TSIM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -841,13 +851,15 @@ int launch_cfg(const CUtensorMap& mq, const CUtensorMap& mc, const TcArgs& a, cu
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = PAIR ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see pdl_wait() in the kernel
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = knob_on("TSIM_NO_PDL") ? 1 : 2;
   TSIM_CUDA(cudaLaunchKernelEx(&cfg, kern, mq, mc, a));
   count_launch();
   return TSIM_OK;
@@ -934,7 +946,7 @@ int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_
   a.self_on = self_on; a.self_off = self_off;
   a.cand = cand; a.thr = thr; a.ladder = ladder;
   a.q_count = q_count; a.q_map = q_map; a.q_skip = q_skip;
-  const bool append = pass == TC_PASS_MAIN && p.append;
+  const bool append = p.append != 0;   // every pass of an append plan (mini sample, sample, main) appends
   a.app_keys = append ? app_keys : nullptr; a.app_cnt = append ? app_cnt : nullptr; a.app_cap = p.app_cap; a.KP = p.KP;
   // every tcgen05 launch of a call claims from its own zeroed area (mini sample | sample | main)
   const int area = pass == TC_PASS_MINI ? 0 : (pass == TC_PASS_SAMPLE || pass == TC_PASS_SAMPLE_REST) ? 1 : 2;
@@ -945,8 +957,12 @@ int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_
   a.hot_scaled = knob_on("TSIM_HOT_SCALED") ? 1 : 0;
 #define TSIM_DISPATCH(FP8)                                                       \
   if (append) {                                                                  \
-    if (p.pair) return launch_cfg<0, 6, true, FP8>(mq, mc, a, st);               \
-    return launch_cfg<0, 4, false, FP8>(mq, mc, a, st);                          \
+    if (pass != TC_PASS_MAIN) {   /* sample passes: loose thresholds, deep staging */  \
+      if (p.pair) return launch_cfg<-kAppStageSample, 4, true, FP8>(mq, mc, a, st);      \
+      return launch_cfg<-kAppStageSample, 3, false, FP8>(mq, mc, a, st);                 \
+    }                                                                            \
+    if (p.pair) return launch_cfg<-kAppStageMain, 6, true, FP8>(mq, mc, a, st);          \
+    return launch_cfg<-kAppStageMain, 4, false, FP8>(mq, mc, a, st);                     \
   }                                                                              \
   if (p.pair) {                                                                  \
     switch (p.KP) {                                                              \

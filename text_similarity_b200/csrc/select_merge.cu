@@ -25,8 +25,27 @@ __device__ __forceinline__ int next_pow2(int n) {
   return p;
 }
 
+// Small inputs (n <= blockDim.x) are sorted by RANK: every thread counts the elements that precede its own (n reads
+// of shared memory, broadcast) and drops it at that position -- two barriers instead of the log^2(n) barrier
+// stages of the bitonic network (28 for n = 128; the two sorts were ~20 % of select_rescore's samples at k = 100).
 // block-wide bitonic sort, DESCENDING, n a power of two, keys in shared memory
 __device__ void sort_keys_desc(uint64_t* a, int n) {
+  if (n <= (int)blockDim.x) {
+    const int t = threadIdx.x;
+    uint64_t mine = 0;
+    int rank = 0;
+    if (t < n) {
+      mine = a[t];
+      for (int j = 0; j < n; ++j) {
+        const uint64_t o = a[j];
+        rank += (o > mine || (o == mine && j < t)) ? 1 : 0;    // equal keys (empty slots) keep their order
+      }
+    }
+    __syncthreads();
+    if (t < n) a[rank] = mine;
+    __syncthreads();
+    return;
+  }
   for (int k = 2; k <= n; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
       for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -117,6 +136,25 @@ __device__ __forceinline__ bool pair_before(double s1, int64_t i1, double s2, in
 }
 
 __device__ void sort_pairs(double* s, int64_t* ix, int n) {
+  if (n <= (int)blockDim.x) {       // rank sort, see sort_keys_desc
+    const int t = threadIdx.x;
+    double ms = 0.0;
+    int64_t mi = -1;
+    int rank = 0;
+    if (t < n) {
+      ms = s[t]; mi = ix[t];
+      for (int j = 0; j < n; ++j) {
+        const double os = s[j];
+        const int64_t oi = ix[j];
+        const bool same = (oi < 0 && mi < 0) || (oi == mi && os == ms);   // padding, or the same pair twice
+        rank += (same ? j < t : pair_before(os, oi, ms, mi)) ? 1 : 0;
+      }
+    }
+    __syncthreads();
+    if (t < n) { s[rank] = ms; ix[rank] = mi; }
+    __syncthreads();
+    return;
+  }
   for (int k = 2; k <= n; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
       for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -174,16 +212,54 @@ __device__ int stream_top_pairs(double* s, int64_t* ix, int* n_sh, int64_t total
 
 // Re-evaluate rows ix[0..m) against query row q with the canonical float64 routine, sort by
 // (score desc, row asc) and write the best k.  ix holds LOCAL corpus rows.
+// `stage` (null: read the rows in place): kRescoreDepth row slots of `stage_row_bytes` per warp, in shared memory.
+// The candidate rows are scattered over the shard (DRAM, not L2), and a warp that reads one row at a time spends
+// a DRAM round trip per row (ncu: 55 % of select_rescore's samples sat on the first use of the loaded row).  With
+// slots, every warp keeps kRescoreDepth rows in flight as cp.async copies and evaluates from shared memory: the
+// gather runs at DRAM bandwidth instead of DRAM latency.  Same routine, same bits either way.
+constexpr int kRescoreDepth = 3;
 __device__ void rescore_and_emit(double* s, int64_t* ix, int m, const void* qrow, int q_dt,
                                  const void* corpus, int c_dt, int64_t c_stride, int64_t D, int k,
                                  int64_t idx_base, float* out_score, double* out_score64,
-                                 int64_t* out_idx) {
+                                 int64_t* out_idx, unsigned char* stage = nullptr, int stage_row_bytes = 0,
+                                 double* qd = nullptr) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int csz = dtype_size(c_dt);
-  for (int j = warp; j < m; j += nw) {
-    const char* crow = (const char*)corpus + (size_t)ix[j] * c_stride * csz;
-    double v = warp_exact_cosine(qrow, q_dt, crow, c_dt, D);
-    if (lane == 0) s[j] = v;
+  const int64_t rowb = D * csz;
+  // qd (shared memory, D doubles, or null): float64 copy of the query row, widened once for all candidate rows
+  if (qd) {
+    for (int64_t e = threadIdx.x; e < qd_len(D); e += blockDim.x) qd[qd_slot(e)] = e < D ? query_elem_f64(qrow, q_dt, e) : 0.0;
+    __syncthreads();
+  }
+  const double qn = warp_query_norm(qrow, q_dt, D);
+  if (stage) {
+    unsigned char* mine = stage + (size_t)warp * kRescoreDepth * stage_row_bytes;
+    const int rounds = m > warp ? (m - warp + nw - 1) / nw : 0;
+    auto issue = [&](int i) {     // row of round i -> slot i % depth (an empty group past the end keeps the counts aligned)
+      if (i < rounds) {
+        const char* r = (const char*)corpus + (size_t)ix[warp + i * nw] * c_stride * csz;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(mine + (size_t)(i % kRescoreDepth) * stage_row_bytes);
+        for (int o = lane * 16; o < rowb; o += 32 * 16)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + o), "l"(r + o) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    for (int i = 0; i < kRescoreDepth; ++i) issue(i);
+    for (int i = 0; i < rounds; ++i) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(kRescoreDepth - 1) : "memory");
+      __syncwarp();
+      const double v = warp_exact_cosine(qrow, q_dt, qd, qn, mine + (size_t)(i % kRescoreDepth) * stage_row_bytes, c_dt, D);
+      if (lane == 0) s[warp + i * nw] = v == v ? v : -INFINITY;   // (NaN would break the sort's total order)
+      __syncwarp();           // every lane is done with the slot before it is refilled
+      issue(i + kRescoreDepth);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else {
+    for (int j = warp; j < m; j += nw) {
+      const char* crow = (const char*)corpus + (size_t)ix[j] * c_stride * csz;
+      double v = warp_exact_cosine(qrow, q_dt, qd, qn, crow, c_dt, D);
+      if (lane == 0) s[j] = v == v ? v : -INFINITY;
+    }
   }
   int np = next_pow2(max(m, 1));
   __syncthreads();
@@ -211,11 +287,16 @@ struct SelArgs {
   void* r_q; int64_t r_q_stride;
   // append mode: the main pass's survivors, app_keys[q][0 .. min(app_cnt[q], app_cap)) (null: lists only)
   const uint64_t* app_keys; const uint32_t* app_cnt; int app_cap;
+  int stage_row_bytes;   // > 0: re-score through shared-memory row slots of this many bytes (rescore_and_emit)
+  int qd_offset;         // ... and keep a float64 copy of the query row at this byte offset of the dynamic window
 };
 
-__global__ void __launch_bounds__(kSelThreads) select_rescore_kernel(SelArgs a) {
-  __shared__ uint64_t keys[kKeyCap];
-  __shared__ uint64_t sel_out[kSelOut];
+__global__ void __launch_bounds__(kSelThreads, 4) select_rescore_kernel(SelArgs a) {
+  // dynamic shared memory: [keys kKeyCap | sel_out kSelOut] while the candidates are selected, then (the keys are
+  // dead by then) the row slots of the re-score, a.stage_row_bytes each (0: rows are read in place)
+  extern __shared__ __align__(16) unsigned char sel_dyn[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(sel_dyn);
+  uint64_t* sel_out = keys + kKeyCap;
   __shared__ uint32_t sel_hist[256];
   __shared__ int sel_sh[4];
   __shared__ double es[128];
@@ -223,6 +304,8 @@ __global__ void __launch_bounds__(kSelThreads) select_rescore_kernel(SelArgs a) 
   __shared__ int n_sh;
   __shared__ double red[kSelThreads / 32];
   const int tid = threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
   const int64_t slot = blockIdx.x;   // position of this query's lists and threshold in the workspace
   int64_t q = slot;                  // query of the call
   if (a.r_in_list) {
@@ -323,10 +406,11 @@ __global__ void __launch_bounds__(kSelThreads) select_rescore_kernel(SelArgs a) 
   flagged = flagged || app_overflow;
 
   for (int j = tid; j < m; j += blockDim.x) { ei[j] = (int64_t)key_idx(keys[j]); es[j] = 0.0; }
-  __syncthreads();
+  __syncthreads();          // keys / sel_out are dead from here on: their memory becomes the row slots
   rescore_and_emit(es, ei, m, qrow, a.q_dt, a.corpus, a.c_dt, a.c_stride, a.D, a.k, a.idx_base,
                    a.out_score + q * a.k, a.out_score64 ? a.out_score64 + q * a.k : nullptr,
-                   a.out_idx + q * a.k);
+                   a.out_idx + q * a.k, a.stage_row_bytes ? sel_dyn : nullptr, a.stage_row_bytes,
+                   a.stage_row_bytes ? reinterpret_cast<double*>(sel_dyn + a.qd_offset) : nullptr);
   // out_flags: 0 answered by the first tensor pass, 2 by the wide retry pass, 1 by the float64 scan
   // (a flagged query keeps / gets 1 here; whichever later stage answers it overwrites that)
   if (tid == 0) {
@@ -355,6 +439,8 @@ __global__ void __launch_bounds__(kSelThreads) tighten_kernel(const uint64_t* ca
   __shared__ uint32_t sel_hist[256];
   __shared__ int sel_sh[4];
   __shared__ int n_sh;
+  pdl_trigger();
+  pdl_wait();
   const int64_t q = blockIdx.x;
   const int tid = threadIdx.x;
   const uint64_t* src = cand + (size_t)q * NC * KP;
@@ -463,6 +549,113 @@ __global__ void __launch_bounds__(kSelThreads) tighten_kernel(const uint64_t* ca
   }
 }
 
+// The same job on an append plan's global lists, one WARP per query (eight queries per block, no block barrier):
+// a warp-private MSB-first radix select (4 passes x 8 bits over the upper 32 key bits, 256-bin histogram in shared
+// memory) finds the KP-th best approximate score among the min(app_cnt, cap) keys appended so far -- a lower bound
+// of the query's final KP-th best, since every appended row reaches select_rescore -- raises thr[q] to it and lays
+// out the threshold ladder exactly as tighten_kernel does (counts = the appended rows at or above each level).
+// Q = 4096, ~1000 keys per query: ~10 us against 77 us for the block-per-query kernel above.
+__global__ void __launch_bounds__(kSelThreads) tighten_app_kernel(const uint64_t* app_keys, const uint32_t* app_cnt,
+                                                                  int cap, int64_t Q, int KP, uint32_t* thr,
+                                                                  uint32_t* ladder) {
+  __shared__ uint32_t hist_all[kSelThreads / 32][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t q = (int64_t)blockIdx.x * (kSelThreads / 32) + warp;
+  pdl_trigger();
+  pdl_wait();
+  if (q >= Q) return;
+  uint32_t* hist = hist_all[warp];
+  const uint32_t n = min(app_cnt[q], (uint32_t)cap);
+  const uint64_t* src = app_keys + (size_t)q * cap;
+  uint32_t* lad = ladder ? ladder + (size_t)q * 2 * kLadder : nullptr;
+  if (n < (uint32_t)KP) {          // not enough rows for a threshold yet: a ladder that never fires
+    if (lad && lane < kLadder) {
+      lad[kLadder + lane] = 0u;
+      lad[lane] = lane == 0 ? __float_as_uint(INFINITY) : 0u;
+    }
+    return;
+  }
+  uint32_t prefix = 0, need = (uint32_t)KP, best = 0;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hist[lane + 32 * i] = 0;
+    __syncwarp();
+    const uint32_t hi_mask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+    for (uint32_t i = lane; i < n; i += 32) {
+      const uint32_t sc = (uint32_t)(__ldg(src + i) >> 32);
+      if (shift == 24) best = max(best, sc);
+      if ((sc & hi_mask) == prefix) atomicAdd(&hist[(sc >> shift) & 255u], 1u);
+    }
+    __syncwarp();
+    // lane l owns buckets 255 - 8l .. 248 - 8l (descending): where does the running count reach `need`?
+    uint32_t c[8], tot = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { c[j] = hist[255 - 8 * lane - j]; tot += c[j]; }
+    uint32_t incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const uint32_t before = incl - tot;
+    const bool mine = before < need && incl >= need;
+    uint32_t bucket = 0, rest = 0;
+    if (mine) {
+      uint32_t run = before;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (run < need && run + c[j] >= need) { bucket = 255u - 8u * lane - j; rest = need - run; }
+        run += c[j];
+      }
+    }
+    const int owner = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;    // exactly one lane (n >= need)
+    bucket = __shfl_sync(0xffffffffu, bucket, owner);
+    need = __shfl_sync(0xffffffffu, rest, owner);
+    prefix |= bucket << shift;
+    __syncwarp();
+  }
+  // prefix = the KP-th best approximate score (ordered-float bits)
+  if (lane == 0) atomicMax(thr + q, prefix);
+  if (!lad) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+  float base = ord_to_f32(prefix);
+  float step = (ord_to_f32(best) - base) * (1.f / 8.f);
+  if (!(step > 0.f) || !(step < INFINITY)) step = 0.f;
+  const float inv = step > 0.f ? 1.f / step : 0.f;
+  if (lane < kLadder) hist[lane] = 0;
+  __syncwarp();
+  for (uint32_t i = lane; i < n; i += 32) {
+    const uint32_t sc = (uint32_t)(__ldg(src + i) >> 32);
+    if (sc >= prefix) {
+      const int j = ladder_level(base, step, inv, ord_to_f32(sc));
+      if (j >= 0) atomicAdd(&hist[j], 1u);
+    }
+  }
+  __syncwarp();
+  if (lane < kLadder) {
+    lad[kLadder + lane] = hist[lane];
+    lad[lane] = lane == 0 ? __float_as_uint(base) : lane == 1 ? __float_as_uint(step) : lane == 2 ? __float_as_uint(inv) : 0u;
+  }
+}
+
+// First kernel of a search (replaces a memset of the control words, a memset of the query padding and a 2-D copy).
+__global__ void __launch_bounds__(256) search_prep_kernel(uint4* zero_base, size_t zero_vecs, const char* q_src,
+                                                          size_t q_src_stride_bytes, char* q_dst, size_t row_vecs,
+                                                          int64_t Q, int64_t q_rows_padded) {
+  pdl_trigger();
+  pdl_wait();
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (size_t i = tid; i < zero_vecs; i += nthr) zero_base[i] = z;
+  if (!q_dst) return;
+  const size_t total = (size_t)q_rows_padded * row_vecs;
+  for (size_t i = tid; i < total; i += nthr) {
+    const size_t r = i / row_vecs, c = i - r * row_vecs;
+    reinterpret_cast<uint4*>(q_dst)[i] = (int64_t)r < Q ? reinterpret_cast<const uint4*>(q_src + r * q_src_stride_bytes)[c] : z;
+  }
+}
+
 struct ExMergeArgs {
   const void* q; int q_dt; int64_t q_stride;
   const void* corpus; int c_dt; int64_t c_stride;
@@ -472,11 +665,13 @@ struct ExMergeArgs {
   float* out_score; double* out_score64; int64_t* out_idx; int32_t* out_flags;
 };
 
-__global__ void __launch_bounds__(kSelThreads) merge_exact_lists_kernel(ExMergeArgs a) {
+__global__ void __launch_bounds__(kSelThreads, 3) merge_exact_lists_kernel(ExMergeArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s = (double*)smem_raw;
   int64_t* ix = (int64_t*)(smem_raw + sizeof(double) * kPairCap);
   __shared__ int n_sh;
+  pdl_trigger();
+  pdl_wait();
   const int64_t slot = blockIdx.x;
   int64_t q = slot;
   if (a.flag_cnt) {
@@ -603,17 +798,49 @@ int launch_select_rescore(const void* q, int q_dt, int64_t q_stride, const void*
   a.r_cap = retry ? retry->cap : 0; a.r_q = retry ? retry->r_q : nullptr; a.r_q_stride = retry ? retry->r_q_stride : 0;
   a.r_skip = retry ? retry->skip : 0; a.r_forward = retry ? retry->forward : 0;
   a.app_keys = app_keys; a.app_cnt = app_cnt; a.app_cap = p.app_cap;
+  // re-score through shared-memory row slots when a row is at most 2 KB and 16-byte granular (cp.async)
+  const int64_t rowb = D * dtype_size(c_dt);
+  const bool stage_ok = rowb <= 2048 && rowb % 16 == 0 && ((uintptr_t)corpus & 15) == 0 &&
+                        (c_stride * dtype_size(c_dt)) % 16 == 0 && !knob_on("TSIM_NO_RESCORE_STAGE");
+  a.stage_row_bytes = stage_ok ? (int)rowb : 0;
+  size_t smem = (size_t)(kKeyCap + kSelOut) * sizeof(uint64_t);
+  const size_t stage_bytes = (size_t)(kSelThreads / 32) * kRescoreDepth * a.stage_row_bytes;
+  a.qd_offset = (int)stage_bytes;
+  if (stage_ok && stage_bytes + (size_t)qd_len(D) * sizeof(double) > smem) smem = stage_bytes + (size_t)qd_len(D) * sizeof(double);
+  // static + dynamic shared memory beyond 48 KB needs the opt-in (the kernel also has ~4 KB of static arrays)
+  if (smem > 40 * 1024)
+    TSIM_CUDA(cudaFuncSetAttribute(select_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // a retry pass launches one block per compact slot: Q = the slot capacity there
-  select_rescore_kernel<<<(unsigned)Q, kSelThreads, 0, st>>>(a);
-  TSIM_CUDA(cudaGetLastError());
+  TSIM_CUDA(launch_pdl(select_rescore_kernel, dim3((unsigned)Q), dim3(kSelThreads), smem, st, a));
   count_launch();
   return TSIM_OK;
 }
 
 int launch_tighten(int64_t Q, const SearchPlan& p, int nslots, const uint64_t* cand, uint32_t* thr,
                    uint32_t* ladder, cudaStream_t st) {
-  tighten_kernel<<<(unsigned)Q, kSelThreads, 0, st>>>(cand, thr, p.NC, p.KP, nslots, ladder);
-  TSIM_CUDA(cudaGetLastError());
+  TSIM_CUDA(launch_pdl(tighten_kernel, dim3((unsigned)Q), dim3(kSelThreads), 0, st, cand, thr, p.NC, p.KP, nslots, ladder));
+  count_launch();
+  return TSIM_OK;
+}
+
+int launch_search_prep(void* zero_base, size_t zero_bytes, const void* q_src, size_t q_src_stride_bytes, void* q_dst,
+                       size_t row_bytes, int64_t Q, int64_t q_rows_padded, cudaStream_t st) {
+  // zero_base is 256-byte aligned and zero_bytes a multiple of 256 (workspace layout); rows are 16-byte multiples
+  const size_t work = zero_bytes / 16 + (q_dst ? (size_t)q_rows_padded * (row_bytes / 16) : 0);
+  size_t blocks = (work + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 1184) blocks = 1184;
+  TSIM_CUDA(launch_pdl(search_prep_kernel, dim3((unsigned)blocks), dim3(256), 0, st, (uint4*)zero_base, zero_bytes / 16,
+                       (const char*)q_src, q_src_stride_bytes, (char*)q_dst, row_bytes / 16, Q, q_rows_padded));
+  count_launch();
+  return TSIM_OK;
+}
+
+int launch_tighten_app(int64_t Q, const SearchPlan& p, const uint64_t* app_keys, const uint32_t* app_cnt,
+                       uint32_t* thr, uint32_t* ladder, cudaStream_t st) {
+  const int per = kSelThreads / 32;
+  TSIM_CUDA(launch_pdl(tighten_app_kernel, dim3((unsigned)((Q + per - 1) / per)), dim3(kSelThreads), 0, st, app_keys, app_cnt,
+                       p.app_cap, Q, p.KP, thr, ladder));
   count_launch();
   return TSIM_OK;
 }
@@ -631,8 +858,7 @@ int launch_merge_exact_lists(const void* q, int q_dt, int64_t q_stride, const vo
   a.flag_cnt = flag_cnt; a.flag_list = flag_list; a.ex_score = ex_score; a.ex_idx = ex_idx;
   a.out_score = out_score; a.out_score64 = out_score64; a.out_idx = out_idx; a.out_flags = out_flags;
   size_t smem = (size_t)kPairCap * (sizeof(double) + sizeof(int64_t));
-  merge_exact_lists_kernel<<<(unsigned)Q, kSelThreads, smem, st>>>(a);
-  TSIM_CUDA(cudaGetLastError());
+  TSIM_CUDA(launch_pdl(merge_exact_lists_kernel, dim3((unsigned)Q), dim3(kSelThreads), smem, st, a));
   count_launch();
   return TSIM_OK;
 }

@@ -147,11 +147,12 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
         p->boot_tpc = best_tpc;
         p->boot_slots = (rest + p->boot_tpc - 1) / p->boot_tpc;
       }
-      // KP >= 32 with a bootstrap sample: the main pass appends to per-query global lists instead of keeping
-      // KP-entry lists in shared memory (search_tc.cu, AppendList); only the sample passes write list slots
-      p->append = (p->boot_tiles && p->KP >= 32 && !knob_on("TSIM_NO_APPEND")) ? 1 : 0;
-      p->app_cap = 4096;
-      if (p->append) p->NC = p->mini_slots + p->boot_slots;
+      // Bootstrapped round-robin plans with KP >= 32 keep no candidate lists at all: every pass (mini sample with
+      // no threshold, rest of the sample, main) APPENDS the rows that beat the query's threshold to one global list
+      // per query (search_tc.cu, AppendList); tighten and select_rescore read that list.
+      p->append = (p->boot_tiles && p->KP >= knob_int("TSIM_APPEND_MIN_KP", 32)) ? 1 : 0;
+      p->app_cap = Q > 65536 ? 2048 : 4096;
+      if (p->append) p->NC = 0;
       else p->NC = p->boot_tiles ? p->mini_slots + p->boot_slots + (T - p->boot_tiles + tpc - 1) / tpc : (T + tpc - 1) / tpc;
     } else {
       p->R = 256;
@@ -319,12 +320,21 @@ static int search_impl(const void* q, int q_dt, int64_t q_stride, const void* co
   const int64_t self_off = exclude_self_base - idx_base;  // local corpus row of query 0's own row
 
   if (p.use_tensor) {
-    // thr, flag_cnt, the unit-claim areas and the retry stage's thr / flag_cnt are adjacent: one memset
+    // thr, flag_cnt, the unit-claim areas, the append counters and the retry stage's thr / flag_cnt are adjacent:
+    // one prep kernel zeroes them and writes the zero-padded copy of the queries (TMA OOB fill is slow)
     const size_t zero_end = p.retry ? p.off_r_flagcnt + 256
                                     : p.append ? p.off_app_cnt + align_up((size_t)Q * sizeof(uint32_t), 256)
                                                : p.off_sched + 3 * p.sched_area;
-    TSIM_CUDA(cudaMemsetAsync(thr, 0, zero_end - p.off_thr, st));
     uint64_t* sched = p.sched_area ? (uint64_t*)(w + p.off_sched) : nullptr;
+    const void* qt = tq;
+    int64_t qt_stride = tq_stride;
+    const int qrows = p.pair ? 256 : 128;
+    const size_t rowb = (size_t)D * dtype_size(t_dt);
+    const bool pad = Q % qrows != 0;
+    rc = launch_search_prep(thr, align_up(zero_end - p.off_thr, 256), tq, (size_t)tq_stride * dtype_size(t_dt),
+                            pad ? w + p.off_qpad : nullptr, rowb, Q, (int64_t)p.QB * qrows, st);
+    if (rc) return rc;
+    if (pad) { qt = w + p.off_qpad; qt_stride = D; }
     const float* c_inv = corpus_inv_norm;
     if (!c_inv) {
       float* tmp = (float*)(w + p.off_invnorm);
@@ -332,40 +342,33 @@ static int search_impl(const void* q, int q_dt, int64_t q_stride, const void* co
       if (rc) return rc;
       c_inv = tmp;
     }
-    const void* qt = tq;
-    int64_t qt_stride = tq_stride;
-    const int qrows = p.pair ? 256 : 128;
-    if (Q % qrows != 0) {
-      char* qp = w + p.off_qpad;
-      const size_t rowb = (size_t)D * dtype_size(t_dt);
-      TSIM_CUDA(cudaMemsetAsync(qp + (size_t)Q * rowb, 0, ((size_t)p.QB * qrows - Q) * rowb, st));
-      TSIM_CUDA(cudaMemcpy2DAsync(qp, rowb, tq, (size_t)tq_stride * dtype_size(t_dt), rowb, (size_t)Q, cudaMemcpyDeviceToDevice, st));
-      qt = qp;
-      qt_stride = D;
-    }
     const bool timed = g_ev_start && g_ev_stop;
     if (timed) TSIM_CUDA(cudaEventRecord(g_ev_start, st));
     uint64_t* cand = (uint64_t*)(w + p.off_cand);
+    uint64_t* app_keys = p.append ? (uint64_t*)(w + p.off_app_keys) : nullptr;
+    uint32_t* app_cnt = p.append ? (uint32_t*)(w + p.off_app_cnt) : nullptr;
     uint32_t* ladder = nullptr;
     if (p.boot_tiles) {
       uint32_t* lad = knob_on("TSIM_NO_LADDER") ? nullptr : (uint32_t*)(w + p.off_ladder);   // experiment knob
       if (p.mini_mult) {
         rc = launch_search_tc(qt, qt_stride, tcorpus, tc_stride, t_dt, c_inv, Q, N, D, self_on, self_off, p,
-                              TC_PASS_MINI, cand, thr, nullptr, sched, st, maps);
+                              TC_PASS_MINI, cand, thr, nullptr, sched, st, maps, nullptr, nullptr, 0, app_keys, app_cnt);
         if (rc) return rc;
-        rc = launch_tighten(Q, p, (int)p.mini_slots, cand, thr, lad, st);
+        rc = p.append ? launch_tighten_app(Q, p, app_keys, app_cnt, thr, lad, st)
+                      : launch_tighten(Q, p, (int)p.mini_slots, cand, thr, lad, st);
         if (rc) return rc;
         ladder = lad;
       }
       rc = launch_search_tc(qt, qt_stride, tcorpus, tc_stride, t_dt, c_inv, Q, N, D, self_on, self_off, p,
-                            p.mini_mult ? TC_PASS_SAMPLE_REST : TC_PASS_SAMPLE, cand, thr, ladder, sched, st, maps);
+                            p.mini_mult ? TC_PASS_SAMPLE_REST : TC_PASS_SAMPLE, cand, thr, ladder, sched, st, maps,
+                            nullptr, nullptr, 0, app_keys, app_cnt);
       if (rc) return rc;
-      rc = launch_tighten(Q, p, (int)(p.mini_slots + p.boot_slots), cand, thr, lad, st);   // re-levels the ladder
+      // re-levels the ladder
+      rc = p.append ? launch_tighten_app(Q, p, app_keys, app_cnt, thr, lad, st)
+                    : launch_tighten(Q, p, (int)(p.mini_slots + p.boot_slots), cand, thr, lad, st);
       if (rc) return rc;
       ladder = lad;
     }
-    uint64_t* app_keys = p.append ? (uint64_t*)(w + p.off_app_keys) : nullptr;
-    uint32_t* app_cnt = p.append ? (uint32_t*)(w + p.off_app_cnt) : nullptr;
     rc = launch_search_tc(qt, qt_stride, tcorpus, tc_stride, t_dt, c_inv, Q, N, D, self_on, self_off, p,
                           p.boot_tiles ? TC_PASS_MAIN : TC_PASS_ALL, cand, thr, ladder, sched, st, maps,
                           nullptr, nullptr, 0, app_keys, app_cnt);

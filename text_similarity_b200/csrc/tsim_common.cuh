@@ -156,6 +156,28 @@ __device__ __forceinline__ int ladder_level(float base, float step, float inv, f
   return j;
 }
 
+// ---- programmatic dependent launch --------------------------------------------------------
+// A search is a chain of ~10 dependent kernels on one stream, several of them tiny (tighten, select, the retry /
+// fallback kernels that usually find nothing to do).  Every kernel of the chain is launched with the
+// programmatic-stream-serialization attribute, calls pdl_trigger() at its top (the next kernel may be scheduled as
+// soon as every CTA of this one has started) and pdl_wait() before it first touches anything its predecessors
+// wrote (blocks until they have completed and flushed): launch latency and prologues (barrier init, TMEM
+// allocation, descriptor prefetch) overlap the predecessor's tail instead of adding up.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = knob_on("TSIM_NO_PDL") ? 0 : 1;   // experiment knob
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- warp helpers ------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum_f64(double v) {
 #pragma unroll
@@ -171,54 +193,193 @@ __device__ __forceinline__ float warp_sum_f32(float v) {
 // The CANONICAL exact cosine of two stored rows, evaluated by one full warp.
 // Every score the library returns is produced by this routine, whichever path nominated the
 // row, so equal stored rows always yield bit-identical scores (ties -> lower index).
-// Products of bf16/fp16/fp8/fp32 values are exact in float64; lane l sums elements
-// l, l+32, ... sequentially, then a fixed xor-butterfly adds the 32 partials.
-template <int QDT, int CDT>
-__device__ __forceinline__ void exact_cosine_sums(const void* q, const void* c, int64_t D, double& dot, double& qq,
-                                                  double& cc) {
-  int64_t d = threadIdx.x & 31;
-  // eight elements per lane per step, loads first (16 in flight), FMAs in the canonical order
-  for (; d + 32 * 7 < D; d += 32 * 8) {
-    float a[8], b[8];
+// Products of bf16/fp16/fp8/fp32 values are exact in float64.  Fixed summation order: lane l owns the
+// 8-element groups g with g % 32 == l (elements 8g .. 8g + 7), adds them in ascending element order with
+// FMAs, then a fixed xor-butterfly adds the 32 partials.  ||q||^2 is summed once per query in the same order
+// (warp_query_norm); dot and ||c||^2 per row.
+// A group is kept as RAW bits (one 16-byte load for bf16 / fp16 rows, 8 bytes for e4m3, 32 for fp32 when the row
+// is aligned; element loads packed the same way otherwise).  The query row is widened ONCE per query into a
+// float64 copy in shared memory where the caller has room, so a corpus element costs one conversion and two FMAs.
+// Widening to float64 goes through float (a shift for bf16) and ONE F2F.F64.F32 per element (2 issue cycles per
+// warp on the XU pipe; doing it with integer bit manipulation costs 6-8 ALU cycles and was measured slower).
+// Raw bits of one 8-element group of a row of element type DT.
+template <int DT> struct Group8;
+template <> struct Group8<TSIM_BF16> {
+  uint32_t w[4];
+  __device__ __forceinline__ void load_vec(const char* p) { const uint4 v = *reinterpret_cast<const uint4*>(p); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+  __device__ __forceinline__ void load_elems(const char* p, int n) {
+    const unsigned short* h = reinterpret_cast<const unsigned short*>(p);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) { a[u] = Elem<QDT>::ld(q, d + 32 * u); b[u] = Elem<CDT>::ld(c, d + 32 * u); }
+    for (int i = 0; i < 4; ++i) w[i] = (2 * i < n ? (uint32_t)h[2 * i] : 0u) | ((2 * i + 1 < n ? (uint32_t)h[2 * i + 1] : 0u) << 16);
+  }
+  __device__ __forceinline__ double get(int i) const {
+    return (double)__uint_as_float((i & 1) ? (w[i >> 1] & 0xffff0000u) : (w[i >> 1] << 16));
+  }
+  static constexpr int kVecAlign = 16, kBytes = 2;
+};
+template <> struct Group8<TSIM_F16> {
+  uint32_t w[4];
+  __device__ __forceinline__ void load_vec(const char* p) { const uint4 v = *reinterpret_cast<const uint4*>(p); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+  __device__ __forceinline__ void load_elems(const char* p, int n) {
+    const unsigned short* h = reinterpret_cast<const unsigned short*>(p);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const double x = (double)a[u], y = (double)b[u];
-      dot = fma(x, y, dot);
-      qq = fma(x, x, qq);
-      cc = fma(y, y, cc);
+    for (int i = 0; i < 4; ++i) w[i] = (2 * i < n ? (uint32_t)h[2 * i] : 0u) | ((2 * i + 1 < n ? (uint32_t)h[2 * i + 1] : 0u) << 16);
+  }
+  __device__ __forceinline__ double get(int i) const {
+    return (double)__half2float(__ushort_as_half((unsigned short)((w[i >> 1] >> ((i & 1) * 16)) & 0xffffu)));
+  }
+  static constexpr int kVecAlign = 16, kBytes = 2;
+};
+template <> struct Group8<TSIM_E4M3> {
+  uint32_t w[2];
+  __device__ __forceinline__ void load_vec(const char* p) { const uint2 v = *reinterpret_cast<const uint2*>(p); w[0] = v.x; w[1] = v.y; }
+  __device__ __forceinline__ void load_elems(const char* p, int n) {
+    const unsigned char* h = reinterpret_cast<const unsigned char*>(p);
+    w[0] = w[1] = 0u;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (i < n) w[i >> 2] |= (uint32_t)h[i] << ((i & 3) * 8);
+  }
+  __device__ __forceinline__ double get(int i) const {
+    __nv_fp8_e4m3 v;
+    v.__x = (__nv_fp8_storage_t)((w[i >> 2] >> ((i & 3) * 8)) & 0xffu);
+    return (double)float(v);
+  }
+  static constexpr int kVecAlign = 8, kBytes = 1;
+};
+template <> struct Group8<TSIM_F32> {
+  uint32_t w[8];
+  __device__ __forceinline__ void load_vec(const char* p) {
+    const uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 16);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+  }
+  __device__ __forceinline__ void load_elems(const char* p, int n) {
+    const uint32_t* h = reinterpret_cast<const uint32_t*>(p);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = i < n ? h[i] : 0u;
+  }
+  __device__ __forceinline__ double get(int i) const { return (double)__uint_as_float(w[i]); }
+  static constexpr int kVecAlign = 16, kBytes = 4;
+};
+// group starting at element e0 of `row` (all-zero bits past D: +0.0, which leaves every FMA chain unchanged)
+template <int DT>
+__device__ __forceinline__ void load_group8(Group8<DT>& g, const void* row, int64_t e0, int64_t D, bool vec) {
+  const char* p = (const char*)row + e0 * Group8<DT>::kBytes;
+  if (e0 + 8 <= D && vec) g.load_vec(p);
+  else g.load_elems(p, e0 < D ? (int)min((int64_t)8, D - e0) : 0);
+}
+
+constexpr int kCosGroups = 3;   // 8-element groups per lane in flight (D = 768: the whole row in one round trip)
+
+// sum of squares of one row in the canonical order (all lanes return the warp total)
+template <int DT>
+__device__ __forceinline__ double canonical_sumsq(const void* r, int64_t D) {
+  const bool vec = ((uintptr_t)r & (Group8<DT>::kVecAlign - 1)) == 0;
+  double acc = 0.0;
+  for (int64_t e0 = (int64_t)(threadIdx.x & 31) * 8; e0 < D; e0 += 256 * kCosGroups) {
+    Group8<DT> g[kCosGroups];
+#pragma unroll
+    for (int u = 0; u < kCosGroups; ++u) load_group8<DT>(g[u], r, e0 + 256 * u, D, vec);
+#pragma unroll
+    for (int u = 0; u < kCosGroups; ++u) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const double x = g[u].get(i); acc = fma(x, x, acc); }
     }
   }
-  for (; d < D; d += 32) {
-    const double x = (double)Elem<QDT>::ld(q, d), y = (double)Elem<CDT>::ld(c, d);
-    dot = fma(x, y, dot);
-    qq = fma(x, x, qq);
-    cc = fma(y, y, cc);
+  return warp_sum_f64(acc);
+}
+// max(||q||, eps) of a query row: the same for every corpus row, so computed once per query
+__device__ __forceinline__ double warp_query_norm(const void* q, int q_dt, int64_t D) {
+  double qq;
+  switch (q_dt) {
+    case TSIM_F32: qq = canonical_sumsq<TSIM_F32>(q, D); break;
+    case TSIM_F16: qq = canonical_sumsq<TSIM_F16>(q, D); break;
+    case TSIM_BF16: qq = canonical_sumsq<TSIM_BF16>(q, D); break;
+    default: qq = canonical_sumsq<TSIM_E4M3>(q, D); break;
+  }
+  return fmax(sqrt(qq), kCosEps);
+}
+
+// element e of a query row as float64 (for filling a shared-memory float64 copy of the query)
+__device__ __forceinline__ double query_elem_f64(const void* q, int q_dt, int64_t e) {
+  return (double)load_elem(q, q_dt, e);
+}
+
+// Position (in doubles) of element e in the lane-interleaved float64 copy of a query row: the pair (2p, 2p + 1) of
+// lane l's group U * 32 + l sits at double2 slot (U * 4 + p) * 32 + l, so a warp's 16-byte reads are conflict free
+// (a plain [D] layout puts the lanes 64 bytes apart: 16-way bank conflicts, measured +25 % on select_rescore).
+// The copy holds qd_len(D) doubles, zero past D.
+__host__ __device__ inline int64_t qd_len(int64_t D) { return (D + 255) / 256 * 256; }
+__device__ __forceinline__ int64_t qd_slot(int64_t e) {
+  const int64_t g = e >> 3, i = e & 7;
+  return ((((g >> 5) * 4 + (i >> 1)) * 32 + (g & 31)) << 1) + (i & 1);
+}
+// dot(q, c) and ||c||^2 in the canonical order.  qd: lane-interleaved float64 copy of the query row (shared
+// memory), or null -> the query's elements are widened from `q` on the fly.
+template <int QDT, int CDT>
+__device__ __forceinline__ void exact_cosine_sums(const void* q, const double* qd, const void* c, int64_t D,
+                                                  double& dot, double& cc) {
+  const bool qvec = ((uintptr_t)q & (Group8<QDT>::kVecAlign - 1)) == 0;
+  const bool cvec = ((uintptr_t)c & (Group8<CDT>::kVecAlign - 1)) == 0;
+  for (int64_t e0 = (int64_t)(threadIdx.x & 31) * 8; e0 < D; e0 += 256 * kCosGroups) {
+    Group8<CDT> b[kCosGroups];
+#pragma unroll
+    for (int u = 0; u < kCosGroups; ++u) load_group8<CDT>(b[u], c, e0 + 256 * u, D, cvec);
+#pragma unroll
+    for (int u = 0; u < kCosGroups; ++u) {
+      const int64_t eu = e0 + 256 * u;
+      if (eu >= D) continue;     // an all-zero group past the end of the row: every FMA would leave its sum unchanged
+      if (qd) {
+        // lane-interleaved float64 copy (qd_slot below): consecutive lanes read consecutive 16-byte words
+        const double2* q2 = reinterpret_cast<const double2*>(qd) + ((eu >> 8) * 4) * 32 + (threadIdx.x & 31);
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          const double2 x = q2[(i >> 1) * 32];
+          const double y0 = b[u].get(i), y1 = b[u].get(i + 1);
+          dot = fma(x.x, y0, dot); cc = fma(y0, y0, cc);
+          dot = fma(x.y, y1, dot); cc = fma(y1, y1, cc);
+        }
+      } else {
+        Group8<QDT> a;
+        load_group8<QDT>(a, q, eu, D, qvec);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const double x = a.get(i), y = b[u].get(i);
+          dot = fma(x, y, dot); cc = fma(y, y, cc);
+        }
+      }
+    }
   }
 }
 
-__device__ __forceinline__ double warp_exact_cosine(const void* q, int q_dt, const void* c, int c_dt,
-                                                    int64_t D) {
-  const int lane = threadIdx.x & 31;
-  double dot = 0.0, qq = 0.0, cc = 0.0;
-  if (q_dt == TSIM_BF16 && c_dt == TSIM_BF16) exact_cosine_sums<TSIM_BF16, TSIM_BF16>(q, c, D, dot, qq, cc);
-  else if (q_dt == TSIM_E4M3 && c_dt == TSIM_E4M3) exact_cosine_sums<TSIM_E4M3, TSIM_E4M3>(q, c, D, dot, qq, cc);
-  else if (q_dt == TSIM_F32 && c_dt == TSIM_F32) exact_cosine_sums<TSIM_F32, TSIM_F32>(q, c, D, dot, qq, cc);
+template <int QDT>
+__device__ __forceinline__ void exact_cosine_sums_c(const void* q, const double* qd, const void* c, int c_dt, int64_t D,
+                                                    double& dot, double& cc) {
+  switch (c_dt) {
+    case TSIM_F32: exact_cosine_sums<QDT, TSIM_F32>(q, qd, c, D, dot, cc); break;
+    case TSIM_F16: exact_cosine_sums<QDT, TSIM_F16>(q, qd, c, D, dot, cc); break;
+    case TSIM_BF16: exact_cosine_sums<QDT, TSIM_BF16>(q, qd, c, D, dot, cc); break;
+    default: exact_cosine_sums<QDT, TSIM_E4M3>(q, qd, c, D, dot, cc); break;
+  }
+}
+
+// qn = warp_query_norm(q, q_dt, D).  All lanes return the score.
+__device__ __forceinline__ double warp_exact_cosine(const void* q, int q_dt, const double* qd, double qn,
+                                                    const void* c, int c_dt, int64_t D) {
+  double dot = 0.0, cc = 0.0;
+  if (q_dt == TSIM_BF16 && c_dt == TSIM_BF16) exact_cosine_sums<TSIM_BF16, TSIM_BF16>(q, qd, c, D, dot, cc);
+  else if (q_dt == TSIM_E4M3 && c_dt == TSIM_E4M3) exact_cosine_sums<TSIM_E4M3, TSIM_E4M3>(q, qd, c, D, dot, cc);
+  else if (q_dt == TSIM_F32 && c_dt == TSIM_F32) exact_cosine_sums<TSIM_F32, TSIM_F32>(q, qd, c, D, dot, cc);
   else {
-    for (int64_t d = lane; d < D; d += 32) {
-      double a = (double)load_elem(q, q_dt, d);
-      double b = (double)load_elem(c, c_dt, d);
-      dot = fma(a, b, dot);
-      qq = fma(a, a, qq);
-      cc = fma(b, b, cc);
+    switch (q_dt) {      // mixed dtypes: same order, same bits, one more switch
+      case TSIM_F32: exact_cosine_sums_c<TSIM_F32>(q, qd, c, c_dt, D, dot, cc); break;
+      case TSIM_F16: exact_cosine_sums_c<TSIM_F16>(q, qd, c, c_dt, D, dot, cc); break;
+      case TSIM_BF16: exact_cosine_sums_c<TSIM_BF16>(q, qd, c, c_dt, D, dot, cc); break;
+      default: exact_cosine_sums_c<TSIM_E4M3>(q, qd, c, c_dt, D, dot, cc); break;
     }
   }
   dot = warp_sum_f64(dot);
-  qq = warp_sum_f64(qq);
   cc = warp_sum_f64(cc);
-  double qn = fmax(sqrt(qq), kCosEps);
-  double cn = fmax(sqrt(cc), kCosEps);
+  const double cn = fmax(sqrt(cc), kCosEps);
   return dot / (qn * cn);
 }
 
@@ -241,9 +402,9 @@ struct SearchPlan {
   // thresholds and a ladder from the first.  Cold lists are expensive (every early row is inserted),
   // so only a handful of tiles ever see them.
   int64_t mini_mult, mini_tiles, mini_slots;
-  // Append mode (round-robin plans with a bootstrap sample and KP >= 32): the MAIN pass keeps no lists; rows that
-  // beat the query's threshold are appended to app_keys[q][0 .. app_cap) (count in app_cnt[q], zeroed with thr).
-  // NC then counts the sample passes' list slots only.
+  // Append mode (round-robin plans with a bootstrap sample and KP >= 32): no candidate lists; in every pass the rows
+  // that beat the query's threshold are appended to app_keys[q][0 .. app_cap) (count in app_cnt[q], zeroed with thr).
+  // NC = 0 then.
   int append;
   int app_cap;
   size_t off_app_keys, off_app_cnt;
@@ -307,6 +468,8 @@ int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_
                      uint64_t* app_keys = nullptr, uint32_t* app_cnt = nullptr);
 int launch_tighten(int64_t Q, const SearchPlan& p, int nslots, const uint64_t* cand, uint32_t* thr,
                    uint32_t* ladder, cudaStream_t st);
+int launch_tighten_app(int64_t Q, const SearchPlan& p, const uint64_t* app_keys, const uint32_t* app_cnt,
+                       uint32_t* thr, uint32_t* ladder, cudaStream_t st);
 int launch_select_rescore(const void* q, int q_dt, int64_t q_stride, const void* corpus, int c_dt,
                           int64_t c_stride, int64_t Q, int64_t N, int64_t D, int k,
                           int64_t idx_base, const SearchPlan& p, const uint64_t* cand,
@@ -330,6 +493,10 @@ int launch_merge_topk(const double* sc, const int64_t* ix, int64_t Q, int64_t n_
                       int64_t* out_idx, cudaStream_t st);
 int launch_row_inv_norm(const void* x, int dt, int64_t N, int64_t D, int64_t stride, float* out,
                         cudaStream_t st);
+// first kernel of a search: zero the control words [zero_base, zero_base + zero_bytes) and, when q_dst is given,
+// copy the Q query rows into the zero-padded block the TMA reads (q_rows_padded rows of row_bytes)
+int launch_search_prep(void* zero_base, size_t zero_bytes, const void* q_src, size_t q_src_stride_bytes, void* q_dst,
+                       size_t row_bytes, int64_t Q, int64_t q_rows_padded, cudaStream_t st);
 
 int device_sm_count();
 void count_launch();       // bumps the counter behind tsim_launch_count()
