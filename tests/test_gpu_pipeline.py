@@ -220,3 +220,42 @@ def test_retrieval_accuracy_meter_matches_dense_argmax():
     assert abs(meter.src2tgt - exp_fwd) < 1e-6 and abs(meter.tgt2src - exp_bwd) < 1e-6
     assert abs(meter.avg - (exp_fwd + exp_bwd) / 2) < 1e-6
     assert len(meter.lines) == int(round((1 - exp_fwd) * 700)) and "INCORRECT" in str(meter)
+
+
+def test_clustering_pipeline_separates_planted_clusters(stack):
+    """ClusteringPipeline (reference src/pipeline/clustering.py:8-31) on the search kernel: three well separated
+    directions must come back as three pure clusters; labels equal a float64 nearest-centroid assignment."""
+    from src.pipeline.clustering import ClusteringPipeline
+    params, model = stack[0], stack[1]
+    g = torch.Generator().manual_seed(4)
+    dirs = torch.nn.functional.normalize(torch.randn(3, 64, generator=g), dim=-1)
+    which = torch.randint(0, 3, (600,), generator=g)
+    x = torch.nn.functional.normalize(dirs[which] + 0.05 * torch.randn(600, 64, generator=g), dim=-1)
+    clu = ClusteringPipeline(3, params, model, seed=1)
+    out = clu(x.cuda(), 3)
+    assert sorted(len(v) for v in out.values()) == sorted(torch.bincount(which, minlength=3).tolist())
+    lab = clu.labels_.cpu()
+    for c in range(3):
+        assert len(set(which[lab == c].tolist())) == 1          # pure clusters
+    want = (x.double() @ clu.cluster_centers_.cpu().double().T).argmax(dim=1)
+    assert torch.equal(lab, want)
+
+
+def test_bf16_autocast_bucketed_encode_matches_fp32_loop(stack):
+    """f2: encoder under torch.autocast(bf16) + token-budget batches.  Pooled unit rows stay
+    within 2^-7 of the reference-shaped fp32 loop, and the search over the rows it stored is exact (== oracle on
+    those rows)."""
+    from text_similarity_b200 import ops
+    params, model, corpus, queries = stack
+    rows_ref, _ = model.encode_text_normalized(corpus, torch.bfloat16)
+    params.encode_dtype, params.token_budget = torch.bfloat16, 2048
+    try:
+        rows, inv = model.encode_text_normalized(corpus, torch.bfloat16)
+        q, _ = model.encode_text_normalized(queries, torch.bfloat16)
+    finally:
+        params.encode_dtype, params.token_budget = None, None
+    assert (rows.float() - rows_ref.float()).abs().max().item() <= 2 ** -7      # tolerance stated by the task
+    s, i, s64 = ops.search_topk(q, rows, 10, corpus_inv_norm=inv, return_score64=True)
+    ev, ei = O.search_exact(q.cpu(), rows.cpu(), 10)
+    assert torch.equal(i.cpu(), ei)
+    np.testing.assert_allclose(s64.cpu().numpy(), ev.numpy(), atol=1e-12)

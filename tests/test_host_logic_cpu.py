@@ -226,3 +226,65 @@ def test_raw_maximum_bound_of_the_epilogue_filter_is_conservative():
         mx = raw.max()
         bound = mx * (inv.max() if mx >= 0 else inv.min())
         assert bound >= scaled.max(), (trial, bound, scaled.max())
+
+
+def test_excluded_reference_classes_are_importable(tmp_path):
+    """the reference's serving / clustering / evaluation entry points import from their
+    own module paths and keep their signatures; what needs a missing dependency says so."""
+    from src.configurations.config import ModelParameters, SearchConfiguration
+    from src.evaluation.eval_sentence_mining import compare_models
+    from src.pipeline.clustering import ClusteringPipeline
+    from src.pipeline.search_pipeline import APISearchPipeline, SemanticSearchPipeline
+    assert issubclass(APISearchPipeline, SemanticSearchPipeline)
+    params = SearchConfiguration(model_parameters=ModelParameters(model_name="m", hidden_size=8), model="m",
+                                 save_path=str(tmp_path), tokenizer=None, device=torch.device("cpu"))
+    pipe = APISearchPipeline(params, 5, str(tmp_path / "index"), model=None)
+    assert pipe.max_n_results == 5 and pipe.session is None and pipe.num_indexed() == 0
+    params.model_path = str(tmp_path / "model.onnx")
+    try:
+        import onnxruntime  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError, match="onnxruntime"):
+            APISearchPipeline(params, 5, str(tmp_path / "index"), model=None)
+    clu = ClusteringPipeline(3, params, None)
+    clu.set_n_clusters(4)
+    assert clu.n_clusters == 4 and clu.method == "k-means"
+    with pytest.raises(ValueError):
+        ClusteringPipeline(3, params, None, method="dbscan")
+    teacher = {0: [(1, "a"), (2, "b")], 1: [(5, "c"), (6, "d")]}
+    student = {0: [(1, "a"), (9, "z")], 1: [(6, "d"), (5, "c")]}
+    assert compare_models(["q0", "q1"], teacher, student) == pytest.approx(75.0)
+
+
+def test_token_budget_bucketing_covers_every_sentence_once():
+    """Length-bucketed batching (encoder._token_budget_batches): every sentence appears exactly once, with the same
+    token ids a per-sentence tokenizer call gives, padded size within the budget, little padding."""
+    from text_similarity_b200.config import ModelParameters, SearchConfiguration
+    from text_similarity_b200.encoder import SentenceTransformerWrapper
+    from text_similarity_b200.utils import SyntheticTokenizer, synthetic_sentences
+    tok = SyntheticTokenizer()
+    params = SearchConfiguration(model_parameters=ModelParameters(model_name="m", hidden_size=8), model="m", save_path=".",
+                                 tokenizer=tok, sequence_max_len=32, batch_size=16, device=torch.device("cpu"),
+                                 token_budget=256)
+
+    class Dummy(torch.nn.Module):
+        config = type("c", (), {"hidden_size": 8})()
+
+    m = SentenceTransformerWrapper(pooler=None, merge_strategy=None, loss=None, params=params,
+                                   context_embedder=Dummy(), parallel_mode=False)
+    docs = synthetic_sentences(200, seed=3)
+    seen, cells, pad = [], 0, 0
+    for rows, feats in m._batches(docs):
+        ids, mask = feats.input_ids, feats.attention_mask
+        assert ids.shape[0] * ids.shape[1] <= 256 or ids.shape[0] == 1
+        for r, i in enumerate(rows.tolist()):
+            ref = tok([docs[i]], max_length=32)["input_ids"][0]
+            n = int(mask[r].sum())
+            assert ids[r, :n].tolist() == ref.tolist() and (ids[r, n:] == 0).all()
+        seen += rows.tolist()
+        cells += ids.numel()
+        pad += int((mask == 0).sum())
+    assert sorted(seen) == list(range(200))
+    assert pad / cells < 0.1
+    params.token_budget = None                      # default: the reference's fixed batches of 16
+    assert [len(r) for r, _ in m._batches(docs)] == [16] * 12 + [8]

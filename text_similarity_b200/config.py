@@ -50,3 +50,7 @@ class SearchConfiguration(Configuration):
     # --- additions for the exact B200 engine (not in the reference) ---
     corpus_dtype: torch.dtype = torch.bfloat16   # storage type of the unit-norm corpus matrix
     search_mode: str = "auto"                    # "auto" | "tensor" | "exact" (include/tsim.h)
+    # encode side.  Defaults reproduce the reference's loop: fp32 encoder, fixed batches of
+    # `batch_size` sentences (sentence_encoder.py:142-167).
+    encode_dtype: Optional[torch.dtype] = None   # torch.bfloat16: run the encoder under torch.autocast(bf16)
+    token_budget: Optional[int] = None           # > 0: length-bucketed batches of at most this many (padded) tokens

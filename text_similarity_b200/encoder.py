@@ -92,7 +92,7 @@ class SentenceTransformerWrapper(BaseEncoderModel):
     # ---- the intent of reference :161 (`self.encode(features, parallel_mode=False)`, which raises
     # as written): the non-parallel branch of forward (:115-124) without the loss
     def embed(self, features: EmbeddingsFeatures) -> torch.Tensor:
-        tokens = self.context_embedder(**features.to_dict())[0]
+        tokens = self._token_embeddings(features)
         return self.projection(self.pooler(tokens, features))
 
     def forward(self, features, return_output=False, head_mask=None):
@@ -109,7 +109,12 @@ class SentenceTransformerWrapper(BaseEncoderModel):
         return self.encode_text(documents, output_np)  # :133-134
 
     def _batches(self, documents: List[str]):
-        """Length-sorted mini-batches, tokenised exactly like reference :138-159."""
+        """Mini-batches as (original positions int64 [b], features).  Default: the reference's loop -- sort by
+        character length, fixed batches of ``params.batch_size``, tokenised per batch exactly like
+        sentence_encoder.py:138-159.  With ``params.token_budget``: length-bucketed batching (below)."""
+        if getattr(self.params, "token_budget", None):
+            yield from self._token_budget_batches(documents)
+            return
         order = np.argsort([len(sen) for sen in documents], kind="stable")
         bs = self.params.batch_size
         for start in range(0, len(documents), bs):
@@ -128,6 +133,55 @@ class SentenceTransformerWrapper(BaseEncoderModel):
                                        attention_mask=enc["attention_mask"].to(self.params.device))
             yield torch.as_tensor(rows, dtype=torch.int64), feats
 
+    def _token_budget_batches(self, documents: List[str]):
+        """Length-bucketed batching: the corpus is tokenised ONCE without padding, sorted by
+        TOKEN count, and cut into batches whose padded size (sentences x longest sentence) stays within
+        ``params.token_budget`` tokens -- hundreds of short sentences or a handful of long ones per encoder call,
+        instead of the reference's fixed 16 (sentence_encoder.py:142) whatever their length.  Padding is at most the
+        spread of lengths inside one bucket; the pooling kernel never reads it anyway."""
+        budget = int(self.params.token_budget)
+        enc = self.params.tokenizer(
+            text=list(documents),
+            add_special_tokens=True,
+            padding=False,
+            truncation=True,
+            max_length=self.params.sequence_max_len,
+            return_attention_mask=False,
+            return_token_type_ids=False,
+            return_tensors=None,
+        )
+        ids = enc["input_ids"]
+        lens = np.asarray([len(x) for x in ids], dtype=np.int64)
+        flat = np.concatenate([np.asarray(x, dtype=np.int64) for x in ids]) if len(ids) else np.zeros(0, np.int64)
+        offs = np.concatenate([[0], np.cumsum(lens)])
+        order = np.argsort(lens, kind="stable")
+        pad_id = getattr(self.params.tokenizer, "pad_token_id", None) or 0
+        start, n = 0, len(ids)
+        while start < n:
+            # sorted ascending: the longest sentence of a candidate batch [start, end) is its last one
+            end = start + 1
+            while end < n and (end + 1 - start) * int(lens[order[end]]) <= budget:
+                end += 1
+            rows = order[start:end]
+            width = int(lens[rows[-1]])
+            live = np.arange(width)[None, :] < lens[rows][:, None]           # [b, width] attention mask
+            batch = np.full((len(rows), width), pad_id, dtype=np.int64)
+            batch[live] = np.concatenate([flat[offs[i]:offs[i + 1]] for i in rows])   # row-major: sentence by sentence
+            feats = EmbeddingsFeatures(
+                input_ids=torch.from_numpy(batch).to(self.params.device, non_blocking=True),
+                attention_mask=torch.from_numpy(live.astype(np.int64)).to(self.params.device, non_blocking=True))
+            yield torch.as_tensor(rows, dtype=torch.int64), feats
+            start = end
+
+    def _token_embeddings(self, feats: EmbeddingsFeatures) -> torch.Tensor:
+        """Encoder forward -> last hidden state.  ``params.encode_dtype = torch.bfloat16`` runs it under
+        ``torch.autocast`` (tensor-core matmuls; whatever dtype comes out, K1 reads it as is)."""
+        dt = getattr(self.params, "encode_dtype", None)
+        if dt in (torch.bfloat16, torch.float16) and torch.device(self.params.device).type == "cuda":
+            with torch.autocast("cuda", dtype=dt):
+                return self.context_embedder(**feats.to_dict())[0]
+        return self.context_embedder(**feats.to_dict())[0]
+
     def encode_text(self, documents: List[str], output_np: bool = False) -> Union[torch.Tensor, np.ndarray]:
         """Text -> [n, D] fp32 mean-pooled embeddings on ``params.device`` (reference :136-173).
         Rows are written by the pooling kernel straight to their un-sorted positions instead of
@@ -140,7 +194,7 @@ class SentenceTransformerWrapper(BaseEncoderModel):
         with torch.no_grad():
             for rows, feats in self._batches(documents):
                 if fused:
-                    tokens = self.context_embedder(**feats.to_dict())[0]
+                    tokens = self._token_embeddings(feats)
                     if out is None:
                         out = torch.empty(n, tokens.shape[-1], dtype=torch.float32, device=tokens.device)
                     from . import ops
@@ -170,7 +224,7 @@ class SentenceTransformerWrapper(BaseEncoderModel):
         out = inv = None
         with torch.no_grad():
             for rows, feats in self._batches(documents):
-                tokens = self.context_embedder(**feats.to_dict())[0]
+                tokens = self._token_embeddings(feats)
                 if out is None:
                     out = torch.empty(n, tokens.shape[-1], dtype=out_dtype, device=tokens.device)
                     inv = torch.empty(n, dtype=torch.float32, device=tokens.device)
@@ -200,7 +254,7 @@ class SentenceTransformerWrapper(BaseEncoderModel):
         store._reserve(n)
         with torch.no_grad():
             for rows, feats in self._batches(documents):
-                tokens = self.context_embedder(**feats.to_dict())[0]
+                tokens = self._token_embeddings(feats)
                 ops.pool_norm(tokens, feats.attention_mask, normalize=True, out=store.rows,
                               out_rows=rows.to(tokens.device) + base, out_inv_norm=store.inv_norm)
         store._register(labels)

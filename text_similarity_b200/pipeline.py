@@ -258,3 +258,58 @@ class SemanticSearchPipeline(SentenceMiningPipeline):
 
     def num_indexed(self):
         return 0 if self.store is None else len(self.store)
+
+
+class APISearchPipeline(SemanticSearchPipeline):
+    """Import- and signature-compatible with the reference's ONNX serving pipeline (search_pipeline.py:178-226):
+    ``APISearchPipeline(params, max_n_results, *args, inference_mode=True, session_options=None, **kwargs)``.
+    The reference builds an ``onnxruntime.InferenceSession`` on ``params.model_path`` at construction and encodes
+    text through it; the search itself is its parent's.  Here the search is the exact CUDA engine, and the ONNX
+    session is optional: with ``onnxruntime`` installed and ``params.model_path`` set it is created and used by
+    ``encode_corpus`` exactly like the reference; otherwise constructing with a model path raises the
+    ``ImportError`` the reference's own ``import onnxruntime`` would, and without one text is encoded by
+    ``model`` (the parent's path)."""
+
+    def __init__(self, params, max_n_results: int, *args, inference_mode: bool = True, session_options=None,
+                 **kwargs):
+        if "index_path" not in kwargs and not args:
+            kwargs["index_path"] = getattr(params, "index_path", None) or os.path.join(
+                getattr(params, "save_path", "."), "index")
+        super().__init__(*args, params=params, **kwargs)
+        self.inference_mode = inference_mode
+        self.sess_options = session_options
+        self.max_n_results = max_n_results
+        self.session = None
+        model_path = getattr(params, "model_path", None)
+        if model_path:
+            try:
+                import onnxruntime
+            except ImportError as exc:  # the reference imports it at module scope (search_pipeline.py:10)
+                raise ImportError("APISearchPipeline with params.model_path needs onnxruntime (not installed): "
+                                  "pass model= and leave model_path unset to encode with the PyTorch encoder") from exc
+            if self.sess_options is None:
+                self.sess_options = onnxruntime.SessionOptions()
+            self.session = onnxruntime.InferenceSession(model_path, self.sess_options)
+
+    def __call__(self, queries: TextOrTensor, max_num_results: Optional[int] = None):
+        return self._search(queries, max_num_results if max_num_results is not None else self.max_n_results)
+
+    def encode_corpus(self, documents, convert_to_numpy: bool = False):
+        """Reference :202-226: length-sorted batches through the ONNX session, un-sorted at the end.  Without a
+        session: the parent's encoder path."""
+        if self.session is None or not isinstance(documents, list):
+            return super().encode_corpus(documents, convert_to_numpy)
+        import numpy as np
+        order = np.argsort([len(sen) for sen in documents], kind="stable")
+        rows = [None] * len(documents)
+        bs = self.params.batch_size
+        for start in range(0, len(documents), bs):
+            idx = order[start:start + bs]
+            enc = self.params.tokenizer(text=[documents[i] for i in idx], add_special_tokens=True, padding="longest",
+                                        truncation=True, max_length=self.params.sequence_max_len,
+                                        return_attention_mask=True, return_token_type_ids=False, return_tensors="np")
+            out = self.session.run(None, {"input_ids": enc["input_ids"], "attention_mask": enc["attention_mask"]})[0]
+            for i, row in zip(idx, out):       # (the reference reshapes the batch to one row, :219-220: repaired)
+                rows[int(i)] = row
+        emb = np.stack(rows) if rows else np.zeros((0, 0), dtype=np.float32)
+        return emb if convert_to_numpy else torch.from_numpy(emb).to(self.params.device)

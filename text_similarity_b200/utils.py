@@ -28,6 +28,11 @@ class SyntheticTokenizer:
         if isinstance(text, str):
             text = [text]
         rows = [self._ids(t, max_length if truncation else None, add_special_tokens) for t in text]
+        if not padding and return_tensors is None:        # HF convention: ragged python lists
+            out = {"input_ids": rows}
+            if return_attention_mask:
+                out["attention_mask"] = [[1] * len(r) for r in rows]
+            return out
         width = max((len(r) for r in rows), default=0)
         if padding == "max_length" and max_length is not None:
             width = max_length
