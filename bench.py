@@ -557,32 +557,8 @@ def main():
     torch.cuda.synchronize()
     regimes = []
 
-    # ---- small-batch (HBM-bound) regimes first: a small-batch search alone does not hit the 1 kW power cap, the
-    # tensor-bound loops below do -------------------------------------------------------------------------
-    if "hbm" in want:
-        for sq in (1, 32):
-            regimes.append(regime_search(ctx, f"hbm_{args.workload.split('_')[0]}_bf16_q{sq}_top{k}", corpus,
-                                         dev_batches[0][:sq].contiguous(), k, N, 2, reps=10, graphed=True, verify=sq))
-    if "cfg4" in want:
-        # BASELINE config 4: 100M x 384 e4m3 rows sharded over the N GPUs of the box (N = 8: 12.5M rows = 4.8 GB per
-        # GPU; N = 1: the whole 38.4 GB on one GPU), batch 1 / 8 / 32, incl. the all-gather + merge at N > 1
-        n4, d4 = 100_000_000, 384
-        a0, a1 = shard_bounds(n4, world, rank)
-        c4 = make_shard(a1 - a0, d4, seed=99 + rank, dev=dev, dtype=torch.float8_e4m3fn)
-        corp4 = ShardedCorpus(c4, idx_base=a0, group=ctx.group)
-        q4 = make_shard(32, d4, seed=77, dev=dev, dtype=torch.float8_e4m3fn)
-        for sq in (1, 8, 32):
-            regimes.append(regime_search(ctx, f"cfg4_100Mx384_e4m3_q{sq}_top10", corp4, q4[:sq].contiguous(), 10, n4, 1,
-                                         reps=10, graphed=True, verify=sq))
-        if world == 1:
-            # the per-GPU shape of the 8-GPU split on its own (first 12.5M rows of the same matrix)
-            corp4s = ShardedCorpus(c4[:12_500_000], inv_norm=corp4.inv_norm[:12_500_000])
-            for sq in (1, 32):
-                regimes.append(regime_search(ctx, f"cfg4_shard_12.5Mx384_e4m3_q{sq}_top10", corp4s, q4[:sq].contiguous(),
-                                             10, 12_500_000, 1, reps=10, graphed=True, verify=sq))
-            del corp4s
-        del corp4, c4
-        torch.cuda.empty_cache()
+    # ---- short regimes first (K1, the HBM-bound small batches, configs 1 and 2): a short search alone does not hit
+    # the 1 kW power cap, the tensor-bound loops below do -----------------------------------------------------
     if "k1" in want:
         # K1: fused masked mean-pool + L2 normalise + bf16 cast (data-parallel: every rank pools its own batch)
         B1, L1, D1 = 16_384, 64, 768
@@ -606,6 +582,20 @@ def main():
                                      "1.6 GB of tokens per call", "traffic": None},
                         "verified": {"rows": 64, "max_abs_err_vs_oracle": k1_err, "mismatches": int(k1_err > 2 ** -8)}})
         del tok, mask, out1
+        torch.cuda.empty_cache()
+    if "hbm" in want:
+        for sq in (1, 32):
+            regimes.append(regime_search(ctx, f"hbm_{args.workload.split('_')[0]}_bf16_q{sq}_top{k}", corpus,
+                                         dev_batches[0][:sq].contiguous(), k, N, 2, reps=10, graphed=True, verify=sq))
+    if "cfg4" in want and world == 1:
+        # the per-GPU shape of config 4's 8-GPU split on its own: 12.5M x 384 e4m3 rows (4.8 GB), batch 1 / 32
+        c4s = make_shard(12_500_000, 384, seed=99, dev=dev, dtype=torch.float8_e4m3fn)
+        corp4s = ShardedCorpus(c4s)
+        q4s = make_shard(32, 384, seed=77, dev=dev, dtype=torch.float8_e4m3fn)
+        for sq in (1, 8, 32):
+            regimes.append(regime_search(ctx, f"cfg4_shard_12.5Mx384_e4m3_q{sq}_top10", corp4s, q4s[:sq].contiguous(),
+                                         10, 12_500_000, 1, reps=10, graphed=True, verify=sq))
+        del corp4s, c4s
         torch.cuda.empty_cache()
     if "cfg1" in want and world == 1:
         regimes.append(regime_cfg1_encode(ctx))
@@ -731,6 +721,22 @@ def main():
             regimes.append(entry("query", msq, {"rows": n5, "mismatches": int(1 - int(same.item())),
                                                 "checked_against": "indices of the corpus-split job on every rank"}))
         del corp5, s5, i5
+
+    if "cfg4" in want:
+        # BASELINE config 4: 100M x 384 e4m3 rows sharded over the N GPUs of the box (N = 8: 12.5M rows = 4.8 GB per
+        # GPU; N = 1: the whole 38.4 GB on one GPU), batch 1 / 8 / 32, incl. the all-gather + merge at N > 1.  Last of
+        # all regimes: seconds of back-to-back HBM streaming leave the memory system throttled for what follows
+        # (K1 measured 0.32 ms right after it, 0.26 ms before).
+        n4, d4 = 100_000_000, 384
+        a0, a1 = shard_bounds(n4, world, rank)
+        c4 = make_shard(a1 - a0, d4, seed=99 + rank, dev=dev, dtype=torch.float8_e4m3fn)
+        corp4 = ShardedCorpus(c4, idx_base=a0, group=ctx.group)
+        q4 = make_shard(32, d4, seed=77, dev=dev, dtype=torch.float8_e4m3fn)
+        for sq in (1, 8, 32):
+            regimes.append(regime_search(ctx, f"cfg4_100Mx384_e4m3_q{sq}_top10", corp4, q4[:sq].contiguous(), 10, n4, 1,
+                                         reps=10, graphed=True, verify=sq))
+        del corp4, c4
+        torch.cuda.empty_cache()
 
     # ---- CPU baselines (rank 0, N = 1 only): bounded samples of the same workload ----------------
     cpu_baseline = None

@@ -1,6 +1,7 @@
 """Interleaved A/B timing of planner knobs (environment variables read per call by libtsim) on the
 bench workload: same process, same box, same thermal state.
     python scripts/ab_probe.py "X=1" "TSIM_CHUNK_ROWS=32768" "TSIM_FORCE_BOOT=1 TSIM_CHUNK_ROWS=16384"
+    ROWS=12500000 D=384 DT=fp8 Q=32 python scripts/ab_probe.py "X=1" "TSIM_NO_FUSED=1"      # config 4's shard
 """
 import os
 import sys
@@ -16,12 +17,13 @@ build.build(experiment=True)      # the knobs below exist only in the -DTSIM_EXP
 _lib.use_experiment_build()
 
 rows = int(os.environ.get("ROWS", "10000000"))
-Q, D, k = int(os.environ.get("Q", "4096")), 768, int(os.environ.get("K", "10"))
+Q, D, k = int(os.environ.get("Q", "4096")), int(os.environ.get("D", "768")), int(os.environ.get("K", "10"))
+dtype = torch.float8_e4m3fn if os.environ.get("DT", "bf16") == "fp8" else torch.bfloat16
 cfgs = [dict(kv.split("=") for kv in c.split()) for c in sys.argv[1:]]
 dev = torch.device("cuda")
-corpus = make_shard(rows, D, 1, dev)
+corpus = make_shard(rows, D, 1, dev, dtype)
 inv = ops.row_inv_norm(corpus)
-q = make_shard(Q, D, 2, dev)
+q = make_shard(Q, D, 2, dev, dtype)
 keys = sorted({k_ for c in cfgs for k_ in c})
 res = {i: [] for i in range(len(cfgs))}
 for rnd in range(4):
@@ -42,4 +44,5 @@ for rnd in range(4):
             res[i].append(e0.elapsed_time(e1) / n)
 for i, c in enumerate(cfgs):
     ms = sorted(res[i])[len(res[i]) // 2]
-    print(f"{str(c):70s} median {ms:8.3f} ms/search  {2.0 * Q * rows * D / (ms * 1e-3) / 1e12:7.0f} TFLOP/s  all={['%.1f' % x for x in res[i]]}")
+    print(f"{str(c):70s} median {ms:8.4f} ms/search  {2.0 * Q * rows * D / (ms * 1e-3) / 1e12:7.0f} TFLOP/s  "
+          f"{rows * (D * corpus.element_size() + 4) / (ms * 1e-3) / 1e9:6.0f} GB/s  all={['%.3f' % x for x in res[i]]}")

@@ -170,6 +170,18 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
       : "memory");
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// The same wait, naming the 32 registers of an earlier tc_ld32 as in/out operands: the load is asynchronous, and
+// nothing else tells the compiler that uses of v must stay BELOW the wait when another load is issued in between.
+__device__ __forceinline__ void tc_ld_wait_on(uint32_t* v) {
+  asm volatile(
+      "tcgen05.wait::ld.sync.aligned;"
+      : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+        "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+        "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+        "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+      :
+      : "memory");
+}
 
 // UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B, 128-byte rows:
 //   start address >> 4 | LBO (unused for swizzled K-major) = 1 | SBO = 1024 B (8 rows) >> 4 |
@@ -190,6 +202,19 @@ struct TcArgs {
   int tile_stride;      // distance between sample tiles (modes 1, 2, 3)
   int tile_mult;        // mode 3: every tile_mult-th sample tile belongs to the mini sample
   int slot_base;        // first candidate-list slot this launch writes
+  // Fused sticky pass (one launch instead of sample -> tighten -> main): every worker first scans its sample
+  // tile(s) (tile_mode / T / slot_base above), the epilogue warps of ALL CTAs meet at a grid barrier, each CTA turns
+  // the sample lists of "its" queries into thresholds + ladders (warp_tighten), a second barrier, then the worker's
+  // main unit (tile mode 2 over T2 tiles, slots from slot_base2).  TMA and MMA warps never wait: they run ahead
+  // into the main unit's tiles while the thresholds are made.
+  int fused; int T2; int slot_base2;
+  // Query replication (sticky lone-CTA plans with Q <= 64): the padded 128-row query block holds the Q <= 128 / qrep
+  // queries qrep times over, so all four TMEM lane quadrants carry the same scores and the four epilogue warps split a
+  // tile's 256 columns between them (each thread: query et % (128 / qrep), columns of part et / (128 / qrep)).  With one
+  // copy, a batch of <= 32 queries keeps ONE warp busy for all 8 column chunks of every tile while three idle -- and
+  // on 384-byte fp8 rows that one warp, not HBM, set the pace.  Sample units are not split (one list per worker).
+  int qrep;
+  uint32_t* gbar;       // [2] grid-barrier counters (zeroed per call)
   int sticky;           // 1: CTA <-> (query block, tile residue class), one list per CTA lifetime
   int Gq;               // sticky: CTAs per query block
   int tpc;              // round-robin: tiles per corpus chunk
@@ -216,15 +241,16 @@ struct TcArgs {
 
 // Logical tile number of this launch -> tile of the corpus.  A bootstrap launch (mode 1) scans a
 // strided sample so every query gets a good threshold before the main launch (mode 2) scans the rest.
-__device__ __forceinline__ int actual_tile(const TcArgs& a, int u) {
-  if (a.tile_mode == 1) return u * a.tile_stride;
-  if (a.tile_mode == 2) return u + u / (a.tile_stride - 1) + 1;
-  if (a.tile_mode == 3) return (u + u / (a.tile_mult - 1) + 1) * a.tile_stride;
+__device__ __forceinline__ int actual_tile(const TcArgs& a, int mode, int u) {
+  if (mode == 1) return u * a.tile_stride;
+  if (mode == 2) return u + u / (a.tile_stride - 1) + 1;
+  if (mode == 3) return (u + u / (a.tile_mult - 1) + 1) * a.tile_stride;
   return u;
 }
 
 // A unit = one candidate list: a query block and the sequence of corpus tiles scanned into it.
-struct Unit { int qb; int slot; int tile0; int tstride; int ntiles; };
+struct Unit { int qb; int slot; int tile0; int tstride; int ntiles; int mode; int split; };   // slot: absolute (first of
+                                                                 // qrep when split); mode: tile mode; split: columns dealt over the parts
 
 // Sticky schedule (few query blocks, the HBM-bound regime): CTA c keeps query block c % QB for its
 // whole life and takes tiles j, j+Gq, ... (j = c / QB): perfect tile balance, neighbouring CTAs
@@ -250,10 +276,13 @@ constexpr uint32_t kNoUnit = 0xffffffffu;
 
 __device__ __forceinline__ bool get_unit(const TcArgs& a, int it, int wid, int nw, bool claimer, Unit& un) {
   if (a.sticky) {
-    if (it > 0 || wid >= a.Gq * a.QB) return false;
+    if (it > (a.fused ? 1 : 0) || wid >= a.Gq * a.QB) return false;
     const int j = wid / a.QB;
-    un.qb = wid % a.QB; un.slot = j; un.tile0 = j; un.tstride = a.Gq;
-    un.ntiles = j < a.T ? (a.T - j + a.Gq - 1) / a.Gq : 0;
+    const int T = it ? a.T2 : a.T;           // fused: unit 0 = the worker's sample tiles, unit 1 = its main tiles
+    un.mode = it ? 2 : a.tile_mode;
+    un.split = (a.qrep > 1 && un.mode != 1) ? 1 : 0;
+    un.qb = wid % a.QB; un.slot = (it ? a.slot_base2 : a.slot_base) + (un.split ? j * a.qrep : j); un.tile0 = j; un.tstride = a.Gq;
+    un.ntiles = j < T ? (T - j + a.Gq - 1) / a.Gq : 0;
     return true;
   }
   int u;
@@ -279,7 +308,8 @@ __device__ __forceinline__ bool get_unit(const TcArgs& a, int it, int wid, int n
     if (u >= a.n_units) return false;
   }
   const int chunk = u / a.QB;
-  un.qb = u - chunk * a.QB; un.slot = chunk; un.tile0 = chunk * a.tpc; un.tstride = 1;
+  un.qb = u - chunk * a.QB; un.slot = a.slot_base + chunk; un.tile0 = chunk * a.tpc; un.tstride = 1; un.mode = a.tile_mode;
+  un.split = 0;
   un.ntiles = min(a.tpc, a.T - un.tile0);
   return true;
 }
@@ -302,7 +332,7 @@ struct Ladder {
     g = lad;
     base = INFINITY; step = 0.f; inv = 0.f;
     if (g) {
-      const uint4 h = __ldg((const uint4*)g);
+      const uint4 h = __ldcg((const uint4*)g);   // (a fused pass reads a ladder another CTA of the same launch wrote)
       base = __uint_as_float(h.x); step = __uint_as_float(h.y); inv = __uint_as_float(h.z);
     }
 #pragma unroll
@@ -548,6 +578,95 @@ template <> struct ListFor<16> { using type = RegList16; };
 template <> struct ListFor<-kAppStageMain> { using type = AppendList<kAppStageMain>; };
 template <> struct ListFor<-kAppStageSample> { using type = AppendList<kAppStageSample>; };
 
+// Thresholds inside a fused sticky pass, by the 128 epilogue threads of a CTA (named barrier 1) for ONE query: the
+// same radix select and ladder as warp_tighten (tsim_common.cuh), but every thread first pulls its share of the
+// keys into registers with independent loads -- one L2 round trip -- and the four passes then run on registers.
+// (A single warp walking 74 keys per lane with a load -> shared-atomic dependency per key took ~45 us, during
+// which every CTA of the launch sat at the grid barrier with HBM idle.)  n <= 128 * kEpiKeys keys; hist: 288 words.
+constexpr int kEpiKeys = 24;
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __noinline__ void epi_tighten(const uint64_t* src, uint32_t n, int KP, uint32_t* thr_q, uint32_t* lad,
+                                         uint32_t* hist, int et) {
+  uint32_t sc[kEpiKeys];
+#pragma unroll
+  for (int i = 0; i < kEpiKeys; ++i) {
+    const uint32_t idx = (uint32_t)et + 128u * i;
+    sc[i] = idx < n ? (uint32_t)(__ldcg(src + idx) >> 32) : 0u;
+  }
+  uint32_t* ctl = hist + 256;      // [0] live keys, [1] best score, [2] bucket, [3] need
+  if (et < 32) ctl[et] = 0u;
+  epi_bar();
+  uint32_t live = 0, best = 0;
+#pragma unroll
+  for (int i = 0; i < kEpiKeys; ++i) { live += sc[i] != 0u; best = max(best, sc[i]); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { live += __shfl_xor_sync(0xffffffffu, live, o); best = max(best, __shfl_xor_sync(0xffffffffu, best, o)); }
+  if ((et & 31) == 0) { atomicAdd(&ctl[0], live); atomicMax(&ctl[1], best); }
+  epi_bar();
+  live = ctl[0]; best = ctl[1];
+  if (live < (uint32_t)KP) {       // not enough rows for a threshold: a ladder that never fires
+    if (lad && et < kLadder) { lad[kLadder + et] = 0u; lad[et] = et == 0 ? __float_as_uint(INFINITY) : 0u; }
+    epi_bar();
+    return;
+  }
+  uint32_t prefix = 0, need = (uint32_t)KP;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    hist[et] = 0u; hist[et + 128] = 0u;
+    epi_bar();
+    const uint32_t hi_mask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+#pragma unroll
+    for (int i = 0; i < kEpiKeys; ++i)
+      if (sc[i] != 0u && (sc[i] & hi_mask) == prefix) atomicAdd(&hist[(sc[i] >> shift) & 255u], 1u);
+    epi_bar();
+    if (et < 32) {
+      // lane l owns buckets 255 - 8l .. 248 - 8l (descending): where does the running count reach `need`?
+      uint32_t c[8], tot = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { c[j] = hist[255 - 8 * et - j]; tot += c[j]; }
+      uint32_t incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (et >= o) incl += v;
+      }
+      const uint32_t before = incl - tot;
+      if (before < need && incl >= need) {
+        uint32_t run = before;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (run < need && run + c[j] >= need) { ctl[2] = 255u - 8u * et - j; ctl[3] = need - run; }
+          run += c[j];
+        }
+      }
+    }
+    epi_bar();
+    prefix |= ctl[2] << shift;
+    need = ctl[3];
+    epi_bar();
+  }
+  if (et == 0) atomicMax(thr_q, prefix);
+  if (lad) {
+    const float base = ord_to_f32(prefix);
+    float step = (ord_to_f32(best) - base) * (1.f / 8.f);
+    if (!(step > 0.f) || !(step < INFINITY)) step = 0.f;
+    const float inv = step > 0.f ? 1.f / step : 0.f;
+    if (et < kLadder) hist[et] = 0u;
+    epi_bar();
+#pragma unroll
+    for (int i = 0; i < kEpiKeys; ++i)
+      if (sc[i] >= prefix) {             // (prefix > 0: empty slots never pass)
+        const int j = ladder_level(base, step, inv, ord_to_f32(sc[i]));
+        if (j >= 0) atomicAdd(&hist[j], 1u);
+      }
+    epi_bar();
+    if (et < kLadder) {
+      lad[kLadder + et] = hist[et];
+      lad[et] = et == 0 ? __float_as_uint(base) : et == 1 ? __float_as_uint(step) : et == 2 ? __float_as_uint(inv) : 0u;
+    }
+  }
+  epi_bar();
+}
+
 template <int KP, int STAGES, bool PAIR, bool FP8>
 __global__ void __launch_bounds__(kThreads, 1)
 search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c, TcArgs a) {
@@ -626,7 +745,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       Unit un;
       for (int it = 0; get_unit(a, it, wid, nw, rank == 0, un); ++it) {
         for (int t = 0; t < un.ntiles; ++t) {
-          const int row0 = actual_tile(a, un.tile0 + t * un.tstride) * BN;
+          const int row0 = actual_tile(a, un.mode, un.tile0 + t * un.tstride) * BN;
           for (int kb = 0; kb < a.kblocks; ++kb) {
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
             const uint32_t sa = smem_u32(tiles + (size_t)stage * STAGE_BYTES);
@@ -690,12 +809,61 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     int acc = 0; uint32_t aphase = 0;
     Unit un;
     for (int it = 0; get_unit(a, it, wid, nw, false, un); ++it) {
-      const int64_t qg = PAIR ? (int64_t)un.qb * (2 * BM) + rank * BM + et : (int64_t)un.qb * BM + et;
+      const int64_t qbase = PAIR ? (int64_t)un.qb * (2 * BM) + rank * BM : (int64_t)un.qb * BM;
+      const int qspan = a.qrep > 1 ? BM / a.qrep : BM;      // distinct queries in this CTA's block (replication, TcArgs)
+      const int part = et / qspan;                          // which share of a tile's columns this thread examines
+      const int64_t qg = qbase + (et & (qspan - 1));
       const bool qvalid = qg < q_live;
+      const bool warp_live = __any_sync(0xffffffffu, qvalid);
+      if (a.fused && it == 1) {
+        // ---- between the sample unit and the main unit of a fused sticky pass ----
+        // (1) every CTA's sample lists are in global memory
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+          atomicAdd(a.gbar, 1u);
+          uint32_t seen;
+          do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.gbar) : "memory"); } while (seen < gridDim.x);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // (2) thresholds + ladders: the 128 queries of this CTA's block half are dealt over the Gq workers that share
+        // the block (query ql belongs to worker ql % Gq), a worker's queries over its four epilogue warps
+        {
+          constexpr int KPv = KP > 0 ? KP : 1;
+          uint32_t* hist = reinterpret_cast<uint32_t*>(cnorm);   // cnorm is idle between units
+          const int j = wid / a.QB;
+          const uint32_t nkeys = (uint32_t)(a.Gq * KPv);
+          if (nkeys <= 128u * kEpiKeys) {
+            // all 128 epilogue threads per query, keys in registers (block-uniform loop: named barriers inside)
+            for (int ql = j; ql < BM; ql += a.Gq) {
+              const int64_t q2 = qbase + ql;
+              if (q2 < q_live)
+                epi_tighten(a.cand + ((size_t)q2 * a.NC + a.slot_base) * KPv, nkeys, KPv, a.thr + q2,
+                            a.ladder ? a.ladder + (size_t)q2 * (2 * kLadder) : nullptr, hist, et);
+            }
+          } else {
+            for (int ql = j + (warp & 3) * a.Gq; ql < BM; ql += 4 * a.Gq) {
+              const int64_t q2 = qbase + ql;
+              if (q2 < q_live)
+                warp_tighten<true>(a.cand + ((size_t)q2 * a.NC + a.slot_base) * KPv, nkeys, KPv, a.thr + q2,
+                                   a.ladder ? a.ladder + (size_t)q2 * (2 * kLadder) : nullptr, hist + (warp & 3) * 256);
+            }
+          }
+        }
+        // (3) ... are visible to every CTA before anybody filters with them
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+          atomicAdd(a.gbar + 1, 1u);
+          uint32_t seen;
+          do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.gbar + 1) : "memory"); } while (seen < gridDim.x);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       const int64_t self_row = a.self_on ? a.self_off + ((a.q_map && qvalid) ? (int64_t)a.q_map[qg] : qg) : -1;
       uint32_t* thr_g = a.thr + (qvalid ? qg : 0);
       Ladder lad;
-      lad.init((a.ladder && qvalid) ? a.ladder + (size_t)qg * (2 * kLadder) : nullptr);
+      lad.init((a.ladder && qvalid && !(a.fused && it == 0)) ? a.ladder + (size_t)qg * (2 * kLadder) : nullptr);
       list.reset();
       if constexpr (KP < 0) list.bind(a.app_keys + (size_t)(qvalid ? qg : 0) * a.app_cap, a.app_cnt + (qvalid ? qg : 0), a.app_cap);
       float thr = qvalid ? -INFINITY : INFINITY;   // padded query lanes never insert
@@ -704,7 +872,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       float nreg[8];
       uint32_t gthr = 0;
       auto fetch_meta = [&](int t) {
-        const int64_t r0 = (int64_t)actual_tile(a, un.tile0 + t * un.tstride) * BN;
+        const int64_t r0 = (int64_t)actual_tile(a, un.mode, un.tile0 + t * un.tstride) * BN;
         const int nc = (int)min((int64_t)BN, a.N - r0);
 #pragma unroll
         for (int i = 0; i < 8; ++i) nreg[i] = (lane + 32 * i < nc) ? __ldg(a.c_inv + r0 + lane + 32 * i) : 0.f;
@@ -712,7 +880,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       };
       if (un.ntiles > 0) fetch_meta(0);
       for (int t = 0; t < un.ntiles; ++t) {
-        const int64_t trow0 = (int64_t)actual_tile(a, un.tile0 + t * un.tstride) * BN;
+        const int64_t trow0 = (int64_t)actual_tile(a, un.mode, un.tile0 + t * un.tstride) * BN;
         const int ncols = (int)min((int64_t)BN, a.N - trow0);
         // each epilogue warp keeps a private copy of the tile's inverse norms: no cross-warp barrier
         // ... followed by, per 32-column chunk, the largest and the smallest of its inverse norms (chunk i = nreg[i]
@@ -732,12 +900,19 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         mbar_wait(smem_u32(&tfull_bar[acc]), aphase);
         tc_fence_after();
         const uint32_t tbase = tmem_base + lane_addr + (uint32_t)acc * BN;
-        const int nchunks = (dbg & 4) ? 0 : (ncols + 31) / 32;
-#pragma unroll 1
-        for (int c = 0; c < nchunks; ++c) {
-          uint32_t v[32];
-          tc_ld32(tbase + c * 32, v);
-          tc_ld_wait();
+        // (a warp whose 32 queries are all padding -- three of the four at Q <= 32 -- has nothing to examine)
+        int nchunks = ((dbg & 4) || !warp_live) ? 0 : (ncols + 31) / 32;
+        int c0 = 0;                                          // this thread's chunks: [c0, nchunks)
+        if (a.qrep > 1) {
+          const int per = (BN / 32) / a.qrep;
+          c0 = un.split ? part * per : 0;
+          nchunks = min(nchunks, un.split ? c0 + per : (part == 0 ? BN / 32 : 0));
+        }
+        // The TMEM loads are software-pipelined: chunk c + 1 is requested before chunk c is examined, so the
+        // tcgen05.ld round trip overlaps the max tree instead of preceding it.  With 384-byte fp8 rows a tile is
+        // only 98 KB -- 2.1 us of HBM time -- and the serial ld -> wait -> examine loop took longer than that:
+        // the epilogue, not HBM, set the pace of config 4 (skipping it: 0.88 -> 0.71 ms per search).
+        auto examine = [&](const uint32_t (&v)[32], int c) {
           // Hot path: FMNMX3 tree over the 32 RAW dot products, one FMUL, one compare.  A scaled score is
           // s_j * inv_j with inv_lo <= inv_j <= inv_hi, so none can exceed  bound = mx * (mx >= 0 ? inv_hi : inv_lo)
           // (float rounding is monotone): bound <= thr proves the chunk holds no candidate without scaling a
@@ -771,6 +946,19 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (__any_sync(0xffffffffu, mx > thr))
               thr = list.slow(sc, thr, trow0 + c * 32, self_row, ncols - c * 32, thr_g, lad);
           }
+        };
+        uint32_t va[32], vb[32];
+        if (c0 < nchunks) tc_ld32(tbase + c0 * 32, va);
+#pragma unroll 1
+        for (int c = c0; c < nchunks; c += 2) {
+          tc_ld_wait_on(va);
+          if (c + 1 < nchunks) tc_ld32(tbase + (c + 1) * 32, vb);
+          examine(va, c);
+          if (c + 1 < nchunks) {
+            tc_ld_wait_on(vb);
+            if (c + 2 < nchunks) tc_ld32(tbase + (c + 2) * 32, va);
+            examine(vb, c + 1);
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -789,7 +977,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
       }
       // flush this unit's list
-      if (qvalid && KP > 0) list.flush(a.cand + ((size_t)qg * a.NC + a.slot_base + un.slot) * KP);
+      if (qvalid && KP > 0 && (un.split || part == 0))
+        list.flush(a.cand + ((size_t)qg * a.NC + un.slot + (un.split ? part : 0)) * KP);
     }
   }
 
@@ -851,7 +1040,7 @@ int launch_cfg(const CUtensorMap& mq, const CUtensorMap& mc, const TcArgs& a, cu
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[3];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = PAIR ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
@@ -860,6 +1049,13 @@ int launch_cfg(const CUtensorMap& mq, const CUtensorMap& mc, const TcArgs& a, cu
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = knob_on("TSIM_NO_PDL") ? 1 : 2;
+  if (a.fused) {
+    // the grid barriers of a fused pass need every CTA resident at once: a cooperative launch is gang-scheduled
+    // (two such searches on two streams cannot interleave their CTAs and dead-lock each other)
+    attr[cfg.numAttrs].id = cudaLaunchAttributeCooperative;
+    attr[cfg.numAttrs].val.cooperative = 1;
+    ++cfg.numAttrs;
+  }
   TSIM_CUDA(cudaLaunchKernelEx(&cfg, kern, mq, mc, a));
   count_launch();
   return TSIM_OK;
@@ -908,7 +1104,7 @@ int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_
                      const float* c_inv, int64_t Q, int64_t N, int64_t D, int self_on, int64_t self_off,
                      const SearchPlan& p, int pass, uint64_t* cand, uint32_t* thr, uint32_t* ladder, uint64_t* sched,
                      cudaStream_t st, MapCache* maps, const int32_t* q_count, const int32_t* q_map, int q_skip,
-                     uint64_t* app_keys, uint32_t* app_cnt) {
+                     uint64_t* app_keys, uint32_t* app_cnt, uint32_t* gbar) {
   CUtensorMap mq, mc;
   const int qrows = p.pair ? 2 * BM : BM;
   // q holds QB * qrows rows (the API pads the last query block with zero rows)
@@ -936,12 +1132,20 @@ int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_
       a.tile_mode = 3; a.tile_stride = (int)p.boot_stride; a.tile_mult = (int)p.mini_mult; a.T = (int)(p.boot_tiles - p.mini_tiles);
       a.tpc = (int)p.boot_tpc; a.slot_base = (int)p.mini_slots;
       break;
+    case TC_PASS_FUSED:         // sticky: the worker's sample tiles, in-kernel thresholds, then its main tiles
+      a.tile_mode = 1; a.tile_stride = (int)p.boot_stride; a.T = (int)p.boot_tiles;
+      break;
     case TC_PASS_MAIN:          // everything that is not a sample tile
       a.tile_mode = 2; a.tile_stride = (int)p.boot_stride; a.T = (int)(T - p.boot_tiles);
       a.slot_base = (int)(p.mini_slots + p.boot_slots);
       break;
     default: break;
   }
+  a.qrep = p.qrep > 1 ? p.qrep : 1;
+  a.fused = pass == TC_PASS_FUSED ? 1 : 0;
+  a.T2 = a.fused ? (int)(T - p.boot_tiles) : 0;
+  a.slot_base2 = a.fused ? (int)(p.mini_slots + p.boot_slots) : 0;
+  a.gbar = gbar;
   a.n_units = p.QB * ((a.T + a.tpc - 1) / (a.tpc > 0 ? a.tpc : 1));
   a.self_on = self_on; a.self_off = self_off;
   a.cand = cand; a.thr = thr; a.ladder = ladder;

@@ -564,85 +564,15 @@ __global__ void __launch_bounds__(kSelThreads) tighten_app_kernel(const uint64_t
   pdl_trigger();
   pdl_wait();
   if (q >= Q) return;
-  uint32_t* hist = hist_all[warp];
   const uint32_t n = min(app_cnt[q], (uint32_t)cap);
-  const uint64_t* src = app_keys + (size_t)q * cap;
-  uint32_t* lad = ladder ? ladder + (size_t)q * 2 * kLadder : nullptr;
-  if (n < (uint32_t)KP) {          // not enough rows for a threshold yet: a ladder that never fires
-    if (lad && lane < kLadder) {
-      lad[kLadder + lane] = 0u;
-      lad[lane] = lane == 0 ? __float_as_uint(INFINITY) : 0u;
-    }
-    return;
-  }
-  uint32_t prefix = 0, need = (uint32_t)KP, best = 0;
-  for (int shift = 24; shift >= 0; shift -= 8) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) hist[lane + 32 * i] = 0;
-    __syncwarp();
-    const uint32_t hi_mask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
-    for (uint32_t i = lane; i < n; i += 32) {
-      const uint32_t sc = (uint32_t)(__ldg(src + i) >> 32);
-      if (shift == 24) best = max(best, sc);
-      if ((sc & hi_mask) == prefix) atomicAdd(&hist[(sc >> shift) & 255u], 1u);
-    }
-    __syncwarp();
-    // lane l owns buckets 255 - 8l .. 248 - 8l (descending): where does the running count reach `need`?
-    uint32_t c[8], tot = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { c[j] = hist[255 - 8 * lane - j]; tot += c[j]; }
-    uint32_t incl = tot;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    const uint32_t before = incl - tot;
-    const bool mine = before < need && incl >= need;
-    uint32_t bucket = 0, rest = 0;
-    if (mine) {
-      uint32_t run = before;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (run < need && run + c[j] >= need) { bucket = 255u - 8u * lane - j; rest = need - run; }
-        run += c[j];
-      }
-    }
-    const int owner = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;    // exactly one lane (n >= need)
-    bucket = __shfl_sync(0xffffffffu, bucket, owner);
-    need = __shfl_sync(0xffffffffu, rest, owner);
-    prefix |= bucket << shift;
-    __syncwarp();
-  }
-  // prefix = the KP-th best approximate score (ordered-float bits)
-  if (lane == 0) atomicMax(thr + q, prefix);
-  if (!lad) return;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
-  float base = ord_to_f32(prefix);
-  float step = (ord_to_f32(best) - base) * (1.f / 8.f);
-  if (!(step > 0.f) || !(step < INFINITY)) step = 0.f;
-  const float inv = step > 0.f ? 1.f / step : 0.f;
-  if (lane < kLadder) hist[lane] = 0;
-  __syncwarp();
-  for (uint32_t i = lane; i < n; i += 32) {
-    const uint32_t sc = (uint32_t)(__ldg(src + i) >> 32);
-    if (sc >= prefix) {
-      const int j = ladder_level(base, step, inv, ord_to_f32(sc));
-      if (j >= 0) atomicAdd(&hist[j], 1u);
-    }
-  }
-  __syncwarp();
-  if (lane < kLadder) {
-    lad[kLadder + lane] = hist[lane];
-    lad[lane] = lane == 0 ? __float_as_uint(base) : lane == 1 ? __float_as_uint(step) : lane == 2 ? __float_as_uint(inv) : 0u;
-  }
+  warp_tighten<false>(app_keys + (size_t)q * cap, n, KP, thr + q, ladder ? ladder + (size_t)q * 2 * kLadder : nullptr,
+                      hist_all[warp]);
 }
 
 // First kernel of a search (replaces a memset of the control words, a memset of the query padding and a 2-D copy).
 __global__ void __launch_bounds__(256) search_prep_kernel(uint4* zero_base, size_t zero_vecs, const char* q_src,
                                                           size_t q_src_stride_bytes, char* q_dst, size_t row_vecs,
-                                                          int64_t Q, int64_t q_rows_padded) {
+                                                          int64_t Q, int64_t q_rows_padded, int q_span) {
   pdl_trigger();
   pdl_wait();
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
@@ -652,7 +582,8 @@ __global__ void __launch_bounds__(256) search_prep_kernel(uint4* zero_base, size
   const size_t total = (size_t)q_rows_padded * row_vecs;
   for (size_t i = tid; i < total; i += nthr) {
     const size_t r = i / row_vecs, c = i - r * row_vecs;
-    reinterpret_cast<uint4*>(q_dst)[i] = (int64_t)r < Q ? reinterpret_cast<const uint4*>(q_src + r * q_src_stride_bytes)[c] : z;
+    const size_t src_row = q_span > 0 ? r % (size_t)q_span : r;      // replicated query block (qrep plans)
+    reinterpret_cast<uint4*>(q_dst)[i] = (int64_t)src_row < Q ? reinterpret_cast<const uint4*>(q_src + src_row * q_src_stride_bytes)[c] : z;
   }
 }
 
@@ -824,14 +755,14 @@ int launch_tighten(int64_t Q, const SearchPlan& p, int nslots, const uint64_t* c
 }
 
 int launch_search_prep(void* zero_base, size_t zero_bytes, const void* q_src, size_t q_src_stride_bytes, void* q_dst,
-                       size_t row_bytes, int64_t Q, int64_t q_rows_padded, cudaStream_t st) {
+                       size_t row_bytes, int64_t Q, int64_t q_rows_padded, int q_span, cudaStream_t st) {
   // zero_base is 256-byte aligned and zero_bytes a multiple of 256 (workspace layout); rows are 16-byte multiples
   const size_t work = zero_bytes / 16 + (q_dst ? (size_t)q_rows_padded * (row_bytes / 16) : 0);
   size_t blocks = (work + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > 1184) blocks = 1184;
   TSIM_CUDA(launch_pdl(search_prep_kernel, dim3((unsigned)blocks), dim3(256), 0, st, (uint4*)zero_base, zero_bytes / 16,
-                       (const char*)q_src, q_src_stride_bytes, (char*)q_dst, row_bytes / 16, Q, q_rows_padded));
+                       (const char*)q_src, q_src_stride_bytes, (char*)q_dst, row_bytes / 16, Q, q_rows_padded, q_span));
   count_launch();
   return TSIM_OK;
 }

@@ -94,11 +94,15 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
       if (Q >= minq && T >= 32 * (int64_t)p->Gq && !knob_on("TSIM_NO_BOOT")) {
         int64_t tpw = knob_int("TSIM_BOOT_TPW", 1);                     // sample tiles per worker
         if (tpw < 1 || tpw > 16) tpw = 1;
-        p->boot_stride = T / (tpw * (int64_t)p->Gq);                    // >= 2
+        // at most tpw sample tiles per worker (rounding the stride DOWN gave Gq + 1 tiles: one worker scanned two
+        // cold tiles while the other 147 waited for it at the fused pass's grid barrier)
+        p->boot_stride = (T + tpw * (int64_t)p->Gq - 1) / (tpw * (int64_t)p->Gq);   // >= 2
         p->boot_tiles = (T + p->boot_stride - 1) / p->boot_stride;      // every multiple of the stride below T
         p->boot_slots = p->Gq;
+        p->fused = knob_on("TSIM_NO_FUSED") ? 0 : 1;   // sample, thresholds and main in one cooperative launch
       }
     }
+    if (p->sticky && !p->pair && !knob_on("TSIM_NO_QREP")) p->qrep = Q <= 32 ? 4 : Q <= 64 ? 2 : 1;
     if (!p->sticky) {
       // Round-robin units (many query blocks).  A unit's list starts empty, so what it filters with is
       // the query's GLOBAL threshold: a strided sample (~1/64 of the tiles) is scanned first and leaves
@@ -156,7 +160,8 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
       else p->NC = p->boot_tiles ? p->mini_slots + p->boot_slots + (T - p->boot_tiles + tpc - 1) / tpc : (T + tpc - 1) / tpc;
     } else {
       p->R = 256;
-      p->NC = p->boot_tiles ? 2 * p->Gq : p->Gq;
+      const int rep = p->qrep > 1 ? p->qrep : 1;          // main-pass lists per worker (sample lists: one)
+      p->NC = p->boot_tiles ? p->Gq + (int64_t)rep * p->Gq : (int64_t)rep * p->Gq;
     }
     p->off_cand = off; off = align_up(off + (size_t)Q * p->NC * p->KP * sizeof(uint64_t), 256);
     if (p->append) { p->off_app_keys = off; off = align_up(off + (size_t)Q * p->app_cap * sizeof(uint64_t), 256); }
@@ -188,6 +193,7 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
   p->sched_area = (p->use_tensor && !p->sticky) ? 256 + (size_t)sms * 32 * sizeof(uint64_t) : 0;
   off += 3 * p->sched_area;
   if (p->append) { p->off_app_cnt = off; off = align_up(off + (size_t)Q * sizeof(uint32_t), 256); }   // zeroed with thr
+  if (p->fused) { p->off_gbar = off; off += 256; }                                                      // zeroed with thr
   // retry stage: its thresholds and level-2 flag count sit in the same zeroed span
   p->retry = 0;   // TSIM_NO_RETRY (experiment knob): flagged queries go straight to the float64 scan
   if (p->use_tensor && !shadow && p->KP < kRetryKP && !knob_on("TSIM_NO_RETRY")) {
@@ -202,7 +208,7 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
   if (p->use_tensor && p->boot_tiles) {
     p->off_ladder = off; off = align_up(off + (size_t)Q * 2 * kLadder * sizeof(uint32_t), 256);
   }
-  if (p->use_tensor && Q % (p->pair ? 256 : 128) != 0) {  // zero-padded copy of the queries (TMA OOB fill is slow)
+  if (p->use_tensor && (Q % (p->pair ? 256 : 128) != 0 || p->qrep > 1)) {  // zero-padded copy of the queries (TMA OOB fill is slow)
     p->off_qpad = off; off = align_up(off + (size_t)p->QB * (p->pair ? 256 : 128) * D * dtype_size(q_dt), 256);
   }
   if (need_invnorm && p->use_tensor) { p->off_invnorm = off; off = align_up(off + (size_t)N * sizeof(float), 256); }
@@ -323,16 +329,17 @@ static int search_impl(const void* q, int q_dt, int64_t q_stride, const void* co
     // thr, flag_cnt, the unit-claim areas, the append counters and the retry stage's thr / flag_cnt are adjacent:
     // one prep kernel zeroes them and writes the zero-padded copy of the queries (TMA OOB fill is slow)
     const size_t zero_end = p.retry ? p.off_r_flagcnt + 256
-                                    : p.append ? p.off_app_cnt + align_up((size_t)Q * sizeof(uint32_t), 256)
-                                               : p.off_sched + 3 * p.sched_area;
+                            : p.fused ? p.off_gbar + 256
+                            : p.append ? p.off_app_cnt + align_up((size_t)Q * sizeof(uint32_t), 256)
+                                       : p.off_sched + 3 * p.sched_area;
     uint64_t* sched = p.sched_area ? (uint64_t*)(w + p.off_sched) : nullptr;
     const void* qt = tq;
     int64_t qt_stride = tq_stride;
     const int qrows = p.pair ? 256 : 128;
     const size_t rowb = (size_t)D * dtype_size(t_dt);
-    const bool pad = Q % qrows != 0;
+    const bool pad = Q % qrows != 0 || p.qrep > 1;
     rc = launch_search_prep(thr, align_up(zero_end - p.off_thr, 256), tq, (size_t)tq_stride * dtype_size(t_dt),
-                            pad ? w + p.off_qpad : nullptr, rowb, Q, (int64_t)p.QB * qrows, st);
+                            pad ? w + p.off_qpad : nullptr, rowb, Q, (int64_t)p.QB * qrows, p.qrep > 1 ? 128 / p.qrep : 0, st);
     if (rc) return rc;
     if (pad) { qt = w + p.off_qpad; qt_stride = D; }
     const float* c_inv = corpus_inv_norm;
@@ -348,6 +355,13 @@ static int search_impl(const void* q, int q_dt, int64_t q_stride, const void* co
     uint64_t* app_keys = p.append ? (uint64_t*)(w + p.off_app_keys) : nullptr;
     uint32_t* app_cnt = p.append ? (uint32_t*)(w + p.off_app_cnt) : nullptr;
     uint32_t* ladder = nullptr;
+    if (p.fused) {
+      uint32_t* lad = knob_on("TSIM_NO_LADDER") ? nullptr : (uint32_t*)(w + p.off_ladder);   // experiment knob
+      rc = launch_search_tc(qt, qt_stride, tcorpus, tc_stride, t_dt, c_inv, Q, N, D, self_on, self_off, p, TC_PASS_FUSED,
+                            cand, thr, lad, sched, st, maps, nullptr, nullptr, 0, nullptr, nullptr,
+                            (uint32_t*)(w + p.off_gbar));
+      if (rc) return rc;
+    } else {
     if (p.boot_tiles) {
       uint32_t* lad = knob_on("TSIM_NO_LADDER") ? nullptr : (uint32_t*)(w + p.off_ladder);   // experiment knob
       if (p.mini_mult) {
@@ -373,6 +387,7 @@ static int search_impl(const void* q, int q_dt, int64_t q_stride, const void* co
                           p.boot_tiles ? TC_PASS_MAIN : TC_PASS_ALL, cand, thr, ladder, sched, st, maps,
                           nullptr, nullptr, 0, app_keys, app_cnt);
     if (rc) return rc;
+    }
     if (timed) TSIM_CUDA(cudaEventRecord(g_ev_stop, st));
     SelRetry first = {nullptr, nullptr, p.retry * kRetryQ, 0, 0, w + p.off_r_q, D};
     rc = launch_select_rescore(q, q_dt, q_stride, corpus, c_dt, c_stride, Q, N, D, k, idx_base, p,

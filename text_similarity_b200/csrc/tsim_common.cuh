@@ -383,6 +383,99 @@ __device__ __forceinline__ double warp_exact_cosine(const void* q, int q_dt, con
   return dot / (qn * cn);
 }
 
+// ---- threshold from a set of candidate keys, by ONE warp ----------------------------------------
+// MSB-first radix select (4 passes x 8 bits over the upper 32 key bits; `hist`: 256 words of shared memory private
+// to the warp) of the KP-th best approximate score among src[0 .. n) (0 = empty slot, skipped): a valid lower bound
+// of the query's final KP-th best whenever every key stands for a row that reaches select_rescore.  Raises *thr_q
+// to it and, if `lad` is given, lays out the query's threshold ladder: 16 evenly spaced levels from that score
+// (level 0) through the best score seen (level 8) to as far again above it, with the number of keys at or above
+// the cut in each level.  Fewer than KP keys: no threshold, a ladder that never fires.
+// L2ONLY: the keys were written by other CTAs of the SAME kernel (fused sticky pass): read them through L2.
+template <bool L2ONLY>
+__device__ __forceinline__ void warp_tighten(const uint64_t* src, uint32_t n, int KP, uint32_t* thr_q, uint32_t* lad,
+                                             uint32_t* hist) {
+  const int lane = threadIdx.x & 31;
+  auto key_at = [&](uint32_t i) -> uint32_t { return (uint32_t)((L2ONLY ? __ldcg(src + i) : __ldg(src + i)) >> 32); };
+  uint32_t prefix = 0, need = (uint32_t)KP, best = 0, live = 0;
+  bool enough = true;
+  for (int shift = 24; shift >= 0 && enough; shift -= 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hist[lane + 32 * i] = 0;
+    __syncwarp();
+    const uint32_t hi_mask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+    for (uint32_t i = lane; i < n; i += 32) {
+      const uint32_t sc = key_at(i);
+      if (sc == 0u) continue;            // empty slot (a real key's ordered score is never 0)
+      if (shift == 24) { best = max(best, sc); ++live; }
+      if ((sc & hi_mask) == prefix) atomicAdd(&hist[(sc >> shift) & 255u], 1u);
+    }
+    __syncwarp();
+    if (shift == 24) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) live += __shfl_xor_sync(0xffffffffu, live, o);
+      enough = live >= (uint32_t)KP;
+      if (!enough) break;
+    }
+    // lane l owns buckets 255 - 8l .. 248 - 8l (descending): where does the running count reach `need`?
+    uint32_t c[8], tot = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { c[j] = hist[255 - 8 * lane - j]; tot += c[j]; }
+    uint32_t incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const uint32_t before = incl - tot;
+    const bool mine = before < need && incl >= need;
+    uint32_t bucket = 0, rest = 0;
+    if (mine) {
+      uint32_t run = before;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (run < need && run + c[j] >= need) { bucket = 255u - 8u * lane - j; rest = need - run; }
+        run += c[j];
+      }
+    }
+    const int owner = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;    // exactly one lane (live >= need)
+    bucket = __shfl_sync(0xffffffffu, bucket, owner);
+    need = __shfl_sync(0xffffffffu, rest, owner);
+    prefix |= bucket << shift;
+    __syncwarp();
+  }
+  if (!enough) {
+    if (lad && lane < kLadder) {
+      lad[kLadder + lane] = 0u;
+      lad[lane] = lane == 0 ? __float_as_uint(INFINITY) : 0u;
+    }
+    return;
+  }
+  // prefix = the KP-th best approximate score (ordered-float bits)
+  if (lane == 0) atomicMax(thr_q, prefix);
+  if (!lad) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+  const float base = ord_to_f32(prefix);
+  float step = (ord_to_f32(best) - base) * (1.f / 8.f);
+  if (!(step > 0.f) || !(step < INFINITY)) step = 0.f;
+  const float inv = step > 0.f ? 1.f / step : 0.f;
+  if (lane < kLadder) hist[lane] = 0;
+  __syncwarp();
+  for (uint32_t i = lane; i < n; i += 32) {
+    const uint32_t sc = key_at(i);
+    if (sc >= prefix) {                  // (prefix > 0: empty slots never pass)
+      const int j = ladder_level(base, step, inv, ord_to_f32(sc));
+      if (j >= 0) atomicAdd(&hist[j], 1u);
+    }
+  }
+  __syncwarp();
+  if (lane < kLadder) {
+    lad[kLadder + lane] = hist[lane];
+    lad[lane] = lane == 0 ? __float_as_uint(base) : lane == 1 ? __float_as_uint(step) : lane == 2 ? __float_as_uint(inv) : 0u;
+  }
+  __syncwarp();
+}
+
 // ---- launch plans shared by the API and the kernels ---------------------------------------
 struct SearchPlan {
   // tensor path
@@ -405,6 +498,10 @@ struct SearchPlan {
   // Append mode (round-robin plans with a bootstrap sample and KP >= 32): no candidate lists; in every pass the rows
   // that beat the query's threshold are appended to app_keys[q][0 .. app_cap) (count in app_cnt[q], zeroed with thr).
   // NC = 0 then.
+  int qrep;            // sticky lone-CTA plans with Q <= 64: the query block holds the queries qrep (2 / 4) times over and
+                       // the epilogue warps split every tile's columns (search_tc.cu, TcArgs::qrep); lists per worker x qrep
+  int fused;           // sticky + bootstrap: one cooperative launch does sample, thresholds and main (TC_PASS_FUSED)
+  size_t off_gbar;     // its two grid-barrier counters (256 bytes, zeroed with thr)
   int append;
   int app_cap;
   size_t off_app_keys, off_app_cnt;
@@ -454,7 +551,8 @@ struct SelRetry {
 // kernels' host launchers (defined in the .cu files)
 // pass: 0 = the whole corpus in one launch; 1 = bootstrap sample (all of it); 2 = main (everything
 // that is not a sample tile); 3 = mini sample (first of two sample launches); 4 = rest of the sample
-enum { TC_PASS_ALL = 0, TC_PASS_SAMPLE = 1, TC_PASS_MAIN = 2, TC_PASS_MINI = 3, TC_PASS_SAMPLE_REST = 4 };
+// 5 = sticky plans: sample + in-kernel thresholds + main in ONE cooperative launch (search_tc.cu, TcArgs::fused)
+enum { TC_PASS_ALL = 0, TC_PASS_SAMPLE = 1, TC_PASS_MAIN = 2, TC_PASS_MINI = 3, TC_PASS_SAMPLE_REST = 4, TC_PASS_FUSED = 5 };
 // TMA descriptors kept by a plan handle (tsim_plan_create), keyed by (base, rows, D, stride, box, element size):
 // a repeated search of the same arrays encodes nothing.  Null: encode per launch.
 struct MapCache;
@@ -465,7 +563,7 @@ int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_
                      int self_on, int64_t self_off, const SearchPlan& p, int pass, uint64_t* cand,
                      uint32_t* thr, uint32_t* ladder, uint64_t* sched, cudaStream_t st, MapCache* maps = nullptr,
                      const int32_t* q_count = nullptr, const int32_t* q_map = nullptr, int q_skip = 0,
-                     uint64_t* app_keys = nullptr, uint32_t* app_cnt = nullptr);
+                     uint64_t* app_keys = nullptr, uint32_t* app_cnt = nullptr, uint32_t* gbar = nullptr);
 int launch_tighten(int64_t Q, const SearchPlan& p, int nslots, const uint64_t* cand, uint32_t* thr,
                    uint32_t* ladder, cudaStream_t st);
 int launch_tighten_app(int64_t Q, const SearchPlan& p, const uint64_t* app_keys, const uint32_t* app_cnt,
@@ -495,8 +593,9 @@ int launch_row_inv_norm(const void* x, int dt, int64_t N, int64_t D, int64_t str
                         cudaStream_t st);
 // first kernel of a search: zero the control words [zero_base, zero_base + zero_bytes) and, when q_dst is given,
 // copy the Q query rows into the zero-padded block the TMA reads (q_rows_padded rows of row_bytes)
+// (q_span > 0: padded row r holds query r % q_span -- the replicated block of a qrep plan)
 int launch_search_prep(void* zero_base, size_t zero_bytes, const void* q_src, size_t q_src_stride_bytes, void* q_dst,
-                       size_t row_bytes, int64_t Q, int64_t q_rows_padded, cudaStream_t st);
+                       size_t row_bytes, int64_t Q, int64_t q_rows_padded, int q_span, cudaStream_t st);
 
 int device_sm_count();
 void count_launch();       // bumps the counter behind tsim_launch_count()
