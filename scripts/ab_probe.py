@@ -31,6 +31,7 @@ for rnd in range(4):
         for k_ in keys:
             os.environ.pop(k_, None)
         os.environ.update(c)
+        ops._destroy_plans()      # plan-time knobs: make a fresh plan under this environment
         ops.search_topk(q, corpus, k, corpus_inv_norm=inv)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -752,8 +752,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (PAIR) {
               // both CTAs' bytes land on the leader's barrier; only the leader arms it (for both)
               const uint32_t fb = map_to_cta(smem_u32(&full_bar[stage]), 0);
-              if (rank == 0) mbar_arrive_expect_tx(smem_u32(&full_bar[stage]), 2 * STAGE_BYTES);
-              tma_load_2d_pair(sa, &tmap_q, fb, kb * BK, un.qb * (2 * BM) + (int)rank * BM);
+              if (rank == 0) mbar_arrive_expect_tx(smem_u32(&full_bar[stage]), 2 * ((dbg & 1) ? B_BYTES : STAGE_BYTES));
+              if (!(dbg & 1)) tma_load_2d_pair(sa, &tmap_q, fb, kb * BK, un.qb * (2 * BM) + (int)rank * BM);
               tma_load_2d_pair(sa + A_BYTES, &tmap_c, fb, kb * BK, row0 + (int)rank * (BN / 2));
             } else {
               const uint32_t fb = smem_u32(&full_bar[stage]);
