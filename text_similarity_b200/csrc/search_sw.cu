@@ -1,0 +1,392 @@
+// K2s (small-batch tensor-core pass): the candidate pass for calls of at most 32 queries -- BASELINE config 4's
+// regime (100M x 384 e4m3 over 8 GPUs, 1 ... 32 queries per call), where a search streams the shard from HBM once.
+//
+// Same job as search_tc.cu (replaces the per-query F.cosine_similarity + torch.topk loop of
+// SentenceMiningPipeline._search, reference src/pipeline/search_pipeline.py:73-79), with the MMA roles SWAPPED:
+// corpus rows are the M side (128 per tile = the 128 TMEM lanes), the <= 32 queries the N side (32 fp32 TMEM columns
+// per accumulator stage), so one tile costs 128 x 32 x D multiply-adds instead of the 128 x 256 x D that
+// search_tc.cu spends when 96-127 of its 128 query rows are padding.
+//
+// Why it exists: power.  Measured on B200 (scripts/ridge_probe.py, profiles/r02b_power_cap_probe.txt): with the
+// queries on the M side an e4m3 12.5M x 384 shard search at Q = 1 holds the board at its 1 kW software power cap --
+// the padded MMAs alone draw ~450 W -- the SM clock sinks to 0.85-0.98 GHz and the search takes 0.870 ms; with the
+// MMAs switched off (diagnosis build) the same TMA stream runs at 1.55 GHz and 0.706 ms = 6.87 TB/s.  An HBM-bound
+// kernel has no business spending half a kilowatt on multiplying zeros.
+//
+// Structure (one persistent CTA per SM, 256 threads: warps 0-3 epilogue, warp 4 TMA, warp 5 MMA, warp 6 TMEM):
+//  * the (zero-padded) 32-query block is loaded ONCE into shared memory, all k-blocks of it ([kblocks][32 rows x 128 B],
+//    128-byte swizzle): it is the B operand of every MMA of the CTA's life;
+//  * everything else of shared memory is a ring of corpus k-blocks ([128 rows x 128 B] = 16 KB per stage, 10-13
+//    stages = 160-208 KB in flight per SM), the A operand;
+//  * eight accumulator stages of 32 TMEM columns: the MMA thread runs up to eight tiles ahead of the epilogue;
+//  * epilogue thread i owns TMEM lane i = corpus row i of the tile: one tcgen05.ld.32x32b.x32 brings its row's 32
+//    scores, one FMUL each by the row's inverse norm, one compare each with the queries' thresholds (a warp-private
+//    shared-memory copy, refreshed per tile); the accumulator stage is handed back BEFORE the (rare) survivors are
+//    appended to their query's global list -- the append lists, ladder counters and thresholds are the ones of
+//    search_tc.cu's append mode, read by tighten_kernel / select_rescore (select_merge.cu).
+//  * Sample pass (SAMPLE = true, <= 24 CTAs): every row of the strided sample tiles becomes a candidate, written
+//    as 16-entry lists (cand[q][8 lists per worker][16]); tighten_kernel turns them into each query's starting
+//    threshold + ladder; the main pass scans every other tile.
+// Completeness: a row is dropped only by score <= thr[q], and thr[q] is always the KP-th best of rows that reach
+// select_rescore or a ladder level with >= KP appended rows at or above it -- the argument of DESIGN.md section 2.
+//
+// Roofline: N * D * e bytes from HBM (the corpus, once); the MMAs are 1/8 of search_tc.cu's.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "tsim_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace tsim {
+namespace {
+
+constexpr int SW_ROWS = 128;       // corpus rows per tile (TMEM lanes, MMA M)
+constexpr int SW_NQ = 32;          // query columns per accumulator stage (MMA N)
+constexpr int SW_ACC = 8;          // accumulator stages
+constexpr int SW_THREADS = 256;
+constexpr int SW_MAX_STAGES = 16;
+constexpr int SW_A_BYTES = SW_ROWS * BK_BYTES;   // 16 KB corpus k-block
+constexpr int SW_Q_BYTES = SW_NQ * BK_BYTES;     // 4 KB query k-block
+
+struct SwArgs {
+  const float* c_inv;     // [N] inverse norms of the stored corpus rows
+  int64_t N; int Q;
+  int kblocks;            // ceil(D * element size / 128)
+  int stages;             // corpus ring depth
+  int T;                  // corpus tiles of 128 rows
+  int ns, stride;         // sample tiles: i * stride, i < ns
+  int self_on; int64_t self_off;
+  uint64_t* cand;         // sample pass: [Q][NC][16] packed keys
+  int64_t NC;
+  uint32_t* thr;          // [Q] ordered-float thresholds
+  uint32_t* ladder;       // [Q][2 * kLadder]
+  uint64_t* app_keys; uint32_t* app_cnt; int app_cap;   // per-query append lists
+  int KP;
+  int dbg;                // TSIM_DEBUG bits (experiment build): 2 skip MMAs, 4 skip the epilogue's compares
+};
+
+// Append one survivor to its query's list, count it in the query's threshold ladder and raise the query's threshold to
+// the highest ladder level that now has >= KP appended rows at or above it (valid: every one of them reaches
+// select_rescore).  Rare: a few hundred calls per query per search.
+__device__ __noinline__ void sw_append(const SwArgs& a, int q, float s, uint32_t row) {
+  const uint32_t pos = atomicAdd(a.app_cnt + q, 1u);
+  if (pos < (uint32_t)a.app_cap) a.app_keys[(size_t)q * a.app_cap + pos] = pack_key(s, row);
+  uint32_t* lad = a.ladder + (size_t)q * (2 * kLadder);
+  const uint4 h = __ldcg(reinterpret_cast<const uint4*>(lad));
+  const float base = __uint_as_float(h.x), step = __uint_as_float(h.y), inv = __uint_as_float(h.z);
+  const int lvl = ladder_level(base, step, inv, s);
+  if (lvl < 0) return;
+  const uint32_t mine = atomicAdd(lad + kLadder + lvl, 1u) + 1u;   // the level's count including this row
+  uint32_t c = 0;
+  int best = -1;
+#pragma unroll
+  for (int i = kLadder / 4 - 1; i >= 0; --i) {
+    const uint4 b = __ldcg(reinterpret_cast<const uint4*>(lad + kLadder) + i);
+    const uint32_t w[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int e = 3; e >= 0; --e) {
+      c += (4 * i + e) == lvl ? max(w[e], mine) : w[e];     // (the load may or may not see our own increment yet)
+      if (best < 0 && c >= (uint32_t)a.KP) best = 4 * i + e;
+    }
+  }
+  if (best >= 0) atomicMax(a.thr + q, f32_to_ord(ladder_value(base, step, best)));
+}
+
+// the u-th tile of worker `w` (of `nw`): sample pass -> sample tile w; main pass -> w, w + nw, ... skipping sample tiles
+__device__ __forceinline__ bool sw_is_sample(const SwArgs& a, int tile) {
+  return a.ns > 0 && tile % a.stride == 0 && tile / a.stride < a.ns;
+}
+
+template <bool FP8, bool SAMPLE>
+__global__ void __launch_bounds__(SW_THREADS, 1)
+search_sw_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c, SwArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  // [kblocks] query k-blocks 4K | [stages] corpus k-blocks 16K | thresholds [4 warps][32] | barriers | tmem ptr
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int BK = FP8 ? BK_BYTES : BK_BYTES / 2;     // elements per k-block
+  // UMMA instruction descriptor: D = f32, A / B = bf16 (kind::f16) or e4m3 (kind::f8f6f4), K-major, N = 32, M = 128
+  constexpr uint32_t IDESC = (1u << 4) | (FP8 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(SW_NQ >> 3) << 17) |
+                             ((uint32_t)(SW_ROWS >> 4) << 24);
+  unsigned char* qtiles = smem;
+  unsigned char* ring = smem + (((size_t)a.kblocks * SW_Q_BYTES + 1023) & ~(size_t)1023);
+  float* thr_s = reinterpret_cast<float*>(ring + (size_t)a.stages * SW_A_BYTES);   // [4][32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(thr_s + 4 * SW_NQ);
+  uint64_t* full_bar = bars;                       // [stages]  TMA -> MMA
+  uint64_t* empty_bar = bars + SW_MAX_STAGES;      // [stages]  MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * SW_MAX_STAGES;  // [SW_ACC]  MMA -> epilogue
+  uint64_t* tempty_bar = tfull_bar + SW_ACC;       // [SW_ACC]  epilogue -> MMA
+  uint64_t* q_bar = tempty_bar + SW_ACC;           // [1]       the query block has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int dbg = TSIM_KNOB_DEV(a.dbg);
+  pdl_trigger();
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_c);
+  }
+  if (warp == 5 && lane == 0) {
+    for (int s = 0; s < a.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int s = 0; s < SW_ACC; ++s) { mbar_init(smem_u32(&tfull_bar[s]), 1); mbar_init(smem_u32(&tempty_bar[s]), 4); }
+    mbar_init(smem_u32(q_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 6) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(SW_ACC * SW_NQ)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // from here on the predecessors' outputs are read (padded queries, thresholds, ladder, counters)
+
+  const int w = (int)blockIdx.x, nw = (int)gridDim.x;
+  // this worker's tiles, the same sequence in every role
+  auto first_tile = [&]() { return SAMPLE ? w * a.stride : w; };
+  auto next_tile = [&](int t) { return SAMPLE ? a.T : t + nw; };     // (a sample worker scans one tile)
+  auto skip = [&](int t) { return !SAMPLE && sw_is_sample(a, t); };
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(smem_u32(q_bar), (uint32_t)a.kblocks * SW_Q_BYTES);
+      for (int kb = 0; kb < a.kblocks; ++kb) tma_load_2d(smem_u32(qtiles + (size_t)kb * SW_Q_BYTES), &tmap_q, smem_u32(q_bar), kb * BK, 0);
+      int stage = 0; uint32_t phase = 0;
+      for (int t = first_tile(); t < a.T; t = next_tile(t)) {
+        if (skip(t)) continue;
+        for (int kb = 0; kb < a.kblocks; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_arrive_expect_tx(fb, SW_A_BYTES);
+          tma_load_2d(smem_u32(ring + (size_t)stage * SW_A_BYTES), &tmap_c, fb, kb * BK, t * SW_ROWS);
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      mbar_wait(smem_u32(q_bar), 0);
+      tc_fence_after();
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t aphase = 0;
+      for (int t = first_tile(); t < a.T; t = next_tile(t)) {
+        if (skip(t)) continue;
+        mbar_wait(smem_u32(&tempty_bar[acc]), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * SW_NQ);
+        for (int kb = 0; kb < a.kblocks; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          const uint64_t adesc = make_umma_desc(smem_u32(ring + (size_t)stage * SW_A_BYTES));     // corpus rows: M side
+          const uint64_t bdesc = make_umma_desc(smem_u32(qtiles + (size_t)kb * SW_Q_BYTES));      // queries: N side
+#pragma unroll
+          for (int k = 0; k < BK_BYTES / UMMA_K_BYTES; ++k) {
+            if (dbg & 2) break;
+            tc_mma<FP8>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (kb | k) ? 1u : 0u);
+          }
+          tc_commit(smem_u32(&empty_bar[stage]));
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(smem_u32(&tfull_bar[acc]));
+        if (++acc == SW_ACC) { acc = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp < 4) {
+    // ===================== epilogue: thread <-> corpus row =====================
+    const int et = threadIdx.x;                                   // 0..127 = TMEM lane = row within the tile
+    const uint32_t lane_addr = ((uint32_t)(warp * 32)) << 16;
+    float* tw = thr_s + warp * SW_NQ;                             // this warp's copy of the 32 thresholds
+    int acc = 0; uint32_t aphase = 0;
+    // Tile metadata -- the row's inverse norm and (lane j) query j's threshold -- is fetched kPf tiles ahead: a tile of
+    // 384-byte rows lasts ~1 us, about one L2 round trip under load (one tile ahead, the epilogue waited for these
+    // loads every tile and paced the whole kernel: 1.2 us per tile)
+    constexpr int kPf = 4;
+    float inv_q[kPf]; uint32_t thr_q[kPf]; int tile_q[kPf];
+    auto advance = [&](int t) { t = next_tile(t); while (t < a.T && skip(t)) t = next_tile(t); return t; };
+    int tnext = first_tile();
+    while (tnext < a.T && skip(tnext)) tnext = next_tile(tnext);
+#pragma unroll
+    for (int i = 0; i < kPf; ++i) {
+      tile_q[i] = tnext; inv_q[i] = 0.f; thr_q[i] = 0u;
+      if (tnext < a.T) {
+        const int64_t r = (int64_t)tnext * SW_ROWS + et;
+        inv_q[i] = r < a.N ? __ldg(a.c_inv + r) : 0.f;
+        if (!SAMPLE) thr_q[i] = lane < a.Q ? __ldcg(a.thr + lane) : 0u;
+        tnext = advance(tnext);
+      }
+    }
+    while (tile_q[0] < a.T) {
+      const int t = tile_q[0];
+      const int64_t row = (int64_t)t * SW_ROWS + et;
+      const float inv = inv_q[0];
+      if (!SAMPLE) {
+        // a query that has no threshold yet (0) accepts everything; padding columns accept nothing
+        tw[lane] = lane < a.Q ? (thr_q[0] ? ord_to_f32(thr_q[0]) : -INFINITY) : INFINITY;
+        __syncwarp();
+      }
+#pragma unroll
+      for (int i = 0; i + 1 < kPf; ++i) { tile_q[i] = tile_q[i + 1]; inv_q[i] = inv_q[i + 1]; thr_q[i] = thr_q[i + 1]; }
+      tile_q[kPf - 1] = tnext; inv_q[kPf - 1] = 0.f; thr_q[kPf - 1] = 0u;
+      if (tnext < a.T) {
+        const int64_t r = (int64_t)tnext * SW_ROWS + et;
+        inv_q[kPf - 1] = r < a.N ? __ldg(a.c_inv + r) : 0.f;
+        if (!SAMPLE) thr_q[kPf - 1] = lane < a.Q ? __ldcg(a.thr + lane) : 0u;
+        tnext = advance(tnext);
+      }
+      mbar_wait(smem_u32(&tfull_bar[acc]), aphase);
+      tc_fence_after();
+      uint32_t v[32];
+      tc_ld32(tmem_base + lane_addr + (uint32_t)(acc * SW_NQ), v);
+      tc_ld_wait_on(v);
+      // the accumulator stage goes back at once: the scores are in registers
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+      if (++acc == SW_ACC) { acc = 0; aphase ^= 1; }
+      float sc[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sc[j] = __uint_as_float(v[j]) * inv;
+      const bool live = row < a.N && !(dbg & 4);
+      // self exclusion: query j's own row is self_off + j
+      const int64_t jself = a.self_on ? row - a.self_off : -1;
+      if (SAMPLE) {
+        // every row of a sample tile is a candidate: lane l of warp w fills entry l % 16 of list 8 * worker + 2 * w + l / 16
+        const int64_t list = (int64_t)w * 8 + warp * 2 + (lane >> 4);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (j < a.Q) {
+            const bool ok = live && jself != j && sc[j] == sc[j] && sc[j] > -INFINITY;   // NaN rows are never returned
+            a.cand[((size_t)j * a.NC + list) * 16 + (lane & 15)] = ok ? pack_key(sc[j], (uint32_t)row) : 0ull;
+          }
+        }
+      } else {
+        uint32_t m = 0;
+        const float4* t4 = reinterpret_cast<const float4*>(tw);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 th = t4[g];
+          m |= (sc[4 * g] > th.x ? 1u : 0u) << (4 * g);
+          m |= (sc[4 * g + 1] > th.y ? 1u : 0u) << (4 * g + 1);
+          m |= (sc[4 * g + 2] > th.z ? 1u : 0u) << (4 * g + 2);
+          m |= (sc[4 * g + 3] > th.w ? 1u : 0u) << (4 * g + 3);
+        }
+        if (!live) m = 0;
+        if (jself >= 0 && jself < 32) m &= ~(1u << (int)jself);
+        if (__any_sync(0xffffffffu, m != 0)) {
+#pragma unroll 1
+          while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            const float s = select32(sc, j);
+            // the threshold may have risen since this tile's copy was made
+            if (f32_to_ord(s) > __ldcg(a.thr + j) && s < INFINITY) sw_append(a, j, s, (uint32_t)row);
+          }
+        }
+        __syncwarp();     // everybody has read tw before the next tile overwrites it
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 6) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(SW_ACC * SW_NQ)) : "memory");
+  }
+}
+
+// Between the sample pass and the main pass, one block of 128 threads per query: the KP-th best of the query's
+// 192 x 16 sample keys becomes its threshold; a ladder of 16 levels is laid out above it with a step taken from the
+// sample's tail slope (epi_tighten, tail_step): the main pass appends rows instead of keeping lists, so the ladder is
+// the ONLY thing that raises a threshold and it has to reach the corpus's own KP-th best -- with search_tc.cu's steps of
+// an eighth of (sample best - threshold) one query in ten ran out of ladder and overflowed its append list.  The
+// sample keys at or above the threshold move to the append list, so that select_rescore reads one short list per query.
+__global__ void __launch_bounds__(128) sw_tighten_kernel(const uint64_t* cand, int64_t NC, int KP, uint32_t* thr,
+                                                         uint32_t* ladder, uint64_t* app_keys, uint32_t* app_cnt, int app_cap) {
+  __shared__ uint32_t hist[288];
+  pdl_trigger();
+  pdl_wait();
+  const int64_t q = blockIdx.x;
+  epi_tighten(cand + (size_t)q * NC * 16, (uint32_t)(NC * 16), KP, thr + q, ladder + (size_t)q * (2 * kLadder), hist,
+              (int)threadIdx.x, 0.25f, app_keys + (size_t)q * app_cap, app_cnt + q, app_cap, /*tail_step=*/true);
+}
+
+size_t sw_smem_bytes(int kblocks, int stages) {
+  return 1024 + (((size_t)kblocks * SW_Q_BYTES + 1023) & ~(size_t)1023) + (size_t)stages * SW_A_BYTES + 4 * SW_NQ * 4 +
+         (2 * SW_MAX_STAGES + 2 * SW_ACC + 1) * 8 + 16;
+}
+
+template <bool FP8, bool SAMPLE>
+int sw_launch(const CUtensorMap& mq, const CUtensorMap& mc, const SwArgs& a, int grid, cudaStream_t st) {
+  const size_t smem = sw_smem_bytes(a.kblocks, a.stages);
+  auto kern = search_sw_kernel<FP8, SAMPLE>;
+  TSIM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(SW_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = knob_on("TSIM_NO_PDL") ? 0 : 1;
+  TSIM_CUDA(cudaLaunchKernelEx(&cfg, kern, mq, mc, a));
+  count_launch();
+  return TSIM_OK;
+}
+
+}  // namespace
+
+// Corpus ring depth for a query block of `kblocks` k-blocks (0: the block does not fit beside a useful ring)
+int search_sw_stages(int kblocks) {
+  int s = SW_MAX_STAGES;
+  while (s >= 6 && sw_smem_bytes(kblocks, s) > 232448) --s;
+  return s >= 6 ? s : 0;
+}
+
+int launch_sw_tighten(int64_t Q, const SearchPlan& p, const uint64_t* cand, uint32_t* thr, uint32_t* ladder,
+                      uint64_t* app_keys, uint32_t* app_cnt, cudaStream_t st) {
+  static_assert(8 * 24 * 16 <= 128 * kEpiKeys, "sample keys per query exceed what epi_tighten holds in registers");
+  TSIM_CUDA(launch_pdl(sw_tighten_kernel, dim3((unsigned)Q), dim3(128), 0, st, cand, p.NC, p.KP, thr, ladder, app_keys,
+                       app_cnt, p.app_cap));
+  count_launch();
+  return TSIM_OK;
+}
+
+// sample == 1: the sample pass (p.sw_ns CTAs, lists into cand); 0: the main pass (appends)
+int launch_search_sw(const void* q, int64_t q_stride, const void* corpus, int64_t c_stride, int dt, const float* c_inv,
+                     int64_t Q, int64_t N, int64_t D, int self_on, int64_t self_off, const SearchPlan& p, int sample,
+                     uint64_t* cand, uint32_t* thr, uint32_t* ladder, uint64_t* app_keys, uint32_t* app_cnt,
+                     cudaStream_t st, MapCache* maps) {
+  const int esz = dt == TSIM_E4M3 ? 1 : 2;
+  CUtensorMap mq, mc;
+  int rc = get_tensor_map(maps, &mq, q, SW_NQ, D, q_stride, SW_NQ, esz);     // the padded block: 32 rows
+  if (rc) return rc;
+  rc = get_tensor_map(maps, &mc, corpus, N, D, c_stride, SW_ROWS, esz);
+  if (rc) return rc;
+  SwArgs a;
+  a.c_inv = c_inv; a.N = N; a.Q = (int)Q;
+  a.kblocks = (int)((D * esz + BK_BYTES - 1) / BK_BYTES);
+  a.stages = search_sw_stages(a.kblocks);
+  a.T = (int)((N + SW_ROWS - 1) / SW_ROWS);
+  a.ns = p.sw_ns; a.stride = p.sw_stride;
+  a.self_on = self_on; a.self_off = self_off;
+  a.cand = cand; a.NC = p.NC; a.thr = thr; a.ladder = ladder;
+  a.app_keys = app_keys; a.app_cnt = app_cnt; a.app_cap = p.app_cap; a.KP = p.KP;
+  a.dbg = knob_int("TSIM_DEBUG", 0);
+  if (a.stages == 0) { set_error("search_sw: query block of %d k-blocks does not fit", a.kblocks); return TSIM_ERR_UNSUPPORTED; }
+  const int sms = device_sm_count();
+  if (sample) {
+    if (dt == TSIM_E4M3) return sw_launch<true, true>(mq, mc, a, p.sw_ns, st);
+    return sw_launch<false, true>(mq, mc, a, p.sw_ns, st);
+  }
+  const int grid = a.T < sms ? a.T : sms;
+  if (dt == TSIM_E4M3) return sw_launch<true, false>(mq, mc, a, grid, st);
+  return sw_launch<false, false>(mq, mc, a, grid, st);
+}
+
+}  // namespace tsim

@@ -24,6 +24,7 @@
 #include <stdlib.h>
 
 #include "tsim_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace tsim {
 namespace {
@@ -31,8 +32,6 @@ namespace {
 constexpr int BM = 128;        // queries per CTA tile (TMEM lanes)
 constexpr int BN = 256;        // corpus rows per tile (TMEM columns per accumulator stage)
 constexpr int kCnStride = BN + 16;   // per-warp copy of a tile's inverse norms + (max, min) per 32-column chunk
-constexpr int BK_BYTES = 128;  // bytes per row per k-block = one 128-byte swizzle atom row (64 bf16 / 128 e4m3)
-constexpr int UMMA_K_BYTES = 32;  // one MMA consumes 32 bytes of K per row (K = 16 bf16 / 32 e4m3)
 constexpr int kThreads = 256;  // warps0-3 epilogue, warp4 TMA, warp5 MMA, warp6 TMEM alloc, warp7 idle (the issue
                                // arbiter favours the higher warp id: the two latency-critical single-thread roles win)
 
@@ -51,145 +50,6 @@ template <bool PAIR> struct Cfg {
                                          ((uint32_t)(MMA_M >> 4) << 24);
   static constexpr uint32_t IDESC_E4M3 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(MMA_M >> 4) << 24);
 };
-
-// ---- PTX wrappers -------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-// 2-CTA variants: the peer's TMA signals the LEADER's barrier; the leader's commit reaches both CTAs
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t cta_rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  // default semantics (release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id): a
-  // cluster-scope release would cost a full memory barrier per tile; the TMEM hand-off is ordered
-  // by tcgen05.fence::before_thread_sync / after_thread_sync around the barrier
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
-}
-__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"((uint16_t)3) : "memory");
-}
-template <bool FP8>
-__device__ __forceinline__ void tc_mma_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  if constexpr (FP8)
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-  else
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-template <bool FP8>
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                       uint32_t accumulate) {
-  if constexpr (FP8)
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-  else
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// The same wait, naming the 32 registers of an earlier tc_ld32 as in/out operands: the load is asynchronous, and
-// nothing else tells the compiler that uses of v must stay BELOW the wait when another load is issued in between.
-__device__ __forceinline__ void tc_ld_wait_on(uint32_t* v) {
-  asm volatile(
-      "tcgen05.wait::ld.sync.aligned;"
-      : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
-        "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
-        "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
-        "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
-      :
-      : "memory");
-}
-
-// UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B, 128-byte rows:
-//   start address >> 4 | LBO (unused for swizzled K-major) = 1 | SBO = 1024 B (8 rows) >> 4 |
-//   version 1 (sm_100) | layout type 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_umma_desc(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr & 0x3ffff) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
-         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
 
 struct TcArgs {
   const float* c_inv;   // [N] inverse norms of the stored corpus rows
@@ -399,18 +259,6 @@ __device__ __forceinline__ uint32_t candidate_mask(const float* sc, float thr, i
   if (ds >= 0 && ds < 32) m &= ~(1u << (int)ds);
   return m;
 }
-__device__ __forceinline__ float select32(const float* sc, int j) {
-  float t16[16], t8[8], t4[4];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) t16[i] = (j & 16) ? sc[16 + i] : sc[i];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) t8[i] = (j & 8) ? t16[8 + i] : t16[i];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) t4[i] = (j & 4) ? t8[4 + i] : t8[i];
-  const float u0 = (j & 2) ? t4[2] : t4[0], u1 = (j & 2) ? t4[3] : t4[1];
-  return (j & 1) ? u1 : u0;
-}
-
 struct RegList16 {
   float a[16]; uint32_t r[16];
   __device__ __forceinline__ RegList16(float*, uint32_t*, int*) {}
@@ -577,95 +425,6 @@ template <int KP> struct ListFor { using type = SmemList<KP>; };
 template <> struct ListFor<16> { using type = RegList16; };
 template <> struct ListFor<-kAppStageMain> { using type = AppendList<kAppStageMain>; };
 template <> struct ListFor<-kAppStageSample> { using type = AppendList<kAppStageSample>; };
-
-// Thresholds inside a fused sticky pass, by the 128 epilogue threads of a CTA (named barrier 1) for ONE query: the
-// same radix select and ladder as warp_tighten (tsim_common.cuh), but every thread first pulls its share of the
-// keys into registers with independent loads -- one L2 round trip -- and the four passes then run on registers.
-// (A single warp walking 74 keys per lane with a load -> shared-atomic dependency per key took ~45 us, during
-// which every CTA of the launch sat at the grid barrier with HBM idle.)  n <= 128 * kEpiKeys keys; hist: 288 words.
-constexpr int kEpiKeys = 24;
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-__device__ __noinline__ void epi_tighten(const uint64_t* src, uint32_t n, int KP, uint32_t* thr_q, uint32_t* lad,
-                                         uint32_t* hist, int et) {
-  uint32_t sc[kEpiKeys];
-#pragma unroll
-  for (int i = 0; i < kEpiKeys; ++i) {
-    const uint32_t idx = (uint32_t)et + 128u * i;
-    sc[i] = idx < n ? (uint32_t)(__ldcg(src + idx) >> 32) : 0u;
-  }
-  uint32_t* ctl = hist + 256;      // [0] live keys, [1] best score, [2] bucket, [3] need
-  if (et < 32) ctl[et] = 0u;
-  epi_bar();
-  uint32_t live = 0, best = 0;
-#pragma unroll
-  for (int i = 0; i < kEpiKeys; ++i) { live += sc[i] != 0u; best = max(best, sc[i]); }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { live += __shfl_xor_sync(0xffffffffu, live, o); best = max(best, __shfl_xor_sync(0xffffffffu, best, o)); }
-  if ((et & 31) == 0) { atomicAdd(&ctl[0], live); atomicMax(&ctl[1], best); }
-  epi_bar();
-  live = ctl[0]; best = ctl[1];
-  if (live < (uint32_t)KP) {       // not enough rows for a threshold: a ladder that never fires
-    if (lad && et < kLadder) { lad[kLadder + et] = 0u; lad[et] = et == 0 ? __float_as_uint(INFINITY) : 0u; }
-    epi_bar();
-    return;
-  }
-  uint32_t prefix = 0, need = (uint32_t)KP;
-  for (int shift = 24; shift >= 0; shift -= 8) {
-    hist[et] = 0u; hist[et + 128] = 0u;
-    epi_bar();
-    const uint32_t hi_mask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
-#pragma unroll
-    for (int i = 0; i < kEpiKeys; ++i)
-      if (sc[i] != 0u && (sc[i] & hi_mask) == prefix) atomicAdd(&hist[(sc[i] >> shift) & 255u], 1u);
-    epi_bar();
-    if (et < 32) {
-      // lane l owns buckets 255 - 8l .. 248 - 8l (descending): where does the running count reach `need`?
-      uint32_t c[8], tot = 0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { c[j] = hist[255 - 8 * et - j]; tot += c[j]; }
-      uint32_t incl = tot;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (et >= o) incl += v;
-      }
-      const uint32_t before = incl - tot;
-      if (before < need && incl >= need) {
-        uint32_t run = before;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (run < need && run + c[j] >= need) { ctl[2] = 255u - 8u * et - j; ctl[3] = need - run; }
-          run += c[j];
-        }
-      }
-    }
-    epi_bar();
-    prefix |= ctl[2] << shift;
-    need = ctl[3];
-    epi_bar();
-  }
-  if (et == 0) atomicMax(thr_q, prefix);
-  if (lad) {
-    const float base = ord_to_f32(prefix);
-    float step = (ord_to_f32(best) - base) * (1.f / 8.f);
-    if (!(step > 0.f) || !(step < INFINITY)) step = 0.f;
-    const float inv = step > 0.f ? 1.f / step : 0.f;
-    if (et < kLadder) hist[et] = 0u;
-    epi_bar();
-#pragma unroll
-    for (int i = 0; i < kEpiKeys; ++i)
-      if (sc[i] >= prefix) {             // (prefix > 0: empty slots never pass)
-        const int j = ladder_level(base, step, inv, ord_to_f32(sc[i]));
-        if (j >= 0) atomicAdd(&hist[j], 1u);
-      }
-    epi_bar();
-    if (et < kLadder) {
-      lad[kLadder + et] = hist[et];
-      lad[et] = et == 0 ? __float_as_uint(base) : et == 1 ? __float_as_uint(step) : et == 2 ? __float_as_uint(inv) : 0u;
-    }
-  }
-  epi_bar();
-}
 
 template <int KP, int STAGES, bool PAIR, bool FP8>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -1076,7 +835,7 @@ struct MapCache {
 MapCache* map_cache_create() { return new MapCache(); }
 void map_cache_destroy(MapCache* c) { delete c; }
 
-static int get_map(MapCache* c, CUtensorMap* m, const void* base, int64_t rows, int64_t D, int64_t stride, int box_rows,
+int get_tensor_map(MapCache* c, CUtensorMap_st* m, const void* base, int64_t rows, int64_t D, int64_t stride, int box_rows,
                    int esz) {
   if (!c) return make_map(m, base, rows, D, stride, box_rows, esz);
   ++c->tick;
@@ -1109,9 +868,9 @@ int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_
   const int qrows = p.pair ? 2 * BM : BM;
   // q holds QB * qrows rows (the API pads the last query block with zero rows)
   const int esz = dt == TSIM_E4M3 ? 1 : 2;
-  int rc = get_map(maps, &mq, q, (int64_t)p.QB * qrows, D, q_stride, BM, esz);
+  int rc = get_tensor_map(maps, &mq, q, (int64_t)p.QB * qrows, D, q_stride, BM, esz);
   if (rc) return rc;
-  rc = get_map(maps, &mc, corpus, N, D, c_stride, p.pair ? BN / 2 : BN, esz);
+  rc = get_tensor_map(maps, &mc, corpus, N, D, c_stride, p.pair ? BN / 2 : BN, esz);
   if (rc) return rc;
   TcArgs a;
   a.c_inv = c_inv; a.Q = Q; a.N = N;

@@ -102,7 +102,22 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
         p->fused = knob_on("TSIM_NO_FUSED") ? 0 : 1;   // sample, thresholds and main in one cooperative launch
       }
     }
-    if (p->sticky && !p->pair && !knob_on("TSIM_NO_QREP")) p->qrep = Q <= 32 ? 4 : Q <= 64 ? 2 : 1;
+    // Small batches on a large shard (config 4): the swapped-role kernel (search_sw.cu) -- the MMA work follows the 32
+    // query columns, not 128 padded query rows, which under the board's power cap is worth 15-25 % of the search
+    {
+      const int64_t T128 = (N + 127) / 128;
+      const int kb = (int)((D * dtype_size(c_dt) + 127) / 128);
+      if (Q <= 32 && p->KP == 16 && !shadow && T128 >= 16 * (int64_t)sms && search_sw_stages(kb) > 0 && !knob_on("TSIM_NO_SWAP")) {
+        p->swapped = 1;
+        p->sticky = 1; p->pair = 0; p->QB = 1; p->Gq = sms; p->fused = 0; p->qrep = 0;
+        p->boot_tiles = 0; p->boot_stride = 0; p->boot_slots = 0;
+        p->sw_ns = 24;                                   // 24 tiles x 128 rows = 3072 sample rows = 192 lists of 16 per query
+        p->sw_stride = (int)(T128 / p->sw_ns);
+        p->append = 1;
+        p->app_cap = 4096;
+      }
+    }
+    if (p->sticky && !p->pair && !p->swapped && !knob_on("TSIM_NO_QREP")) p->qrep = Q <= 32 ? 4 : Q <= 64 ? 2 : 1;
     if (!p->sticky) {
       // Round-robin units (many query blocks).  A unit's list starts empty, so what it filters with is
       // the query's GLOBAL threshold: a strided sample (~1/64 of the tiles) is scanned first and leaves
@@ -158,6 +173,9 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
       p->app_cap = Q > 65536 ? 2048 : 4096;
       if (p->append) p->NC = 0;
       else p->NC = p->boot_tiles ? p->mini_slots + p->boot_slots + (T - p->boot_tiles + tpc - 1) / tpc : (T + tpc - 1) / tpc;
+    } else if (p->swapped) {
+      p->R = 128;
+      p->NC = 8 * (int64_t)p->sw_ns;
     } else {
       p->R = 256;
       const int rep = p->qrep > 1 ? p->qrep : 1;          // main-pass lists per worker (sample lists: one)
@@ -205,11 +223,11 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
     p->off_r_flagcnt = off; off += 256;
   }
   p->off_flaglist = off; off = align_up(off + (size_t)Q * sizeof(int32_t), 256);
-  if (p->use_tensor && p->boot_tiles) {
+  if (p->use_tensor && (p->boot_tiles || p->swapped)) {
     p->off_ladder = off; off = align_up(off + (size_t)Q * 2 * kLadder * sizeof(uint32_t), 256);
   }
   if (p->use_tensor && (Q % (p->pair ? 256 : 128) != 0 || p->qrep > 1)) {  // zero-padded copy of the queries (TMA OOB fill is slow)
-    p->off_qpad = off; off = align_up(off + (size_t)p->QB * (p->pair ? 256 : 128) * D * dtype_size(q_dt), 256);
+    p->off_qpad = off; off = align_up(off + (size_t)p->QB * (p->pair ? 256 : 128) * D * dtype_size(q_dt), 256);   // (swapped plans use 32 rows of it)
   }
   if (need_invnorm && p->use_tensor) { p->off_invnorm = off; off = align_up(off + (size_t)N * sizeof(float), 256); }
   if (p->retry) {
@@ -335,7 +353,7 @@ static int search_impl(const void* q, int q_dt, int64_t q_stride, const void* co
     uint64_t* sched = p.sched_area ? (uint64_t*)(w + p.off_sched) : nullptr;
     const void* qt = tq;
     int64_t qt_stride = tq_stride;
-    const int qrows = p.pair ? 256 : 128;
+    const int qrows = p.swapped ? 32 : p.pair ? 256 : 128;
     const size_t rowb = (size_t)D * dtype_size(t_dt);
     const bool pad = Q % qrows != 0 || p.qrep > 1;
     rc = launch_search_prep(thr, align_up(zero_end - p.off_thr, 256), tq, (size_t)tq_stride * dtype_size(t_dt),
@@ -355,7 +373,18 @@ static int search_impl(const void* q, int q_dt, int64_t q_stride, const void* co
     uint64_t* app_keys = p.append ? (uint64_t*)(w + p.off_app_keys) : nullptr;
     uint32_t* app_cnt = p.append ? (uint32_t*)(w + p.off_app_cnt) : nullptr;
     uint32_t* ladder = nullptr;
-    if (p.fused) {
+    if (p.swapped) {
+      // small batches: sample tiles -> 16-entry lists, thresholds + ladders, then the main pass appends
+      uint32_t* lad = (uint32_t*)(w + p.off_ladder);
+      rc = launch_search_sw(qt, qt_stride, tcorpus, tc_stride, t_dt, c_inv, Q, N, D, self_on, self_off, p, 1, cand, thr, lad,
+                            app_keys, app_cnt, st, maps);
+      if (rc) return rc;
+      rc = launch_sw_tighten(Q, p, cand, thr, lad, app_keys, app_cnt, st);
+      if (rc) return rc;
+      rc = launch_search_sw(qt, qt_stride, tcorpus, tc_stride, t_dt, c_inv, Q, N, D, self_on, self_off, p, 0, cand, thr, lad,
+                            app_keys, app_cnt, st, maps);
+      if (rc) return rc;
+    } else if (p.fused) {
       uint32_t* lad = knob_on("TSIM_NO_LADDER") ? nullptr : (uint32_t*)(w + p.off_ladder);   // experiment knob
       rc = launch_search_tc(qt, qt_stride, tcorpus, tc_stride, t_dt, c_inv, Q, N, D, self_on, self_off, p, TC_PASS_FUSED,
                             cand, thr, lad, sched, st, maps, nullptr, nullptr, 0, nullptr, nullptr,
@@ -390,7 +419,9 @@ static int search_impl(const void* q, int q_dt, int64_t q_stride, const void* co
     }
     if (timed) TSIM_CUDA(cudaEventRecord(g_ev_stop, st));
     SelRetry first = {nullptr, nullptr, p.retry * kRetryQ, 0, 0, w + p.off_r_q, D};
-    rc = launch_select_rescore(q, q_dt, q_stride, corpus, c_dt, c_stride, Q, N, D, k, idx_base, p,
+    SearchPlan psel = p;
+    if (p.swapped) psel.NC = 0;        // the sample keys that matter were moved to the append lists (sw_tighten_kernel)
+    rc = launch_select_rescore(q, q_dt, q_stride, corpus, c_dt, c_stride, Q, N, D, k, idx_base, psel,
                                (const uint64_t*)(w + p.off_cand), thr, flag_cnt, flag_list,
                                out_score, out_score64, out_idx, out_flags, st, p.retry ? &first : nullptr,
                                app_keys, app_cnt);

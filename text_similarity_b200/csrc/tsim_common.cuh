@@ -9,6 +9,8 @@
 
 #include "../../include/tsim.h"
 
+struct CUtensorMap_st;   // <cuda.h>: CUtensorMap
+
 namespace tsim {
 
 constexpr double kCosEps = 1e-8;   // F.cosine_similarity eps, reference search_pipeline.py:77
@@ -500,6 +502,10 @@ struct SearchPlan {
   // NC = 0 then.
   int qrep;            // sticky lone-CTA plans with Q <= 64: the query block holds the queries qrep (2 / 4) times over and
                        // the epilogue warps split every tile's columns (search_tc.cu, TcArgs::qrep); lists per worker x qrep
+  // Small-batch plans (search_sw.cu: Q <= 32 on a large shard): corpus rows on the MMA's M side, the queries resident
+  // on the N side.  Tiles of 128 rows; sample tiles i * sw_stride (i < sw_ns) are scanned first into 16-entry lists
+  // (cand[q][8 * sw_ns][16]), tighten_kernel makes thresholds + ladders, the main pass appends (app_keys / app_cnt).
+  int swapped, sw_ns, sw_stride;
   int fused;           // sticky + bootstrap: one cooperative launch does sample, thresholds and main (TC_PASS_FUSED)
   size_t off_gbar;     // its two grid-barrier counters (256 bytes, zeroed with thr)
   int append;
@@ -558,6 +564,17 @@ enum { TC_PASS_ALL = 0, TC_PASS_SAMPLE = 1, TC_PASS_MAIN = 2, TC_PASS_MINI = 3, 
 struct MapCache;
 MapCache* map_cache_create();
 void map_cache_destroy(MapCache* c);
+// 2-D row-major [rows, D] tensor map (bf16, or 1-byte e4m3) with a [box_rows, 128 bytes] box and 128-byte swizzle, from
+// the cache `c` when it holds one (null: encode)
+int get_tensor_map(MapCache* c, CUtensorMap_st* m, const void* base, int64_t rows, int64_t D, int64_t stride, int box_rows,
+                   int esz);
+int launch_sw_tighten(int64_t Q, const SearchPlan& p, const uint64_t* cand, uint32_t* thr, uint32_t* ladder,
+                      uint64_t* app_keys, uint32_t* app_cnt, cudaStream_t st);
+int search_sw_stages(int kblocks);   // corpus ring depth of the small-batch kernel for this many query k-blocks (0: no fit)
+int launch_search_sw(const void* q, int64_t q_stride, const void* corpus, int64_t c_stride, int dt, const float* c_inv,
+                     int64_t Q, int64_t N, int64_t D, int self_on, int64_t self_off, const SearchPlan& p, int sample,
+                     uint64_t* cand, uint32_t* thr, uint32_t* ladder, uint64_t* app_keys, uint32_t* app_cnt,
+                     cudaStream_t st, MapCache* maps);
 int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_t c_stride, int dt,
                      const float* c_inv, int64_t Q, int64_t N, int64_t D,
                      int self_on, int64_t self_off, const SearchPlan& p, int pass, uint64_t* cand,
