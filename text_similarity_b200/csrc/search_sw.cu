@@ -18,7 +18,9 @@
 //    128-byte swizzle): it is the B operand of every MMA of the CTA's life;
 //  * everything else of shared memory is a ring of corpus k-blocks ([128 rows x 128 B] = 16 KB per stage, 10-13
 //    stages = 160-208 KB in flight per SM), the A operand;
-//  * eight accumulator stages of 32 TMEM columns: the MMA thread runs up to eight tiles ahead of the epilogue;
+//  * sixteen accumulator stages of 32 TMEM columns: the TMA and MMA warps start streaming the corpus the moment the
+//    CTA is resident and run up to sixteen tiles ahead, while the epilogue warps still wait (griddepcontrol.wait) for
+//    the thresholds the previous kernel is making;
 //  * epilogue thread i owns TMEM lane i = corpus row i of the tile: one tcgen05.ld.32x32b.x32 brings its row's 32
 //    scores, one FMUL each by the row's inverse norm, one compare each with the queries' thresholds (a warp-private
 //    shared-memory copy, refreshed per tile); the accumulator stage is handed back BEFORE the (rare) survivors are
@@ -42,7 +44,8 @@ namespace {
 
 constexpr int SW_ROWS = 128;       // corpus rows per tile (TMEM lanes, MMA M)
 constexpr int SW_NQ = 32;          // query columns per accumulator stage (MMA N)
-constexpr int SW_ACC = 8;          // accumulator stages
+constexpr int SW_ACC = 16;         // accumulator stages (tiles in flight between the MMA thread and the epilogue): all 512 columns
+constexpr int SW_ACC_COLS = SW_NQ;                   // TMEM columns per accumulator stage
 constexpr int SW_THREADS = 256;
 constexpr int SW_MAX_STAGES = 16;
 constexpr int SW_A_BYTES = SW_ROWS * BK_BYTES;   // 16 KB corpus k-block
@@ -120,7 +123,6 @@ search_sw_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int dbg = TSIM_KNOB_DEV(a.dbg);
-  pdl_trigger();
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_c);
@@ -133,14 +135,19 @@ search_sw_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 6) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(SW_ACC * SW_NQ)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(SW_ACC * SW_ACC_COLS)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();      // from here on the predecessors' outputs are read (padded queries, thresholds, ladder, counters)
+  // Programmatic dependent launch.  The sample pass reads what search_prep wrote (the padded query block) and lets its
+  // successors start only after it has waited for that kernel; the main pass can therefore load the query block and
+  // stream the corpus at once (its grid cannot start before the threshold kernel's, which cannot start before every
+  // sample CTA is past its wait) -- only its epilogue warps wait, for the thresholds, ladders and append counters.
+  if (SAMPLE) { pdl_wait(); pdl_trigger(); }
+  else { pdl_trigger(); if (warp < 4) pdl_wait(); }
 
   const int w = (int)blockIdx.x, nw = (int)gridDim.x;
   // this worker's tiles, the same sequence in every role
@@ -148,51 +155,64 @@ search_sw_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   auto next_tile = [&](int t) { return SAMPLE ? a.T : t + nw; };     // (a sample worker scans one tile)
   auto skip = [&](int t) { return !SAMPLE && sw_is_sample(a, t); };
 
+  // The two single-thread roles run WARP-UNIFORM: all 32 lanes walk the loop and wait on the barriers, one elected lane
+  // issues the TMA / MMA / commit.  Written as `if (lane == 0) { whole loop }` every operand of the tcgen05 / TMA
+  // instructions (uniform registers) went through ELECT + R2UR.BROADCAST sequences inside divergent code, and the MMA
+  // thread's loop body -- ~700 clocks per k-block, with no wait in it -- paced the kernel (ncu: 6.0 TB/s, tensor pipe
+  // 9 % busy, the epilogue waiting for accumulators).
   if (warp == 4) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(smem_u32(q_bar), (uint32_t)a.kblocks * SW_Q_BYTES);
       for (int kb = 0; kb < a.kblocks; ++kb) tma_load_2d(smem_u32(qtiles + (size_t)kb * SW_Q_BYTES), &tmap_q, smem_u32(q_bar), kb * BK, 0);
-      int stage = 0; uint32_t phase = 0;
-      for (int t = first_tile(); t < a.T; t = next_tile(t)) {
-        if (skip(t)) continue;
-        for (int kb = 0; kb < a.kblocks; ++kb) {
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-          const uint32_t fb = smem_u32(&full_bar[stage]);
-          mbar_arrive_expect_tx(fb, SW_A_BYTES);
-          tma_load_2d(smem_u32(ring + (size_t)stage * SW_A_BYTES), &tmap_c, fb, kb * BK, t * SW_ROWS);
-          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+    }
+    __syncwarp();
+    const uint32_t ring0 = smem_u32(ring), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+    int stage = 0; uint32_t phase = 0;
+    for (int t = first_tile(); t < a.T; t = next_tile(t)) {
+      if (skip(t)) continue;
+      for (int kb = 0; kb < a.kblocks; ++kb) {
+        mbar_wait(empty0 + 8u * stage, phase ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(full0 + 8u * stage, SW_A_BYTES);
+          tma_load_2d(ring0 + (uint32_t)stage * SW_A_BYTES, &tmap_c, full0 + 8u * stage, kb * BK, t * SW_ROWS);
         }
+        __syncwarp();
+        if (++stage == a.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 5) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      mbar_wait(smem_u32(q_bar), 0);
+    mbar_wait(smem_u32(q_bar), 0);
+    tc_fence_after();
+    // descriptors advance linearly with the shared-memory address (>> 4): 16 KB per corpus stage, 4 KB per query k-block
+    const uint64_t adesc0 = make_umma_desc(smem_u32(ring)), bdesc0 = make_umma_desc(smem_u32(qtiles));
+    const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), tfull0 = smem_u32(tfull_bar), tempty0 = smem_u32(tempty_bar);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t aphase = 0;
+    for (int t = first_tile(); t < a.T; t = next_tile(t)) {
+      if (skip(t)) continue;
+      mbar_wait(tempty0 + 8u * acc, aphase ^ 1);
       tc_fence_after();
-      int stage = 0; uint32_t phase = 0;
-      int acc = 0; uint32_t aphase = 0;
-      for (int t = first_tile(); t < a.T; t = next_tile(t)) {
-        if (skip(t)) continue;
-        mbar_wait(smem_u32(&tempty_bar[acc]), aphase ^ 1);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * SW_ACC_COLS);
+      for (int kb = 0; kb < a.kblocks; ++kb) {
+        mbar_wait(full0 + 8u * stage, phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * SW_NQ);
-        for (int kb = 0; kb < a.kblocks; ++kb) {
-          mbar_wait(smem_u32(&full_bar[stage]), phase);
-          tc_fence_after();
-          const uint64_t adesc = make_umma_desc(smem_u32(ring + (size_t)stage * SW_A_BYTES));     // corpus rows: M side
-          const uint64_t bdesc = make_umma_desc(smem_u32(qtiles + (size_t)kb * SW_Q_BYTES));      // queries: N side
+        if (elect_one()) {
+          const uint64_t adesc = adesc0 + (uint64_t)(stage * (SW_A_BYTES >> 4));     // corpus rows: M side
+          const uint64_t bdesc = bdesc0 + (uint64_t)(kb * (SW_Q_BYTES >> 4));        // queries: N side
 #pragma unroll
           for (int k = 0; k < BK_BYTES / UMMA_K_BYTES; ++k) {
             if (dbg & 2) break;
             tc_mma<FP8>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (kb | k) ? 1u : 0u);
           }
-          tc_commit(smem_u32(&empty_bar[stage]));
-          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+          tc_commit(empty0 + 8u * stage);
+          if (kb == a.kblocks - 1) tc_commit(tfull0 + 8u * acc);
         }
-        tc_commit(smem_u32(&tfull_bar[acc]));
-        if (++acc == SW_ACC) { acc = 0; aphase ^= 1; }
+        __syncwarp();
+        if (++stage == a.stages) { stage = 0; phase ^= 1; }
       }
+      if (++acc == SW_ACC) { acc = 0; aphase ^= 1; }
     }
   } else if (warp < 4) {
     // ===================== epilogue: thread <-> corpus row =====================
@@ -239,7 +259,7 @@ search_sw_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       mbar_wait(smem_u32(&tfull_bar[acc]), aphase);
       tc_fence_after();
       uint32_t v[32];
-      tc_ld32(tmem_base + lane_addr + (uint32_t)(acc * SW_NQ), v);
+      tc_ld32(tmem_base + lane_addr + (uint32_t)(acc * SW_ACC_COLS), v);
       tc_ld_wait_on(v);
       // the accumulator stage goes back at once: the scores are in registers
       tc_fence_before();
@@ -294,7 +314,7 @@ search_sw_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   __syncthreads();
   if (warp == 6) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(SW_ACC * SW_NQ)) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(SW_ACC * SW_ACC_COLS)) : "memory");
   }
 }
 
