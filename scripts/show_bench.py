@@ -11,6 +11,7 @@ for r in d["regimes"]:
     rf = r.get("roofline", {})
     print(f"{r['name']:44s} n={r.get('n_gpus')} {r['value']:12.1f} {r['unit']:11s} ms {r.get('ms_per_step', 0):9.4f} eager {r.get('ms_per_step_eager') or 0:8.4f} "
           f"{rf.get('bound', '-'):6s} {rf.get('achieved', 0):8.1f} frac {rf.get('frac', 0):.3f} whole {rf.get('achieved_whole_call') or 0:7.1f} "
-          f"mism {(r.get('verified') or {}).get('mismatches')}")
+          f"mism {(r.get('verified') or {}).get('mismatches')}"
+          + (f"  sustained {r['sustained']['ms_per_step']:.4f} ms = {r['sustained']['whole_call_gbs']:.0f} GB/s whole call" if r.get("sustained") else ""))
 print("cpu:", d.get("cpu_baseline"))
 print("clocks:", d.get("clocks"))

@@ -10,7 +10,8 @@ from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
 
-N_SW = 320_000          # > 16 * 148 * 128 = 303,104 rows: the planner picks the small-batch kernel
+N_SW = 320_000          # > 16 * 148 * 128 = 303,104 rows: the planner picks the small-batch kernel (rows of at most 512
+                        # bytes at any Q <= 32, wider rows at 8 < Q <= 32; the other cases below run search_tc.cu)
 
 
 @pytest.fixture(scope="module")
@@ -71,7 +72,7 @@ def test_small_batch_matches_exact_scan(ops, Q, dtype, D):
 def test_small_batch_uses_the_swapped_kernel(ops):
     """The plan for Q <= 32 on a large shard is the 3-launch chain (sample, thresholds, main): fewer MMAs, and
     select_rescore reads 192 sample lists + the append list instead of 4 lists per SM."""
-    c, q = _rows(N_SW, 384, 3, torch.bfloat16), _rows(8, 384, 4, torch.bfloat16)
+    c, q = _rows(N_SW, 384, 3, torch.bfloat16), _rows(16, 384, 4, torch.bfloat16)
     inv = ops.row_inv_norm(c)
     ops.search_topk(q, c, 10, corpus_inv_norm=inv)
     _, n_small = _launches(ops, lambda: ops.search_topk(q, c, 10, corpus_inv_norm=inv))

@@ -18,9 +18,13 @@
 //    128-byte swizzle): it is the B operand of every MMA of the CTA's life;
 //  * everything else of shared memory is a ring of corpus k-blocks ([128 rows x 128 B] = 16 KB per stage, 10-13
 //    stages = 160-208 KB in flight per SM), the A operand;
-//  * sixteen accumulator stages of 32 TMEM columns: the TMA and MMA warps start streaming the corpus the moment the
-//    CTA is resident and run up to sixteen tiles ahead, while the epilogue warps still wait (griddepcontrol.wait) for
-//    the thresholds the previous kernel is making;
+//  * eight accumulator stages (all 512 TMEM columns): the TMA and MMA warps start streaming the corpus the moment the
+//    CTA is resident and run up to eight tiles ahead, while the epilogue warps still wait (griddepcontrol.wait) for
+//    the thresholds the previous kernel is making.  A stage is TWO partial accumulators of 32 columns, for the even
+//    and the odd 32-byte K sub-steps: an N = 32 MMA is 16 clocks of tensor work but its result is ~180 clocks away,
+//    and the 4 x kblocks MMAs of a tile on ONE accumulator are one dependent chain -- 48 x 180 clocks = 4.6 us per
+//    tile of 768-wide bf16 rows, more than the tile's 4.1 us of HBM time (measured: 6.6 TB/s).  Two interleaved
+//    chains halve that; the epilogue adds the two partial sums;
 //  * epilogue thread i owns TMEM lane i = corpus row i of the tile: one tcgen05.ld.32x32b.x32 brings its row's 32
 //    scores, one FMUL each by the row's inverse norm, one compare each with the queries' thresholds (a warp-private
 //    shared-memory copy, refreshed per tile); the accumulator stage is handed back BEFORE the (rare) survivors are
@@ -44,8 +48,9 @@ namespace {
 
 constexpr int SW_ROWS = 128;       // corpus rows per tile (TMEM lanes, MMA M)
 constexpr int SW_NQ = 32;          // query columns per accumulator stage (MMA N)
-constexpr int SW_ACC = 16;         // accumulator stages (tiles in flight between the MMA thread and the epilogue): all 512 columns
-constexpr int SW_ACC_COLS = SW_NQ;                   // TMEM columns per accumulator stage
+constexpr int SW_KSPLIT = 2;       // partial accumulators per stage (see below)
+constexpr int SW_ACC_COLS = SW_KSPLIT * SW_NQ;       // TMEM columns per accumulator stage
+constexpr int SW_ACC = 512 / SW_ACC_COLS;            // accumulator stages (tiles in flight between the MMA thread and the epilogue)
 constexpr int SW_THREADS = 256;
 constexpr int SW_MAX_STAGES = 16;
 constexpr int SW_A_BYTES = SW_ROWS * BK_BYTES;   // 16 KB corpus k-block
@@ -68,27 +73,20 @@ struct SwArgs {
   int dbg;                // TSIM_DEBUG bits (experiment build): 2 skip MMAs, 4 skip the epilogue's compares
 };
 
-// Append one survivor to its query's list, count it in the query's threshold ladder and raise the query's threshold to
-// the highest ladder level that now has >= KP appended rows at or above it (valid: every one of them reaches
-// select_rescore).  Rare: a few hundred calls per query per search.
-__device__ __noinline__ void sw_append(const SwArgs& a, int q, float s, uint32_t row) {
-  const uint32_t pos = atomicAdd(a.app_cnt + q, 1u);
-  if (pos < (uint32_t)a.app_cap) a.app_keys[(size_t)q * a.app_cap + pos] = pack_key(s, row);
-  uint32_t* lad = a.ladder + (size_t)q * (2 * kLadder);
-  const uint4 h = __ldcg(reinterpret_cast<const uint4*>(lad));
-  const float base = __uint_as_float(h.x), step = __uint_as_float(h.y), inv = __uint_as_float(h.z);
-  const int lvl = ladder_level(base, step, inv, s);
-  if (lvl < 0) return;
-  const uint32_t mine = atomicAdd(lad + kLadder + lvl, 1u) + 1u;   // the level's count including this row
+// A query's threshold follows its ladder (tsim_common.cuh): raise thr[q] to the highest level that has >= KP appended
+// rows at or above it -- valid, because every one of them reaches select_rescore.  One lane per query; counts read a
+// little stale only delay a raise.
+__device__ __forceinline__ void sw_ladder_raise(const SwArgs& a, int q, float base, float step) {
+  const uint32_t* cnt = a.ladder + (size_t)q * (2 * kLadder) + kLadder;
   uint32_t c = 0;
   int best = -1;
 #pragma unroll
   for (int i = kLadder / 4 - 1; i >= 0; --i) {
-    const uint4 b = __ldcg(reinterpret_cast<const uint4*>(lad + kLadder) + i);
+    const uint4 b = __ldcg(reinterpret_cast<const uint4*>(cnt) + i);
     const uint32_t w[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
     for (int e = 3; e >= 0; --e) {
-      c += (4 * i + e) == lvl ? max(w[e], mine) : w[e];     // (the load may or may not see our own increment yet)
+      c += w[e];
       if (best < 0 && c >= (uint32_t)a.KP) best = 4 * i + e;
     }
   }
@@ -104,7 +102,7 @@ template <bool FP8, bool SAMPLE>
 __global__ void __launch_bounds__(SW_THREADS, 1)
 search_sw_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c, SwArgs a) {
   extern __shared__ unsigned char smem_raw[];
-  // [kblocks] query k-blocks 4K | [stages] corpus k-blocks 16K | thresholds [4 warps][32] | barriers | tmem ptr
+  // [kblocks] query k-blocks 4K | [stages] corpus k-blocks 16K | thresholds [4 warps][32] | ladders [32] | barriers | tmem ptr
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int BK = FP8 ? BK_BYTES : BK_BYTES / 2;     // elements per k-block
   // UMMA instruction descriptor: D = f32, A / B = bf16 (kind::f16) or e4m3 (kind::f8f6f4), K-major, N = 32, M = 128
@@ -113,7 +111,8 @@ search_sw_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   unsigned char* qtiles = smem;
   unsigned char* ring = smem + (((size_t)a.kblocks * SW_Q_BYTES + 1023) & ~(size_t)1023);
   float* thr_s = reinterpret_cast<float*>(ring + (size_t)a.stages * SW_A_BYTES);   // [4][32]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(thr_s + 4 * SW_NQ);
+  float4* lad_s = reinterpret_cast<float4*>(thr_s + 4 * SW_NQ);                    // [32] ladder (base, step, 1 / step) per query
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lad_s + SW_NQ);
   uint64_t* full_bar = bars;                       // [stages]  TMA -> MMA
   uint64_t* empty_bar = bars + SW_MAX_STAGES;      // [stages]  MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * SW_MAX_STAGES;  // [SW_ACC]  MMA -> epilogue
@@ -204,7 +203,8 @@ search_sw_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
           for (int k = 0; k < BK_BYTES / UMMA_K_BYTES; ++k) {
             if (dbg & 2) break;
-            tc_mma<FP8>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (kb | k) ? 1u : 0u);
+            tc_mma<FP8>(d_tmem + (uint32_t)((k % SW_KSPLIT) * SW_NQ), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC,
+                        (kb | (k / SW_KSPLIT)) ? 1u : 0u);
           }
           tc_commit(empty0 + 8u * stage);
           if (kb == a.kblocks - 1) tc_commit(tfull0 + 8u * acc);
@@ -219,22 +219,32 @@ search_sw_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const int et = threadIdx.x;                                   // 0..127 = TMEM lane = row within the tile
     const uint32_t lane_addr = ((uint32_t)(warp * 32)) << 16;
     float* tw = thr_s + warp * SW_NQ;                             // this warp's copy of the 32 thresholds
+    // the queries' ladders (laid out by the threshold kernel; only their counters change during this pass)
+    float lbase = INFINITY, lstep = 0.f;
+    if (!SAMPLE) {
+      uint4 h = make_uint4(__float_as_uint(INFINITY), 0u, 0u, 0u);
+      if (lane < a.Q) h = __ldcg(reinterpret_cast<const uint4*>(a.ladder + (size_t)lane * (2 * kLadder)));
+      lbase = __uint_as_float(h.x); lstep = __uint_as_float(h.y);
+      if (warp == 0) lad_s[lane] = make_float4(lbase, lstep, __uint_as_float(h.z), 0.f);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     int acc = 0; uint32_t aphase = 0;
     // Tile metadata -- the row's inverse norm and (lane j) query j's threshold -- is fetched kPf tiles ahead: a tile of
     // 384-byte rows lasts ~1 us, about one L2 round trip under load (one tile ahead, the epilogue waited for these
     // loads every tile and paced the whole kernel: 1.2 us per tile)
     constexpr int kPf = 4;
-    float inv_q[kPf]; uint32_t thr_q[kPf]; int tile_q[kPf];
+    float inv_q[kPf]; int tile_q[kPf];
+    uint32_t thr_q[2] = {0u, 0u};       // thresholds travel two tiles ahead only: a raise should bite soon
+    if (!SAMPLE && lane < a.Q) thr_q[0] = thr_q[1] = __ldcg(a.thr + lane);
     auto advance = [&](int t) { t = next_tile(t); while (t < a.T && skip(t)) t = next_tile(t); return t; };
     int tnext = first_tile();
     while (tnext < a.T && skip(tnext)) tnext = next_tile(tnext);
 #pragma unroll
     for (int i = 0; i < kPf; ++i) {
-      tile_q[i] = tnext; inv_q[i] = 0.f; thr_q[i] = 0u;
+      tile_q[i] = tnext; inv_q[i] = 0.f;
       if (tnext < a.T) {
         const int64_t r = (int64_t)tnext * SW_ROWS + et;
         inv_q[i] = r < a.N ? __ldg(a.c_inv + r) : 0.f;
-        if (!SAMPLE) thr_q[i] = lane < a.Q ? __ldcg(a.thr + lane) : 0u;
         tnext = advance(tnext);
       }
     }
@@ -248,19 +258,22 @@ search_sw_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         __syncwarp();
       }
 #pragma unroll
-      for (int i = 0; i + 1 < kPf; ++i) { tile_q[i] = tile_q[i + 1]; inv_q[i] = inv_q[i + 1]; thr_q[i] = thr_q[i + 1]; }
-      tile_q[kPf - 1] = tnext; inv_q[kPf - 1] = 0.f; thr_q[kPf - 1] = 0u;
+      for (int i = 0; i + 1 < kPf; ++i) { tile_q[i] = tile_q[i + 1]; inv_q[i] = inv_q[i + 1]; }
+      tile_q[kPf - 1] = tnext; inv_q[kPf - 1] = 0.f;
+      thr_q[0] = thr_q[1];
+      if (!SAMPLE && lane < a.Q) thr_q[1] = __ldcg(a.thr + lane);
       if (tnext < a.T) {
         const int64_t r = (int64_t)tnext * SW_ROWS + et;
         inv_q[kPf - 1] = r < a.N ? __ldg(a.c_inv + r) : 0.f;
-        if (!SAMPLE) thr_q[kPf - 1] = lane < a.Q ? __ldcg(a.thr + lane) : 0u;
         tnext = advance(tnext);
       }
       mbar_wait(smem_u32(&tfull_bar[acc]), aphase);
       tc_fence_after();
-      uint32_t v[32];
+      uint32_t v[32], u[32];
       tc_ld32(tmem_base + lane_addr + (uint32_t)(acc * SW_ACC_COLS), v);
+      tc_ld32(tmem_base + lane_addr + (uint32_t)(acc * SW_ACC_COLS + SW_NQ), u);
       tc_ld_wait_on(v);
+      tc_ld_wait_on(u);
       // the accumulator stage goes back at once: the scores are in registers
       tc_fence_before();
       __syncwarp();
@@ -268,7 +281,7 @@ search_sw_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       if (++acc == SW_ACC) { acc = 0; aphase ^= 1; }
       float sc[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) sc[j] = __uint_as_float(v[j]) * inv;
+      for (int j = 0; j < 32; ++j) sc[j] = (__uint_as_float(v[j]) + __uint_as_float(u[j])) * inv;
       const bool live = row < a.N && !(dbg & 4);
       // self exclusion: query j's own row is self_off + j
       const int64_t jself = a.self_on ? row - a.self_off : -1;
@@ -296,14 +309,24 @@ search_sw_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         if (!live) m = 0;
         if (jself >= 0 && jself < 32) m &= ~(1u << (int)jself);
         if (__any_sync(0xffffffffu, m != 0)) {
+          // Cold path (a few hundred rows per query per search): append the survivor to its query's list and count
+          // it on the query's ladder -- two atomics per row, nothing waited for but the list position -- then ONE
+          // lane per touched query re-reads that query's counters and raises its threshold.
+          const uint32_t touched = __reduce_or_sync(0xffffffffu, m);
 #pragma unroll 1
           while (m) {
             const int j = __ffs(m) - 1;
             m &= m - 1;
             const float s = select32(sc, j);
-            // the threshold may have risen since this tile's copy was made
-            if (f32_to_ord(s) > __ldcg(a.thr + j) && s < INFINITY) sw_append(a, j, s, (uint32_t)row);
+            if (!(s < INFINITY)) continue;
+            const uint32_t pos = atomicAdd(a.app_cnt + j, 1u);
+            if (pos < (uint32_t)a.app_cap) a.app_keys[(size_t)j * a.app_cap + pos] = pack_key(s, (uint32_t)row);
+            const float4 ld = lad_s[j];
+            const int lvl = ladder_level(ld.x, ld.y, ld.z, s);
+            if (lvl >= 0) atomicAdd(a.ladder + (size_t)j * (2 * kLadder) + kLadder + lvl, 1u);
           }
+          __syncwarp();
+          if ((touched >> lane) & 1u) sw_ladder_raise(a, lane, lbase, lstep);
         }
         __syncwarp();     // everybody has read tw before the next tile overwrites it
       }
@@ -326,7 +349,7 @@ search_sw_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 // sample keys at or above the threshold move to the append list, so that select_rescore reads one short list per query.
 __global__ void __launch_bounds__(128) sw_tighten_kernel(const uint64_t* cand, int64_t NC, int KP, uint32_t* thr,
                                                          uint32_t* ladder, uint64_t* app_keys, uint32_t* app_cnt, int app_cap) {
-  __shared__ uint32_t hist[288];
+  __shared__ uint32_t hist[544];
   pdl_trigger();
   pdl_wait();
   const int64_t q = blockIdx.x;
@@ -336,7 +359,7 @@ __global__ void __launch_bounds__(128) sw_tighten_kernel(const uint64_t* cand, i
 
 size_t sw_smem_bytes(int kblocks, int stages) {
   return 1024 + (((size_t)kblocks * SW_Q_BYTES + 1023) & ~(size_t)1023) + (size_t)stages * SW_A_BYTES + 4 * SW_NQ * 4 +
-         (2 * SW_MAX_STAGES + 2 * SW_ACC + 1) * 8 + 16;
+         SW_NQ * 16 + (2 * SW_MAX_STAGES + 2 * SW_ACC + 1) * 8 + 16;
 }
 
 template <bool FP8, bool SAMPLE>

@@ -175,7 +175,7 @@ __device__ __forceinline__ float select32(const float* sc, int j) {
 // same radix select and ladder as warp_tighten (tsim_common.cuh), but every thread first pulls its share of the
 // keys into registers with independent loads -- one L2 round trip -- and the four passes then run on registers.
 // (A single warp walking 74 keys per lane with a load -> shared-atomic dependency per key took ~45 us, during
-// which every CTA of the launch sat at the grid barrier with HBM idle.)  n <= 128 * kEpiKeys keys; hist: 288 words.
+// which every CTA of the launch sat at the grid barrier with HBM idle.)  n <= 128 * kEpiKeys keys; hist: 288 words (544 with tail_step).
 constexpr int kEpiKeys = 24;
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 // ladder_frac: ladder step as a fraction of (sample best - KP-th best): 1/8 puts the sample's best at level 8.
@@ -215,34 +215,45 @@ __device__ __noinline__ void epi_tighten(const uint64_t* src, uint32_t n, int KP
     epi_bar();
     return;
   }
-  // MSB-first radix select over the registers: the `want`-th best ordered score
-  auto select_rank = [&](uint32_t want) {
-    uint32_t prefix = 0, need = want;
+  // MSB-first radix select over the registers: the `want`-th best ordered score -- and, in the same four passes (second
+  // histogram at hist + 288, scanned by the second warp), the `want2`-th best when want2 != 0
+  uint32_t prefix = 0, lower = 0;
+  {
+    const uint32_t want2 = (tail_step && live >= 4u * (uint32_t)KP) ? 4u * (uint32_t)KP : 0u;
+    uint32_t* hist2 = hist + 288;
+    uint32_t need = (uint32_t)KP, need2 = want2;
     for (int shift = 24; shift >= 0; shift -= 8) {
       hist[et] = 0u; hist[et + 128] = 0u;
+      if (want2) { hist2[et] = 0u; hist2[et + 128] = 0u; }
       epi_bar();
       const uint32_t hi_mask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
 #pragma unroll
       for (int i = 0; i < kEpiKeys; ++i)
-        if (sc[i] != 0u && (sc[i] & hi_mask) == prefix) atomicAdd(&hist[(sc[i] >> shift) & 255u], 1u);
+        if (sc[i] != 0u) {
+          if ((sc[i] & hi_mask) == prefix) atomicAdd(&hist[(sc[i] >> shift) & 255u], 1u);
+          if (want2 && (sc[i] & hi_mask) == lower) atomicAdd(&hist2[(sc[i] >> shift) & 255u], 1u);
+        }
       epi_bar();
-      if (et < 32) {
+      if (et < 32 || (want2 && et < 64)) {
         // lane l owns buckets 255 - 8l .. 248 - 8l (descending): where does the running count reach `need`?
+        const uint32_t* h = et < 32 ? hist : hist2;
+        const uint32_t nd = et < 32 ? need : need2;
+        const int l = et & 31;
         uint32_t c[8], tot = 0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { c[j] = hist[255 - 8 * et - j]; tot += c[j]; }
+        for (int j = 0; j < 8; ++j) { c[j] = h[255 - 8 * l - j]; tot += c[j]; }
         uint32_t incl = tot;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-          if (et >= o) incl += v;
+          if (l >= o) incl += v;
         }
         const uint32_t before = incl - tot;
-        if (before < need && incl >= need) {
+        if (before < nd && incl >= nd) {
           uint32_t run = before;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            if (run < need && run + c[j] >= need) { ctl[2] = 255u - 8u * et - j; ctl[3] = need - run; }
+            if (run < nd && run + c[j] >= nd) { ctl[et < 32 ? 2 : 4] = 255u - 8u * l - j; ctl[et < 32 ? 3 : 5] = nd - run; }
             run += c[j];
           }
         }
@@ -250,20 +261,16 @@ __device__ __noinline__ void epi_tighten(const uint64_t* src, uint32_t n, int KP
       epi_bar();
       prefix |= ctl[2] << shift;
       need = ctl[3];
+      if (want2) { lower |= ctl[4] << shift; need2 = ctl[5]; }
       epi_bar();
     }
-    return prefix;
-  };
-  const uint32_t prefix = select_rank((uint32_t)KP);
+    if (!want2) lower = 0;
+  }
   // tail_step (append plans of search_sw.cu): the ladder step comes from the sample's own tail slope -- the gap between
   // its KP-th and 4 KP-th best, i.e. ln 4 in rank -- not from its best score: a query whose twin sits in the sample
   // (score 1.0, common: queries are often corpus rows) would stretch an eighth-of-(best - base) ladder so far that no
   // level beyond the first ever collects KP rows.  0.43 = 0.6 / ln 4: 15 steps span ~9 e-foldings of rank.
-  float robust_step = 0.f;
-  if (tail_step && live >= 4u * (uint32_t)KP) {
-    const uint32_t lower = select_rank(4u * (uint32_t)KP);
-    robust_step = (ord_to_f32(prefix) - ord_to_f32(lower)) * 0.43f;
-  }
+  const float robust_step = lower ? (ord_to_f32(prefix) - ord_to_f32(lower)) * 0.43f : 0.f;
   if (et == 0) atomicMax(thr_q, prefix);
   if (lad) {
     const float base = ord_to_f32(prefix);
