@@ -403,6 +403,188 @@ __global__ void __launch_bounds__(kExThreads, MINB) search_exact_mma_kernel(ExAr
   }
 }
 
+// ---- the same scan with an asynchronous raw-row pipeline (round 2) ---------------------------------------------------
+// search_exact_mma_kernel above fetches the next (tile, chunk) into registers, widens it to float64 and stores it to
+// shared memory between TWO block barriers per 32-wide chunk: ncu showed the DMMA sub-pipe 46 % busy, 583 staging
+// instructions per 64 DMMAs, and the kernel stopped at 68 % of the measured DMMA peak.  Here the rows travel RAW:
+// every thread issues 16-byte cp.async copies (LDGSTS) of the chunk after next into a ring of kAStages stages -- no
+// registers, no conversion, no store instructions -- there is ONE barrier per chunk, and a fragment element is
+// widened when it is loaded (one 2/4-byte shared-memory load + one conversion instead of one 8-byte load: half the
+// shared-memory wavefronts).  Row stride in a stage = 32 elements + 16 bytes: 144 / 80 / 48 bytes for 4 / 2 / 1-byte
+// elements puts the 8 fragment rows x 4 k of a load on 32 distinct banks (2- and 1-byte elements share words within
+// a row: broadcast).  Needs q_dt == c_dt, 16-byte aligned bases and row pitches, D * element size % 16 == 0; anything
+// else takes the kernel above.  Same lists, same output, bit-identical results.
+template <int DT> struct AsyncCfg {
+  static constexpr int ESZ = DT == TSIM_F32 ? 4 : DT == TSIM_E4M3 ? 1 : 2;
+  static constexpr int ROWB = kMDC * ESZ + 16;            // bytes per staged row
+  static constexpr int PPR = kMDC * ESZ / 16;             // 16-byte pieces per row
+  static constexpr int STAGE = 2 * kMRows * ROWB;         // 64 corpus rows + 64 queries
+};
+
+__device__ __forceinline__ void cp_async_16_zfill(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+
+template <int DT, int kAStages>
+__global__ void __launch_bounds__(kExThreads, 2) search_exact_mma_async_kernel(ExArgs a) {
+  using C = AsyncCfg<DT>;
+  constexpr int QG = 64;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char* ring = smem_raw;                                        // [kAStages][128 rows][ROWB]
+  double* rinv = (double*)(ring + (size_t)kAStages * C::STAGE);          // [2][kMRows] 1 / row norm, by tile parity
+  double* qn_s = rinv + 2 * kMRows;                                      // [QG] 1 / query norm
+  double* ls_all = qn_s + QG;                                            // [QG][k]
+  uint32_t* li_all = (uint32_t*)(ls_all + (size_t)QG * a.k);             // [QG][k]
+  int* cnt_s = (int*)(li_all + (size_t)QG * a.k);                        // [QG] list lengths (warp-private)
+  int32_t* qid_s = cnt_s + QG;                                           // [QG] query number of the slot
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int fr = lane >> 2, fk = lane & 3;
+  pdl_trigger();
+  pdl_wait();
+  const int64_t nq = a.flag_cnt ? (int64_t)*a.flag_cnt : a.Q;
+  const int64_t ngroups = (nq + QG - 1) / QG;
+  const int slice = blockIdx.x;
+  const int64_t row_begin = (int64_t)slice * a.slice_rows;
+  const int64_t row_end = min(a.N, row_begin + a.slice_rows);
+  const int nchunks = (int)((a.D + kMDC - 1) / kMDC);
+  const int64_t ntiles = row_end > row_begin ? (row_end - row_begin + kMRows - 1) / kMRows : 0;
+  const int64_t total = ntiles * nchunks;
+  const int64_t row_bytes = a.D * C::ESZ;
+  const int64_t c_pitch = a.c_stride * C::ESZ, q_pitch = a.q_stride * C::ESZ;
+
+  for (int64_t g = blockIdx.y; g < ngroups; g += gridDim.y) {
+    const int64_t slot0 = g * QG + warp * 8;
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) {
+      const int64_t slot = min(slot0 + j, nq - 1);
+      const int64_t qid = a.flag_list ? (int64_t)a.flag_list[slot] : slot;
+      const char* qrow = (const char*)a.q + (size_t)qid * q_pitch;
+      double qq = 0.0;
+      for (int64_t d = lane; d < a.D; d += 32) {
+        double v = (double)Elem<DT>::ld(qrow, d);
+        qq = fma(v, v, qq);
+      }
+      qq = warp_sum_f64(qq);
+      if (lane == 0) {
+        qn_s[warp * 8 + j] = 1.0 / fmax(sqrt(qq), kCosEps);
+        cnt_s[warp * 8 + j] = 0;
+        qid_s[warp * 8 + j] = (int32_t)qid;
+      }
+    }
+    __syncthreads();      // qid_s is read by every thread's copies
+
+    // issue the copies of iteration `it` (tile it / nchunks, chunk it % nchunks) into its stage
+    auto issue = [&](int64_t it) {
+      if (it < total) {
+        const int64_t tile = it / nchunks;
+        const int c = (int)(it - tile * nchunks);
+        const int64_t r0 = row_begin + tile * kMRows;
+        unsigned char* st = ring + (size_t)(it % kAStages) * C::STAGE;
+#pragma unroll
+        for (int p = tid; p < 2 * kMRows * C::PPR; p += kExThreads) {
+          const int row = p / C::PPR, piece = p - row * C::PPR;
+          const int64_t boff = (int64_t)c * (kMDC * C::ESZ) + piece * 16;      // byte offset within the source row
+          const char* src;
+          bool ok = boff < row_bytes;
+          if (row < kMRows) {
+            ok = ok && r0 + row < row_end;
+            src = (const char*)a.corpus + (size_t)(ok ? r0 + row : row_begin) * c_pitch + (ok ? boff : 0);
+          } else {
+            ok = ok && g * QG + (row - kMRows) < nq;
+            src = (const char*)a.q + (size_t)qid_s[row - kMRows] * q_pitch + (ok ? boff : 0);
+          }
+          cp_async_16_zfill(st + (size_t)row * C::ROWB + piece * 16, src, ok);
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int i = 0; i < kAStages - 1; ++i) issue(i);
+
+    double acc[kMNF][2];
+    int c = 0;
+    int64_t r0 = row_begin, tile_no = 0;
+    for (int64_t it = 0; it < total; ++it) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(kAStages - 2) : "memory");
+      if (c == 0 && tid < kMRows) rinv[(tile_no & 1) * kMRows + tid] = r0 + tid < row_end ? a.rinv[r0 + tid] : 0.0;
+      __syncthreads();          // this chunk has landed for everybody; everybody is done with the stage refilled next
+      issue(it + kAStages - 1);
+      if (c == 0) {
+#pragma unroll
+        for (int ni = 0; ni < kMNF; ++ni) acc[ni][0] = acc[ni][1] = 0.0;
+      }
+      const unsigned char* st = ring + (size_t)(it % kAStages) * C::STAGE;
+      const unsigned char* tf = st + (size_t)fr * C::ROWB;                          // corpus rows fr + 8 ni
+      const unsigned char* qf = st + (size_t)(kMRows + warp * 8 + fr) * C::ROWB;    // this warp's query fr
+#pragma unroll
+      for (int ks = 0; ks < kMDC / 4; ++ks) {
+        const double af = (double)Elem<DT>::ld(qf, ks * 4 + fk);
+        double bf[kMNF];
+#pragma unroll
+        for (int ni = 0; ni < kMNF; ++ni) bf[ni] = (double)Elem<DT>::ld(tf + (size_t)ni * 8 * C::ROWB, ks * 4 + fk);
+#pragma unroll
+        for (int ni = 0; ni < kMNF; ++ni) dmma_8x8x4(acc[ni], af, bf[ni]);
+      }
+
+      if (c == nchunks - 1) {
+        const double* ri_t = rinv + (tile_no & 1) * kMRows;
+        const int ql = warp * 8 + fr;
+        const int64_t qid = qid_s[ql];
+        const bool live = g * QG + ql < nq;
+        const double qn = qn_s[ql];
+#pragma unroll
+        for (int ni = 0; ni < kMNF; ++ni) {
+          const int cnt = cnt_s[ql];
+          const double thr = cnt < a.k ? -INFINITY : ls_all[(size_t)ql * a.k + a.k - 1];
+          const int col = ni * 8 + 2 * fk;
+          const double2 ri = *reinterpret_cast<const double2*>(ri_t + col);
+          const double s0 = acc[ni][0] * qn * ri.x, s1 = acc[ni][1] * qn * ri.y;
+          const int64_t row = r0 + col;
+          const bool w0 = live && row < row_end && !(a.self_on && row == a.self_off + qid) && s0 > thr;
+          const bool w1 = live && row + 1 < row_end && !(a.self_on && row + 1 == a.self_off + qid) && s1 > thr;
+          unsigned m0 = __ballot_sync(0xffffffffu, w0), m1 = __ballot_sync(0xffffffffu, w1);
+          while (m0 | m1) {
+            const int src = __ffs(m0 | m1) - 1;
+            const bool first = (m0 >> src) & 1u;
+            if (first) m0 &= ~(1u << src); else m1 &= ~(1u << src);
+            const double s = __shfl_sync(0xffffffffu, first ? s0 : s1, src);
+            const int qsrc = warp * 8 + (src >> 2);
+            warp_list_insert_call(ls_all + (size_t)qsrc * a.k, li_all + (size_t)qsrc * a.k, cnt_s + qsrc, a.k, s,
+                                  (uint32_t)(r0 + ni * 8 + 2 * (src & 3) + (first ? 0 : 1)));
+          }
+        }
+      }
+      if (++c == nchunks) { c = 0; r0 += kMRows; ++tile_no; }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // write this warp's (slot, slice) lists
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) {
+      const int64_t slot = slot0 + j;
+      if (slot >= nq) break;
+      const double* ls = ls_all + (size_t)(warp * 8 + j) * a.k;
+      const uint32_t* li = li_all + (size_t)(warp * 8 + j) * a.k;
+      const int cnt = cnt_s[warp * 8 + j];
+      double* os = a.ex_score + ((size_t)slot * a.S + slice) * a.k;
+      uint32_t* oi = a.ex_idx + ((size_t)slot * a.S + slice) * a.k;
+      for (int i = lane; i < a.k; i += 32) {
+        os[i] = i < cnt ? ls[i] : 0.0;
+        oi[i] = i < cnt ? li[i] : 0xffffffffu;
+      }
+    }
+    __syncthreads();      // the next group rewrites qid_s / the ring
+  }
+}
+
+size_t mma_async_smem_bytes(int k, int dt, int stages) {
+  const int esz = dtype_size(dt);
+  const size_t stage = 2 * (size_t)kMRows * (kMDC * esz + 16);
+  return stages * stage + sizeof(double) * (2 * kMRows + 64 + 64 * (size_t)k) + sizeof(uint32_t) * 64 * (size_t)k + 2 * sizeof(int) * 64;
+}
+
 size_t mma_smem_bytes(int k, int MF) {
   const size_t QG = 64 * (size_t)MF;
   return sizeof(double) * ((QG + kMRows) * kMStride + kMRows + QG + QG * k) + sizeof(uint32_t) * QG * k + 2 * sizeof(int) * QG;
@@ -441,6 +623,28 @@ int launch_search_exact(const void* q, int q_dt, int64_t q_stride, const void* c
                            c_stride, N, D, flag_cnt, ex_rinv));
       count_launch();
       dim3 mgrid((unsigned)p.S, (unsigned)(mgroups < 4096 ? mgroups : 4096));
+      // asynchronous raw-row pipeline when the operands allow 16-byte cp.async copies
+      const int esz = dtype_size(c_dt);
+      // (4 stages, or 3 when that is what lets two CTAs share an SM -- one multiplies while the other waits at its
+      // barrier; with one CTA per SM -- long lists, k > ~75 on 4-byte rows -- the kernel above measured faster)
+      const size_t two_per_sm = (227 * 1024) / 2 - 1024;
+      const int nst = mma_async_smem_bytes(k, c_dt, 4) <= two_per_sm ? 4 : 3;
+      const size_t asmem = mma_async_smem_bytes(k, c_dt, nst);
+      const bool async_ok = q_dt == c_dt && MF == 1 && variant == 12 && (((uintptr_t)q | (uintptr_t)corpus) & 15) == 0 &&
+                            (q_stride * esz) % 16 == 0 && (c_stride * esz) % 16 == 0 && (D * esz) % 16 == 0 &&
+                            asmem <= two_per_sm && !knob_on("TSIM_NO_ASYNC_SCAN");
+      if (async_ok) {
+#define TSIM_ASYNC_KERN(NST) (c_dt == TSIM_F32 ? search_exact_mma_async_kernel<TSIM_F32, NST>             \
+                              : c_dt == TSIM_F16 ? search_exact_mma_async_kernel<TSIM_F16, NST>           \
+                              : c_dt == TSIM_BF16 ? search_exact_mma_async_kernel<TSIM_BF16, NST>         \
+                                                  : search_exact_mma_async_kernel<TSIM_E4M3, NST>)
+        auto akern = nst == 4 ? TSIM_ASYNC_KERN(4) : TSIM_ASYNC_KERN(3);
+#undef TSIM_ASYNC_KERN
+        TSIM_CUDA(cudaFuncSetAttribute(akern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asmem));
+        TSIM_CUDA(launch_pdl(akern, mgrid, dim3(kExThreads), asmem, st, a));
+        count_launch();
+        return TSIM_OK;
+      }
       auto kern = MF == 2 ? search_exact_mma_kernel<2, 1> : minb == 2 ? search_exact_mma_kernel<1, 2> : search_exact_mma_kernel<1, 1>;
       TSIM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
       TSIM_CUDA(launch_pdl(kern, mgrid, dim3(kExThreads), msmem, st, a));
