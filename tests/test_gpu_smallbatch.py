@@ -69,6 +69,15 @@ def test_small_batch_matches_exact_scan(ops, Q, dtype, D):
     assert (d <= 0).all() and ((i[:, 1:] > i[:, :-1]) | (d < 0)).all()
 
 
+@pytest.mark.parametrize("k", [1, 24])
+def test_small_batch_other_k(ops, k):
+    """k <= 24 (candidate proofs over 16 or 32 rows) takes the same kernel; k = 25 and beyond the list kernel."""
+    c, q = _rows(N_SW, 256, 21, torch.bfloat16), _rows(12, 256, 22, torch.bfloat16)
+    c[250_000:250_030] = c[40:70]
+    s, i, s64, fl = _same_as_exact(ops, q, c, k)
+    assert (fl == 0).all()
+
+
 def test_small_batch_uses_the_swapped_kernel(ops):
     """The plan for Q <= 32 on a large shard is the 3-launch chain (sample, thresholds, main): fewer MMAs, and
     select_rescore reads 192 sample lists + the append list instead of 4 lists per SM."""

@@ -112,7 +112,7 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
       const int64_t T128 = (N + 127) / 128;
       const int kb = (int)((D * dtype_size(c_dt) + 127) / 128);
       const bool narrow = kb <= 4;
-      if (Q <= 32 && (narrow || Q > 8 || knob_on("TSIM_SWAP_ALL")) && p->KP == 16 && !shadow && T128 >= 16 * (int64_t)sms &&
+      if (Q <= 32 && (narrow || Q > 8 || knob_on("TSIM_SWAP_ALL")) && p->KP <= 32 && !shadow && T128 >= 16 * (int64_t)sms &&
           search_sw_stages(kb) > 0 && !knob_on("TSIM_NO_SWAP")) {
         p->swapped = 1;
         p->sticky = 1; p->pair = 0; p->QB = 1; p->Gq = sms; p->fused = 0; p->qrep = 0;
