@@ -135,3 +135,31 @@ def test_small_batch_shards_plus_merge_equal_single_search(ops):
     parts = [ops.search_topk(q, c[r * per:(r + 1) * per], k, idx_base=r * per, return_score64=True) for r in range(G)]
     ms, ms64, mi = ops.merge_topk(torch.cat([p[2] for p in parts], 1), torch.cat([p[1] for p in parts], 1), k, G)
     assert torch.equal(mi, full[1]) and torch.equal(ms64, full[2])
+
+
+def test_small_batch_graph_replay_and_two_streams(ops):
+    """The 3-launch chain replays from a CUDA graph (ShardedCorpus.search_graphed) with fresh queries each time, and
+    two streams can run small-batch searches side by side (no grid barrier in these kernels, one workspace per stream)."""
+    from text_similarity_b200.sharded import ShardedCorpus
+    c = (_rows(N_SW, 384, 31, torch.float32) * 16.0).to(torch.float8_e4m3fn)
+    corp = ShardedCorpus(c)
+    for seed in (32, 33, 34):
+        q = (_rows(8, 384, seed, torch.float32) * 16.0).to(torch.float8_e4m3fn)
+        gs, gi = corp.search_graphed(q, 10)
+        gs, gi = gs.clone(), gi.clone()
+        es, ei = ops.search_topk(q, c, 10, mode="exact")
+        assert torch.equal(gi, ei) and torch.equal(gs, es)
+    qa = (_rows(16, 384, 41, torch.float32) * 16.0).to(torch.float8_e4m3fn)
+    qb = (_rows(3, 384, 42, torch.float32) * 16.0).to(torch.float8_e4m3fn)
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    outs = {}
+    for _ in range(3):
+        with torch.cuda.stream(sa):
+            outs["a"] = ops.search_topk(qa, c, 10, corpus_inv_norm=corp.inv_norm)
+        with torch.cuda.stream(sb):
+            outs["b"] = ops.search_topk(qb, c, 10, corpus_inv_norm=corp.inv_norm)
+    torch.cuda.synchronize()
+    for key, q in (("a", qa), ("b", qb)):
+        es, ei = ops.search_topk(q, c, 10, mode="exact")
+        assert torch.equal(outs[key][1], ei) and torch.equal(outs[key][0], es)
