@@ -640,6 +640,60 @@ __global__ void __launch_bounds__(256) row_inv_norm_kernel(const void* x, int64_
   }
 }
 
+// e4m3 rows: the sums of squares come off the tensor cores.  Converting an e4m3 byte to float and squaring it costs
+// ~2.5 instructions per BYTE on the CUDA cores: the kernel above ran at 36 % of HBM on e4m3 rows (4 ms per 25M x 384).
+// mma.sync.m16n8k32 (e4m3 x e4m3 -> f32) multiplies a 16 x 32 block of A by a 32 x 8 block of B; feeding 16 rows as A
+// and THE SAME registers as B -- rows 0-7 for one MMA, rows 8-15 for a second -- gives blocks of X X^T whose diagonal
+// is the rows' sums of squares (products exact, float accumulation).  Any assignment of a row's bytes to the k
+// positions is fine as long as A and B agree, and they do by construction (thread (g, kq) holds bytes kq * 16 .. + 15
+// of a 64-byte step of row g in the registers that the fragment layout calls row g / column g): two 16-byte loads and
+// four MMAs per thread per 16 rows x 64 bytes, ~10 instructions per KILOBYTE.
+__device__ __forceinline__ void mma_e4m3_16x8x32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                 uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k32.row.col.f32.e4m3.e4m3.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+               "{%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256) row_inv_norm_e4m3_mma_kernel(const unsigned char* x, int64_t N, int64_t D,
+                                                                    int64_t stride, float* out) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, kq = lane & 3;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  for (int64_t row0 = gw * 16; row0 < N; row0 += nwarps * 16) {
+    const int64_t ra = min(row0 + g, N - 1), rb = min(row0 + g + 8, N - 1);    // (rows past the end: clamped, not stored)
+    const unsigned char* pa = x + ra * stride + kq * 16;
+    const unsigned char* pb = x + rb * stride + kq * 16;
+    float d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int64_t b0 = 0; b0 < D; b0 += 256) {                // four 64-byte steps per round: eight loads in flight
+      uint4 w[4], v[4];
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const int64_t off = b0 + s * 64;
+        const bool ok = off + kq * 16 < D;
+        w[s] = ok ? __ldg(reinterpret_cast<const uint4*>(pa + off)) : zero;
+        v[s] = ok ? __ldg(reinterpret_cast<const uint4*>(pb + off)) : zero;
+      }
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        mma_e4m3_16x8x32(d1, w[s].x, v[s].x, w[s].y, v[s].y, w[s].x, w[s].y);   // columns = rows 0-7
+        mma_e4m3_16x8x32(d2, w[s].x, v[s].x, w[s].y, v[s].y, v[s].x, v[s].y);   // columns = rows 8-15
+        mma_e4m3_16x8x32(d1, w[s].z, v[s].z, w[s].w, v[s].w, w[s].z, w[s].w);
+        mma_e4m3_16x8x32(d2, w[s].z, v[s].z, w[s].w, v[s].w, v[s].z, v[s].w);
+      }
+    }
+    // diagonals: (row g, column g) sits in thread (g, kq = g / 2), element g % 2 of d1; (row g + 8, column g) in d2[2 + g % 2]
+    if (kq == (g >> 1)) {
+      const float sa = (g & 1) ? d1[1] : d1[0], sb = (g & 1) ? d2[3] : d2[2];
+      if (row0 + g < N) out[row0 + g] = 1.f / fmaxf(sqrtf(sa), (float)kCosEps);
+      if (row0 + g + 8 < N) out[row0 + g + 8] = 1.f / fmaxf(sqrtf(sb), (float)kCosEps);
+    }
+  }
+}
+
 template <int DT, int VEC>
 int launch_pool(const PoolArgs& a, cudaStream_t st) {
   const int nvec = (int)(a.D / VEC);
@@ -735,6 +789,13 @@ int launch_row_inv_norm(const void* x, int dt, int64_t N, int64_t D, int64_t str
   int64_t want = (N + 4 * wpb - 1) / (4 * wpb);
   const int64_t cap = (int64_t)device_sm_count() * 8;      // persistent: 8 CTAs per SM, grid-stride over rows
   unsigned grid = (unsigned)(want < cap ? want : cap);
+  if (dt == TSIM_E4M3 && vec_ok && !knob_on("TSIM_NO_MMA_NORM")) {      // tensor-core sums of squares, 16 rows per warp
+    int64_t want16 = (N + 16 * wpb - 1) / (16 * wpb);
+    row_inv_norm_e4m3_mma_kernel<<<(unsigned)(want16 < cap ? want16 : cap), wpb * 32, 0, st>>>((const unsigned char*)x, N, D, stride, out);
+    TSIM_CUDA(cudaGetLastError());
+    count_launch();
+    return TSIM_OK;
+  }
   switch (dt) {
     case TSIM_F32: row_inv_norm_kernel<TSIM_F32><<<grid, wpb * 32, 0, st>>>(x, N, D, stride, out, vec_ok); break;
     case TSIM_F16: row_inv_norm_kernel<TSIM_F16><<<grid, wpb * 32, 0, st>>>(x, N, D, stride, out, vec_ok); break;
