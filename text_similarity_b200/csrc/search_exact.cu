@@ -418,7 +418,6 @@ template <int DT> struct AsyncCfg {
   static constexpr int ESZ = DT == TSIM_F32 ? 4 : DT == TSIM_E4M3 ? 1 : 2;
   static constexpr int ROWB = kMDC * ESZ + 16;            // bytes per staged row
   static constexpr int PPR = kMDC * ESZ / 16;             // 16-byte pieces per row
-  static constexpr int STAGE = 2 * kMRows * ROWB;         // 64 corpus rows + 64 queries
 };
 
 __device__ __forceinline__ void cp_async_16_zfill(void* smem_dst, const void* gsrc, bool valid) {
@@ -427,13 +426,17 @@ __device__ __forceinline__ void cp_async_16_zfill(void* smem_dst, const void* gs
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
 }
 
-template <int DT, int kAStages>
+// MF = query fragments per warp (8 MF queries per warp, 64 MF per CTA): with two, a k-step is 2 + 8 fragment loads
+// and conversions for 16 DMMAs instead of 1 + 8 for 8.
+template <int DT, int kAStages, int MF>
 __global__ void __launch_bounds__(kExThreads, 2) search_exact_mma_async_kernel(ExArgs a) {
   using C = AsyncCfg<DT>;
-  constexpr int QG = 64;
+  constexpr int QW = 8 * MF, QG = 64 * MF;
+  constexpr int SROWS = kMRows + QG;                       // rows per stage: 64 corpus rows + the CTA's queries
+  constexpr int STAGE = SROWS * C::ROWB;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned char* ring = smem_raw;                                        // [kAStages][128 rows][ROWB]
-  double* rinv = (double*)(ring + (size_t)kAStages * C::STAGE);          // [2][kMRows] 1 / row norm, by tile parity
+  double* rinv = (double*)(ring + (size_t)kAStages * STAGE);          // [2][kMRows] 1 / row norm, by tile parity
   double* qn_s = rinv + 2 * kMRows;                                      // [QG] 1 / query norm
   double* ls_all = qn_s + QG;                                            // [QG][k]
   uint32_t* li_all = (uint32_t*)(ls_all + (size_t)QG * a.k);             // [QG][k]
@@ -456,9 +459,9 @@ __global__ void __launch_bounds__(kExThreads, 2) search_exact_mma_async_kernel(E
   const int64_t c_pitch = a.c_stride * C::ESZ, q_pitch = a.q_stride * C::ESZ;
 
   for (int64_t g = blockIdx.y; g < ngroups; g += gridDim.y) {
-    const int64_t slot0 = g * QG + warp * 8;
+    const int64_t slot0 = g * QG + warp * QW;
 #pragma unroll 1
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < QW; ++j) {
       const int64_t slot = min(slot0 + j, nq - 1);
       const int64_t qid = a.flag_list ? (int64_t)a.flag_list[slot] : slot;
       const char* qrow = (const char*)a.q + (size_t)qid * q_pitch;
@@ -469,9 +472,9 @@ __global__ void __launch_bounds__(kExThreads, 2) search_exact_mma_async_kernel(E
       }
       qq = warp_sum_f64(qq);
       if (lane == 0) {
-        qn_s[warp * 8 + j] = 1.0 / fmax(sqrt(qq), kCosEps);
-        cnt_s[warp * 8 + j] = 0;
-        qid_s[warp * 8 + j] = (int32_t)qid;
+        qn_s[warp * QW + j] = 1.0 / fmax(sqrt(qq), kCosEps);
+        cnt_s[warp * QW + j] = 0;
+        qid_s[warp * QW + j] = (int32_t)qid;
       }
     }
     __syncthreads();      // qid_s is read by every thread's copies
@@ -482,9 +485,9 @@ __global__ void __launch_bounds__(kExThreads, 2) search_exact_mma_async_kernel(E
         const int64_t tile = it / nchunks;
         const int c = (int)(it - tile * nchunks);
         const int64_t r0 = row_begin + tile * kMRows;
-        unsigned char* st = ring + (size_t)(it % kAStages) * C::STAGE;
+        unsigned char* st = ring + (size_t)(it % kAStages) * STAGE;
 #pragma unroll
-        for (int p = tid; p < 2 * kMRows * C::PPR; p += kExThreads) {
+        for (int p = tid; p < SROWS * C::PPR; p += kExThreads) {
           const int row = p / C::PPR, piece = p - row * C::PPR;
           const int64_t boff = (int64_t)c * (kMDC * C::ESZ) + piece * 16;      // byte offset within the source row
           const char* src;
@@ -504,7 +507,7 @@ __global__ void __launch_bounds__(kExThreads, 2) search_exact_mma_async_kernel(E
 #pragma unroll
     for (int i = 0; i < kAStages - 1; ++i) issue(i);
 
-    double acc[kMNF][2];
+    double acc[MF][kMNF][2];
     int c = 0;
     int64_t r0 = row_begin, tile_no = 0;
     for (int64_t it = 0; it < total; ++it) {
@@ -514,24 +517,31 @@ __global__ void __launch_bounds__(kExThreads, 2) search_exact_mma_async_kernel(E
       issue(it + kAStages - 1);
       if (c == 0) {
 #pragma unroll
-        for (int ni = 0; ni < kMNF; ++ni) acc[ni][0] = acc[ni][1] = 0.0;
+        for (int mi = 0; mi < MF; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < kMNF; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
       }
-      const unsigned char* st = ring + (size_t)(it % kAStages) * C::STAGE;
+      const unsigned char* st = ring + (size_t)(it % kAStages) * STAGE;
       const unsigned char* tf = st + (size_t)fr * C::ROWB;                          // corpus rows fr + 8 ni
-      const unsigned char* qf = st + (size_t)(kMRows + warp * 8 + fr) * C::ROWB;    // this warp's query fr
+      const unsigned char* qf = st + (size_t)(kMRows + warp * QW + fr) * C::ROWB;   // this warp's queries fr + 8 mi
 #pragma unroll
       for (int ks = 0; ks < kMDC / 4; ++ks) {
-        const double af = (double)Elem<DT>::ld(qf, ks * 4 + fk);
-        double bf[kMNF];
+        double af[MF], bf[kMNF];
+#pragma unroll
+        for (int mi = 0; mi < MF; ++mi) af[mi] = (double)Elem<DT>::ld(qf + (size_t)mi * 8 * C::ROWB, ks * 4 + fk);
 #pragma unroll
         for (int ni = 0; ni < kMNF; ++ni) bf[ni] = (double)Elem<DT>::ld(tf + (size_t)ni * 8 * C::ROWB, ks * 4 + fk);
 #pragma unroll
-        for (int ni = 0; ni < kMNF; ++ni) dmma_8x8x4(acc[ni], af, bf[ni]);
+        for (int mi = 0; mi < MF; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < kMNF; ++ni) dmma_8x8x4(acc[mi][ni], af[mi], bf[ni]);
       }
 
       if (c == nchunks - 1) {
         const double* ri_t = rinv + (tile_no & 1) * kMRows;
-        const int ql = warp * 8 + fr;
+#pragma unroll
+        for (int mi = 0; mi < MF; ++mi) {
+        const int ql = warp * QW + mi * 8 + fr;
         const int64_t qid = qid_s[ql];
         const bool live = g * QG + ql < nq;
         const double qn = qn_s[ql];
@@ -541,7 +551,7 @@ __global__ void __launch_bounds__(kExThreads, 2) search_exact_mma_async_kernel(E
           const double thr = cnt < a.k ? -INFINITY : ls_all[(size_t)ql * a.k + a.k - 1];
           const int col = ni * 8 + 2 * fk;
           const double2 ri = *reinterpret_cast<const double2*>(ri_t + col);
-          const double s0 = acc[ni][0] * qn * ri.x, s1 = acc[ni][1] * qn * ri.y;
+          const double s0 = acc[mi][ni][0] * qn * ri.x, s1 = acc[mi][ni][1] * qn * ri.y;
           const int64_t row = r0 + col;
           const bool w0 = live && row < row_end && !(a.self_on && row == a.self_off + qid) && s0 > thr;
           const bool w1 = live && row + 1 < row_end && !(a.self_on && row + 1 == a.self_off + qid) && s1 > thr;
@@ -551,10 +561,11 @@ __global__ void __launch_bounds__(kExThreads, 2) search_exact_mma_async_kernel(E
             const bool first = (m0 >> src) & 1u;
             if (first) m0 &= ~(1u << src); else m1 &= ~(1u << src);
             const double s = __shfl_sync(0xffffffffu, first ? s0 : s1, src);
-            const int qsrc = warp * 8 + (src >> 2);
+            const int qsrc = warp * QW + mi * 8 + (src >> 2);
             warp_list_insert_call(ls_all + (size_t)qsrc * a.k, li_all + (size_t)qsrc * a.k, cnt_s + qsrc, a.k, s,
                                   (uint32_t)(r0 + ni * 8 + 2 * (src & 3) + (first ? 0 : 1)));
           }
+        }
         }
       }
       if (++c == nchunks) { c = 0; r0 += kMRows; ++tile_no; }
@@ -562,12 +573,12 @@ __global__ void __launch_bounds__(kExThreads, 2) search_exact_mma_async_kernel(E
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     // write this warp's (slot, slice) lists
 #pragma unroll 1
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < QW; ++j) {
       const int64_t slot = slot0 + j;
       if (slot >= nq) break;
-      const double* ls = ls_all + (size_t)(warp * 8 + j) * a.k;
-      const uint32_t* li = li_all + (size_t)(warp * 8 + j) * a.k;
-      const int cnt = cnt_s[warp * 8 + j];
+      const double* ls = ls_all + (size_t)(warp * QW + j) * a.k;
+      const uint32_t* li = li_all + (size_t)(warp * QW + j) * a.k;
+      const int cnt = cnt_s[warp * QW + j];
       double* os = a.ex_score + ((size_t)slot * a.S + slice) * a.k;
       uint32_t* oi = a.ex_idx + ((size_t)slot * a.S + slice) * a.k;
       for (int i = lane; i < a.k; i += 32) {
@@ -579,10 +590,11 @@ __global__ void __launch_bounds__(kExThreads, 2) search_exact_mma_async_kernel(E
   }
 }
 
-size_t mma_async_smem_bytes(int k, int dt, int stages) {
+size_t mma_async_smem_bytes(int k, int dt, int stages, int mf) {
   const int esz = dtype_size(dt);
-  const size_t stage = 2 * (size_t)kMRows * (kMDC * esz + 16);
-  return stages * stage + sizeof(double) * (2 * kMRows + 64 + 64 * (size_t)k) + sizeof(uint32_t) * 64 * (size_t)k + 2 * sizeof(int) * 64;
+  const size_t qg = 64 * (size_t)mf;
+  const size_t stage = (kMRows + qg) * (kMDC * esz + 16);
+  return stages * stage + sizeof(double) * (2 * kMRows + qg + qg * k) + sizeof(uint32_t) * qg * k + 2 * sizeof(int) * qg;
 }
 
 size_t mma_smem_bytes(int k, int MF) {
@@ -628,17 +640,26 @@ int launch_search_exact(const void* q, int q_dt, int64_t q_stride, const void* c
       // (4 stages, or 3 when that is what lets two CTAs share an SM -- one multiplies while the other waits at its
       // barrier; with one CTA per SM -- long lists, k > ~75 on 4-byte rows -- the kernel above measured faster)
       const size_t two_per_sm = (227 * 1024) / 2 - 1024;
-      const int nst = mma_async_smem_bytes(k, c_dt, 4) <= two_per_sm ? 4 : 3;
-      const size_t asmem = mma_async_smem_bytes(k, c_dt, nst);
+      // two query fragments per warp (128 queries per CTA) when there are enough queries and the lists still leave
+      // room for two CTAs per SM; experiment knob TSIM_ASYNC_MF=1 keeps one
+      int amf = (Q >= 1024 && !flag_cnt && mma_async_smem_bytes(k, c_dt, 3, 2) <= two_per_sm) ? 2 : 1;
+      if (knob_int("TSIM_ASYNC_MF", 0) == 1) amf = 1;
+      const int nst = mma_async_smem_bytes(k, c_dt, 4, amf) <= two_per_sm ? 4 : 3;
+      const size_t asmem = mma_async_smem_bytes(k, c_dt, nst, amf);
+      if (amf == 2) {
+        const int64_t g2 = (Q + 127) / 128;
+        mgrid.y = (unsigned)(g2 < 4096 ? g2 : 4096);
+      }
       const bool async_ok = q_dt == c_dt && MF == 1 && variant == 12 && (((uintptr_t)q | (uintptr_t)corpus) & 15) == 0 &&
                             (q_stride * esz) % 16 == 0 && (c_stride * esz) % 16 == 0 && (D * esz) % 16 == 0 &&
                             asmem <= two_per_sm && !knob_on("TSIM_NO_ASYNC_SCAN");
       if (async_ok) {
-#define TSIM_ASYNC_KERN(NST) (c_dt == TSIM_F32 ? search_exact_mma_async_kernel<TSIM_F32, NST>             \
-                              : c_dt == TSIM_F16 ? search_exact_mma_async_kernel<TSIM_F16, NST>           \
-                              : c_dt == TSIM_BF16 ? search_exact_mma_async_kernel<TSIM_BF16, NST>         \
-                                                  : search_exact_mma_async_kernel<TSIM_E4M3, NST>)
-        auto akern = nst == 4 ? TSIM_ASYNC_KERN(4) : TSIM_ASYNC_KERN(3);
+#define TSIM_ASYNC_KERN(NST, MFA) (c_dt == TSIM_F32 ? search_exact_mma_async_kernel<TSIM_F32, NST, MFA>        \
+                                   : c_dt == TSIM_F16 ? search_exact_mma_async_kernel<TSIM_F16, NST, MFA>      \
+                                   : c_dt == TSIM_BF16 ? search_exact_mma_async_kernel<TSIM_BF16, NST, MFA>    \
+                                                       : search_exact_mma_async_kernel<TSIM_E4M3, NST, MFA>)
+        auto akern = amf == 2 ? (nst == 4 ? TSIM_ASYNC_KERN(4, 2) : TSIM_ASYNC_KERN(3, 2))
+                              : (nst == 4 ? TSIM_ASYNC_KERN(4, 1) : TSIM_ASYNC_KERN(3, 1));
 #undef TSIM_ASYNC_KERN
         TSIM_CUDA(cudaFuncSetAttribute(akern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asmem));
         TSIM_CUDA(launch_pdl(akern, mgrid, dim3(kExThreads), asmem, st, a));
