@@ -163,3 +163,25 @@ def test_small_batch_graph_replay_and_two_streams(ops):
     for key, q in (("a", qa), ("b", qb)):
         es, ei = ops.search_topk(q, c, 10, mode="exact")
         assert torch.equal(outs[key][1], ei) and torch.equal(outs[key][0], es)
+
+
+def test_small_batch_randomized_shapes(ops):
+    """Seeded random shapes around the planner's boundaries (shard size, row width, Q, k, dtype, un-normalised rows,
+    strided views): the tensor path -- whichever kernel the planner picks -- must equal the float64 exact scan."""
+    rng = np.random.default_rng(1234)
+    for case in range(8):
+        fp8 = bool(rng.integers(0, 2))
+        D = int(rng.choice([64, 128, 272, 384, 512, 768, 1024])) if not fp8 else int(rng.choice([64, 128, 384, 512, 1040]))
+        N = int(rng.integers(300_000, 420_000))
+        Q = int(rng.integers(1, 33))
+        k = int(rng.choice([1, 5, 10, 24]))
+        unit = bool(rng.integers(0, 2))
+        scale = 16.0 if fp8 else 1.0
+        dtype = torch.float8_e4m3fn if fp8 else torch.bfloat16
+        base = (_rows(N, D + 16, 100 + case, torch.float32, unit=unit) * scale).to(dtype)
+        c = base[:, :D]                                        # a strided view: row pitch D + 16 elements
+        q = (_rows(Q, D, 200 + case, torch.float32, unit=unit) * scale).to(dtype)
+        src = torch.randint(0, N, (50,), device="cuda")
+        c[torch.randint(0, N, (50,), device="cuda")] = c[src]  # exact duplicates
+        s, i, s64, fl = _same_as_exact(ops, q, c, k)
+        assert (i >= 0).all() and (i < N).all(), (case, fp8, D, N, Q, k)
