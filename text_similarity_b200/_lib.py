@@ -39,6 +39,7 @@ SIGNATURES = {
                                         c_int64, c_int64, c_int64, c_int, c_int64, c_int64,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tsim_plan_create": (c_void_p, [c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int]),
+    "tsim_plan_create_split_shadow": (c_void_p, [c_int64, c_int64, c_int64, c_int, c_int, c_int]),
     "tsim_plan_destroy": (None, [c_void_p]),
     "tsim_plan_workspace_bytes": (c_size_t, [c_void_p]),
     "tsim_plan_search": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p,

@@ -58,13 +58,15 @@ static bool tensor_shape_ok(int64_t Q, int64_t N, int64_t D, int k, int q_dt, in
 }
 
 int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt, int mode,
-                     bool need_invnorm, bool shadow, SearchPlan* p) {
+                     bool need_invnorm, int shadow_kind, SearchPlan* p) {
+  const bool shadow = shadow_kind == 1;      // the rounded shadow: wide margin, widest lists, k <= 24
+  const bool split = shadow_kind == 2;       // the split shadow: D here is 3 x the rows' width, ordinary lists
   memset(p, 0, sizeof(*p));
   __atomic_add_fetch(&g_plans, 1ull, __ATOMIC_RELAXED);
   const int sms = device_sm_count();
   // a shadow pass needs the widest lists: the candidates must reach 2 * kShadowEps below the k-th best
   const bool ok = tensor_shape_ok(Q, N, D, k, q_dt, c_dt) && (!shadow || k <= 24);
-  p->eps = shadow ? shadow_eps(D) : approx_eps(D, dtype_size(c_dt));
+  p->eps = shadow ? shadow_eps(D) : split ? split_shadow_eps(D / 3) : approx_eps(D, dtype_size(c_dt));
   if (mode == TSIM_MODE_TENSOR && !ok) {
     set_error("search: TSIM_MODE_TENSOR needs bf16 (D %% 8 == 0) or e4m3 (D %% 16 == 0) queries AND corpus, k <= 100 "
               "(got q_dt=%d c_dt=%d D=%lld k=%d)", q_dt, c_dt, (long long)D, k);
@@ -112,7 +114,7 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
       const int64_t T128 = (N + 127) / 128;
       const int kb = (int)((D * dtype_size(c_dt) + 127) / 128);
       const bool narrow = kb <= 4;
-      if (Q <= 32 && (narrow || Q > 8 || knob_on("TSIM_SWAP_ALL")) && p->KP <= 32 && !shadow && T128 >= 16 * (int64_t)sms &&
+      if (Q <= 32 && (narrow || Q > 8 || knob_on("TSIM_SWAP_ALL")) && p->KP <= 32 && !shadow && !split && T128 >= 16 * (int64_t)sms &&
           search_sw_stages(kb) > 0 && !knob_on("TSIM_NO_SWAP")) {
         p->swapped = 1;
         p->sticky = 1; p->pair = 0; p->QB = 1; p->Gq = sms; p->fused = 0; p->qrep = 0;
@@ -220,7 +222,7 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
   if (p->fused) { p->off_gbar = off; off += 256; }                                                      // zeroed with thr
   // retry stage: its thresholds and level-2 flag count sit in the same zeroed span
   p->retry = 0;   // TSIM_NO_RETRY (experiment knob): flagged queries go straight to the float64 scan
-  if (p->use_tensor && !shadow && p->KP < kRetryKP && !knob_on("TSIM_NO_RETRY")) {
+  if (p->use_tensor && !shadow && !split && p->KP < kRetryKP && !knob_on("TSIM_NO_RETRY")) {
     const int64_t rounds = (Q + kRetryQ - 1) / kRetryQ;
     p->retry = (int)(rounds < kRetryMaxRounds ? rounds : kRetryMaxRounds);
   }
@@ -293,21 +295,21 @@ extern "C" size_t tsim_search_workspace_bytes(int64_t Q, int64_t N, int64_t D, i
                                               int mode) {
   if (check_search_args(Q, N, D, k, q_dt, c_dt, mode) != TSIM_OK) return 0;
   SearchPlan p;
-  if (make_search_plan(Q, N, D, k, q_dt, c_dt, mode, /*need_invnorm=*/true, /*shadow=*/false, &p) != TSIM_OK) return 0;
+  if (make_search_plan(Q, N, D, k, q_dt, c_dt, mode, /*need_invnorm=*/true, /*shadow=*/0, &p) != TSIM_OK) return 0;
   return p.total;
 }
 
 extern "C" size_t tsim_search_shadow_workspace_bytes(int64_t Q, int64_t N, int64_t D, int k, int shadow_dt) {
   if (check_search_args(Q, N, D, k, shadow_dt, shadow_dt, TSIM_MODE_AUTO) != TSIM_OK) return 0;
   SearchPlan p;
-  if (make_search_plan(Q, N, D, k, shadow_dt, shadow_dt, TSIM_MODE_AUTO, true, /*shadow=*/true, &p) != TSIM_OK) return 0;
+  if (make_search_plan(Q, N, D, k, shadow_dt, shadow_dt, TSIM_MODE_AUTO, true, /*shadow=*/1, &p) != TSIM_OK) return 0;
   return p.total;
 }
 
 // q / corpus: the rows results are defined on (re-score, exact scan).  tq / tcorpus (dtype t_dt): what the
 // tensor pass reads -- the same arrays, or bf16 shadows of fp32 / fp16 rows (`shadow`).
 static int search_impl(const void* q, int q_dt, int64_t q_stride, const void* corpus, int c_dt, int64_t c_stride,
-                       const void* tq, int64_t tq_stride, const void* tcorpus, int64_t tc_stride, int t_dt, bool shadow,
+                       const void* tq, int64_t tq_stride, const void* tcorpus, int64_t tc_stride, int t_dt, int shadow,
                        const float* corpus_inv_norm, int64_t Q, int64_t N,
                        int64_t D, int k, int64_t idx_base, int64_t exclude_self_base, int mode,
                        float* out_score, double* out_score64, int64_t* out_idx,
@@ -321,8 +323,9 @@ static int search_impl(const void* q, int q_dt, int64_t q_stride, const void* co
   TSIM_CHECK_ARG(q_stride >= D && c_stride >= D, "search: row stride smaller than D");
   cudaStream_t st = (cudaStream_t)stream;
   SearchPlan p;
+  const int64_t Dt = shadow == 2 ? 3 * D : D;      // width of what the tensor pass reads (a split shadow is 3 D wide)
   if (prepared) p = *prepared;     // a plan handle (tsim_plan_create): no planning, cached TMA descriptors
-  else rc = make_search_plan(Q, N, D, k, shadow ? t_dt : q_dt, shadow ? t_dt : c_dt, mode, true, shadow, &p);
+  else rc = make_search_plan(Q, N, Dt, k, shadow ? t_dt : q_dt, shadow ? t_dt : c_dt, mode, true, shadow, &p);
   if (rc) return rc;
   if (!ws || ws_bytes < p.total) {
     set_error("search: workspace too small (%zu < %zu bytes)", ws_bytes, p.total);
@@ -360,16 +363,18 @@ static int search_impl(const void* q, int q_dt, int64_t q_stride, const void* co
     const void* qt = tq;
     int64_t qt_stride = tq_stride;
     const int qrows = p.swapped ? 32 : p.pair ? 256 : 128;
-    const size_t rowb = (size_t)D * dtype_size(t_dt);
+    const size_t rowb = (size_t)Dt * dtype_size(t_dt);
     const bool pad = Q % qrows != 0 || p.qrep > 1;
     rc = launch_search_prep(thr, align_up(zero_end - p.off_thr, 256), tq, (size_t)tq_stride * dtype_size(t_dt),
                             pad ? w + p.off_qpad : nullptr, rowb, Q, (int64_t)p.QB * qrows, p.qrep > 1 ? 128 / p.qrep : 0, st);
     if (rc) return rc;
-    if (pad) { qt = w + p.off_qpad; qt_stride = D; }
+    if (pad) { qt = w + p.off_qpad; qt_stride = Dt; }
     const float* c_inv = corpus_inv_norm;
     if (!c_inv) {
       float* tmp = (float*)(w + p.off_invnorm);
-      rc = launch_row_inv_norm(tcorpus, t_dt, N, D, tc_stride, tmp, st);
+      // (a split shadow's rows are [hi | lo | hi]: their own norm is not the row's -- take it from the originals)
+      rc = shadow == 2 ? launch_row_inv_norm(corpus, c_dt, N, D, c_stride, tmp, st)
+                       : launch_row_inv_norm(tcorpus, t_dt, N, D, tc_stride, tmp, st);
       if (rc) return rc;
       c_inv = tmp;
     }
@@ -382,17 +387,17 @@ static int search_impl(const void* q, int q_dt, int64_t q_stride, const void* co
     if (p.swapped) {
       // small batches: sample tiles -> 16-entry lists, thresholds + ladders, then the main pass appends
       uint32_t* lad = (uint32_t*)(w + p.off_ladder);
-      rc = launch_search_sw(qt, qt_stride, tcorpus, tc_stride, t_dt, c_inv, Q, N, D, self_on, self_off, p, 1, cand, thr, lad,
+      rc = launch_search_sw(qt, qt_stride, tcorpus, tc_stride, t_dt, c_inv, Q, N, Dt, self_on, self_off, p, 1, cand, thr, lad,
                             app_keys, app_cnt, st, maps);
       if (rc) return rc;
       rc = launch_sw_tighten(Q, p, cand, thr, lad, app_keys, app_cnt, st);
       if (rc) return rc;
-      rc = launch_search_sw(qt, qt_stride, tcorpus, tc_stride, t_dt, c_inv, Q, N, D, self_on, self_off, p, 0, cand, thr, lad,
+      rc = launch_search_sw(qt, qt_stride, tcorpus, tc_stride, t_dt, c_inv, Q, N, Dt, self_on, self_off, p, 0, cand, thr, lad,
                             app_keys, app_cnt, st, maps);
       if (rc) return rc;
     } else if (p.fused) {
       uint32_t* lad = knob_on("TSIM_NO_LADDER") ? nullptr : (uint32_t*)(w + p.off_ladder);   // experiment knob
-      rc = launch_search_tc(qt, qt_stride, tcorpus, tc_stride, t_dt, c_inv, Q, N, D, self_on, self_off, p, TC_PASS_FUSED,
+      rc = launch_search_tc(qt, qt_stride, tcorpus, tc_stride, t_dt, c_inv, Q, N, Dt, self_on, self_off, p, TC_PASS_FUSED,
                             cand, thr, lad, sched, st, maps, nullptr, nullptr, 0, nullptr, nullptr,
                             (uint32_t*)(w + p.off_gbar));
       if (rc) return rc;
@@ -400,7 +405,7 @@ static int search_impl(const void* q, int q_dt, int64_t q_stride, const void* co
     if (p.boot_tiles) {
       uint32_t* lad = knob_on("TSIM_NO_LADDER") ? nullptr : (uint32_t*)(w + p.off_ladder);   // experiment knob
       if (p.mini_mult) {
-        rc = launch_search_tc(qt, qt_stride, tcorpus, tc_stride, t_dt, c_inv, Q, N, D, self_on, self_off, p,
+        rc = launch_search_tc(qt, qt_stride, tcorpus, tc_stride, t_dt, c_inv, Q, N, Dt, self_on, self_off, p,
                               TC_PASS_MINI, cand, thr, nullptr, sched, st, maps, nullptr, nullptr, 0, app_keys, app_cnt);
         if (rc) return rc;
         rc = p.append ? launch_tighten_app(Q, p, app_keys, app_cnt, thr, lad, st)
@@ -408,7 +413,7 @@ static int search_impl(const void* q, int q_dt, int64_t q_stride, const void* co
         if (rc) return rc;
         ladder = lad;
       }
-      rc = launch_search_tc(qt, qt_stride, tcorpus, tc_stride, t_dt, c_inv, Q, N, D, self_on, self_off, p,
+      rc = launch_search_tc(qt, qt_stride, tcorpus, tc_stride, t_dt, c_inv, Q, N, Dt, self_on, self_off, p,
                             p.mini_mult ? TC_PASS_SAMPLE_REST : TC_PASS_SAMPLE, cand, thr, ladder, sched, st, maps,
                             nullptr, nullptr, 0, app_keys, app_cnt);
       if (rc) return rc;
@@ -418,7 +423,7 @@ static int search_impl(const void* q, int q_dt, int64_t q_stride, const void* co
       if (rc) return rc;
       ladder = lad;
     }
-    rc = launch_search_tc(qt, qt_stride, tcorpus, tc_stride, t_dt, c_inv, Q, N, D, self_on, self_off, p,
+    rc = launch_search_tc(qt, qt_stride, tcorpus, tc_stride, t_dt, c_inv, Q, N, Dt, self_on, self_off, p,
                           p.boot_tiles ? TC_PASS_MAIN : TC_PASS_ALL, cand, thr, ladder, sched, st, maps,
                           nullptr, nullptr, 0, app_keys, app_cnt);
     if (rc) return rc;
@@ -484,7 +489,7 @@ extern "C" int tsim_search_topk(const void* q, int q_dt, int64_t q_stride, const
                                 int64_t D, int k, int64_t idx_base, int64_t exclude_self_base, int mode,
                                 float* out_score, double* out_score64, int64_t* out_idx,
                                 int32_t* out_flags, void* ws, size_t ws_bytes, void* stream) {
-  return search_impl(q, q_dt, q_stride, corpus, c_dt, c_stride, q, q_stride, corpus, c_stride, c_dt, false,
+  return search_impl(q, q_dt, q_stride, corpus, c_dt, c_stride, q, q_stride, corpus, c_stride, c_dt, 0,
                      corpus_inv_norm, Q, N, D, k, idx_base, exclude_self_base, mode, out_score, out_score64, out_idx,
                      out_flags, ws, ws_bytes, stream);
 }
@@ -500,13 +505,13 @@ extern "C" int tsim_search_topk_shadow(const void* q, int q_dt, int64_t q_stride
   TSIM_CHECK_ARG(shadow_dt == TSIM_BF16, "search_shadow: the shadow must be bf16 (got dtype %d)", shadow_dt);
   TSIM_CHECK_ARG(qs_stride >= D && cs_stride >= D, "search_shadow: row stride smaller than D");
   return search_impl(q, q_dt, q_stride, corpus, c_dt, c_stride, q_shadow, qs_stride, corpus_shadow, cs_stride,
-                     shadow_dt, true, shadow_inv_norm, Q, N, D, k, idx_base, exclude_self_base, TSIM_MODE_AUTO,
+                     shadow_dt, 1, shadow_inv_norm, Q, N, D, k, idx_base, exclude_self_base, TSIM_MODE_AUTO,
                      out_score, out_score64, out_idx, out_flags, ws, ws_bytes, stream);
 }
 
 // ---- test hooks ---------------------------------------------------------------------------------
 extern "C" float tsim_debug_eps(int64_t D, int dt, int shadow) {
-  return shadow ? shadow_eps(D) : approx_eps(D, dtype_size(dt) ? dtype_size(dt) : 2);
+  return shadow == 2 ? split_shadow_eps(D) : shadow ? shadow_eps(D) : approx_eps(D, dtype_size(dt) ? dtype_size(dt) : 2);
 }
 
 extern "C" int tsim_debug_tensor_pass(const void* q, int64_t q_stride, const void* corpus, int64_t c_stride, int dt,
@@ -536,24 +541,36 @@ struct tsim_plan {
   SearchPlan p;
   int64_t Q, N, D;
   int k, q_dt, c_dt, mode, shadow_dt;   // shadow_dt < 0: no shadow
+  int shadow_kind;                      // 0 none, 1 rounded shadow (D wide), 2 split shadow (3 D wide)
   MapCache* maps;
 };
 
-extern "C" tsim_plan_t* tsim_plan_create(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt, int mode,
-                                         int shadow_dt) {
-  const bool shadow = shadow_dt >= 0;
+static tsim_plan_t* plan_create(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt, int mode, int shadow_dt,
+                                int shadow_kind) {
+  const bool shadow = shadow_kind != 0;
   if (shadow && shadow_dt != TSIM_BF16) { set_error("plan: the shadow must be bf16 (got dtype %d)", shadow_dt); return nullptr; }
   if (check_search_args(Q, N, D, k, q_dt, c_dt, shadow ? TSIM_MODE_AUTO : mode) != TSIM_OK) return nullptr;
   tsim_plan* h = new (std::nothrow) tsim_plan();
   if (!h) { set_error("plan: out of host memory"); return nullptr; }
   h->Q = Q; h->N = N; h->D = D; h->k = k; h->q_dt = q_dt; h->c_dt = c_dt;
-  h->mode = shadow ? TSIM_MODE_AUTO : mode; h->shadow_dt = shadow ? shadow_dt : -1;
-  if (make_search_plan(Q, N, D, k, shadow ? shadow_dt : q_dt, shadow ? shadow_dt : c_dt, h->mode, true, shadow, &h->p) != TSIM_OK) {
+  h->mode = shadow ? TSIM_MODE_AUTO : mode; h->shadow_dt = shadow ? shadow_dt : -1; h->shadow_kind = shadow_kind;
+  if (make_search_plan(Q, N, shadow_kind == 2 ? 3 * D : D, k, shadow ? shadow_dt : q_dt, shadow ? shadow_dt : c_dt, h->mode, true,
+                       shadow_kind, &h->p) != TSIM_OK) {
     delete h;
     return nullptr;
   }
   h->maps = map_cache_create();
   return h;
+}
+
+extern "C" tsim_plan_t* tsim_plan_create(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt, int mode,
+                                         int shadow_dt) {
+  return plan_create(Q, N, D, k, q_dt, c_dt, mode, shadow_dt, shadow_dt >= 0 ? 1 : 0);
+}
+
+extern "C" tsim_plan_t* tsim_plan_create_split_shadow(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt) {
+  if (D % 8 != 0) { set_error("plan: a split shadow needs D %% 8 == 0 (got %lld)", (long long)D); return nullptr; }
+  return plan_create(Q, N, D, k, q_dt, c_dt, TSIM_MODE_AUTO, TSIM_BF16, 2);
 }
 
 extern "C" void tsim_plan_destroy(tsim_plan_t* h) {
@@ -573,12 +590,13 @@ extern "C" int tsim_plan_search(tsim_plan_t* h, const void* q, int64_t q_stride,
   const bool shadow = h->shadow_dt >= 0;
   if (shadow) {
     TSIM_CHECK_ARG(q_shadow && (h->N == 0 || corpus_shadow), "plan_search: this plan needs the bf16 shadows");
-    TSIM_CHECK_ARG(qs_stride >= h->D && cs_stride >= h->D, "plan_search: shadow row stride smaller than D");
+    const int64_t sw = h->shadow_kind == 2 ? 3 * h->D : h->D;
+    TSIM_CHECK_ARG(qs_stride >= sw && cs_stride >= sw, "plan_search: shadow row stride smaller than the shadow's width");
     return search_impl(q, h->q_dt, q_stride, corpus, h->c_dt, c_stride, q_shadow, qs_stride, corpus_shadow, cs_stride,
-                       h->shadow_dt, true, corpus_inv_norm, h->Q, h->N, h->D, h->k, idx_base, exclude_self_base,
+                       h->shadow_dt, h->shadow_kind, corpus_inv_norm, h->Q, h->N, h->D, h->k, idx_base, exclude_self_base,
                        TSIM_MODE_AUTO, out_score, out_score64, out_idx, out_flags, ws, ws_bytes, stream, &h->p, h->maps);
   }
-  return search_impl(q, h->q_dt, q_stride, corpus, h->c_dt, c_stride, q, q_stride, corpus, c_stride, h->c_dt, false,
+  return search_impl(q, h->q_dt, q_stride, corpus, h->c_dt, c_stride, q, q_stride, corpus, c_stride, h->c_dt, 0,
                      corpus_inv_norm, h->Q, h->N, h->D, h->k, idx_base, exclude_self_base, h->mode, out_score,
                      out_score64, out_idx, out_flags, ws, ws_bytes, stream, &h->p, h->maps);
 }

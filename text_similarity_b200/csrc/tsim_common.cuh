@@ -39,6 +39,11 @@ __host__ __device__ inline float approx_eps(int64_t D, int esz) {
 // the tensor-core term (5e-5 up to D = 1664; shadow_eps adds what approx_eps exceeds that by): 5.93e-3, rounded up.
 constexpr float kShadowEps = 6e-3f;
 __host__ __device__ inline float shadow_eps(int64_t D) { return kShadowEps + (approx_eps(D, 2) - kApproxEpsFloor); }
+// SPLIT shadow of fp32 / fp16 rows (k up to 100): x = hi + lo + r with hi = bf16(x), lo = bf16(x - hi), |r| <= 2^-18 |x|;
+// the tensor pass multiplies [qh | qh | ql] by [ch | cl | ch] (3 D wide), i.e. qh.ch + qh.cl + ql.ch.  What is
+// missing from q.c is ql.cl + (qh + ql).rc + rq.c: each at most 2^-18 ||q|| ||c|| (3.8e-6); together 1.15e-5,
+// rounded up to 1.5e-5, plus the tensor-core term of a 3 D-wide bf16 dot product.
+__host__ __device__ inline float split_shadow_eps(int64_t D) { return approx_eps(3 * D, 2) + 1.5e-5f; }
 
 // Threshold ladder (search_tc.cu / select_merge.cu): per query, kLadder ascending score levels
 // level(i) = base + i * step and the number of candidate rows seen so far in [level(i), level(i+1));
@@ -540,8 +545,9 @@ constexpr int kRetryKP = 112;
 constexpr int kRetryMaxRounds = 4;
 
 // q_dt / c_dt: the dtypes the tensor pass reads (the shadow's when `shadow`)
+// shadow: 0 none; 1 rounded bf16 shadow (D wide, k <= 24, 112 candidates); 2 split shadow (pass D = 3 x the rows' width)
 int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt, int mode,
-                     bool need_invnorm, bool shadow, SearchPlan* plan);
+                     bool need_invnorm, int shadow, SearchPlan* plan);
 
 // How select_rescore takes part in the retry stage (null: plain call, flagged queries go to flag_list).
 //  * first pass (in_list == null): a flagged query also copies its row into r_q[position in flag_list]

@@ -52,7 +52,7 @@ class ShardedCorpus:
     """One rank's block of the corpus embedding matrix plus what the search needs with it."""
 
     def __init__(self, shard: torch.Tensor, idx_base: int = 0, group=None,
-                 inv_norm: Optional[torch.Tensor] = None, bf16_shadow: bool = True):
+                 inv_norm: Optional[torch.Tensor] = None, bf16_shadow: bool = True, split_shadow: bool = False):
         if shard.dim() != 2:
             raise ValueError("shard must be [rows, D]")
         self.shard = shard
@@ -72,10 +72,18 @@ class ShardedCorpus:
         if (bf16_shadow and shard.is_cuda and shard.shape[0] and shard.dtype in (torch.float32, torch.float16)
                 and shard.shape[1] % 8 == 0):
             self.shadow, self.shadow_inv = ops.make_shadow(shard)
+        # ... and a split (hi + lo) shadow, 3 D wide (+150 % / +300 %), carries 24 < k <= 100 on the tensor cores as
+        # well (opt-in: without it those calls take the float64 scan)
+        self.split = self.split_inv = None
+        if (split_shadow and shard.is_cuda and shard.shape[0] and shard.dtype in (torch.float32, torch.float16)
+                and shard.shape[1] % 8 == 0):
+            self.split, self.split_inv = ops.make_shadow(shard, split=True)
         self._gather_buf = {}
         self._graphs = {}
 
-    def _shadow_kw(self):
+    def _shadow_kw(self, k: int = 10):
+        if self.split is not None and (k > 24 or self.shadow is None) and k <= 100:
+            return {"corpus_shadow": self.split, "shadow_inv_norm": self.split_inv}
         return {} if self.shadow is None else {"corpus_shadow": self.shadow, "shadow_inv_norm": self.shadow_inv}
 
     # -- CUDA-graph replay of the local search -------------------------------------------------------
@@ -97,15 +105,17 @@ class ShardedCorpus:
         # The graph replays raw pointers: it owns its workspace (kept alive in self._graphs next to the graph),
         # never the growable per-stream cache of ops, whose buffers are replaced -- and freed -- when a later
         # call on a recycled stream handle needs more room.
-        shadowed = self.shadow is not None and mode == "auto"
+        skw = self._shadow_kw(k) if mode == "auto" else {}
+        is_split = bool(skw) and skw["corpus_shadow"] is self.split
+        shadowed = bool(skw) and not is_split
         ws = torch.empty(ops.search_workspace_bytes(Q, self.shard.shape[0], self.shard.shape[1], k, dtype,
-                                                    self.shard.dtype, mode, shadow=shadowed, device=dev),
+                                                    self.shard.dtype, mode, shadow=shadowed, device=dev, split=is_split),
                          dtype=torch.uint8, device=dev)
 
         def run():
             ops.search_topk(q_static, self.shard, k, corpus_inv_norm=self.inv_norm, idx_base=self.idx_base,
                             exclude_self_base=exclude_self_base, mode=mode, out_scores=scores,
-                            out_score64=s64, out_idx=idx, workspace=ws, **self._shadow_kw())
+                            out_score64=s64, out_idx=idx, workspace=ws, **skw)
 
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -137,7 +147,7 @@ class ShardedCorpus:
 
     def search_local(self, queries: torch.Tensor, k: int, **kw):
         return ops.search_topk(queries, self.shard, k, corpus_inv_norm=self.inv_norm,
-                               idx_base=self.idx_base, **self._shadow_kw(), **kw)
+                               idx_base=self.idx_base, **self._shadow_kw(k), **kw)
 
     def search(self, queries: torch.Tensor, k: int, exclude_self_base: int = -1, mode: str = "auto",
                return_score64: bool = False):
@@ -157,7 +167,7 @@ class ShardedCorpus:
         # the search kernels write their float64 scores and int64 rows straight into the send buffer
         ops.search_topk(queries, self.shard, k, corpus_inv_norm=self.inv_norm, idx_base=self.idx_base,
                         exclude_self_base=exclude_self_base, mode=mode,
-                        out_score64=send[0].view(torch.float64), out_idx=send[1], **self._shadow_kw())
+                        out_score64=send[0].view(torch.float64), out_idx=send[1], **self._shadow_kw(k))
         import torch.distributed as dist
         dist.all_gather_into_tensor(recv, send, group=self.group)        # THE collective of the search
         scores, m64, rows = ops.merge_gathered(recv, Q, k, self.world)   # K3 reads the rank-major buffer in place
