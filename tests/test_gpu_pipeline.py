@@ -106,6 +106,11 @@ def test_sentence_mining_pipeline_tensors(stack):
     s, i = pipe.search_tensors(queries.cuda(), 7)
     assert torch.equal(i.cpu(), ei)
     np.testing.assert_allclose(s.cpu().numpy(), ev.numpy(), atol=1e-5)
+    # fp32 tensors, 24 < k <= 100: the split (hi + lo) bf16 shadow, made on first use, chunks merged -- same answer
+    s50, i50 = pipe.search_tensors(queries.cuda(), 50)
+    ev50, ei50 = O.search_exact(queries, corpus, 50)
+    assert torch.equal(i50.cpu(), ei50)
+    np.testing.assert_allclose(s50.cpu().numpy(), ev50.numpy(), atol=1e-5)
     # bf16 tensors: tcgen05 path, k larger than the corpus is clamped (reference clamps by #queries, A6)
     cb = corpus[:9].to(torch.bfloat16)
     s, i = pipe.search_tensors(queries.to(torch.bfloat16).cuda(), 100, corpus=cb.cuda())

@@ -60,6 +60,17 @@ class _EncodedCorpus:
         if rows.dtype in (torch.float32, torch.float16) and rows.shape[0] and rows.shape[1] % 8 == 0:
             shadow, shadow_inv = ops.make_shadow(rows)
             self.shadow_kw = {"corpus_shadow": shadow, "shadow_inv_norm": shadow_inv}
+        self._split_kw = None
+
+    def shadow_for(self, k: int) -> dict:
+        """Shadow arguments of ``ops.search_topk`` for a top-k call: the rounded shadow up to k = 24; for 24 < k <= 100
+        the split (hi + lo) shadow, 3 D wide, made on first use (without it those calls take the float64 scan)."""
+        if not self.shadow_kw or k <= 24 or k > 100:
+            return self.shadow_kw
+        if self._split_kw is None:
+            shadow, inv = ops.make_shadow(self.rows, split=True)
+            self._split_kw = {"corpus_shadow": shadow, "shadow_inv_norm": inv}
+        return self._split_kw
 
 
 class SentenceMiningPipeline(SearchPipeline):
@@ -140,12 +151,12 @@ class SentenceMiningPipeline(SearchPipeline):
             begin, enc = chunks[0]
             qq = q if q.dtype == enc.rows.dtype or enc.rows.dtype == torch.float32 else q.to(enc.rows.dtype)
             return ops.search_topk(qq, enc.rows, k, corpus_inv_norm=enc.inv_norm, idx_base=begin, mode=mode,
-                                   **enc.shadow_kw)
+                                   **enc.shadow_for(k))
         s64_parts, idx_parts = [], []
         for begin, enc in chunks:
             qq = q if q.dtype == enc.rows.dtype or enc.rows.dtype == torch.float32 else q.to(enc.rows.dtype)
             _, idx, s64 = ops.search_topk(qq, enc.rows, k, corpus_inv_norm=enc.inv_norm, idx_base=begin,
-                                          mode=mode, return_score64=True, **enc.shadow_kw)
+                                          mode=mode, return_score64=True, **enc.shadow_for(k))
             s64_parts.append(s64)
             idx_parts.append(idx)
         # cross-chunk merge, absent in the reference (:83,88 overwrite): K3 second pass
