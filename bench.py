@@ -51,7 +51,7 @@ WORKLOADS = {
 }
 DEFAULT_WORKLOAD = "10Mx768_q4096_top10"
 METRIC = "queries/sec exact top-10 over 10Mx768 bf16 corpus"
-ALL_REGIMES = ("hbm", "cfg1", "cfg2", "cfg3", "cfg4", "cfg5", "k1", "cpu_loop")
+ALL_REGIMES = ("hbm", "cfg1", "cfg2", "cfg3", "cfg4", "cfg5", "k1", "cpu_loop", "fp32")
 
 
 def load_peaks():
@@ -618,6 +618,22 @@ def main():
         regimes.append(regime_search(ctx, "cfg2_1Mx768_q1024_top10", corp2, dev_batches[1][:1024].contiguous(), 10,
                                      1_000_000, 2, reps=20, verify=64))
         del corp2
+    if "fp32" in want and world == 1:
+        # fp32 rows (what the reference's encode_text returns, config 1 keeps them) at config 2's shape with k = 100:
+        # the split (hi + lo) bf16 shadow on the tensor cores + float64 re-score on the fp32 rows, against the float64
+        # scan of the same call (FP64 tensor cores), both verified against each other by the spot check
+        g32 = torch.Generator(device=dev).manual_seed(4242)
+        c32 = torch.randn(1_000_000, 768, generator=g32, device=dev)
+        c32 /= c32.norm(dim=-1, keepdim=True)
+        q32 = torch.randn(1024, 768, generator=g32, device=dev)
+        corp32 = ShardedCorpus(c32, split_shadow=True)
+        r32 = regime_search(ctx, "fp32_1Mx768_q1024_top100_split_shadow", corp32, q32, 100, 1_000_000, 4, reps=10, verify=32,
+                            extra={"note": "tensor pass is 3 D wide (qh.ch + qh.cl + ql.ch): 3x the nominal flops counted here"})
+        ms_scan, _ = ctx.timed(lambda: corp32.search(q32, 100, mode="exact"), 2, warm=1)
+        r32["float64_scan_ms"] = ms_scan
+        regimes.append(r32)
+        del corp32, c32, q32
+        torch.cuda.empty_cache()
     torch.cuda.synchronize()
     time.sleep(0.5)
 
