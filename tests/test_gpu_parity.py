@@ -168,6 +168,22 @@ def test_exact_scan_tensor_cores(ops, monkeypatch, N, Q, D, k, dtype):
     assert torch.equal(i0, i1) and torch.equal(d0, d1) and torch.equal(s0, s1)
 
 
+@pytest.mark.parametrize("N,Q,D,k,dtype", [
+    (60_000, 1100, 256, 10, torch.float32),     # two query fragments per warp (128 queries per CTA), ragged last group (76)
+    (50_000, 1030, 128, 60, torch.float32),     # lists too long for four stages at two CTAs per SM: the 3-stage ring
+    (45_000, 100, 256, 10, torch.float16),      # 2-byte rows: 80-byte staged rows
+    (45_077, 70, 40, 3, torch.bfloat16),        # one partial 32-wide chunk (80 of 64 ... bytes: pieces past the row are zero-filled)
+])
+def test_exact_scan_async_pipeline_variants(ops, N, Q, D, k, dtype):
+    """The cp.async raw-row pipeline of the float64 scan (search_exact_mma_async_kernel) in its stage-count /
+    fragment-count variants, against the CPU oracle (indices exact, float64 scores to 1e-12)."""
+    q, c = _make(N, Q, D, dtype, seed=N + Q + k, dup_frac=0.01)
+    c[13] = 0
+    tol = TOL_F32 if dtype == torch.float32 else TOL_BF16
+    _check(ops, q, c, k, tol, mode="exact")
+    _check(ops, q[:Q // 2], c, k, tol, mode="exact", idx_base=500, exclude_self_base=500 + 3)
+
+
 def test_exact_scan_tensor_cores_fp8(ops):
     q, c = _make(40_000, 64, 128, torch.float32, seed=77, normalize=False)
     _check(ops, (q * 2).to(torch.float8_e4m3fn), (c * 4).to(torch.float8_e4m3fn), 10, TOL_BF16, mode="exact")
