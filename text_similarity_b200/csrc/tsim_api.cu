@@ -125,7 +125,13 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
         p->app_cap = 4096;
       }
     }
-    if (p->sticky && !p->pair && !p->swapped && !knob_on("TSIM_NO_QREP")) p->qrep = Q <= 32 ? 4 : Q <= 64 ? 2 : 1;
+    // Query replication (search_tc.cu, TcArgs::qrep) spreads the epilogue of a tile over the four lane quadrants -- what
+    // rows of at most 512 bytes need, whose tiles last ~2 us.  On wider rows one warp keeps up, and the replicas cost
+    // power: zero rows are cheaper to multiply than copies (10M x 768 bf16 under a sustained stream: Q = 32 2.69 ms
+    // with, 2.46 ms without; Q = 8 2.46 vs 2.40 ms).
+    if (p->sticky && !p->pair && !p->swapped && !knob_on("TSIM_NO_QREP") &&
+        ((D * dtype_size(c_dt) + 127) / 128 <= 4 || knob_on("TSIM_QREP_WIDE")))
+      p->qrep = Q <= 32 ? 4 : Q <= 64 ? 2 : 1;
     if (!p->sticky) {
       // Round-robin units (many query blocks).  A unit's list starts empty, so what it filters with is
       // the query's GLOBAL threshold: a strided sample (~1/64 of the tiles) is scanned first and leaves
