@@ -11,7 +11,7 @@ from oracle import oracle as O
 pytestmark = pytest.mark.gpu
 
 N_SW = 320_000          # > 16 * 148 * 128 = 303,104 rows: the planner picks the small-batch kernel (rows of at most 512
-                        # bytes at any Q <= 32, wider rows at 8 < Q <= 32; the other cases below run search_tc.cu)
+                        # bytes at any Q <= 32, wider rows at 8 <= Q <= 32; the other cases below run search_tc.cu)
 
 
 @pytest.fixture(scope="module")

@@ -106,15 +106,15 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
     }
     // Small batches on a large shard (config 4): the swapped-role kernel (search_sw.cu) -- corpus rows on the MMA's M
     // side, the queries resident on the N side -- which under the board's 1 kW power cap is worth 10-20 % of a
-    // sustained stream of searches (profiles/README.md, "small batches").  Rows wider than 512 bytes with at most 8
-    // queries stay on search_tc.cu: its replicated query block is mostly zero rows then (cheap MMAs), and a swapped
+    // sustained stream of searches (profiles/README.md, "small batches").  Rows wider than 512 bytes with fewer than 8
+    // queries stay on search_tc.cu: its query block is mostly zero rows then (cheap MMAs), and a swapped
     // MMA occupies the tensor pipe for ~146 clocks per 128 rows x 32 bytes whatever its N, which caps that kernel at
     // ~6.6 TB/s on 1536-byte rows where search_tc.cu streams 7.2 TB/s in a burst.
     {
       const int64_t T128 = (N + 127) / 128;
       const int kb = (int)((D * dtype_size(c_dt) + 127) / 128);
       const bool narrow = kb <= 4;
-      if (Q <= 32 && (narrow || Q > 8 || knob_on("TSIM_SWAP_ALL")) && p->KP <= 32 && !shadow && !split && T128 >= 16 * (int64_t)sms &&
+      if (Q <= 32 && (narrow || Q >= 8 || knob_on("TSIM_SWAP_ALL")) && p->KP <= 32 && !shadow && !split && T128 >= 16 * (int64_t)sms &&
           search_sw_stages(kb) > 0 && !knob_on("TSIM_NO_SWAP")) {
         p->swapped = 1;
         p->sticky = 1; p->pair = 0; p->QB = 1; p->Gq = sms; p->fused = 0; p->qrep = 0;
