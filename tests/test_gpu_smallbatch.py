@@ -185,3 +185,22 @@ def test_small_batch_randomized_shapes(ops):
         c[torch.randint(0, N, (50,), device="cuda")] = c[src]  # exact duplicates
         s, i, s64, fl = _same_as_exact(ops, q, c, k)
         assert (i >= 0).all() and (i < N).all(), (case, fp8, D, N, Q, k)
+
+
+def test_small_batch_dense_cluster_overflows_to_the_retry_pass(ops):
+    """6000 rows crowd around one query, far above anything the 3072-row sample suggests: the query's append list
+    (4096 entries) overflows, which must flag it -- the wide retry pass answers it -- and never lose a row."""
+    N, D = N_SW, 256
+    c = _rows(N, D, 71, torch.float32)
+    q = _rows(3, D, 72, torch.float32)
+    g = torch.Generator(device="cuda").manual_seed(73)
+    where = torch.randperm(N, generator=g, device="cuda")[:6000]
+    noise = torch.randn(6000, D, generator=g, device="cuda")
+    noise = noise / noise.norm(dim=-1, keepdim=True)
+    eps_ = torch.linspace(0.05, 0.45, 6000, device="cuda")[:, None]
+    v = q[1][None, :] + eps_ * noise
+    c[where] = v / v.norm(dim=-1, keepdim=True)
+    cb, qb = c.to(torch.bfloat16), q.to(torch.bfloat16)
+    s, i, s64, fl = _same_as_exact(ops, qb, cb, 10)
+    assert fl[1].item() == 2 and fl[0].item() == 0 and fl[2].item() == 0      # 2 = answered by the retry pass
+    assert set(i[1].tolist()) <= set(where.tolist())
