@@ -56,6 +56,8 @@ constexpr int SW_MAX_STAGES = 16;
 constexpr int SW_A_BYTES = SW_ROWS * BK_BYTES;   // 16 KB corpus k-block
 constexpr int SW_Q_BYTES = SW_NQ * BK_BYTES;     // 4 KB query k-block
 constexpr int SW_PEND = 64;        // survivors a warp parks in shared memory between two flushes to the global lists
+constexpr int SW_RETIGHTEN = 1024; // a query's append list reaching a multiple of this gets its threshold re-made from its
+constexpr int SW_RT_KEYS = 512;    // ... most recent SW_RT_KEYS entries
 
 struct SwArgs {
   const float* c_inv;     // [N] inverse norms of the stored corpus rows
@@ -94,6 +96,62 @@ __device__ __forceinline__ void sw_ladder_raise(const SwArgs& a, int q, float ba
   if (best >= 0) atomicMax(a.thr + q, f32_to_ord(ladder_value(base, step, best)));
 }
 
+// The KP-th best ordered score among n <= 512 keys (0 = empty slot), by ONE warp: every lane pulls its 16 keys into
+// registers with independent loads (one L2 round trip), then an MSB-first radix select of 4 passes x 8 bits runs on the
+// registers (hist: 256 words of shared memory private to the warp).  0: fewer than KP keys.
+__device__ __noinline__ uint32_t sw_kth_best(const uint64_t* src, uint32_t n, int KP, uint32_t* hist) {
+  const int lane = threadIdx.x & 31;
+  uint32_t sc[SW_RT_KEYS / 32];
+  uint32_t live = 0;
+#pragma unroll
+  for (int i = 0; i < SW_RT_KEYS / 32; ++i) {
+    const uint32_t idx = (uint32_t)lane + 32u * i;
+    sc[i] = idx < n ? (uint32_t)(__ldcg(src + idx) >> 32) : 0u;
+  }
+#pragma unroll
+  for (int i = 0; i < SW_RT_KEYS / 32; ++i) live += sc[i] != 0u;
+  live = __reduce_add_sync(0xffffffffu, live);
+  if (live < (uint32_t)KP) return 0u;
+  uint32_t prefix = 0, need = (uint32_t)KP;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hist[lane + 32 * i] = 0u;
+    __syncwarp();
+    const uint32_t hi_mask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+#pragma unroll
+    for (int i = 0; i < SW_RT_KEYS / 32; ++i)
+      if (sc[i] != 0u && (sc[i] & hi_mask) == prefix) atomicAdd(&hist[(sc[i] >> shift) & 255u], 1u);
+    __syncwarp();
+    // lane l owns buckets 255 - 8l .. 248 - 8l (descending): where does the running count reach `need`?
+    uint32_t c[8], tot = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { c[j] = hist[255 - 8 * lane - j]; tot += c[j]; }
+    uint32_t incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const uint32_t before = incl - tot;
+    const bool mine = before < need && incl >= need;
+    uint32_t bucket = 0, rest = 0;
+    if (mine) {
+      uint32_t run = before;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (run < need && run + c[j] >= need) { bucket = 255u - 8u * lane - j; rest = need - run; }
+        run += c[j];
+      }
+    }
+    const int owner = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;     // exactly one lane (live >= need)
+    bucket = __shfl_sync(0xffffffffu, bucket, owner);
+    need = __shfl_sync(0xffffffffu, rest, owner);
+    prefix |= bucket << shift;
+    __syncwarp();
+  }
+  return prefix;
+}
+
 // the u-th tile of worker `w` (of `nw`): sample pass -> sample tile w; main pass -> w, w + nw, ... skipping sample tiles
 __device__ __forceinline__ bool sw_is_sample(const SwArgs& a, int tile) {
   return a.ns > 0 && tile % a.stride == 0 && tile / a.stride < a.ns;
@@ -116,7 +174,8 @@ search_sw_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   float4* lad_s = reinterpret_cast<float4*>(thr_s + 4 * SW_NQ);                    // [32] ladder (base, step, 1 / step) per query
   uint64_t* pend_k = reinterpret_cast<uint64_t*>(lad_s + SW_NQ);                   // [4 warps][SW_PEND] parked survivors: key
   int* pend_q = reinterpret_cast<int*>(pend_k + 4 * SW_PEND);                      //                                  ... query
-  uint64_t* bars = reinterpret_cast<uint64_t*>(pend_q + 4 * SW_PEND);
+  uint32_t* rt_hist = reinterpret_cast<uint32_t*>(pend_q + 4 * SW_PEND);           // [4 warps][256] radix histogram (re-tighten)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rt_hist + 4 * 256);
   uint64_t* full_bar = bars;                       // [stages]  TMA -> MMA
   uint64_t* empty_bar = bars + SW_MAX_STAGES;      // [stages]  MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * SW_MAX_STAGES;  // [SW_ACC]  MMA -> epilogue
@@ -261,7 +320,7 @@ search_sw_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     int npend = 0, tiles_done = 0;
     const int flush_mask = a.kblocks <= 4 ? 7 : 0;
     auto flush = [&]() {
-      uint32_t touched = 0;
+      uint32_t touched = 0, crowded = 0;
       for (int base = 0; base < npend; base += 32) {
         const int i = base + lane;
         if (i < npend) {
@@ -269,6 +328,7 @@ search_sw_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           const int j = pq[i];
           const uint32_t pos = atomicAdd(a.app_cnt + j, 1u);
           if (pos < (uint32_t)a.app_cap) a.app_keys[(size_t)j * a.app_cap + pos] = key;
+          if ((pos + 1) % SW_RETIGHTEN == 0 && pos < (uint32_t)a.app_cap) crowded |= 1u << j;
           const float4 ld = lad_s[j];
           const int lvl = ladder_level(ld.x, ld.y, ld.z, key_score(key));
           if (lvl >= 0) atomicAdd(a.ladder + (size_t)j * (2 * kLadder) + kLadder + lvl, 1u);
@@ -276,8 +336,25 @@ search_sw_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
       }
       touched = __reduce_or_sync(0xffffffffu, touched);
+      crowded = __reduce_or_sync(0xffffffffu, crowded);
       __syncwarp();
       if ((touched >> lane) & 1u) sw_ladder_raise(a, lane, lbase, lstep);
+      // A list that keeps filling although its threshold sits on the ladder's top level -- a dense cluster of rows
+      // around the query that the sample could not foresee -- would overflow (4096 entries: the query is flagged and the
+      // retry pass answers it, a second scan of the shard).  The warp whose row made the list reach a multiple of 1024
+      // re-makes the threshold from the list itself: the KP-th best of its most recent 512 rows -- KP appended rows at or
+      // above it exist, so it is valid (slots other CTAs have reserved but not written yet read as 0 = empty -- the
+      // prep kernel zeroes the lists of these plans -- which only lowers the result).  At most three times per query per
+      // search, a few microseconds of one warp each.
+#pragma unroll 1
+      while (crowded) {
+        const int j = __ffs(crowded) - 1;
+        crowded &= crowded - 1;
+        const uint32_t cnt = min(__ldcg(a.app_cnt + j), (uint32_t)a.app_cap);
+        const uint32_t first = cnt > SW_RT_KEYS ? cnt - SW_RT_KEYS : 0u;
+        const uint32_t t = sw_kth_best(a.app_keys + (size_t)j * a.app_cap + first, cnt - first, a.KP, rt_hist + warp * 256);
+        if (t && lane == 0) atomicMax(a.thr + j, t);
+      }
       npend = 0;
       __syncwarp();
     };
@@ -395,7 +472,7 @@ __global__ void __launch_bounds__(128) sw_tighten_kernel(const uint64_t* cand, i
 
 size_t sw_smem_bytes(int kblocks, int stages) {
   return 1024 + (((size_t)kblocks * SW_Q_BYTES + 1023) & ~(size_t)1023) + (size_t)stages * SW_A_BYTES + 4 * SW_NQ * 4 +
-         SW_NQ * 16 + 4 * SW_PEND * 12 + (2 * SW_MAX_STAGES + 2 * SW_ACC + 1) * 8 + 16;
+         SW_NQ * 16 + 4 * SW_PEND * 12 + 4 * 256 * 4 + (2 * SW_MAX_STAGES + 2 * SW_ACC + 1) * 8 + 16;
 }
 
 template <bool FP8, bool SAMPLE>

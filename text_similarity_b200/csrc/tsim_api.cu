@@ -371,7 +371,10 @@ static int search_impl(const void* q, int q_dt, int64_t q_stride, const void* co
     const int qrows = p.swapped ? 32 : p.pair ? 256 : 128;
     const size_t rowb = (size_t)Dt * dtype_size(t_dt);
     const bool pad = Q % qrows != 0 || p.qrep > 1;
-    rc = launch_search_prep(thr, align_up(zero_end - p.off_thr, 256), tq, (size_t)tq_stride * dtype_size(t_dt),
+    // (small-batch plans: the append lists, which sit right below thr, are zeroed as well -- search_sw.cu re-makes a
+    // crowded query's threshold from its list and must not read a previous call's keys)
+    const size_t zero_begin = p.swapped ? p.off_app_keys : p.off_thr;
+    rc = launch_search_prep(w + zero_begin, align_up(zero_end - zero_begin, 256), tq, (size_t)tq_stride * dtype_size(t_dt),
                             pad ? w + p.off_qpad : nullptr, rowb, Q, (int64_t)p.QB * qrows, p.qrep > 1 ? 128 / p.qrep : 0, st);
     if (rc) return rc;
     if (pad) { qt = w + p.off_qpad; qt_stride = Dt; }
