@@ -102,6 +102,7 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.first = 0        # samples [first, ...) belong to the timed region (mark())
 
     def start(self):
         try:
@@ -112,6 +113,10 @@ class ClockSampler:
             self.thread.start()
         except Exception:
             self.proc = None
+
+    def mark(self):
+        """Samples from here on are the timed region's (the process was started earlier, see main())."""
+        self.first = len(self.lines)
 
     def _pump(self):
         for line in self.proc.stdout:
@@ -128,7 +133,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[self.first:]:
             parts = [x.strip() for x in ln.split(",")]
             if len(parts) < 7:
                 continue
@@ -642,12 +647,17 @@ def main():
     ev_k1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     for ev in ev_k0 + ev_k1:
         ev.record()  # torch creates the CUDA event lazily: materialise the handles up front
-    for i in range(warmup):
-        corpus.search(dev_batches[i % nbatch], k)
-    ctx.barrier()
+    # the clock sampler (one looping nvidia-smi process) starts BEFORE the warm-up steps: its start-up -- process spawn,
+    # NVML initialisation -- was seen to stall the stream for tens of milliseconds when it fell into the timed region
+    # (a run with kernel time 43.3 ms per step reported 46.5 ms per step); it keeps sampling through the timed steps
     sampler = ClockSampler(ctx.local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.3)
+    for i in range(warmup):
+        corpus.search(dev_batches[i % nbatch], k)
+    ctx.barrier()
+    sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = lib.tsim_launch_count()
     last = None
