@@ -454,19 +454,20 @@ search_sw_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   }
 }
 
-// Between the sample pass and the main pass, one block of 128 threads per query: the KP-th best of the query's
+// Between the sample pass and the main pass, one block of 512 threads per query (six sample keys a thread): the KP-th best of the query's
 // 192 x 16 sample keys becomes its threshold; a ladder of 16 levels is laid out above it with a step taken from the
 // sample's tail slope (epi_tighten, tail_step): the main pass appends rows instead of keeping lists, so the ladder is
 // the ONLY thing that raises a threshold and it has to reach the corpus's own KP-th best -- with search_tc.cu's steps of
 // an eighth of (sample best - threshold) one query in ten ran out of ladder and overflowed its append list.  The
 // sample keys at or above the threshold move to the append list, so that select_rescore reads one short list per query.
-__global__ void __launch_bounds__(128) sw_tighten_kernel(const uint64_t* cand, int64_t NC, int KP, uint32_t* thr,
+constexpr int SW_TT = 512, SW_TK = 6;   // sw_tighten: threads per query, sample keys per thread
+__global__ void __launch_bounds__(SW_TT) sw_tighten_kernel(const uint64_t* cand, int64_t NC, int KP, uint32_t* thr,
                                                          uint32_t* ladder, uint64_t* app_keys, uint32_t* app_cnt, int app_cap) {
   __shared__ uint32_t hist[544];
   pdl_trigger();
   pdl_wait();
   const int64_t q = blockIdx.x;
-  epi_tighten(cand + (size_t)q * NC * 16, (uint32_t)(NC * 16), KP, thr + q, ladder + (size_t)q * (2 * kLadder), hist,
+  epi_tighten<SW_TT, SW_TK>(cand + (size_t)q * NC * 16, (uint32_t)(NC * 16), KP, thr + q, ladder + (size_t)q * (2 * kLadder), hist,
               (int)threadIdx.x, 0.25f, app_keys + (size_t)q * app_cap, app_cnt + q, app_cap, /*tail_step=*/true);
 }
 
@@ -506,8 +507,8 @@ int search_sw_stages(int kblocks) {
 
 int launch_sw_tighten(int64_t Q, const SearchPlan& p, const uint64_t* cand, uint32_t* thr, uint32_t* ladder,
                       uint64_t* app_keys, uint32_t* app_cnt, cudaStream_t st) {
-  static_assert(8 * 24 * 16 <= 128 * kEpiKeys, "sample keys per query exceed what epi_tighten holds in registers");
-  TSIM_CUDA(launch_pdl(sw_tighten_kernel, dim3((unsigned)Q), dim3(128), 0, st, cand, p.NC, p.KP, thr, ladder, app_keys,
+  static_assert(8 * 24 * 16 <= SW_TT * SW_TK, "sample keys per query exceed what epi_tighten holds in registers");
+  TSIM_CUDA(launch_pdl(sw_tighten_kernel, dim3((unsigned)Q), dim3(SW_TT), 0, st, cand, p.NC, p.KP, thr, ladder, app_keys,
                        app_cnt, p.app_cap));
   count_launch();
   return TSIM_OK;

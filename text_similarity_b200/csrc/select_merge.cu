@@ -71,15 +71,39 @@ constexpr int kSelOut = 512;
 __device__ int keep_top_scores(uint64_t* keys, int n, int keep, uint64_t* out, uint32_t* hist, int* sh) {
   if (n <= keep) return n;
   const int tid = threadIdx.x;
-  uint32_t prefix = 0;   // score bits decided so far (upper bits)
-  int need = keep;
-  for (int shift = 24; shift >= 0; shift -= 8) {
-    for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
-    __syncthreads();
-    const uint32_t hi_mask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+  // The scores of one list share their upper bits (cosines of a narrow band), and a first pass that drops every key into
+  // one bucket serialises on that bucket's shared-memory atomic.  Select over (score - worst) instead, starting at the top
+  // bit of the span: the first pass then spreads over 128+ buckets and passes whose bits are all equal are never run.
+  if (tid == 0) { hist[0] = 0u; hist[1] = 0xffffffffu; }
+  __syncthreads();
+  {
+    uint32_t mx = 0u, mn = 0xffffffffu;
     for (int i = tid; i < n; i += blockDim.x) {
       const uint32_t sc = (uint32_t)(keys[i] >> 32);
-      if ((sc & hi_mask) == prefix) atomicAdd(&hist[(sc >> shift) & 255u], 1u);
+      mx = max(mx, sc); mn = min(mn, sc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    if ((tid & 31) == 0) { atomicMax(&hist[0], mx); atomicMin(&hist[1], mn); }
+  }
+  __syncthreads();
+  const uint32_t worst = hist[1];
+  int hi = 32 - __clz(hist[0] - worst);   // bits >= hi of (score - worst) are zero in every key
+  __syncthreads();
+  uint32_t prefix = 0;   // bits of (k-th best - worst) decided so far (upper bits)
+  int need = keep;
+  while (hi > 0) {
+    const int shift = hi > 8 ? hi - 8 : 0;
+    const uint32_t bmask = (1u << (hi - shift)) - 1u;
+    const uint32_t pre_hi = hi < 32 ? prefix >> hi : 0u;
+    for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {
+      const uint32_t rel = (uint32_t)(keys[i] >> 32) - worst;
+      if ((hi < 32 ? rel >> hi : 0u) == pre_hi) atomicAdd(&hist[(rel >> shift) & bmask], 1u);
     }
     __syncthreads();
     if (tid < 32) {
@@ -106,8 +130,10 @@ __device__ int keep_top_scores(uint64_t* keys, int n, int keep, uint64_t* out, u
     __syncthreads();
     prefix |= (uint32_t)sh[0] << shift;
     need = sh[1];
+    hi = shift;
     __syncthreads();
   }
+  prefix += worst;
   // prefix = the keep-th best score; everything at or above it survives
   if (tid == 0) sh[2] = 0;
   __syncthreads();

@@ -176,64 +176,81 @@ __device__ __forceinline__ float select32(const float* sc, int j) {
 // keys into registers with independent loads -- one L2 round trip -- and the four passes then run on registers.
 // (A single warp walking 74 keys per lane with a load -> shared-atomic dependency per key took ~45 us, during
 // which every CTA of the launch sat at the grid barrier with HBM idle.)  n <= 128 * kEpiKeys keys; hist: 288 words (544 with tail_step).
+// NT threads x NK keys each: 128 x 24 inside the fused pass; the stand-alone kernel of search_sw.cu runs 512 x 6 (the
+// same 3072 keys: at 24 keys a thread the ~3100 instructions per warp of this latency chain took 17 us, one warp per
+// scheduler).
 constexpr int kEpiKeys = 24;
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+template <int NT>
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 // ladder_frac: ladder step as a fraction of (sample best - KP-th best): 1/8 puts the sample's best at level 8.
 // app_keys / app_cnt (optional): also copy every sample key at or above the new threshold to the query's append list
 // (the sample lists then need not be read again by select_rescore).
+template <int NT = 128, int NK = kEpiKeys>
 __device__ __noinline__ void epi_tighten(const uint64_t* src, uint32_t n, int KP, uint32_t* thr_q, uint32_t* lad,
                                          uint32_t* hist, int et, float ladder_frac = 0.125f,
                                          uint64_t* app_keys = nullptr, uint32_t* app_cnt = nullptr, int app_cap = 0,
                                          bool tail_step = false) {
-  uint32_t sc[kEpiKeys];
+  uint32_t sc[NK];
 #pragma unroll
-  for (int i = 0; i < kEpiKeys; ++i) {
-    const uint32_t idx = (uint32_t)et + 128u * i;
+  for (int i = 0; i < NK; ++i) {
+    const uint32_t idx = (uint32_t)et + (uint32_t)NT * i;
     sc[i] = idx < n ? (uint32_t)(__ldcg(src + idx) >> 32) : 0u;
   }
-  uint32_t* ctl = hist + 256;      // [0] live keys, [1] best score, [2] bucket, [3] need
-  if (et < 32) ctl[et] = 0u;
-  epi_bar();
-  uint32_t live = 0, best = 0;
+  uint32_t* ctl = hist + 256;      // [0] live keys, [1] best score, [2] bucket, [3] need, [4] [5] same for want2, [6] worst
+  if (et < 32) ctl[et] = et == 6 ? 0xffffffffu : 0u;
+  epi_bar<NT>();
+  uint32_t live = 0, best = 0, worst = 0xffffffffu;
 #pragma unroll
-  for (int i = 0; i < kEpiKeys; ++i) { live += sc[i] != 0u; best = max(best, sc[i]); }
+  for (int i = 0; i < NK; ++i) {
+    live += sc[i] != 0u; best = max(best, sc[i]);
+    if (sc[i] != 0u) worst = min(worst, sc[i]);
+  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { live += __shfl_xor_sync(0xffffffffu, live, o); best = max(best, __shfl_xor_sync(0xffffffffu, best, o)); }
-  if ((et & 31) == 0) { atomicAdd(&ctl[0], live); atomicMax(&ctl[1], best); }
-  epi_bar();
-  live = ctl[0]; best = ctl[1];
+  for (int o = 16; o > 0; o >>= 1) {
+    live += __shfl_xor_sync(0xffffffffu, live, o);
+    best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    worst = min(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+  }
+  if ((et & 31) == 0) { atomicAdd(&ctl[0], live); atomicMax(&ctl[1], best); atomicMin(&ctl[6], worst); }
+  epi_bar<NT>();
+  live = ctl[0]; best = ctl[1]; worst = ctl[6];
   if (live < (uint32_t)KP) {       // not enough rows for a threshold: a ladder that never fires
     if (lad && et < kLadder) { lad[kLadder + et] = 0u; lad[et] = et == 0 ? __float_as_uint(INFINITY) : 0u; }
     if (app_keys) {                // no threshold: every live sample key stays a candidate
 #pragma unroll
-      for (int i = 0; i < kEpiKeys; ++i)
+      for (int i = 0; i < NK; ++i)
         if (sc[i] != 0u) {
           const uint32_t pos = atomicAdd(app_cnt, 1u);
-          if (pos < (uint32_t)app_cap) app_keys[pos] = __ldcg(src + (uint32_t)et + 128u * i);
+          if (pos < (uint32_t)app_cap) app_keys[pos] = __ldcg(src + (uint32_t)et + (uint32_t)NT * i);
         }
     }
-    epi_bar();
+    epi_bar<NT>();
     return;
   }
-  // MSB-first radix select over the registers: the `want`-th best ordered score -- and, in the same four passes (second
-  // histogram at hist + 288, scanned by the second warp), the `want2`-th best when want2 != 0
+  // MSB-first radix select over the registers: the `want`-th best ordered score -- and, in the same passes (second
+  // histogram at hist + 288, scanned by the second warp), the `want2`-th best when want2 != 0.  The select runs over
+  // (score - worst) from the top bit of the span down: a sample's scores share their upper bits, and a pass that drops
+  // every key into one bucket serialises on that bucket's shared-memory atomic.
   uint32_t prefix = 0, lower = 0;
   {
     const uint32_t want2 = (tail_step && live >= 4u * (uint32_t)KP) ? 4u * (uint32_t)KP : 0u;
     uint32_t* hist2 = hist + 288;
     uint32_t need = (uint32_t)KP, need2 = want2;
-    for (int shift = 24; shift >= 0; shift -= 8) {
-      hist[et] = 0u; hist[et + 128] = 0u;
-      if (want2) { hist2[et] = 0u; hist2[et + 128] = 0u; }
-      epi_bar();
-      const uint32_t hi_mask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+    int hi = 32 - __clz(best - worst);   // bits >= hi of (score - worst) are zero in every live key
+    while (hi > 0) {
+      const int shift = hi > 8 ? hi - 8 : 0;
+      const uint32_t bmask = (1u << (hi - shift)) - 1u;
+      const uint32_t pre_hi = hi < 32 ? prefix >> hi : 0u, low_hi = hi < 32 ? lower >> hi : 0u;
+      for (int i = et; i < 256; i += NT) { hist[i] = 0u; if (want2) hist2[i] = 0u; }
+      epi_bar<NT>();
 #pragma unroll
-      for (int i = 0; i < kEpiKeys; ++i)
+      for (int i = 0; i < NK; ++i)
         if (sc[i] != 0u) {
-          if ((sc[i] & hi_mask) == prefix) atomicAdd(&hist[(sc[i] >> shift) & 255u], 1u);
-          if (want2 && (sc[i] & hi_mask) == lower) atomicAdd(&hist2[(sc[i] >> shift) & 255u], 1u);
+          const uint32_t rel = sc[i] - worst, top = hi < 32 ? rel >> hi : 0u;
+          if (top == pre_hi) atomicAdd(&hist[(rel >> shift) & bmask], 1u);
+          if (want2 && top == low_hi) atomicAdd(&hist2[(rel >> shift) & bmask], 1u);
         }
-      epi_bar();
+      epi_bar<NT>();
       if (et < 32 || (want2 && et < 64)) {
         // lane l owns buckets 255 - 8l .. 248 - 8l (descending): where does the running count reach `need`?
         const uint32_t* h = et < 32 ? hist : hist2;
@@ -258,12 +275,15 @@ __device__ __noinline__ void epi_tighten(const uint64_t* src, uint32_t n, int KP
           }
         }
       }
-      epi_bar();
+      epi_bar<NT>();
       prefix |= ctl[2] << shift;
       need = ctl[3];
       if (want2) { lower |= ctl[4] << shift; need2 = ctl[5]; }
-      epi_bar();
+      hi = shift;
+      epi_bar<NT>();
     }
+    prefix += worst;
+    lower += worst;
     if (!want2) lower = 0;
   }
   // tail_step (append plans of search_sw.cu): the ladder step comes from the sample's own tail slope -- the gap between
@@ -278,14 +298,14 @@ __device__ __noinline__ void epi_tighten(const uint64_t* src, uint32_t n, int KP
     if (!(step > 0.f) || !(step < INFINITY)) step = 0.f;
     const float inv = step > 0.f ? 1.f / step : 0.f;
     if (et < kLadder) hist[et] = 0u;
-    epi_bar();
+    epi_bar<NT>();
 #pragma unroll
-    for (int i = 0; i < kEpiKeys; ++i)
+    for (int i = 0; i < NK; ++i)
       if (sc[i] >= prefix) {             // (prefix > 0: empty slots never pass)
         const int j = ladder_level(base, step, inv, ord_to_f32(sc[i]));
         if (j >= 0) atomicAdd(&hist[j], 1u);
       }
-    epi_bar();
+    epi_bar<NT>();
     if (et < kLadder) {
       lad[kLadder + et] = hist[et];
       lad[et] = et == 0 ? __float_as_uint(base) : et == 1 ? __float_as_uint(step) : et == 2 ? __float_as_uint(inv) : 0u;
@@ -293,13 +313,13 @@ __device__ __noinline__ void epi_tighten(const uint64_t* src, uint32_t n, int KP
   }
   if (app_keys) {
 #pragma unroll
-    for (int i = 0; i < kEpiKeys; ++i)
+    for (int i = 0; i < NK; ++i)
       if (sc[i] >= prefix) {
         const uint32_t pos = atomicAdd(app_cnt, 1u);
-        if (pos < (uint32_t)app_cap) app_keys[pos] = __ldcg(src + (uint32_t)et + 128u * i);
+        if (pos < (uint32_t)app_cap) app_keys[pos] = __ldcg(src + (uint32_t)et + (uint32_t)NT * i);
       }
   }
-  epi_bar();
+  epi_bar<NT>();
 }
 
 }  // namespace
