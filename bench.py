@@ -633,7 +633,7 @@ def main():
         q32 = torch.randn(1024, 768, generator=g32, device=dev)
         corp32 = ShardedCorpus(c32, split_shadow=True)
         r32 = regime_search(ctx, "fp32_1Mx768_q1024_top100_split_shadow", corp32, q32, 100, 1_000_000, 4, reps=10, verify=32,
-                            extra={"note": "tensor pass is 3 D wide (qh.ch + qh.cl + ql.ch): 3x the nominal flops counted here"})
+                            extra={"note": "tensor pass is three segments long (qh.ch + ql.ch + qh.cl): 3x the nominal flops counted here"})
         ms_scan, _ = ctx.timed(lambda: corp32.search(q32, 100, mode="exact"), 2, warm=1)
         r32["float64_scan_ms"] = ms_scan
         regimes.append(r32)

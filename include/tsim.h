@@ -167,12 +167,15 @@ typedef struct tsim_plan tsim_plan_t;
 tsim_plan_t* tsim_plan_create(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt, int mode,
                               int shadow_dt);
 /* Plan for fp32 / fp16 rows with a SPLIT bf16 shadow (k <= 100): every element x is carried as hi = bf16(x) and
- * lo = bf16(x - hi); corpus_shadow rows are [hi | lo | hi] and q_shadow rows [hi | hi | lo], both 3 D wide, so that one
- * bf16 tensor pass computes qh.ch + qh.cl + ql.ch = q.c to ~1e-5 of ||q|| ||c|| -- tight enough for the ordinary
- * candidate-list proof at k = 100, where the rounded shadow of tsim_search_topk_shadow (error 6e-3) stops at k = 24.
+ * lo = bf16(x - hi).  With Dp = D rounded up to a multiple of 64 (zero padded): corpus_shadow rows are [hi | lo], 2 Dp
+ * wide; q_shadow rows are 3 Dp wide and hold, for every 64-element block j, the triple (hi_j, lo_j, hi_j).  One bf16
+ * tensor pass of 3 Dp / 64 k-blocks multiplies query block 3 j + r with corpus block hi_j (r < 2) or lo_j (r == 2):
+ * qh.ch + ql.ch + qh.cl = q.c to ~1e-5 of ||q|| ||c|| -- tight enough for the ordinary candidate-list proof at
+ * k = 100, where the rounded shadow of tsim_search_topk_shadow (error 6e-3) stops at k = 24.  The corpus shadow costs
+ * as many bytes as fp32 rows do (the second read of hi_j is an L2 hit).
  * corpus_inv_norm must be 1 / ||row|| of the ORIGINAL rows (tsim_row_inv_norm on them; null: computed per call).
  * Results are defined on, and re-scored in float64 from, the original rows (reference lines replaced: the same,
- * src/pipeline/search_pipeline.py:73-79).  D % 8 == 0. */
+ * src/pipeline/search_pipeline.py:73-79). */
 tsim_plan_t* tsim_plan_create_split_shadow(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt);
 void tsim_plan_destroy(tsim_plan_t* plan);
 size_t tsim_plan_workspace_bytes(const tsim_plan_t* plan);

@@ -111,6 +111,13 @@ def test_sentence_mining_pipeline_tensors(stack):
     ev50, ei50 = O.search_exact(queries, corpus, 50)
     assert torch.equal(i50.cpu(), ei50)
     np.testing.assert_allclose(s50.cpu().numpy(), ev50.numpy(), atol=1e-5)
+    # fp32 rows whose width is no multiple of 8 (no rounded shadow): the split shadow pads its segments, any k <= 100
+    odd = torch.randn(6000, 100, generator=g)
+    qo = torch.randn(9, 100, generator=g)
+    so, io = pipe.search_tensors(qo.cuda(), 10, corpus=odd.cuda())
+    evo, eio = O.search_exact(qo, odd, 10)
+    assert torch.equal(io.cpu(), eio)
+    np.testing.assert_allclose(so.cpu().numpy(), evo.numpy(), atol=1e-5)
     # bf16 tensors: tcgen05 path, k larger than the corpus is clamped (reference clamps by #queries, A6)
     cb = corpus[:9].to(torch.bfloat16)
     s, i = pipe.search_tensors(queries.to(torch.bfloat16).cuda(), 100, corpus=cb.cuda())

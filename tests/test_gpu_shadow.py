@@ -95,7 +95,7 @@ def test_fp32_corpora_take_the_shadow_path_in_the_sharded_and_pipeline_apis(ops)
 # ---------------------------------------------------------------------------- split (hi + lo) shadow: k up to 100
 def _split_same_as_exact(ops, q, c, k, max_flag_frac=0.05, **kw):
     shadow, sinv = ops.make_shadow(c, split=True)
-    assert shadow.shape == (c.shape[0], 3 * c.shape[1]) and shadow.dtype == torch.bfloat16
+    assert shadow.shape == (c.shape[0], 2 * ((c.shape[1] + 63) // 64 * 64)) and shadow.dtype == torch.bfloat16
     a = ops.search_topk(q, c, k, corpus_shadow=shadow, shadow_inv_norm=sinv, return_score64=True, return_flags=True, **kw)
     b = ops.search_topk(q, c, k, mode="exact", return_score64=True, **kw)
     torch.cuda.synchronize()
@@ -107,7 +107,8 @@ def _split_same_as_exact(ops, q, c, k, max_flag_frac=0.05, **kw):
 
 @pytest.mark.parametrize("N,Q,D,k,dtype", [(300_000, 200, 768, 100, torch.float32), (120_000, 1100, 384, 50, torch.float32),
                                             (500_000, 40, 256, 100, torch.float32), (150_000, 64, 256, 30, torch.float16),
-                                            (2_000, 5, 64, 100, torch.float32), (200_000, 300, 768, 10, torch.float32)])
+                                            (2_000, 5, 64, 100, torch.float32), (200_000, 300, 768, 10, torch.float32),
+                                            (60_000, 33, 100, 20, torch.float32), (40_000, 150, 203, 100, torch.float32)])
 def test_split_shadow_matches_exact_scan(ops, N, Q, D, k, dtype):
     c = _rows(N, D, 61).to(dtype)
     c[N // 2:N // 2 + 30] = c[10:40]                 # exact duplicates
@@ -150,7 +151,7 @@ def test_split_shadow_error_bound(ops):
         ch, cl = ops._split_bf16(c)
         qh, ql = ops._split_bf16(q)
         cs, qs = torch.cat([ch, cl, ch], 1).contiguous(), torch.cat([qh, qh, ql], 1).contiguous()
-        approx = (qs.double() @ cs.double().T)                 # what an error-free 3 D-wide bf16 pass would compute
+        approx = (qs.double() @ cs.double().T)                 # what an error-free three-segment bf16 pass would compute
         exact = q.double() @ c.double().T
         scale = q.double().norm(dim=1)[:, None] * c.double().norm(dim=1)[None, :]
         err = ((approx - exact).abs() / scale).max().item()

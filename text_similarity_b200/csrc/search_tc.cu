@@ -55,6 +55,7 @@ struct TcArgs {
   const float* c_inv;   // [N] inverse norms of the stored corpus rows
   int64_t Q, N;
   int kblocks;          // ceil(D * element size / 128)
+  int ksplit;           // split shadow: corpus k-block of pass k-block 3 j + r is j (r < 2) or ksplit + j (r == 2); 0: kb
   int QB;               // query blocks (128 queries; 256 when CTA pairs are used)
   int T;                // corpus tiles (of 256 rows) THIS launch scans (see tile_mode); all tile arithmetic is 32-bit
   int tile_mode;        // 0: tiles 0..T-1; 1: the tiles i * tile_stride; 2: every tile that is not a multiple of
@@ -505,7 +506,12 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       for (int it = 0; get_unit(a, it, wid, nw, rank == 0, un); ++it) {
         for (int t = 0; t < un.ntiles; ++t) {
           const int row0 = actual_tile(a, un.mode, un.tile0 + t * un.tstride) * BN;
+          int cj = 0, cr = 0;
           for (int kb = 0; kb < a.kblocks; ++kb) {
+            // corpus k-block: a split shadow's rows are [hi | lo] and the pass walks (hi_j, hi_j, lo_j) against the
+            // query shadow's (hi_j, lo_j, hi_j) -- the second read of hi_j comes from L2
+            const int ckb = a.ksplit ? (cr < 2 ? cj : a.ksplit + cj) : kb;
+            if (++cr == 3) { cr = 0; ++cj; }
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
             const uint32_t sa = smem_u32(tiles + (size_t)stage * STAGE_BYTES);
             if (PAIR) {
@@ -513,12 +519,12 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
               const uint32_t fb = map_to_cta(smem_u32(&full_bar[stage]), 0);
               if (rank == 0) mbar_arrive_expect_tx(smem_u32(&full_bar[stage]), 2 * ((dbg & 1) ? B_BYTES : STAGE_BYTES));
               if (!(dbg & 1)) tma_load_2d_pair(sa, &tmap_q, fb, kb * BK, un.qb * (2 * BM) + (int)rank * BM);
-              tma_load_2d_pair(sa + A_BYTES, &tmap_c, fb, kb * BK, row0 + (int)rank * (BN / 2));
+              tma_load_2d_pair(sa + A_BYTES, &tmap_c, fb, ckb * BK, row0 + (int)rank * (BN / 2));
             } else {
               const uint32_t fb = smem_u32(&full_bar[stage]);
               mbar_arrive_expect_tx(fb, (dbg & 1) ? B_BYTES : STAGE_BYTES);
               if (!(dbg & 1)) tma_load_2d(sa, &tmap_q, fb, kb * BK, un.qb * BM);
-              tma_load_2d(sa + A_BYTES, &tmap_c, fb, kb * BK, row0);
+              tma_load_2d(sa + A_BYTES, &tmap_c, fb, ckb * BK, row0);
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -870,11 +876,12 @@ int launch_search_tc(const void* q, int64_t q_stride, const void* corpus, int64_
   const int esz = dt == TSIM_E4M3 ? 1 : 2;
   int rc = get_tensor_map(maps, &mq, q, (int64_t)p.QB * qrows, D, q_stride, BM, esz);
   if (rc) return rc;
-  rc = get_tensor_map(maps, &mc, corpus, N, D, c_stride, p.pair ? BN / 2 : BN, esz);
+  rc = get_tensor_map(maps, &mc, corpus, N, p.ksplit ? 2 * (int64_t)p.ksplit * 64 : D, c_stride, p.pair ? BN / 2 : BN, esz);
   if (rc) return rc;
   TcArgs a;
   a.c_inv = c_inv; a.Q = Q; a.N = N;
   a.kblocks = (int)((D * esz + BK_BYTES - 1) / BK_BYTES);
+  a.ksplit = p.ksplit;
   const int64_t T = (N + BN - 1) / BN;
   a.QB = p.QB; a.sticky = p.sticky; a.Gq = p.Gq; a.tpc = (int)(p.R / BN);
   a.NC = p.NC;

@@ -60,8 +60,9 @@ static bool tensor_shape_ok(int64_t Q, int64_t N, int64_t D, int k, int q_dt, in
 int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt, int mode,
                      bool need_invnorm, int shadow_kind, SearchPlan* p) {
   const bool shadow = shadow_kind == 1;      // the rounded shadow: wide margin, widest lists, k <= 24
-  const bool split = shadow_kind == 2;       // the split shadow: D here is 3 x the rows' width, ordinary lists
+  const bool split = shadow_kind == 2;       // the split shadow: D here is 3 x the segment width, ordinary lists
   memset(p, 0, sizeof(*p));
+  p->ksplit = split ? (int)(D / 3 / 64) : 0;
   __atomic_add_fetch(&g_plans, 1ull, __ATOMIC_RELAXED);
   const int sms = device_sm_count();
   // a shadow pass needs the widest lists: the candidates must reach 2 * kShadowEps below the k-th best
@@ -329,7 +330,8 @@ static int search_impl(const void* q, int q_dt, int64_t q_stride, const void* co
   TSIM_CHECK_ARG(q_stride >= D && c_stride >= D, "search: row stride smaller than D");
   cudaStream_t st = (cudaStream_t)stream;
   SearchPlan p;
-  const int64_t Dt = shadow == 2 ? 3 * D : D;      // width of what the tensor pass reads (a split shadow is 3 D wide)
+  // width of what the tensor pass reads: a split shadow's pass is three segments long (the query shadow's width)
+  const int64_t Dt = shadow == 2 ? 3 * split_shadow_seg(D) : D;
   if (prepared) p = *prepared;     // a plan handle (tsim_plan_create): no planning, cached TMA descriptors
   else rc = make_search_plan(Q, N, Dt, k, shadow ? t_dt : q_dt, shadow ? t_dt : c_dt, mode, true, shadow, &p);
   if (rc) return rc;
@@ -563,7 +565,7 @@ static tsim_plan_t* plan_create(int64_t Q, int64_t N, int64_t D, int k, int q_dt
   if (!h) { set_error("plan: out of host memory"); return nullptr; }
   h->Q = Q; h->N = N; h->D = D; h->k = k; h->q_dt = q_dt; h->c_dt = c_dt;
   h->mode = shadow ? TSIM_MODE_AUTO : mode; h->shadow_dt = shadow ? shadow_dt : -1; h->shadow_kind = shadow_kind;
-  if (make_search_plan(Q, N, shadow_kind == 2 ? 3 * D : D, k, shadow ? shadow_dt : q_dt, shadow ? shadow_dt : c_dt, h->mode, true,
+  if (make_search_plan(Q, N, shadow_kind == 2 ? 3 * split_shadow_seg(D) : D, k, shadow ? shadow_dt : q_dt, shadow ? shadow_dt : c_dt, h->mode, true,
                        shadow_kind, &h->p) != TSIM_OK) {
     delete h;
     return nullptr;
@@ -578,7 +580,6 @@ extern "C" tsim_plan_t* tsim_plan_create(int64_t Q, int64_t N, int64_t D, int k,
 }
 
 extern "C" tsim_plan_t* tsim_plan_create_split_shadow(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt) {
-  if (D % 8 != 0) { set_error("plan: a split shadow needs D %% 8 == 0 (got %lld)", (long long)D); return nullptr; }
   return plan_create(Q, N, D, k, q_dt, c_dt, TSIM_MODE_AUTO, TSIM_BF16, 2);
 }
 
@@ -599,8 +600,9 @@ extern "C" int tsim_plan_search(tsim_plan_t* h, const void* q, int64_t q_stride,
   const bool shadow = h->shadow_dt >= 0;
   if (shadow) {
     TSIM_CHECK_ARG(q_shadow && (h->N == 0 || corpus_shadow), "plan_search: this plan needs the bf16 shadows");
-    const int64_t sw = h->shadow_kind == 2 ? 3 * h->D : h->D;
-    TSIM_CHECK_ARG(qs_stride >= sw && cs_stride >= sw, "plan_search: shadow row stride smaller than the shadow's width");
+    const int64_t seg = h->shadow_kind == 2 ? split_shadow_seg(h->D) : h->D;
+    TSIM_CHECK_ARG(qs_stride >= (h->shadow_kind == 2 ? 3 : 1) * seg && cs_stride >= (h->shadow_kind == 2 ? 2 : 1) * seg,
+                   "plan_search: shadow row stride smaller than the shadow's width");
     return search_impl(q, h->q_dt, q_stride, corpus, h->c_dt, c_stride, q_shadow, qs_stride, corpus_shadow, cs_stride,
                        h->shadow_dt, h->shadow_kind, corpus_inv_norm, h->Q, h->N, h->D, h->k, idx_base, exclude_self_base,
                        TSIM_MODE_AUTO, out_score, out_score64, out_idx, out_flags, ws, ws_bytes, stream, &h->p, h->maps);

@@ -44,6 +44,8 @@ __host__ __device__ inline float shadow_eps(int64_t D) { return kShadowEps + (ap
 // missing from q.c is ql.cl + (qh + ql).rc + rq.c: each at most 2^-18 ||q|| ||c|| (3.8e-6); together 1.15e-5,
 // rounded up to 1.5e-5, plus the tensor-core term of a 3 D-wide bf16 dot product.
 __host__ __device__ inline float split_shadow_eps(int64_t D) { return approx_eps(3 * D, 2) + 1.5e-5f; }
+// segment width of a split shadow: D rounded up to whole 64-element (128-byte) k-blocks, zero padded
+__host__ __device__ inline int64_t split_shadow_seg(int64_t D) { return (D + 63) / 64 * 64; }
 
 // Threshold ladder (search_tc.cu / select_merge.cu): per query, kLadder ascending score levels
 // level(i) = base + i * step and the number of candidate rows seen so far in [level(i), level(i+1));
@@ -511,6 +513,9 @@ struct SearchPlan {
   // on the N side.  Tiles of 128 rows; sample tiles i * sw_stride (i < sw_ns) are scanned first into 16-entry lists
   // (cand[q][8 * sw_ns][16]), tighten_kernel makes thresholds + ladders, the main pass appends (app_keys / app_cnt).
   int swapped, sw_ns, sw_stride;
+  // split shadow (make_search_plan shadow_kind 2): 64-element k-blocks per segment of the corpus shadow's [hi | lo] rows;
+  // k-block 3 j + r of the pass reads corpus block j (r < 2: hi) or ksplit + j (r == 2: lo).  0: plain rows
+  int ksplit;
   int fused;           // sticky + bootstrap: one cooperative launch does sample, thresholds and main (TC_PASS_FUSED)
   size_t off_gbar;     // its two grid-barrier counters (256 bytes, zeroed with thr)
   int append;

@@ -188,21 +188,45 @@ def _split_bf16(rows: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     return hi, lo
 
 
+def _split_seg(D: int) -> int:
+    """Segment width of a split shadow: D rounded up to whole 64-element k-blocks (tsim.h, split_shadow_seg)."""
+    return (D + 63) // 64 * 64
+
+
+def _split_query_shadow(queries: torch.Tensor) -> torch.Tensor:
+    """[Q, 3 Dp] query shadow of a split pass: per 64-element block j the triple (hi_j, lo_j, hi_j), which the kernel
+    multiplies with the corpus shadow's (hi_j, hi_j, lo_j)."""
+    Q, D = queries.shape
+    Dp = _split_seg(D)
+    qh, ql = _split_bf16(queries)
+    if Dp != D:
+        qh = torch.nn.functional.pad(qh, (0, Dp - D))
+        ql = torch.nn.functional.pad(ql, (0, Dp - D))
+    qh, ql = qh.view(Q, Dp // 64, 64), ql.view(Q, Dp // 64, 64)
+    return torch.stack([qh, ql, qh], dim=2).reshape(Q, 3 * Dp).contiguous()
+
+
 def make_shadow(rows: torch.Tensor, split: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
     """bf16 shadow of fp32 / fp16 rows plus the inverse norms that go with it: what ``search_topk`` needs
     (``corpus_shadow=``, ``shadow_inv_norm=``) to search such rows at tensor-core speed, still exactly.
 
     Default: the rows rounded to bf16, [N, D] (+50 % memory on fp32 rows) -- good for k <= 24 (the proof has to span
     the 6e-3 the rounding can move a cosine, so 112 candidates are re-scored per query).
-    ``split=True``: [N, 3 D] rows [hi | lo | hi] (+150 %): one 3 D-wide bf16 pass computes qh.ch + qh.cl + ql.ch, q.c to
-    ~1e-5 -- the ordinary candidate lists then prove k up to 100 (1M x 768 fp32, Q = 1024, k = 100: ~5 ms instead of the
-    70 ms float64 scan)."""
+    ``split=True``: [N, 2 Dp] rows [hi | lo], Dp = D rounded up to 64 (+100 % on fp32 rows): one bf16 pass of three
+    segments computes qh.ch + ql.ch + qh.cl, q.c to ~1e-5 -- the ordinary candidate lists then prove k up to 100
+    (1M x 768 fp32, Q = 1024, k = 100: ~4 ms instead of the 70 ms float64 scan)."""
     _require_cuda(rows)
     if not split:
         shadow = rows.to(torch.bfloat16).contiguous()
         return shadow, row_inv_norm(shadow)
-    hi, lo = _split_bf16(rows)
-    return torch.cat([hi, lo, hi], dim=1).contiguous(), row_inv_norm(rows.contiguous())
+    N, D = rows.shape
+    Dp = _split_seg(D)
+    shadow = (torch.zeros if Dp != D else torch.empty)((N, 2 * Dp), dtype=torch.bfloat16, device=rows.device)
+    for s in range(0, N, 1 << 20):          # in slabs: the fp32 temporaries of a 10M-row shard would not fit beside it
+        hi, lo = _split_bf16(rows[s:s + (1 << 20)])
+        shadow[s:s + (1 << 20), :D] = hi
+        shadow[s:s + (1 << 20), Dp:Dp + D] = lo
+    return shadow, row_inv_norm(rows.contiguous())
 
 
 def search_topk(queries: torch.Tensor, corpus: torch.Tensor, k: int, *,
@@ -255,13 +279,12 @@ def search_topk(queries: torch.Tensor, corpus: torch.Tensor, k: int, *,
     if shadow:
         # fp32 / fp16 rows: candidates from the bf16 shadows on the tensor cores, float64 re-score on the originals
         _require_cuda(corpus_shadow, shadow_inv_norm)
-        split = corpus_shadow.dim() == 2 and corpus_shadow.shape == (N, 3 * D)
+        split = corpus_shadow.dim() == 2 and corpus_shadow.shape == (N, 2 * _split_seg(D))
         if ((corpus_shadow.shape != corpus.shape and not split) or corpus_shadow.dtype != torch.bfloat16
                 or corpus_shadow.stride(1) != 1):
-            raise ValueError("corpus_shadow must be a bfloat16 [N, D] (rounded) or [N, 3 D] (split) tensor with contiguous rows")
+            raise ValueError("corpus_shadow must be a bfloat16 [N, D] (rounded) or [N, 2 * ceil64(D)] (split) tensor with contiguous rows")
         if split:
-            qh, ql = _split_bf16(queries)
-            q_shadow = torch.cat([qh, qh, ql], dim=1).contiguous()
+            q_shadow = _split_query_shadow(queries)
         else:
             q_shadow = queries.to(torch.bfloat16).contiguous()
     plan = _plan(dev, Q, N, D, k, _dt(queries), _dt(corpus), _lib.MODE_AUTO if shadow else _MODES[mode],

@@ -57,15 +57,18 @@ class _EncodedCorpus:
         self.rows, self.inv_norm = rows, inv_norm
         # fp32 / fp16 tensors: bf16 shadow for the tensor-core candidate pass (results stay exact on `rows`)
         self.shadow_kw = {}
-        if rows.dtype in (torch.float32, torch.float16) and rows.shape[0] and rows.shape[1] % 8 == 0:
+        self._can_shadow = bool(rows.dtype in (torch.float32, torch.float16) and rows.shape[0])
+        if self._can_shadow and rows.shape[1] % 8 == 0:
             shadow, shadow_inv = ops.make_shadow(rows)
             self.shadow_kw = {"corpus_shadow": shadow, "shadow_inv_norm": shadow_inv}
         self._split_kw = None
 
     def shadow_for(self, k: int) -> dict:
         """Shadow arguments of ``ops.search_topk`` for a top-k call: the rounded shadow up to k = 24; for 24 < k <= 100
-        the split (hi + lo) shadow, 3 D wide, made on first use (without it those calls take the float64 scan)."""
-        if not self.shadow_kw or k <= 24 or k > 100:
+        the split (hi + lo) shadow, made on first use (without it those calls take the float64 scan).  Rows whose width
+        is no multiple of 8 have no rounded shadow (TMA rows are 16-byte aligned); the split shadow pads its segments
+        and serves them at every k <= 100."""
+        if not self._can_shadow or k > 100 or (self.shadow_kw and k <= 24):
             return self.shadow_kw
         if self._split_kw is None:
             shadow, inv = ops.make_shadow(self.rows, split=True)

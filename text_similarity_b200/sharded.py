@@ -72,11 +72,10 @@ class ShardedCorpus:
         if (bf16_shadow and shard.is_cuda and shard.shape[0] and shard.dtype in (torch.float32, torch.float16)
                 and shard.shape[1] % 8 == 0):
             self.shadow, self.shadow_inv = ops.make_shadow(shard)
-        # ... and a split (hi + lo) shadow, 3 D wide (+150 % / +300 %), carries 24 < k <= 100 on the tensor cores as
+        # ... and a split (hi + lo) shadow (+100 % / +200 %) carries 24 < k <= 100 on the tensor cores as
         # well (opt-in: without it those calls take the float64 scan)
         self.split = self.split_inv = None
-        if (split_shadow and shard.is_cuda and shard.shape[0] and shard.dtype in (torch.float32, torch.float16)
-                and shard.shape[1] % 8 == 0):
+        if split_shadow and shard.is_cuda and shard.shape[0] and shard.dtype in (torch.float32, torch.float16):
             self.split, self.split_inv = ops.make_shadow(shard, split=True)
         self._gather_buf = {}
         self._graphs = {}
