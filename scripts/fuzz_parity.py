@@ -2,7 +2,7 @@
 k, data distribution, view, shard offset, self exclusion) must give exactly what the float64 exact scan of the same
 library gives -- same indices, same float64 score bits (tests/test_gpu_parity.py pins that scan to the CPU oracle).
 
-    python scripts/fuzz_parity.py --seconds 240 --seed 1 [--max-rows 2500000]
+    python scripts/fuzz_parity.py --seconds 240 --seed 1 [--max-rows 2500000] [--big]
 
 Prints one line per failing case (with everything needed to replay it: --only CASE) and a summary; exit status 1 on
 any mismatch.  Data distributions: Gaussian, unit rows, tight clusters (near-duplicates closer than bf16 resolution),
@@ -23,7 +23,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--seconds", type=float, default=240.0)
 ap.add_argument("--seed", type=int, default=1)
 ap.add_argument("--max-rows", type=int, default=2_500_000)
+ap.add_argument("--big", action="store_true", help="shards of >= 290K rows and batches up to 4096 queries only "
+                "(round-robin plans, sample passes, append lists: the headline's code path)")
 ap.add_argument("--only", type=int, default=-1, help="replay one case number of this seed")
+ap.add_argument("--cases", default="", help="replay a comma list of case numbers of this seed")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 
@@ -35,13 +38,15 @@ def make(case: int):
     dtype = [torch.bfloat16, torch.float8_e4m3fn, torch.float32, torch.float16][int(rng.integers(0, 4))]
     step = 16 if dtype == torch.float8_e4m3fn else 8
     D = int(rng.choice([1, 2, 3, 5, 8, 16, 17, 24, 32, 33, 48, 64, 96, 97, 128])) * step
-    size_class = int(rng.integers(0, 4))
+    size_class = int(rng.integers(2, 4)) if a.big else int(rng.integers(0, 4))
     hi = [2_000, 60_000, 420_000, a.max_rows][size_class]
     lo = [1, 2_000, 290_000, 420_000][size_class]
     # keep the corpus under ~2 GB of elements
     hi = max(lo + 1, min(hi, int(2.0e9 / (D * 4))))
     N = int(rng.integers(lo, hi))
     Q = int(rng.choice([1, 2, 7, 8, 9, 31, 32, 33, 64, 100, 127, 128, 129, 200, 240, 256, 257, 511, 600, 1024, 1500]))
+    if a.big:
+        Q = int(rng.choice([129, 600, 1200, 1700, 2500, 4096, 5000]))
     if N * Q * D > 6e12:
         Q = max(1, int(6e12 / (N * D)))
     k = int(rng.choice([1, 2, 5, 10, 16, 24, 25, 40, 64, 100, 101, 128]))
@@ -127,7 +132,8 @@ def run(case: int):
 
 t0 = time.time()
 n_cases = fails = 0
-case = 0 if a.only < 0 else a.only
+replay = [int(x) for x in a.cases.split(",") if x] or ([a.only] if a.only >= 0 else [])
+case = replay[0] if replay else 0
 while True:
     try:
         bad_i, bad_s, bad_f, desc = run(case)
@@ -142,10 +148,15 @@ while True:
     if bad_i or bad_s or bad_f:
         fails += 1
         print(f"MISMATCH idx={bad_i} s64={bad_s} s32={bad_f} {desc}", flush=True)
-    elif a.only >= 0 or n_cases % 20 == 0:
+    elif replay or n_cases % 20 == 0:
         print(f"ok {desc}", flush=True)
+    if replay:
+        if n_cases == len(replay):
+            break
+        case = replay[n_cases]
+        continue
     case += 1
-    if a.only >= 0 or time.time() - t0 > a.seconds:
+    if time.time() - t0 > a.seconds:
         break
 print(f"fuzz: {n_cases} cases, {fails} failing, seed {a.seed}, {time.time() - t0:.0f} s")
 sys.exit(1 if fails else 0)

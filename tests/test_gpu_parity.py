@@ -268,6 +268,44 @@ def test_heavy_duplicates_fall_back_and_stay_exact(ops):
     assert torch.equal(i, i2) and torch.equal(s, s2)
 
 
+def _clusters(N, Q, D, noise, seed):
+    """Near-duplicate clusters: 16 centres, rows = centre + noise * N(0, 1) (closer than bf16 can tell apart for small
+    noise), queries near the centres -- hundreds of rows within 2 eps of every query's k-th best."""
+    g = torch.Generator().manual_seed(seed)
+    cent = torch.randn(16, D, generator=g)
+    c = cent[torch.randint(0, 16, (N,), generator=g)] + noise * torch.randn(N, D, generator=g)
+    q = cent[torch.randint(0, 16, (Q,), generator=g)] + 0.05 * torch.randn(Q, D, generator=g)
+    return q, c
+
+
+@pytest.mark.parametrize("noise", [1e-1, 1e-2, 1e-3])
+@pytest.mark.parametrize("N,Q,D,k,dtype", [(17_080, 31, 64, 100, torch.bfloat16), (23_351, 31, 64, 64, torch.bfloat16),
+                                            (4_481, 7, 64, 1, torch.float16), (37_413, 7, 192, 2, torch.float32),
+                                            (8_086, 7, 16, 100, torch.float16), (300_000, 20, 64, 100, torch.bfloat16)])
+def test_clusters_on_a_shard_whose_lists_never_fill(ops, N, Q, D, k, dtype, noise):
+    """Found by scripts/fuzz_parity.py: with at most a tile per worker and 112-entry lists no list ever fills, no
+    threshold is ever set, and select_rescore receives EVERY row -- its own truncation to the best 112 approximate
+    scores owes the completeness proof just like a threshold does (it used to skip it when thr == 0 and returned
+    wrong rows, unflagged, on near-duplicate clusters).  fp32 / fp16 rows go through both shadows."""
+    q, c = _clusters(N, Q, D, noise, seed=N + k)
+    q, c = q.to(dtype).cuda(), c.to(dtype).cuda()
+    ref = ops.search_topk(q, c, k, mode="exact", return_score64=True)
+    variants = [{}]
+    if dtype != torch.bfloat16:
+        variants = []
+        for split in ([True] if k > 24 else [False, True]):
+            sh, sinv = ops.make_shadow(c, split=split)
+            variants.append(dict(corpus_shadow=sh, shadow_inv_norm=sinv))
+    for kw in variants:
+        got = ops.search_topk(q, c, k, mode="auto", return_score64=True, **kw)
+        torch.cuda.synchronize()
+        assert torch.equal(got[1], ref[1]), f"{(got[1] != ref[1]).sum().item()} index mismatches"
+        assert torch.equal(got[2], ref[2])
+    if N <= 40_000:
+        ev, ei = O.search_exact(q.cpu(), c.cpu(), k)
+        assert torch.equal(ref[1].cpu(), ei)
+
+
 def test_adversarial_ascending_corpus(ops):
     # rows sorted by increasing similarity to query 0: every row beats the running threshold
     g = torch.Generator().manual_seed(31)

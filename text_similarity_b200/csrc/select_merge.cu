@@ -359,6 +359,7 @@ __global__ void __launch_bounds__(kSelThreads, 4) select_rescore_kernel(SelArgs 
     if (app_overflow) app_n = (uint32_t)a.app_cap;
   }
   int n = 0;
+  bool truncated = false;   // (block-uniform) this kernel itself dropped keys: more than KP candidates reached it
   for (int part = 0; part < 2; ++part) {
     const uint64_t* src = part == 0 ? a.cand + (size_t)slot * a.NC * a.KP : a.app_keys + (size_t)slot * a.app_cap;
     const int64_t total = part == 0 ? a.NC * a.KP : (int64_t)app_n;
@@ -380,6 +381,7 @@ __global__ void __launch_bounds__(kSelThreads, 4) select_rescore_kernel(SelArgs 
       __syncthreads();
       n = n_sh;
       if ((cursor < total || part == 0) && n > kKeyCap / 2) {
+        truncated = true;             // (kKeyCap / 2 > KP: something goes)
         const int kept = keep_top_scores(keys, n, a.KP, sel_out, sel_hist, sel_sh);
         if (kept == n) {              // massive ties: sort and truncate
           int np = next_pow2(n);
@@ -398,6 +400,7 @@ __global__ void __launch_bounds__(kSelThreads, 4) select_rescore_kernel(SelArgs 
   {
     // only the best KP matter: radix-select them (ties at the cut included), then sort those few -- a bitonic
     // sort of every survivor was 3/4 of this kernel's instructions at Q = 1 (148 lists, 69 us; ncu)
+    truncated = truncated || n > a.KP;
     n = keep_top_scores(keys, n, a.KP, sel_out, sel_hist, sel_sh);
     int np = next_pow2(max(n, 1));
     for (int i = n + tid; i < np; i += blockDim.x) keys[i] = 0;
@@ -425,8 +428,12 @@ __global__ void __launch_bounds__(kSelThreads, 4) select_rescore_kernel(SelArgs 
   // it was either evicted from a full unit list or rejected by a threshold that was the minimum
   // of a full list.  With |approx - exact * ||q||| <= eps * ||q||, a gap a_k - a_KP > 2 eps ||q||
   // proves such a row (and any candidate ranked beyond KP) is below the exact k-th best.
+  // The proof is owed whenever ANY row was left out on its approximate score: by a threshold of the candidate passes
+  // (thr_ord != 0) or by the truncation to KP right here (`truncated`: lists that never filled -- a shard of a few
+  // tiles per worker, KP = 112 -- hand over every row, and near-duplicate clusters put hundreds of them within
+  // 2 eps of the k-th best; scripts/fuzz_parity.py found those answers wrong and unflagged).
   bool flagged = false;
-  if (thr_ord != 0) {
+  if (thr_ord != 0 || truncated) {
     int kk = min(a.k, m);
     float a_k = key_score(keys[kk - 1]);
     float a_kp = key_score(keys[m - 1]);
