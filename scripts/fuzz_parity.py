@@ -31,6 +31,7 @@ a = ap.parse_args()
 dev = torch.device("cuda", 0)
 
 DIST = ["gauss", "unit", "clusters", "dups", "few_distinct", "zeros", "range", "dense_cluster"]
+DIST2 = ["scale", "ints", "onehot"]      # added later, drawn from a second generator so that old case numbers replay
 
 
 def make(case: int):
@@ -51,6 +52,9 @@ def make(case: int):
         Q = max(1, int(6e12 / (N * D)))
     k = int(rng.choice([1, 2, 5, 10, 16, 24, 25, 40, 64, 100, 101, 128]))
     dist = DIST[int(rng.integers(0, len(DIST)))]
+    rng2 = np.random.default_rng([a.seed, case, 7])
+    if rng2.integers(0, 11) < len(DIST2):
+        dist = DIST2[int(rng2.integers(0, len(DIST2)))]
     g = torch.Generator(device=dev).manual_seed(int(rng.integers(0, 2 ** 31)))
     pitch = D + (step * int(rng.integers(0, 3)) if rng.integers(0, 3) == 0 else 0)
     base = torch.randn(N, pitch, generator=g, device=dev)
@@ -83,6 +87,19 @@ def make(case: int):
         n_c = int(min(N // 2, rng.choice([300, 6000, 50_000])))
         rows = torch.randperm(N, generator=g, device=dev)[:n_c]
         c[rows] = q[0] + torch.randn(n_c, D, generator=g, device=dev) * 0.02
+    elif dist == "scale" and dtype in (torch.bfloat16, torch.float32):
+        # rows 24 orders of magnitude apart (cosine is scale free; nothing under- or overflows in fp32)
+        c *= 10.0 ** (torch.rand(N, 1, generator=g, device=dev) * 24 - 12)
+        q *= 10.0 ** (torch.rand(Q, 1, generator=g, device=dev) * 24 - 12)
+    elif dist == "ints":
+        # small integers: distinct rows with exactly equal cosines (the tie rule decides), exact zeros
+        c.copy_(torch.randint(-2, 3, (N, D), generator=g, device=dev).float())
+        q.copy_(torch.randint(-2, 3, (Q, D), generator=g, device=dev).float())
+    elif dist == "onehot":
+        c.zero_()
+        c[torch.arange(N, device=dev), torch.randint(0, D, (N,), generator=g, device=dev)] = 1.0
+        if D > 1:
+            c[torch.arange(N, device=dev), torch.randint(0, D, (N,), generator=g, device=dev)] += 0.5
     if dtype == torch.float8_e4m3fn:
         c.clamp_(-30, 30); q.clamp_(-30, 30)
         c *= 8; q *= 8
