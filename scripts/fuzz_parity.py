@@ -26,6 +26,8 @@ ap.add_argument("--max-rows", type=int, default=2_500_000)
 ap.add_argument("--big", action="store_true", help="shards of >= 290K rows and batches up to 4096 queries only "
                 "(round-robin plans, sample passes, append lists: the headline's code path)")
 ap.add_argument("--only", type=int, default=-1, help="replay one case number of this seed")
+ap.add_argument("--explain", action="store_true", help="on a mismatch print, for a few queries, the rows either answer "
+                "holds with their float64 torch scores (exact for small-integer rows)")
 ap.add_argument("--cases", default="", help="replay a comma list of case numbers of this seed")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
@@ -139,6 +141,28 @@ def run(case: int):
     ref = ops.search_topk(q, c, k, mode="exact", return_score64=True, **kw)
     torch.cuda.synchronize()
     bad_i = int((got[1] != ref[1]).sum())
+    if a.explain and bad_i:
+        base = kw.get("idx_base", 0)
+        c64 = c.double()
+        cn = c64.pow(2).sum(-1).sqrt().clamp_min(1e-8)
+        for qi in (got[1] != ref[1]).any(1).nonzero().flatten()[:3].tolist():
+            q64 = q[qi].double()
+            sc = (c64 @ q64) / (q64.pow(2).sum().sqrt().clamp_min(1e-8) * cn)
+            if "exclude_self_base" in kw:
+                sc[kw["exclude_self_base"] - base + qi] = -float("inf")
+            order = torch.sort(sc, descending=True, stable=True)[1][:k]
+            g, r = (got[1][qi] - base).tolist(), (ref[1][qi] - base).tolist()
+            t = order.tolist()
+            print(f"  query {qi} flag={int(got[3][qi])}: tensor-path == torch {g == t}, scan == torch {r == t}")
+            for pos in range(k):
+                if g[pos] != r[pos] or g[pos] != t[pos]:
+                    print(f"    pos {pos}: tensor {g[pos]} ({float(sc[g[pos]]).hex()}, returned {float(got[2][qi][pos]).hex()})  "
+                          f"scan {r[pos]} ({float(sc[r[pos]]).hex()}, returned {float(ref[2][qi][pos]).hex()})  "
+                          f"torch {t[pos]} ({float(sc[t[pos]]).hex()})")
+            kth = float(sc[t[-1]])
+            tied = ((sc - kth).abs() <= 1e-12).nonzero().flatten().tolist()
+            print(f"    rows within 1e-12 of the k-th score: {len(tied)}: {tied[:12]}  "
+                  f"distinct bit patterns {len(set(float(sc[x]).hex() for x in tied))}")
     # (-inf == -inf; NaN never appears in the output)
     bad_s = int((got[2] != ref[2]).sum())
     bad_f = int((got[0] != ref[0]).sum())

@@ -31,7 +31,7 @@ struct ExArgs {
   int S; int64_t slice_rows;
   const int32_t* flag_cnt; const int32_t* flag_list;
   double* ex_score; uint32_t* ex_idx;
-  const double* rinv;   // [N] 1 / max(||row||, eps), tensor-core scan only
+  const double* rinv;   // [N] 1 / max(||row||, eps), then [N] max(||row||, eps) itself; tensor-core scan only
 };
 
 // insert (s, r) into a descending list ls/li of length *cnt (capacity k); whole warp calls
@@ -248,9 +248,19 @@ __global__ void __launch_bounds__(256) row_rinv_f64_kernel(const void* corpus, i
       sq = fma(v, v, sq);
     }
     sq = warp_sum_f64(sq);
-    if (lane == 0) rinv[row] = 1.0 / fmax(sqrt(sq), kCosEps);
+    if (lane == 0) { const double cn = fmax(sqrt(sq), kCosEps); rinv[row] = 1.0 / cn; rinv[N + row] = cn; }
   }
 }
+
+// The tensor-core scans scale a tile's dot products by RECIPROCAL norms (acc * (1 / ||q||) * (1 / ||c||): two
+// multiplies per score), the canonical routine (tsim_common.cuh) divides (dot / (||q|| ||c||)): one ulp apart now and
+// then.  For rows whose sums are exact in any order -- small integers, one-hot / count vectors: the rows where two
+// DISTINCT rows can have the same cosine, 3 / sqrt(18) = 1 / sqrt(2) -- that ulp was the only difference between a
+// scan's score and the canonical one, and it could drop the lower-index row of a tie at the k-th place before the
+// canonical re-score saw it (scripts/fuzz_parity.py, `ints`).  So the reciprocal form only FILTERS, with a margin far
+// above its rounding: what passes is inserted with the divided form, whose bits equal the canonical score whenever
+// the sums are exact (and differ from it only by summation-order noise on rows that cannot tie unless identical).
+constexpr double kScanBand = 1e-9;
 
 template <int MF, int MINB>
 __global__ void __launch_bounds__(kExThreads, MINB) search_exact_mma_kernel(ExArgs a) {
@@ -261,7 +271,8 @@ __global__ void __launch_bounds__(kExThreads, MINB) search_exact_mma_kernel(ExAr
   double* tile = qs + QG * kMStride;                    // [kMRows][kMStride]
   double* rinv = tile + kMRows * kMStride;              // [kMRows] 1 / row norm of the tile being finished
   double* qn_s = rinv + kMRows;                         // [QG] 1 / query norm
-  double* ls_all = qn_s + QG;                           // [QG][k]
+  double* qnc_s = qn_s + QG;                            // [QG] the query norm itself (scores that enter a list are divided)
+  double* ls_all = qnc_s + QG;                          // [QG][k]
   uint32_t* li_all = (uint32_t*)(ls_all + (size_t)QG * a.k);  // [QG][k]
   int* cnt_s = (int*)(li_all + (size_t)QG * a.k);       // [QG] list lengths (warp-private)
   int32_t* qid_s = cnt_s + QG;                          // [QG] query number of the slot (its row, self exclusion)
@@ -296,6 +307,7 @@ __global__ void __launch_bounds__(kExThreads, MINB) search_exact_mma_kernel(ExAr
       qq = warp_sum_f64(qq);
       if (lane == 0) {
         qn_s[warp * QW + j] = 1.0 / fmax(sqrt(qq), kCosEps);
+        qnc_s[warp * QW + j] = fmax(sqrt(qq), kCosEps);
         cnt_s[warp * QW + j] = 0;
         qid_s[warp * QW + j] = (int32_t)qid;
       }
@@ -361,7 +373,7 @@ __global__ void __launch_bounds__(kExThreads, MINB) search_exact_mma_kernel(ExAr
 #pragma unroll
           for (int ni = 0; ni < kMNF; ++ni) {
             const int cnt = cnt_s[ql];
-            const double thr = cnt < a.k ? -INFINITY : ls_all[(size_t)ql * a.k + a.k - 1];
+            const double thr = (cnt < a.k ? -INFINITY : ls_all[(size_t)ql * a.k + a.k - 1]) - kScanBand;   // a filter (kScanBand)
             const int col = ni * 8 + 2 * fk;
             const double2 ri = *reinterpret_cast<const double2*>(rinv + col);
             const double s0 = acc[mi][ni][0] * qn * ri.x, s1 = acc[mi][ni][1] * qn * ri.y;
@@ -374,10 +386,11 @@ __global__ void __launch_bounds__(kExThreads, MINB) search_exact_mma_kernel(ExAr
               const int src = __ffs(m0 | m1) - 1;
               const bool first = (m0 >> src) & 1u;
               if (first) m0 &= ~(1u << src); else m1 &= ~(1u << src);
-              const double s = __shfl_sync(0xffffffffu, first ? s0 : s1, src);
+              const double dsrc = __shfl_sync(0xffffffffu, first ? acc[mi][ni][0] : acc[mi][ni][1], src);
               const int qsrc = warp * QW + mi * 8 + (src >> 2);
-              warp_list_insert_call(ls_all + (size_t)qsrc * a.k, li_all + (size_t)qsrc * a.k, cnt_s + qsrc, a.k, s,
-                                    (uint32_t)(r0 + ni * 8 + 2 * (src & 3) + (first ? 0 : 1)));
+              const int64_t rsrc = r0 + ni * 8 + 2 * (src & 3) + (first ? 0 : 1);
+              const double s = dsrc / (qnc_s[qsrc] * a.rinv[a.N + rsrc]);      // the canonical routine's last step
+              warp_list_insert_call(ls_all + (size_t)qsrc * a.k, li_all + (size_t)qsrc * a.k, cnt_s + qsrc, a.k, s, (uint32_t)rsrc);
             }
           }
         }
@@ -438,7 +451,8 @@ __global__ void __launch_bounds__(kExThreads, 2) search_exact_mma_async_kernel(E
   unsigned char* ring = smem_raw;                                        // [kAStages][128 rows][ROWB]
   double* rinv = (double*)(ring + (size_t)kAStages * STAGE);          // [2][kMRows] 1 / row norm, by tile parity
   double* qn_s = rinv + 2 * kMRows;                                      // [QG] 1 / query norm
-  double* ls_all = qn_s + QG;                                            // [QG][k]
+  double* qnc_s = qn_s + QG;                                             // [QG] the query norm itself
+  double* ls_all = qnc_s + QG;                                           // [QG][k]
   uint32_t* li_all = (uint32_t*)(ls_all + (size_t)QG * a.k);             // [QG][k]
   int* cnt_s = (int*)(li_all + (size_t)QG * a.k);                        // [QG] list lengths (warp-private)
   int32_t* qid_s = cnt_s + QG;                                           // [QG] query number of the slot
@@ -473,6 +487,7 @@ __global__ void __launch_bounds__(kExThreads, 2) search_exact_mma_async_kernel(E
       qq = warp_sum_f64(qq);
       if (lane == 0) {
         qn_s[warp * QW + j] = 1.0 / fmax(sqrt(qq), kCosEps);
+        qnc_s[warp * QW + j] = fmax(sqrt(qq), kCosEps);
         cnt_s[warp * QW + j] = 0;
         qid_s[warp * QW + j] = (int32_t)qid;
       }
@@ -548,7 +563,7 @@ __global__ void __launch_bounds__(kExThreads, 2) search_exact_mma_async_kernel(E
 #pragma unroll
         for (int ni = 0; ni < kMNF; ++ni) {
           const int cnt = cnt_s[ql];
-          const double thr = cnt < a.k ? -INFINITY : ls_all[(size_t)ql * a.k + a.k - 1];
+          const double thr = (cnt < a.k ? -INFINITY : ls_all[(size_t)ql * a.k + a.k - 1]) - kScanBand;   // a filter (kScanBand)
           const int col = ni * 8 + 2 * fk;
           const double2 ri = *reinterpret_cast<const double2*>(ri_t + col);
           const double s0 = acc[mi][ni][0] * qn * ri.x, s1 = acc[mi][ni][1] * qn * ri.y;
@@ -560,10 +575,11 @@ __global__ void __launch_bounds__(kExThreads, 2) search_exact_mma_async_kernel(E
             const int src = __ffs(m0 | m1) - 1;
             const bool first = (m0 >> src) & 1u;
             if (first) m0 &= ~(1u << src); else m1 &= ~(1u << src);
-            const double s = __shfl_sync(0xffffffffu, first ? s0 : s1, src);
+            const double dsrc = __shfl_sync(0xffffffffu, first ? acc[mi][ni][0] : acc[mi][ni][1], src);
             const int qsrc = warp * QW + mi * 8 + (src >> 2);
-            warp_list_insert_call(ls_all + (size_t)qsrc * a.k, li_all + (size_t)qsrc * a.k, cnt_s + qsrc, a.k, s,
-                                  (uint32_t)(r0 + ni * 8 + 2 * (src & 3) + (first ? 0 : 1)));
+            const int64_t rsrc = r0 + ni * 8 + 2 * (src & 3) + (first ? 0 : 1);
+            const double s = dsrc / (qnc_s[qsrc] * a.rinv[a.N + rsrc]);        // the canonical routine's last step
+            warp_list_insert_call(ls_all + (size_t)qsrc * a.k, li_all + (size_t)qsrc * a.k, cnt_s + qsrc, a.k, s, (uint32_t)rsrc);
           }
         }
         }
@@ -594,12 +610,12 @@ size_t mma_async_smem_bytes(int k, int dt, int stages, int mf) {
   const int esz = dtype_size(dt);
   const size_t qg = 64 * (size_t)mf;
   const size_t stage = (kMRows + qg) * (kMDC * esz + 16);
-  return stages * stage + sizeof(double) * (2 * kMRows + qg + qg * k) + sizeof(uint32_t) * qg * k + 2 * sizeof(int) * qg;
+  return stages * stage + sizeof(double) * (2 * kMRows + 2 * qg + qg * k) + sizeof(uint32_t) * qg * k + 2 * sizeof(int) * qg;
 }
 
 size_t mma_smem_bytes(int k, int MF) {
   const size_t QG = 64 * (size_t)MF;
-  return sizeof(double) * ((QG + kMRows) * kMStride + kMRows + QG + QG * k) + sizeof(uint32_t) * QG * k + 2 * sizeof(int) * QG;
+  return sizeof(double) * ((QG + kMRows) * kMStride + kMRows + 2 * QG + QG * k) + sizeof(uint32_t) * QG * k + 2 * sizeof(int) * QG;
 }
 
 }  // namespace

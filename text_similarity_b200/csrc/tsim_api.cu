@@ -254,7 +254,7 @@ int make_search_plan(int64_t Q, int64_t N, int64_t D, int k, int q_dt, int c_dt,
   }
   if (Q > 32 && N > 0) {   // float64 scan on the FP64 tensor cores (whole call, or the flagged-query fallback): row norms once per call
     p->has_ex_rinv = 1;
-    p->off_ex_rinv = off; off = align_up(off + (size_t)N * sizeof(double), 256);
+    p->off_ex_rinv = off; off = align_up(off + 2 * (size_t)N * sizeof(double), 256);   // [N] 1 / norm, then [N] the norms
   }
   p->off_ex_score = off; off = align_up(off + (size_t)Q * p->S * k * sizeof(double), 256);
   p->off_ex_idx = off; off = align_up(off + (size_t)Q * p->S * k * sizeof(uint32_t), 256);
