@@ -306,6 +306,34 @@ def test_clusters_on_a_shard_whose_lists_never_fill(ops, N, Q, D, k, dtype, nois
         assert torch.equal(ref[1].cpu(), ei)
 
 
+@pytest.mark.parametrize("N,Q,D,k,dtype", [(53_425, 127, 16, 2, torch.float32), (45_468, 127, 24, 100, torch.float32),
+                                            (7_375, 300, 32, 25, torch.float8_e4m3fn), (331_133, 64, 16, 16, torch.float16),
+                                            (44_404, 257, 16, 40, torch.bfloat16), (20_000, 9, 8, 10, torch.bfloat16)])
+def test_distinct_rows_that_tie_in_exact_arithmetic(ops, N, Q, D, k, dtype):
+    """Small-integer rows: every sum is exact in any order, and DISTINCT rows share a cosine (3 / sqrt(18) =
+    1 / sqrt(2)), so the tie rule -- lower row first -- decides at the k-th place.  The oracle's float64 formula
+    dot / (||q|| ||c||) is then exact to the bit, and so must be every path of the library: found by
+    scripts/fuzz_parity.py, the tensor-core scans used to score with reciprocal norms (an ulp off now and then)
+    and dropped the lower row of such a tie."""
+    g = torch.Generator().manual_seed(N + k)
+    c = torch.randint(-2, 3, (N, D), generator=g).float()
+    q = torch.randint(-2, 3, (Q, D), generator=g).float()
+    ev, ei = O.search_exact(q, c, k)
+    qd, cd = q.to(dtype).cuda(), c.to(dtype).cuda()
+    runs = [dict(mode="exact")]
+    if dtype in (torch.bfloat16, torch.float8_e4m3fn):
+        runs.append(dict(mode="tensor"))
+    else:
+        for split in ([True] if k > 24 else [False, True]):
+            sh, sinv = ops.make_shadow(cd, split=split)
+            runs.append(dict(mode="auto", corpus_shadow=sh, shadow_inv_norm=sinv))
+    for kw in runs:
+        s, i, s64 = ops.search_topk(qd, cd, k, return_score64=True, **kw)
+        torch.cuda.synchronize()
+        assert torch.equal(i.cpu(), ei), f"{kw.get('mode')}: {(i.cpu() != ei).sum().item()} index mismatches"
+        assert torch.equal(s64.cpu(), ev), f"{kw.get('mode')}: float64 scores differ from the oracle's bits"
+
+
 def test_adversarial_ascending_corpus(ops):
     # rows sorted by increasing similarity to query 0: every row beats the running threshold
     g = torch.Generator().manual_seed(31)
