@@ -20,6 +20,7 @@ from text_similarity_b200 import ops  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--seconds", type=float, default=60.0)
 ap.add_argument("--seed", type=int, default=1)
+ap.add_argument("--max-cases", type=int, default=0, help="stop after this many cases (0: run out the clock)")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 
@@ -106,5 +107,7 @@ while time.time() - t0 < a.seconds:
     elif n_cases % 50 == 0:
         print(f"ok {desc}", flush=True)
     case += 1
+    if a.max_cases and n_cases >= a.max_cases:
+        break
 print(f"fuzz_merge: {n_cases} cases, {fails} failing, seed {a.seed}, {time.time() - t0:.0f} s")
 sys.exit(1 if fails else 0)

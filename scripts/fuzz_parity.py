@@ -22,6 +22,7 @@ from text_similarity_b200 import ops  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--seconds", type=float, default=240.0)
 ap.add_argument("--seed", type=int, default=1)
+ap.add_argument("--max-cases", type=int, default=0, help="stop after this many cases (0: run out the clock)")
 ap.add_argument("--max-rows", type=int, default=2_500_000)
 ap.add_argument("--big", action="store_true", help="shards of >= 290K rows and batches up to 4096 queries only "
                 "(round-robin plans, sample passes, append lists: the headline's code path)")
@@ -201,7 +202,7 @@ while True:
         case = replay[n_cases]
         continue
     case += 1
-    if time.time() - t0 > a.seconds:
+    if time.time() - t0 > a.seconds or (a.max_cases and n_cases >= a.max_cases):
         break
 print(f"fuzz: {n_cases} cases, {fails} failing, seed {a.seed}, {time.time() - t0:.0f} s")
 sys.exit(1 if fails else 0)
