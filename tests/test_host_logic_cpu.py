@@ -57,6 +57,22 @@ def test_product_package_does_not_import_the_oracle():
                         f"{dirpath}/{fn} imports the oracle"
 
 
+def test_scripts_compile_and_stay_off_the_oracle():
+    """scripts/ are measurement drivers and fuzzers, not tests: they compile, and none of them may use oracle/ (only
+    tests/, smoke() and bench.py's CPU legs may) -- the fuzzers check against the library's float64 scan and plain
+    torch formulas."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    n = 0
+    for fn in sorted(os.listdir(os.path.join(root, "scripts"))):
+        if fn.endswith(".py"):
+            path = os.path.join(root, "scripts", fn)
+            text = open(path).read()
+            compile(text, path, "exec")
+            assert "import oracle" not in text and "from oracle" not in text, f"scripts/{fn} imports the oracle"
+            n += 1
+    assert n >= 3
+
+
 def test_synthetic_tokenizer_follows_hf_call_shape():
     from text_similarity_b200.utils import SyntheticTokenizer, synthetic_sentences
     tok = SyntheticTokenizer()
