@@ -38,6 +38,32 @@ def test_version_and_workspace_planning(lib):
     assert lib.tsim_pool_workspace_bytes(16, 256, 384) > 0
 
 
+def test_planner_sweep_over_legal_shapes_never_wraps_or_crashes(lib):
+    """Host-side planning (no GPU needed: 148 SMs assumed) over random legal shapes up to the ABI's limits: the
+    workspace size is positive, holds at least the float64 fallback lists (Q * k * 12 bytes: catches 32-bit
+    wrap-around in the offset arithmetic); illegal shapes are errors with a message, never a crash."""
+    import numpy as np
+    from text_similarity_b200 import _lib
+    rng = np.random.default_rng(7)
+    dts = [_lib.BF16, _lib.E4M3, _lib.F32, _lib.F16]
+    for _ in range(3000):
+        Q = int(rng.choice([1, 2, 31, 32, 33, 128, 129, 4096, 100_000, 2 ** 31 - 1]))
+        N = int(rng.choice([0, 1, 255, 256, 257, 303_103, 303_104, 10_000_000, 100_000_000, 4_000_000_000]))
+        D = int(rng.choice([8, 16, 24, 64, 384, 768, 1000, 4096, 65_536]))
+        k = int(rng.choice([1, 10, 11, 24, 25, 52, 53, 100, 101, 1024]))
+        qd, cd = int(rng.choice(dts)), int(rng.choice(dts))
+        mode = int(rng.choice([_lib.MODE_AUTO, _lib.MODE_EXACT]))
+        nb = lib.tsim_search_workspace_bytes(Q, N, D, k, qd, cd, mode)
+        assert nb >= Q * k * 12, (Q, N, D, k, qd, cd, mode, nb, lib.tsim_last_error())
+        if D % 8 == 0 and N > 0:
+            for sdt in (_lib.BF16,):
+                ns = lib.tsim_search_shadow_workspace_bytes(Q, N, D, k, sdt)
+                assert ns >= Q * k * 12, (Q, N, D, k, ns, lib.tsim_last_error())
+    for bad in [(-1, 10, 8, 1), (1, -1, 8, 1), (1, 10, 0, 1), (1, 10, 8, 0), (1, 10, 8, 1025), (1, 2 ** 32, 8, 1), (2 ** 31, 10, 8, 1)]:
+        assert lib.tsim_search_workspace_bytes(*bad, _lib.BF16, _lib.BF16, _lib.MODE_AUTO) == 0
+        assert len(lib.tsim_last_error()) > 0
+
+
 def test_argument_errors_do_not_touch_the_gpu(lib):
     from text_similarity_b200 import _lib
     rc = lib.tsim_merge_topk(None, None, 4, 100, 100, 10, None, None, None, None)
